@@ -1,0 +1,554 @@
+// dfm_api.cu -- the C-ABI (include/dfm_b200.h): handle, workspace, H2D/D2H staging and the launch
+// sequences of every entry point.  Host code here only orchestrates; all arithmetic runs in the
+// kernels.  There is no CPU compute path: without a CUDA device dfm_create fails.
+#include "../../include/dfm_b200.h"
+#include "dfm_common.cuh"
+#include "dfm_kernels_np.cuh"
+#include "dfm_kernels_em.cuh"
+#include <algorithm>
+#include <new>
+#include <vector>
+#ifndef DFM_EMU
+#include <dlfcn.h>
+#endif
+
+#ifdef DFM_EMU
+// ---- minimal CUDA-runtime stand-ins for the host-emulation test build -------------------------
+typedef int cudaError_t;
+enum { cudaSuccess = 0 };
+enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+static inline cudaError_t cudaMalloc(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 2; }
+static inline cudaError_t cudaFree(void* p) { free(p); return 0; }
+static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return 0; }
+static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { memset(d, v, n); return 0; }
+static inline cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = nullptr; return 0; }
+static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+static inline cudaError_t cudaSetDevice(int) { return 0; }
+static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return 0; }
+static inline cudaError_t cudaGetLastError() { return 0; }
+static inline const char* cudaGetErrorString(cudaError_t) { return "emu"; }
+#define DFM_SET_SMEM(kern, bytes) ((void)0)
+#else
+#define DFM_SET_SMEM(kern, bytes) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))
+#endif
+
+using namespace dfm;
+
+struct dfm_handle {
+  int device;
+  cudaStream_t stream;
+  bool own_stream;
+  char* ws;
+  size_t ws_bytes;
+  long long launches;
+  char err[256];
+};
+
+namespace {
+
+const size_t kMaxSmem = 220 * 1024;
+
+struct Arena {
+  char* base; size_t off;
+  explicit Arena(char* b) : base(b), off(0) {}
+  template <typename Tp> Tp* get(size_t n) {
+    size_t bytes = (n * sizeof(Tp) + 255) & ~(size_t)255;
+    Tp* p = base ? reinterpret_cast<Tp*>(base + off) : nullptr;
+    off += bytes;
+    return p;
+  }
+};
+
+int fail(dfm_handle* h, int code, const char* msg) {
+  if (h) { snprintf(h->err, sizeof(h->err), "%s", msg); }
+  return code;
+}
+
+#define CK(call)                                                                                   \
+  do { cudaError_t e__ = (call); if (e__ != cudaSuccess) {                                         \
+    snprintf(h->err, sizeof(h->err), "%s:%d %s", __FILE__, __LINE__, cudaGetErrorString(e__));    \
+    return DFM_ERR_CUDA; } } while (0)
+
+#define L(kern, gx, gy, nt, smem, ...)                                                             \
+  do { DFM_LAUNCH(kern, gx, gy, nt, smem, h->stream, __VA_ARGS__); h->launches++; } while (0)
+
+int ensure_ws(dfm_handle* h, size_t bytes) {
+  if (bytes <= h->ws_bytes) return DFM_OK;
+  if (h->ws) { CK(cudaStreamSynchronize(h->stream)); CK(cudaFree(h->ws)); h->ws = nullptr; h->ws_bytes = 0; }
+  size_t want = bytes + (bytes >> 3) + (1 << 20);
+  void* p = nullptr;
+  CK(cudaMalloc(&p, want));
+  h->ws = (char*)p; h->ws_bytes = want;
+  return DFM_OK;
+}
+
+// input staging: returns device pointer for `src` (copying if it lives on the host)
+template <typename Tp>
+int stage_in(dfm_handle* h, const Tp* src, Tp* dev_buf, size_t n, int mem, const Tp** out) {
+  if (mem == DFM_MEM_DEVICE) { *out = src; return DFM_OK; }
+  CK(cudaMemcpyAsync(dev_buf, src, n * sizeof(Tp), cudaMemcpyHostToDevice, h->stream));
+  *out = dev_buf;
+  return DFM_OK;
+}
+template <typename Tp>
+int copy_out(dfm_handle* h, Tp* dst, const Tp* dev, size_t n, int mem) {
+  if (!dst || dst == dev) return DFM_OK;
+  CK(cudaMemcpyAsync(dst, dev, n * sizeof(Tp), mem == DFM_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+  return DFM_OK;
+}
+
+int finish(dfm_handle* h, int mem) {
+  CK(cudaGetLastError());
+  if (mem == DFM_MEM_HOST) CK(cudaStreamSynchronize(h->stream));
+  return DFM_OK;
+}
+
+// threads per block for the thread-per-period kernels: ws doubles of shared memory per thread
+int tpt_threads(int ws_doubles) {
+  int nt = (int)((96 * 1024) / ((size_t)ws_doubles * 8));
+  nt = (nt / 32) * 32;
+  return std::max(32, std::min(128, nt));
+}
+
+}  // namespace
+
+extern "C" {
+
+int dfm_version(void) { return DFM_VERSION; }
+
+const char* dfm_status_string(int s) {
+  switch (s) {
+    case DFM_OK: return "ok";
+    case DFM_ERR_ARG: return "bad argument";
+    case DFM_ERR_TOO_FEW_OBS: return "too few observations";
+    case DFM_ERR_NOT_PD: return "matrix not positive definite";
+    case DFM_ERR_NOT_CONVERGED: return "not converged (max_iter reached)";
+    case DFM_ERR_CUDA: return "CUDA error / no device";
+    case DFM_ERR_UNSUPPORTED: return "unsupported problem size";
+    case DFM_ERR_NCCL: return "NCCL error";
+  }
+  return "unknown";
+}
+
+int dfm_create_on_stream(int device, void* cuda_stream, dfm_handle** out) {
+  if (!out) return DFM_ERR_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return DFM_ERR_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return DFM_ERR_CUDA;
+  dfm_handle* h = new (std::nothrow) dfm_handle();
+  if (!h) return DFM_ERR_CUDA;
+  h->device = device; h->ws = nullptr; h->ws_bytes = 0; h->launches = 0; h->err[0] = 0;
+  if (cuda_stream) { h->stream = (cudaStream_t)cuda_stream; h->own_stream = false; }
+  else { if (cudaStreamCreate(&h->stream) != cudaSuccess) { delete h; return DFM_ERR_CUDA; } h->own_stream = true; }
+  DFM_SET_SMEM(k_em_filter_smooth, kMaxSmem); DFM_SET_SMEM(k_als_factor, kMaxSmem); DFM_SET_SMEM(k_em_contract, kMaxSmem);
+  DFM_SET_SMEM(k_lyapunov, kMaxSmem); DFM_SET_SMEM(k_var, kMaxSmem); DFM_SET_SMEM(k_pca_finish, kMaxSmem);
+  DFM_SET_SMEM(k_jacobi, kMaxSmem); DFM_SET_SMEM(k_loading, kMaxSmem); DFM_SET_SMEM(k_als_lambda, kMaxSmem);
+  if (cudaGetLastError() != cudaSuccess) { delete h; return DFM_ERR_CUDA; }
+  *out = h;
+  return DFM_OK;
+}
+int dfm_create(int device, dfm_handle** out) { return dfm_create_on_stream(device, nullptr, out); }
+
+int dfm_destroy(dfm_handle* h) {
+  if (!h) return DFM_ERR_ARG;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  if (h->ws) cudaFree(h->ws);
+  if (h->own_stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return DFM_OK;
+}
+int dfm_sync(dfm_handle* h) { if (!h) return DFM_ERR_ARG; CK(cudaStreamSynchronize(h->stream)); return DFM_OK; }
+long long dfm_launch_count(const dfm_handle* h) { return h ? h->launches : -1; }
+const char* dfm_last_error(const dfm_handle* h) { return h ? h->err : "null handle"; }
+
+int dfm_shard_range(long long n_rep, int rank, int world, long long* begin, long long* end) {
+  if (n_rep < 0 || world <= 0 || rank < 0 || rank >= world || !begin || !end) return DFM_ERR_ARG;
+  *begin = n_rep * rank / world; *end = n_rep * (rank + 1) / world;
+  return DFM_OK;
+}
+
+// ------------------------------------------------------------------------------------ a2
+int dfm_standardize(dfm_handle* h, const double* X, int T, int N, int batch, int mem, double* Xs, double* xmean,
+                    double* xstd) {
+  if (!h || !X || !Xs || T <= 0 || N <= 0 || batch <= 0) return fail(h, DFM_ERR_ARG, "dfm_standardize: bad argument");
+  CK(cudaSetDevice(h->device));
+  size_t B = batch, TN = (size_t)T * N;
+  for (int pass = 0; pass < 2; ++pass) {
+    Arena a(pass ? h->ws : nullptr);
+    double* dX = mem == DFM_MEM_HOST ? a.get<double>(B * TN) : nullptr;
+    double* dXs = mem == DFM_MEM_HOST ? a.get<double>(B * TN) : Xs;
+    double* dm = a.get<double>(B * N); double* ds = a.get<double>(B * N);
+    if (!pass) { int rc = ensure_ws(h, a.off); if (rc) return rc; continue; }
+    const double* x; int rc = stage_in(h, X, dX, B * TN, mem, &x); if (rc) return rc;
+    L(k_standardize, N, batch, 128, 48 * 8, x, T, N, dXs, dm, ds, (double*)nullptr, (int*)nullptr);
+    if (mem == DFM_MEM_HOST) { rc = copy_out(h, Xs, dXs, B * TN, mem); if (rc) return rc; }
+    rc = copy_out(h, xmean, dm, B * N, mem); if (rc) return rc;
+    rc = copy_out(h, xstd, ds, B * N, mem); if (rc) return rc;
+  }
+  return finish(h, mem);
+}
+
+// ------------------------------------------------------------------------------------ PCA helper
+// device-side PCA of the balanced columns of dXs into dF.  nmax = min(N,T) <= 256.
+static int run_pca(dfm_handle* h, const double* dXs, int T, int N, int r, int batch, const int* col_n /*null = all cols*/,
+                   int* bal_idx, int* nbal, double* G, double* V, double* dF, int* status, AlsState* st) {
+  int nmax = std::min(N, T);
+  if (col_n) L(k_balanced_cols, batch, 1, 1, 0, col_n, T, N, bal_idx, nbal);
+  else L(k_all_cols, batch, 1, 128, 0, N, bal_idx, nbal);
+  int gx = (int)std::min<long long>(((long long)nmax * nmax + 255) / 256, 4096);
+  L(k_gram, gx, batch, 256, 0, dXs, T, N, bal_idx, nbal, G, nmax);
+  L(k_jacobi, batch, 1, 256, (size_t)(nmax + 2 + 48) * 8, G, V, nbal, T, nmax, 60, (int*)nullptr);
+  L(k_pca_finish, batch, 1, 128, (size_t)(r / 2 + 2 + 48 + N) * 8, dXs, T, N, bal_idx, nbal, G, V, nmax, r, dF, status, st);
+  return DFM_OK;
+}
+
+int dfm_pca_score(dfm_handle* h, const double* X, int T, int N, int r, int batch, int mem, double* score) {
+  if (!h || !X || !score || T <= 0 || N <= 0 || r <= 0 || batch <= 0 || r > std::min(T, N)) return fail(h, DFM_ERR_ARG, "dfm_pca_score: bad argument");
+  if (std::min(N, T) > 256) return fail(h, DFM_ERR_UNSUPPORTED, "dfm_pca_score: min(T,N) > 256 not supported yet");
+  CK(cudaSetDevice(h->device));
+  size_t B = batch, TN = (size_t)T * N; int nmax = std::min(N, T);
+  for (int pass = 0; pass < 2; ++pass) {
+    Arena a(pass ? h->ws : nullptr);
+    double* dX = mem == DFM_MEM_HOST ? a.get<double>(B * TN) : nullptr;
+    double* dF = mem == DFM_MEM_HOST ? a.get<double>(B * T * r) : score;
+    int* bal = a.get<int>(B * N); int* nbal = a.get<int>(B); int* status = a.get<int>(B);
+    double* G = a.get<double>(B * nmax * nmax); double* V = a.get<double>(B * nmax * nmax);
+    if (!pass) { int rc = ensure_ws(h, a.off); if (rc) return rc; continue; }
+    const double* x; int rc = stage_in(h, X, dX, B * TN, mem, &x); if (rc) return rc;
+    CK(cudaMemsetAsync(status, 0, B * sizeof(int), h->stream));
+    rc = run_pca(h, x, T, N, r, batch, nullptr, bal, nbal, G, V, dF, status, nullptr); if (rc) return rc;
+    if (mem == DFM_MEM_HOST) { rc = copy_out(h, score, dF, B * T * r, mem); if (rc) return rc; }
+  }
+  return finish(h, mem);
+}
+
+// ------------------------------------------------------------------------------------ a7
+int dfm_estimate_factor(dfm_handle* h, const double* X, const dfm_factor_opts* o, const double* F_init, double* F,
+                        double* Lambda, double* R2, double* xmean, double* xstd, dfm_factor_stats* stats) {
+  if (!h || !X || !o) return fail(h, DFM_ERR_ARG, "dfm_estimate_factor: null argument");
+  int T = o->T, N = o->N, r = o->r, batch = o->batch, mem = o->mem;
+  if (T <= 1 || N <= 0 || r <= 0 || batch <= 0 || r > 64 || r > N || r > T || o->max_iter < 1 || o->n_constr < 0 ||
+      (o->n_constr > 0 && (!o->constr_index || !o->constr_R || !o->constr_r)) || o->n_constr > 64)
+    return fail(h, DFM_ERR_ARG, "dfm_estimate_factor: bad shape/options");
+  if (!F_init && std::min(N, T) > 256) return fail(h, DFM_ERR_UNSUPPORTED, "PCA init: min(T,N) > 256 not supported yet (pass F_init)");
+  CK(cudaSetDevice(h->device));
+  size_t B = batch, TN = (size_t)T * N; int nmax = std::min(N, T), np = r * (r + 1) / 2, nc = o->n_constr;
+  int ntF = tpt_threads(np + r);
+  int nblk = (T + ntF - 1) / ntF;
+  for (int pass = 0; pass < 2; ++pass) {
+    Arena a(pass ? h->ws : nullptr);
+    double* dX = mem == DFM_MEM_HOST ? a.get<double>(B * TN) : nullptr;
+    double* dXs = a.get<double>(B * TN);
+    double* dm = a.get<double>(B * N); double* ds = a.get<double>(B * N); double* css = a.get<double>(B * N);
+    int* cn = a.get<int>(B * N); AlsState* st = a.get<AlsState>(B);
+    int* bal = a.get<int>(B * N); int* nbal = a.get<int>(B); int* active = a.get<int>(4);
+    double* G = F_init ? nullptr : a.get<double>(B * nmax * nmax); double* V = F_init ? nullptr : a.get<double>(B * nmax * nmax);
+    double* dF = a.get<double>(B * T * r); double* dLam = a.get<double>(B * N * r); double* dR2 = a.get<double>(B * N);
+    double* FtF = a.get<double>(B * r * r); double* LtL = a.get<double>(B * r * r); double* ssrp = a.get<double>(B * nblk);
+    int* cidx = a.get<int>(nc + 1); double* cR = a.get<double>((size_t)nc * r + 1); double* cr = a.get<double>(nc + 1);
+    if (!pass) { int rc = ensure_ws(h, a.off); if (rc) return rc; continue; }
+    const double* x; int rc = stage_in(h, X, dX, B * TN, mem, &x); if (rc) return rc;
+    if (nc > 0) {
+      CK(cudaMemcpyAsync(cidx, o->constr_index, nc * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+      CK(cudaMemcpyAsync(cR, o->constr_R, (size_t)nc * r * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      CK(cudaMemcpyAsync(cr, o->constr_r, nc * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    }
+    L(k_standardize, N, batch, 128, 48 * 8, x, T, N, dXs, dm, ds, css, cn);            // :339
+    L(k_als_init_state, batch, 1, 128, 48 * 8, st, css, cn, N);                        // :342-343
+    if (F_init) { const double* fi; rc = stage_in(h, F_init, dF, B * T * r, mem, &fi); if (rc) return rc;
+                  if (fi != dF) CK(cudaMemcpyAsync(dF, fi, B * T * r * sizeof(double), cudaMemcpyDeviceToDevice, h->stream)); }
+    else { rc = run_pca(h, dXs, T, N, r, batch, cn, bal, nbal, G, V, dF, nullptr, st); if (rc) return rc; }   // :345-348
+    size_t smL = (size_t)(2 * np + 2 * r + 8 + (size_t)r * nc + (size_t)nc * (nc + 1) / 2 + nc) * 8;
+    size_t smF = ((size_t)(np + r) * ntF + 48) * 8;
+    long long it = 0;
+    int h_active = batch;
+    while (it < o->max_iter && h_active > 0) {                                       // :352
+      if (nc > 0) L(k_gram_small, batch, 1, 128, 0, dF, T, r, FtF, st);
+      L(k_als_lambda, N, batch, 64, smL, dXs, dF, T, N, r, o->nt_min, 0, dLam, (double*)nullptr, FtF, nc, cidx, cR, cr, ds, st);   // :355-362
+      L(k_gram_small, batch, 1, 128, 0, dLam, N, r, LtL, st);
+      L(k_als_factor, nblk, batch, ntF, smF, dXs, dLam, LtL, T, N, r, dF, ssrp, st);                                             // :364-366
+      L(k_als_check, batch, 1, 1, 0, st, ssrp, nblk, o->tol, T, N, o->max_iter);                                                // :367-368
+      ++it;
+      if ((it & 1) == 0 || it >= o->max_iter || it < 2) {
+        L(k_count_active, 1, 1, 128, 48 * 8, st, batch, active);
+        CK(cudaMemcpyAsync(&h_active, active, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+      }
+    }
+    if (o->compute_r2 && R2)                                                          // :372-380
+      L(k_als_lambda, N, batch, 64, smL, dXs, dF, T, N, r, o->nt_min, 1, (double*)nullptr, dR2, FtF, 0, cidx, cR, cr, ds, (AlsState*)nullptr);
+    rc = copy_out(h, F, dF, B * T * r, mem); if (rc) return rc;
+    rc = copy_out(h, Lambda, dLam, B * N * r, mem); if (rc) return rc;
+    if (o->compute_r2) { rc = copy_out(h, R2, dR2, B * N, mem); if (rc) return rc; }
+    rc = copy_out(h, xmean, dm, B * N, mem); if (rc) return rc;
+    rc = copy_out(h, xstd, ds, B * N, mem); if (rc) return rc;
+    if (stats) {
+      std::vector<AlsState> hs(B);
+      CK(cudaMemcpyAsync(hs.data(), st, B * sizeof(AlsState), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      for (size_t b = 0; b < B; ++b) { stats[b].ssr = hs[b].ssr; stats[b].tss = hs[b].tss; stats[b].nobs = hs[b].nobs; stats[b].iters = hs[b].iters; stats[b].status = hs[b].status; }
+    }
+  }
+  return finish(h, mem);
+}
+
+// ------------------------------------------------------------------------------------ a9
+int dfm_estimate_loading(dfm_handle* h, const double* data, const double* F, const dfm_loading_opts* o, double* lambda,
+                         double* r2, double* uar_coef, double* uar_ser) {
+  if (!h || !data || !F || !o) return fail(h, DFM_ERR_ARG, "dfm_estimate_loading: null argument");
+  int T = o->T, ns = o->ns, r = o->r, batch = o->batch, mem = o->mem, L_ = o->n_uarlag, nc = o->n_constr;
+  if (T <= 1 || ns <= 0 || r <= 0 || r > 64 || batch <= 0 || L_ <= 0 || L_ > 16 || nc < 0 || nc > 64 ||
+      (nc > 0 && (!o->constr_index || !o->constr_R || !o->constr_r)))
+    return fail(h, DFM_ERR_ARG, "dfm_estimate_loading: bad shape/options");
+  CK(cudaSetDevice(h->device));
+  size_t B = batch; int K = r + 1, np = K * (K + 1) / 2;
+  for (int pass = 0; pass < 2; ++pass) {
+    Arena a(pass ? h->ws : nullptr);
+    double* dD = mem == DFM_MEM_HOST ? a.get<double>(B * T * ns) : nullptr;
+    double* dFb = mem == DFM_MEM_HOST ? a.get<double>(B * T * r) : nullptr;
+    double* dl = a.get<double>(B * ns * r); double* dr2 = a.get<double>(B * ns);
+    double* dac = a.get<double>(B * ns * L_); double* dser = a.get<double>(B * ns);
+    double* scr = a.get<double>(B * ns * T); int* status = a.get<int>(B);
+    int* cidx = a.get<int>(nc + 1); double* cR = a.get<double>((size_t)nc * r + 1); double* cr = a.get<double>(nc + 1);
+    if (!pass) { int rc = ensure_ws(h, a.off); if (rc) return rc; continue; }
+    const double* d; const double* f;
+    int rc = stage_in(h, data, dD, B * T * ns, mem, &d); if (rc) return rc;
+    rc = stage_in(h, F, dFb, B * T * r, mem, &f); if (rc) return rc;
+    if (nc > 0) {
+      CK(cudaMemcpyAsync(cidx, o->constr_index, nc * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+      CK(cudaMemcpyAsync(cR, o->constr_R, (size_t)nc * r * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      CK(cudaMemcpyAsync(cr, o->constr_r, nc * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    }
+    CK(cudaMemsetAsync(status, 0, B * sizeof(int), h->stream));
+    size_t wk = std::max<size_t>((size_t)K * nc + (size_t)nc * (nc + 1) / 2 + nc, (size_t)L_ * (L_ + 1) / 2 + L_);
+    size_t sm = (size_t)(np + K + 8 + wk) * 8;
+    L(k_loading, ns, batch, 64, sm, d, f, T, ns, r, o->nt_min, L_, dl, dr2, dac, dser, scr, nc, cidx, cR, cr, status);
+    rc = copy_out(h, lambda, dl, B * ns * r, mem); if (rc) return rc;
+    rc = copy_out(h, r2, dr2, B * ns, mem); if (rc) return rc;
+    rc = copy_out(h, uar_coef, dac, B * ns * L_, mem); if (rc) return rc;
+    rc = copy_out(h, uar_ser, dser, B * ns, mem); if (rc) return rc;
+  }
+  return finish(h, mem);
+}
+
+// ------------------------------------------------------------------------------------ a10
+int dfm_estimate_var(dfm_handle* h, const double* F, int T, int r, int p, int withconst, int batch, int mem,
+                     double* betahat, double* resid, double* seps, double* M, double* Q, double* G) {
+  if (!h || !F || T <= 0 || r <= 0 || p <= 0 || batch <= 0) return fail(h, DFM_ERR_ARG, "dfm_estimate_var: bad argument");
+  int k = r * p, K = k + (withconst ? 1 : 0);
+  if (T - p <= K) return fail(h, DFM_ERR_TOO_FEW_OBS, "dfm_estimate_var: T - p <= K");
+  size_t sm = ((size_t)K * K + (size_t)K * r + (size_t)r * r + 16) * 8;
+  if (sm > kMaxSmem) return fail(h, DFM_ERR_UNSUPPORTED, "dfm_estimate_var: r*p too large");
+  CK(cudaSetDevice(h->device));
+  size_t B = batch;
+  for (int pass = 0; pass < 2; ++pass) {
+    Arena a(pass ? h->ws : nullptr);
+    double* dFb = mem == DFM_MEM_HOST ? a.get<double>(B * T * r) : nullptr;
+    double* db = a.get<double>(B * K * r); double* dres = a.get<double>(B * T * r); double* dse = a.get<double>(B * r * r);
+    double* dM = a.get<double>(B * k * k); double* dQ = a.get<double>(B * r * k); double* dG = a.get<double>(B * k * r);
+    int* status = a.get<int>(B);
+    if (!pass) { int rc = ensure_ws(h, a.off); if (rc) return rc; continue; }
+    const double* f; int rc = stage_in(h, F, dFb, B * T * r, mem, &f); if (rc) return rc;
+    CK(cudaMemsetAsync(status, 0, B * sizeof(int), h->stream));
+    L(k_var, batch, 1, 128, sm, f, T, r, p, withconst, 0, db, dres, dse, dM, dQ, dG, (double*)nullptr, status);
+    rc = copy_out(h, betahat, db, B * K * r, mem); if (rc) return rc;
+    rc = copy_out(h, resid, dres, B * T * r, mem); if (rc) return rc;
+    rc = copy_out(h, seps, dse, B * r * r, mem); if (rc) return rc;
+    rc = copy_out(h, M, dM, B * k * k, mem); if (rc) return rc;
+    rc = copy_out(h, Q, dQ, B * r * k, mem); if (rc) return rc;
+    rc = copy_out(h, G, dG, B * k * r, mem); if (rc) return rc;
+    std::vector<int> hs(B);
+    CK(cudaMemcpyAsync(hs.data(), status, B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (size_t b = 0; b < B; ++b) if (hs[b]) return fail(h, hs[b], "dfm_estimate_var: regression failed");
+  }
+  return finish(h, mem);
+}
+
+// ------------------------------------------------------------------------------------ a11
+int dfm_irf(dfm_handle* h, const double* M, const double* Q, const double* G, int k, int r, int H, int n_shock,
+            const int* shock_ids, int batch, int mem, double* irf) {
+  if (!h || !M || !Q || !G || !shock_ids || !irf || k <= 0 || r <= 0 || H <= 0 || n_shock <= 0 || batch <= 0)
+    return fail(h, DFM_ERR_ARG, "dfm_irf: bad argument");
+  for (int j = 0; j < n_shock; ++j) if (shock_ids[j] < 0 || shock_ids[j] >= r) return fail(h, DFM_ERR_ARG, "dfm_irf: shock id out of range");
+  CK(cudaSetDevice(h->device));
+  size_t B = batch;
+  for (int pass = 0; pass < 2; ++pass) {
+    Arena a(pass ? h->ws : nullptr);
+    double* dM = mem == DFM_MEM_HOST ? a.get<double>(B * k * k) : nullptr;
+    double* dQ = mem == DFM_MEM_HOST ? a.get<double>(B * r * k) : nullptr;
+    double* dG = mem == DFM_MEM_HOST ? a.get<double>(B * k * r) : nullptr;
+    double* dI = mem == DFM_MEM_HOST ? a.get<double>(B * r * H * n_shock) : irf;
+    int* ids = a.get<int>(n_shock);
+    if (!pass) { int rc = ensure_ws(h, a.off); if (rc) return rc; continue; }
+    const double *m, *q, *g;
+    int rc = stage_in(h, M, dM, B * k * k, mem, &m); if (rc) return rc;
+    rc = stage_in(h, Q, dQ, B * r * k, mem, &q); if (rc) return rc;
+    rc = stage_in(h, G, dG, B * k * r, mem, &g); if (rc) return rc;
+    CK(cudaMemcpyAsync(ids, shock_ids, n_shock * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    L(k_irf, n_shock, batch, 64, (size_t)(2 * k + 8) * 8, m, q, g, k, r, H, n_shock, ids, dI);
+    if (mem == DFM_MEM_HOST) { rc = copy_out(h, irf, dI, B * r * H * n_shock, mem); if (rc) return rc; }
+  }
+  return finish(h, mem);
+}
+
+// ------------------------------------------------------------------------------------ a' init
+int dfm_em_init_from_factors(dfm_handle* h, const double* Xs, const double* F, int T, int N, int r, int p, int batch,
+                             int mem, double* Lam, double* R, double* A, double* Q) {
+  if (!h || !Xs || !F || T <= 0 || N <= 0 || r <= 0 || r > 64 || p <= 0 || batch <= 0) return fail(h, DFM_ERR_ARG, "dfm_em_init_from_factors: bad argument");
+  int k = r * p;
+  if (T - p <= k) return fail(h, DFM_ERR_TOO_FEW_OBS, "dfm_em_init_from_factors: T - p <= r*p");
+  size_t smV = ((size_t)k * k + (size_t)k * r + (size_t)r * r + 16) * 8;
+  if (smV > kMaxSmem) return fail(h, DFM_ERR_UNSUPPORTED, "r*p too large");
+  CK(cudaSetDevice(h->device));
+  size_t B = batch, TN = (size_t)T * N; int np = r * (r + 1) / 2;
+  for (int pass = 0; pass < 2; ++pass) {
+    Arena a(pass ? h->ws : nullptr);
+    double* dX = mem == DFM_MEM_HOST ? a.get<double>(B * TN) : nullptr;
+    double* dFb = mem == DFM_MEM_HOST ? a.get<double>(B * T * r) : nullptr;
+    double* dL = a.get<double>(B * N * r); double* dR = a.get<double>(B * N);
+    double* dA = a.get<double>(B * r * k); double* dQ = a.get<double>(B * r * r); double* dres = a.get<double>(B * T * r);
+    int* status = a.get<int>(B);
+    if (!pass) { int rc = ensure_ws(h, a.off); if (rc) return rc; continue; }
+    const double *x, *f;
+    int rc = stage_in(h, Xs, dX, B * TN, mem, &x); if (rc) return rc;
+    rc = stage_in(h, F, dFb, B * T * r, mem, &f); if (rc) return rc;
+    CK(cudaMemsetAsync(status, 0, B * sizeof(int), h->stream));
+    size_t smL = (size_t)(2 * np + 2 * r + 8) * 8;
+    L(k_als_lambda, N, batch, 64, smL, x, f, T, N, r, 0, 2, dL, dR, (const double*)nullptr, 0, (const int*)nullptr,
+      (const double*)nullptr, (const double*)nullptr, (const double*)nullptr, (AlsState*)nullptr);
+    L(k_var, batch, 1, 128, smV, f, T, r, p, 0, 1, (double*)nullptr, dres, dQ, (double*)nullptr, (double*)nullptr,
+      (double*)nullptr, dA, status);
+    rc = copy_out(h, Lam, dL, B * N * r, mem); if (rc) return rc;
+    rc = copy_out(h, R, dR, B * N, mem); if (rc) return rc;
+    rc = copy_out(h, A, dA, B * r * k, mem); if (rc) return rc;
+    rc = copy_out(h, Q, dQ, B * r * r, mem); if (rc) return rc;
+  }
+  return finish(h, mem);
+}
+
+// ------------------------------------------------------------------------------------ a'
+#ifndef DFM_EMU
+int dfm_em_kalman_fused(dfm_handle* h, const double* dX, const dfm_em_opts* o, double* dLam, double* dR, double* dA,
+                        double* dQ, const double* dP0, double* dFs, double* dPsF, double* dll, int* diters, int* dstatus,
+                        long long* launches);   // dfm_fast.cu
+int dfm_em_fused_supported(const dfm_em_opts* o);
+#endif
+
+int dfm_em_kalman(dfm_handle* h, const double* X, const dfm_em_opts* o, const dfm_em_init* init, const dfm_em_out* out) {
+  if (!h || !X || !o || !init || !out || !init->Lam || !init->R || !init->A || !init->Q)
+    return fail(h, DFM_ERR_ARG, "dfm_em_kalman: null argument");
+  int T = o->T, N = o->N, r = o->r, p = o->p, batch = o->batch, mem = o->mem, mi = o->max_iter;
+  if (T <= 1 || N <= 0 || r <= 0 || r > 64 || p <= 0 || batch <= 0 || mi <= 0 || o->tol < 0)
+    return fail(h, DFM_ERR_ARG, "dfm_em_kalman: bad shape/options");
+  size_t smFS = em_fs_smem_doubles(r, p) * 8;
+  if (smFS > kMaxSmem) return fail(h, DFM_ERR_UNSUPPORTED, "dfm_em_kalman: state dimension r*p too large for the general path");
+  CK(cudaSetDevice(h->device));
+  size_t B = batch, TN = (size_t)T * N; int k = r * p, kk = k * k, rr = r * r, rk = r * k, np = r * (r + 1) / 2;
+  int ntC = tpt_threads(np + r);
+  int nblkC = (T + ntC - 1) / ntC;
+  bool fused = false;
+#ifndef DFM_EMU
+  fused = (o->path == 2) || (o->path == 0 && dfm_em_fused_supported(o));
+  if (o->path == 2 && !dfm_em_fused_supported(o)) return fail(h, DFM_ERR_UNSUPPORTED, "dfm_em_kalman: fused path does not support this shape");
+#endif
+  for (int pass = 0; pass < 2; ++pass) {
+    Arena a(pass ? h->ws : nullptr);
+    double* dXb = mem == DFM_MEM_HOST ? a.get<double>(B * TN) : nullptr;
+    double* dL = a.get<double>(B * N * r); double* dR = a.get<double>(B * N);
+    double* dA = a.get<double>(B * rk); double* dQ = a.get<double>(B * rr); double* dP0 = a.get<double>(B * kk);
+    double* dFs = a.get<double>(B * T * r); double* dPsF = a.get<double>(B * T * np);
+    double* dll = a.get<double>(B * mi); EmState* st = a.get<EmState>(B);
+    int* dit = a.get<int>(B); int* dstat = a.get<int>(B); int* active = a.get<int>(4);
+    double* dPFfull = out->PF ? a.get<double>(B * T * rr) : nullptr;
+    double *dAn = nullptr, *dQn = nullptr, *dW = nullptr, *dlogR = nullptr, *dC = nullptr, *dBt = nullptr, *dqt = nullptr,
+           *dslr = nullptr, *dCt = nullptr, *dzp = nullptr, *dzf = nullptr, *dPp = nullptr, *dPf = nullptr, *dSff = nullptr;
+    int* dnt = nullptr;
+    if (!fused) {
+      dAn = a.get<double>(B * rk); dQn = a.get<double>(B * rr); dW = a.get<double>(B * N * r); dlogR = a.get<double>(B * N);
+      dC = a.get<double>(B * rr); dBt = a.get<double>(B * T * r); dqt = a.get<double>(B * T); dslr = a.get<double>(B * T);
+      dnt = a.get<int>(B * T); dCt = a.get<double>(B * T * np); dzp = a.get<double>(B * T * k); dzf = a.get<double>(B * T * k);
+      dPp = a.get<double>(B * T * kk); dPf = a.get<double>(B * T * kk); dSff = a.get<double>(B * rr);
+    }
+    if (!pass) { int rc = ensure_ws(h, a.off); if (rc) return rc; continue; }
+    const double* x; int rc = stage_in(h, X, dXb, B * TN, mem, &x); if (rc) return rc;
+    cudaMemcpyKind kin = mem == DFM_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    CK(cudaMemcpyAsync(dL, init->Lam, B * N * r * 8, kin, h->stream));
+    CK(cudaMemcpyAsync(dR, init->R, B * N * 8, kin, h->stream));
+    CK(cudaMemcpyAsync(dA, init->A, B * rk * 8, kin, h->stream));
+    CK(cudaMemcpyAsync(dQ, init->Q, B * rr * 8, kin, h->stream));
+    if (init->P0) CK(cudaMemcpyAsync(dP0, init->P0, B * kk * 8, kin, h->stream));
+    else L(k_lyapunov, batch, 1, 128, (size_t)(3 * kk + 8) * 8, dA, dQ, r, p, dP0, 12);
+    {
+      long long n = (long long)B * mi;
+      L(k_fill, (int)std::min<long long>((n + 255) / 256, 1024), 1, 256, 0, dll, n, DFM_NAN);
+    }
+    if (fused) {
+#ifndef DFM_EMU
+      rc = dfm_em_kalman_fused(h, x, o, dL, dR, dA, dQ, dP0, dFs, dPsF, dll, dit, dstat, &h->launches);
+      if (rc) return fail(h, rc, "dfm_em_kalman: fused path failed");
+#endif
+    } else {
+      L(k_em_state_init, batch, 1, 1, 0, st);
+      L(k_em_scan, N, batch, 64, 0, x, dL, T, N, r, st);
+      L(k_em_prep, batch, 1, 128, 0, dL, dR, N, r, p, dW, dlogR, dC, dA, dAn, dQ, dQn, st, mi, 0);
+      int h_active = batch;
+      for (int it = 0; it < mi && h_active > 0; ++it) {
+        L(k_em_contract, nblkC, batch, ntC, ((size_t)(np + r) * ntC + 8) * 8, x, dL, dW, dR, dlogR, dC, T, N, r, dBt, dqt, dslr, dnt, dCt, st);
+        L(k_em_filter_smooth, batch, 1, 128, smFS, dA, dQ, dP0, dC, dBt, dqt, dslr, dnt, dCt, T, r, p, dzp, dzf, dPp, dPf,
+          dFs, dPsF, dSff, dAn, dQn, dll, mi, o->tol, st);
+        L(k_em_mstep_series, N, batch, 64, (size_t)(2 * np + r + 8) * 8, x, dFs, dPsF, dSff, T, N, r, dL, dR, st);
+        L(k_em_prep, batch, 1, 128, 0, dL, dR, N, r, p, dW, dlogR, dC, dA, dAn, dQ, dQn, st, mi, 1);
+        if (o->tol > 0 && ((it & 3) == 3)) {
+          L(k_em_count_active, 1, 1, 128, 48 * 8, st, batch, active);
+          CK(cudaMemcpyAsync(&h_active, active, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+          CK(cudaStreamSynchronize(h->stream));
+        }
+      }
+      L(k_em_collect, batch, 1, 1, 0, st, dit, dstat);
+    }
+    rc = copy_out(h, out->Lam, dL, B * N * r, mem); if (rc) return rc;
+    rc = copy_out(h, out->R, dR, B * N, mem); if (rc) return rc;
+    rc = copy_out(h, out->A, dA, B * rk, mem); if (rc) return rc;
+    rc = copy_out(h, out->Q, dQ, B * rr, mem); if (rc) return rc;
+    rc = copy_out(h, out->P0, dP0, B * kk, mem); if (rc) return rc;
+    rc = copy_out(h, out->F, dFs, B * T * r, mem); if (rc) return rc;
+    if (out->PF) {
+      long long n = (long long)T * rr;
+      L(k_unpack_psf, (int)std::min<long long>((n + 255) / 256, 1024), batch, 256, 0, dPsF, T, r, dPFfull);
+      rc = copy_out(h, out->PF, dPFfull, B * T * rr, mem); if (rc) return rc;
+    }
+    rc = copy_out(h, out->loglik, dll, B * mi, mem); if (rc) return rc;
+    rc = copy_out(h, out->iters, dit, B, mem); if (rc) return rc;
+    rc = copy_out(h, out->status, dstat, B, mem); if (rc) return rc;
+  }
+  return finish(h, mem);
+}
+
+// ------------------------------------------------------------------------------------ (e)
+int dfm_allgather_results(dfm_handle* h, void* nccl_comm, const double* send, double* recv, long long count) {
+  if (!h || !nccl_comm || !send || !recv || count <= 0) return fail(h, DFM_ERR_ARG, "dfm_allgather_results: bad argument");
+#ifdef DFM_EMU
+  return DFM_ERR_NCCL;
+#else
+  typedef int (*allgather_fn)(const void*, void*, size_t, int, void*, cudaStream_t);
+  static allgather_fn fn = nullptr;
+  if (!fn) {
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* lib = nullptr;
+    for (const char* n : names) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+    if (!lib) return fail(h, DFM_ERR_NCCL, "libnccl not found");
+    fn = (allgather_fn)dlsym(lib, "ncclAllGather");
+    if (!fn) return fail(h, DFM_ERR_NCCL, "ncclAllGather not found");
+  }
+  CK(cudaSetDevice(h->device));
+  int rc = fn(send, recv, (size_t)count, /*ncclFloat64*/ 8, nccl_comm, h->stream);
+  if (rc != 0) return fail(h, DFM_ERR_NCCL, "ncclAllGather failed");
+  return DFM_OK;
+#endif
+}
+
+}  // extern "C"

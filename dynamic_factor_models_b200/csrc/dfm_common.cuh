@@ -1,0 +1,215 @@
+// dfm_common.cuh -- launch/sync abstraction + block-cooperative small dense FP64 helpers.
+//
+// Product build: nvcc -gencode arch=compute_100a,code=sm_100a (real CUDA).
+// DFM_EMU build (tests/emu only, never shipped or loaded by the package): the SAME kernel
+// source compiled by g++ with one "thread" per block, so index/algebra logic can be checked in
+// the GPU-less build container.  It is a test harness for the kernel source, not a fallback:
+// libdfm_b200.so contains no host compute path.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+#ifdef DFM_EMU
+// ------------------------------------------------------------------ host emulation layer
+#include <cstdlib>
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+struct dfm_emu_ctx { int bx, by, gx, gy; };
+static thread_local dfm_emu_ctx g_emu;
+static thread_local double g_emu_smem[1 << 19];   // 4 MB of "shared memory"
+#define DFM_TID 0
+#define DFM_NT 1
+#define DFM_BX (g_emu.bx)
+#define DFM_BY (g_emu.by)
+#define DFM_GX (g_emu.gx)
+#define DFM_SYNC() ((void)0)
+#define DFM_SMEM(name) double* name = g_emu_smem
+static inline double atomicAdd(double* p, double v) { double o = *p; *p += v; return o; }
+static inline int atomicAdd(int* p, int v) { int o = *p; *p += v; return o; }
+static inline int atomicMax(int* p, int v) { int o = *p; if (v > o) *p = v; return o; }
+typedef void* cudaStream_t;
+#define DFM_LAUNCH(kern, gx_, gy_, nt_, smem_, stream_, ...)                          \
+  do {                                                                               \
+    g_emu.gx = (gx_); g_emu.gy = (gy_);                                              \
+    for (int by__ = 0; by__ < (gy_); ++by__)                                         \
+      for (int bx__ = 0; bx__ < (gx_); ++bx__) { g_emu.bx = bx__; g_emu.by = by__; kern(__VA_ARGS__); } \
+  } while (0)
+#else
+// ------------------------------------------------------------------ real CUDA
+#include <cuda_runtime.h>
+#define DFM_TID ((int)threadIdx.x)
+#define DFM_NT ((int)blockDim.x)
+#define DFM_BX ((int)blockIdx.x)
+#define DFM_BY ((int)blockIdx.y)
+#define DFM_GX ((int)gridDim.x)
+#define DFM_SYNC() __syncthreads()
+#define DFM_SMEM(name) extern __shared__ double name[]
+#define DFM_LAUNCH(kern, gx_, gy_, nt_, smem_, stream_, ...) \
+  kern<<<dim3((unsigned)(gx_), (unsigned)(gy_)), (unsigned)(nt_), (size_t)(smem_), (stream_)>>>(__VA_ARGS__)
+#endif
+
+#define DFM_NAN (nan(""))
+
+namespace dfm {
+
+__device__ __forceinline__ bool is_nan(double x) { return x != x; }
+
+// Sum over the block.  `red` = >= 33 doubles of shared scratch.  All threads get the result.
+__device__ __forceinline__ double block_sum(double v, double* red) {
+#ifdef DFM_EMU
+  (void)red;
+  return v;
+#else
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    double s = (lane < nw) ? red[lane] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) red[32] = s;
+  }
+  __syncthreads();
+  double out = red[32];
+  __syncthreads();
+  return out;
+#endif
+}
+
+// packed lower-triangular index, a >= c
+__device__ __forceinline__ int pidx(int a, int c) { return a * (a + 1) / 2 + c; }
+
+// ---- thread-private solve: packed lower SPD matrix A (element (a,c) at A[pidx(a,c)*stride]),
+// rhs b (b[a*stride]); overwrites A with its Cholesky factor and b with the solution.
+// returns 0 ok, 1 not PD.
+__device__ inline int chol_solve_packed(double* A, double* b, int n, int stride) {
+  for (int j = 0; j < n; ++j) {
+    double d = A[pidx(j, j) * stride];
+    for (int c = 0; c < j; ++c) { double l = A[pidx(j, c) * stride]; d -= l * l; }
+    if (!(d > 0.0)) return 1;
+    d = sqrt(d);
+    A[pidx(j, j) * stride] = d;
+    double inv = 1.0 / d;
+    for (int i = j + 1; i < n; ++i) {
+      double s = A[pidx(i, j) * stride];
+      for (int c = 0; c < j; ++c) s -= A[pidx(i, c) * stride] * A[pidx(j, c) * stride];
+      A[pidx(i, j) * stride] = s * inv;
+    }
+  }
+  for (int i = 0; i < n; ++i) {          // L y = b
+    double s = b[i * stride];
+    for (int c = 0; c < i; ++c) s -= A[pidx(i, c) * stride] * b[c * stride];
+    b[i * stride] = s / A[pidx(i, i) * stride];
+  }
+  for (int i = n - 1; i >= 0; --i) {     // L' x = y
+    double s = b[i * stride];
+    for (int c = i + 1; c < n; ++c) s -= A[pidx(c, i) * stride] * b[c * stride];
+    b[i * stride] = s / A[pidx(i, i) * stride];
+  }
+  return 0;
+}
+
+// solve with an already factored packed lower L (as left by chol_solve_packed)
+__device__ inline void chol_resolve_packed(const double* L, double* b, int n, int stride) {
+  for (int i = 0; i < n; ++i) {
+    double s = b[i * stride];
+    for (int c = 0; c < i; ++c) s -= L[pidx(i, c) * stride] * b[c * stride];
+    b[i * stride] = s / L[pidx(i, i) * stride];
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    double s = b[i * stride];
+    for (int c = i + 1; c < n; ++c) s -= L[pidx(c, i) * stride] * b[c * stride];
+    b[i * stride] = s / L[pidx(i, i) * stride];
+  }
+}
+
+// ================= block-cooperative dense ops on column-major matrices (shared or global) =====
+// Every routine ends with DFM_SYNC(); outputs must not alias inputs unless stated.
+
+// C(m x n) = beta*C + alpha * opA(A) * opB(B);  opA(A) is m x kk, opB(B) is kk x n.
+__device__ inline void bm_gemm(double* C, int ldc, const double* A, int lda, bool ta, const double* B, int ldb,
+                               bool tb, int m, int n, int kk, double alpha, double beta) {
+  for (int e = DFM_TID; e < m * n; e += DFM_NT) {
+    int i = e % m, j = e / m;
+    double s = 0.0;
+    for (int l = 0; l < kk; ++l) {
+      double a = ta ? A[l + lda * i] : A[i + lda * l];
+      double b = tb ? B[j + ldb * l] : B[l + ldb * j];
+      s += a * b;
+    }
+    double c0 = (beta == 0.0) ? 0.0 : beta * C[i + ldc * j];
+    C[i + ldc * j] = c0 + alpha * s;
+  }
+  DFM_SYNC();
+}
+
+__device__ inline void bm_copy(double* D, int ldd, const double* S, int lds, int m, int n) {
+  for (int e = DFM_TID; e < m * n; e += DFM_NT) { int i = e % m, j = e / m; D[i + ldd * j] = S[i + lds * j]; }
+  DFM_SYNC();
+}
+
+// A <- (A + A')/2  (n x n)
+__device__ inline void bm_symmetrize(double* A, int ld, int n) {
+  for (int e = DFM_TID; e < n * n; e += DFM_NT) {
+    int i = e % n, j = e / n;
+    if (i > j) { double v = 0.5 * (A[i + ld * j] + A[j + ld * i]); A[i + ld * j] = v; A[j + ld * i] = v; }
+  }
+  DFM_SYNC();
+}
+
+// In-place lower Cholesky of the n x n SPD matrix A (upper triangle is ZEROED so A can be used
+// as a full matrix afterwards).  *info (shared int) is set to 1 on a non-positive pivot.
+__device__ inline void bm_chol(double* A, int ld, int n, int* info) {
+  for (int j = 0; j < n; ++j) {
+    if (DFM_TID == 0) {
+      double d = A[j + ld * j];
+      if (!(d > 0.0)) { *info = 1; d = 1.0; }
+      A[j + ld * j] = sqrt(d);
+    }
+    DFM_SYNC();
+    double inv = 1.0 / A[j + ld * j];
+    for (int i = j + 1 + DFM_TID; i < n; i += DFM_NT) A[i + ld * j] *= inv;
+    DFM_SYNC();
+    int m = n - j - 1;   // trailing update of the lower triangle, columns j+1..n-1
+    for (int e = DFM_TID; e < m * m; e += DFM_NT) {
+      int i = j + 1 + e % m, c = j + 1 + e / m;
+      if (i >= c) A[i + ld * c] -= A[i + ld * j] * A[c + ld * j];
+    }
+    DFM_SYNC();
+  }
+  for (int e = DFM_TID; e < n * n; e += DFM_NT) { int i = e % n, j = e / n; if (i < j) A[i + ld * j] = 0.0; }
+  DFM_SYNC();
+}
+
+// B (n x m) <- L^-1 B   (L lower, n x n); one thread per right-hand-side column.
+__device__ inline void bm_trsm_lower(const double* L, int ldl, int n, double* B, int ldb, int m) {
+  for (int c = DFM_TID; c < m; c += DFM_NT) {
+    double* x = B + (size_t)ldb * c;
+    for (int i = 0; i < n; ++i) {
+      double s = x[i];
+      for (int l = 0; l < i; ++l) s -= L[i + ldl * l] * x[l];
+      x[i] = s / L[i + ldl * i];
+    }
+  }
+  DFM_SYNC();
+}
+
+// B (n x m) <- L^-T B
+__device__ inline void bm_trsm_lowerT(const double* L, int ldl, int n, double* B, int ldb, int m) {
+  for (int c = DFM_TID; c < m; c += DFM_NT) {
+    double* x = B + (size_t)ldb * c;
+    for (int i = n - 1; i >= 0; --i) {
+      double s = x[i];
+      for (int l = i + 1; l < n; ++l) s -= L[l + ldl * i] * x[l];
+      x[i] = s / L[i + ldl * i];
+    }
+  }
+  DFM_SYNC();
+}
+
+}  // namespace dfm

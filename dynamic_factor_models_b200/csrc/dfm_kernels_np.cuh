@@ -1,0 +1,670 @@
+// dfm_kernels_np.cuh -- kernels of the NON-PARAMETRIC path (rows a2..a11 of SURVEY.md section 8):
+// standardise, PCA (Gram + Jacobi), ALS / least-squares-EM sweep, loadings + idiosyncratic AR,
+// factor VAR + companion form, IRF.  All FP64, column-major, batched over blockIdx.y = panel.
+// Reference lines cited as dfm_functions.ipynb:<raw JSON line>.
+#pragma once
+#include "dfm_common.cuh"
+
+namespace dfm {
+
+struct AlsState {          // one per panel, device resident
+  double ssr, ssr_old, tss;
+  long long nobs;
+  int iters, done, status, pad;
+};
+
+// ---------------------------------------------------------------- K1 standardize_data :501-509
+// grid (N, B); block per column.  Also per-column sum of squares / count for tss, nobs (:342-343).
+__global__ void k_standardize(const double* __restrict__ X, int T, int N, double* __restrict__ Xs,
+                              double* __restrict__ xmean, double* __restrict__ xstd,
+                              double* __restrict__ col_ss, int* __restrict__ col_n) {
+  DFM_SMEM(sm);
+  int i = DFM_BX, b = DFM_BY;
+  const double* x = X + ((size_t)b * N + i) * T;
+  double* xs = Xs + ((size_t)b * N + i) * T;
+  double s = 0.0, n = 0.0;
+  for (int t = DFM_TID; t < T; t += DFM_NT) { double v = x[t]; if (!is_nan(v)) { s += v; n += 1.0; } }
+  s = block_sum(s, sm); n = block_sum(n, sm);
+  double mean = (n > 0) ? s / n : DFM_NAN;
+  double v2 = 0.0;
+  for (int t = DFM_TID; t < T; t += DFM_NT) { double v = x[t]; if (!is_nan(v)) { double d = v - mean; v2 += d * d; } }
+  v2 = block_sum(v2, sm);
+  double sd = (n > 0) ? sqrt(v2 / n) : DFM_NAN;      // population std  (:504-506)
+  double ss = 0.0;
+  for (int t = DFM_TID; t < T; t += DFM_NT) {
+    double v = (x[t] - mean) / sd;
+    xs[t] = v;
+    if (!is_nan(v)) ss += v * v;
+  }
+  ss = block_sum(ss, sm);
+  if (DFM_TID == 0) {
+    if (xmean) xmean[(size_t)b * N + i] = mean;
+    if (xstd) xstd[(size_t)b * N + i] = sd;
+    if (col_ss) col_ss[(size_t)b * N + i] = ss;
+    if (col_n) col_n[(size_t)b * N + i] = (int)n;
+  }
+}
+
+// tss / nobs totals + state reset.  grid (B), 1 block.
+__global__ void k_als_init_state(AlsState* st, const double* col_ss, const int* col_n, int N) {
+  DFM_SMEM(sm);
+  int b = DFM_BX;
+  double ss = 0.0, n = 0.0;
+  for (int i = DFM_TID; i < N; i += DFM_NT) { ss += col_ss[(size_t)b * N + i]; n += col_n[(size_t)b * N + i]; }
+  ss = block_sum(ss, sm); n = block_sum(n, sm);
+  if (DFM_TID == 0) {
+    st[b].tss = ss; st[b].nobs = (long long)n; st[b].ssr = 0.0; st[b].ssr_old = 0.0;
+    st[b].iters = 0; st[b].done = 0; st[b].status = 0;
+  }
+}
+
+// ---------------------------------------------------------------- K2 PCA  (pca_score :179-183)
+// balanced columns (drop_missing_col :167-170).  grid (B), single thread.
+__global__ void k_balanced_cols(const int* col_n, int T, int N, int* bal_idx, int* nbal) {
+  if (DFM_TID != 0) return;
+  int b = DFM_BX, n = 0;
+  for (int i = 0; i < N; ++i) if (col_n[(size_t)b * N + i] == T) bal_idx[(size_t)b * N + n++] = i;
+  nbal[b] = n;
+}
+__global__ void k_all_cols(int N, int* bal_idx, int* nbal) {
+  int b = DFM_BX;
+  for (int i = DFM_TID; i < N; i += DFM_NT) bal_idx[(size_t)b * N + i] = i;
+  if (DFM_TID == 0) nbal[b] = N;
+}
+
+// Gram of the balanced block: mode 0 (nbal <= T): G = Xb'Xb (nbal x nbal); mode 1: G = Xb Xb' (T x T).
+// G stored dense with leading dimension n = min(nbal, T).  grid (ceil(nmax^2/NT), B).
+__global__ void k_gram(const double* __restrict__ Xs, int T, int N, const int* __restrict__ bal_idx,
+                       const int* __restrict__ nbal, double* __restrict__ G, int nmax) {
+  int b = DFM_BY;
+  int nb = nbal[b];
+  int mode = (nb <= T) ? 0 : 1;
+  int n = mode ? T : nb;
+  const double* X = Xs + (size_t)b * T * N;
+  const int* idx = bal_idx + (size_t)b * N;
+  double* g = G + (size_t)b * nmax * nmax;
+  for (long long e = (long long)DFM_BX * DFM_NT + DFM_TID; e < (long long)n * n; e += (long long)DFM_GX * DFM_NT) {
+    int a = (int)(e % n), c = (int)(e / n);
+    if (a < c) continue;
+    double s = 0.0;
+    if (mode == 0) {
+      const double* xa = X + (size_t)idx[a] * T; const double* xc = X + (size_t)idx[c] * T;
+      for (int t = 0; t < T; ++t) s += xa[t] * xc[t];
+    } else {
+      for (int j = 0; j < nb; ++j) { const double* col = X + (size_t)idx[j] * T; s += col[a] * col[c]; }
+    }
+    g[a + (size_t)n * c] = s; g[c + (size_t)n * a] = s;
+  }
+}
+
+// Cyclic Jacobi eigen-solver with round-robin parallel ordering.  grid (B), one block per panel.
+// G (n x n, destroyed: diagonal = eigenvalues), V (n x n eigenvectors in columns).
+__global__ void k_jacobi(double* __restrict__ Gall, double* __restrict__ Vall, const int* __restrict__ nbal,
+                         int T, int nmax, int max_sweeps, int* __restrict__ sweeps_out) {
+  DFM_SMEM(sm);
+  int b = DFM_BX;
+  int nb = nbal[b];
+  int n = (nb <= T) ? nb : T;
+  double* G = Gall + (size_t)b * nmax * nmax;
+  double* V = Vall + (size_t)b * nmax * nmax;
+  int m = (n + 1) & ~1;                  // even number of players
+  double* cs = sm;                       // [m/2][2]
+  double* red = sm + m;                  // 33
+  int* flag = (int*)(red + 40);
+  for (int e = DFM_TID; e < n * n; e += DFM_NT) { int i = e % n, j = e / n; V[i + (size_t)n * j] = (i == j) ? 1.0 : 0.0; }
+  DFM_SYNC();
+  int sweep = 0;
+  for (; sweep < max_sweeps; ++sweep) {
+    double off = 0.0, dg = 0.0;
+    for (int e = DFM_TID; e < n * n; e += DFM_NT) {
+      int i = e % n, j = e / n; double v = G[i + (size_t)n * j];
+      if (i > j) off += v * v; else if (i == j) dg += v * v;
+    }
+    off = block_sum(off, red); dg = block_sum(dg, red);
+    if (off <= 1e-32 * dg) break;
+    for (int s = 0; s < m - 1; ++s) {
+      // phase 1: rotation angles for the m/2 disjoint pairs of this round
+      for (int i = DFM_TID; i < m / 2; i += DFM_NT) {
+        int j1 = i, j2 = m - 1 - i;
+        int p = (j1 == 0) ? 0 : ((j1 - 1 + s) % (m - 1)) + 1;
+        int q = (j2 == 0) ? 0 : ((j2 - 1 + s) % (m - 1)) + 1;
+        if (p > q) { int t_ = p; p = q; q = t_; }
+        double c = 1.0, sn = 0.0;
+        if (q < n) {
+          double app = G[p + (size_t)n * p], aqq = G[q + (size_t)n * q], apq = G[p + (size_t)n * q];
+          if (fabs(apq) > 1e-300 && fabs(apq) > 1e-18 * sqrt(fabs(app * aqq))) {
+            double tau = (aqq - app) / (2.0 * apq);
+            double t = ((tau >= 0.0) ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+            c = 1.0 / sqrt(1.0 + t * t); sn = t * c;
+          }
+        }
+        cs[2 * i] = c; cs[2 * i + 1] = sn;
+      }
+      DFM_SYNC();
+      // phase 2: G <- J' G  (rows p, q)
+      for (int e = DFM_TID; e < (m / 2) * n; e += DFM_NT) {
+        int i = e / n, j = e % n;
+        int j1 = i, j2 = m - 1 - i;
+        int p = (j1 == 0) ? 0 : ((j1 - 1 + s) % (m - 1)) + 1;
+        int q = (j2 == 0) ? 0 : ((j2 - 1 + s) % (m - 1)) + 1;
+        if (p > q) { int t_ = p; p = q; q = t_; }
+        if (q >= n) continue;
+        double c = cs[2 * i], sn = cs[2 * i + 1];
+        double gp = G[p + (size_t)n * j], gq = G[q + (size_t)n * j];
+        G[p + (size_t)n * j] = c * gp - sn * gq;
+        G[q + (size_t)n * j] = sn * gp + c * gq;
+      }
+      DFM_SYNC();
+      // phase 3: G <- G J, V <- V J  (columns p, q)
+      for (int e = DFM_TID; e < (m / 2) * n; e += DFM_NT) {
+        int i = e / n, j = e % n;
+        int j1 = i, j2 = m - 1 - i;
+        int p = (j1 == 0) ? 0 : ((j1 - 1 + s) % (m - 1)) + 1;
+        int q = (j2 == 0) ? 0 : ((j2 - 1 + s) % (m - 1)) + 1;
+        if (p > q) { int t_ = p; p = q; q = t_; }
+        if (q >= n) continue;
+        double c = cs[2 * i], sn = cs[2 * i + 1];
+        double gp = G[j + (size_t)n * p], gq = G[j + (size_t)n * q];
+        G[j + (size_t)n * p] = c * gp - sn * gq;
+        G[j + (size_t)n * q] = sn * gp + c * gq;
+        double vp = V[j + (size_t)n * p], vq = V[j + (size_t)n * q];
+        V[j + (size_t)n * p] = c * vp - sn * vq;
+        V[j + (size_t)n * q] = sn * vp + c * vq;
+      }
+      DFM_SYNC();
+    }
+  }
+  if (DFM_TID == 0 && sweeps_out) sweeps_out[b] = sweep;
+  (void)flag;
+}
+
+// Pick the r largest eigenpairs and form scores.  grid (B), one block.
+// mode 0: score_j = Xb v_j ; mode 1: score_j = u_j * sqrt(lambda_j).  Sign: the entry of largest
+// magnitude of the right singular vector v_j is made positive.
+__global__ void k_pca_finish(const double* __restrict__ Xs, int T, int N, const int* __restrict__ bal_idx,
+                             const int* __restrict__ nbal, const double* __restrict__ Gall,
+                             const double* __restrict__ Vall, int nmax, int r, double* __restrict__ score,
+                             int* __restrict__ status, AlsState* st) {
+  DFM_SMEM(sm);
+  int b = DFM_BX;
+  int nb = nbal[b];
+  int mode = (nb <= T) ? 0 : 1;
+  int n = mode ? T : nb;
+  const double* X = Xs + (size_t)b * T * N;
+  const int* idx = bal_idx + (size_t)b * N;
+  const double* G = Gall + (size_t)b * nmax * nmax;
+  const double* V = Vall + (size_t)b * nmax * nmax;
+  double* sc = score + (size_t)b * T * r;
+  int* order = (int*)sm;                 // r ints
+  double* red = sm + ((r + 1) / 2 + 1);  // 33+
+  double* vtmp = red + 40;               // nb doubles (mode 1)
+  if (n < r) { if (DFM_TID == 0) { if (status) status[b] = 2; if (st) { st[b].status = 2; st[b].done = 1; } } return; }
+  if (DFM_TID == 0) {                    // selection of the r largest diagonal entries
+    for (int j = 0; j < r; ++j) {
+      int best = -1; double bv = -1e300;
+      for (int i = 0; i < n; ++i) {
+        bool used = false;
+        for (int l = 0; l < j; ++l) if (order[l] == i) used = true;
+        double v = G[i + (size_t)n * i];
+        if (!used && v > bv) { bv = v; best = i; }
+      }
+      order[j] = best;
+    }
+  }
+  DFM_SYNC();
+  for (int j = 0; j < r; ++j) {
+    const double* v = V + (size_t)n * order[j];
+    if (mode == 0) {
+      // sign from v itself (thread 0; n is small)
+      if (DFM_TID == 0) {
+        double best = 0.0, sg = 1.0;
+        for (int i = 0; i < n; ++i) if (fabs(v[i]) > best) { best = fabs(v[i]); sg = (v[i] < 0) ? -1.0 : 1.0; }
+        red[36] = sg;
+      }
+      DFM_SYNC();
+      double sg = red[36];
+      for (int t = DFM_TID; t < T; t += DFM_NT) {
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) s += X[t + (size_t)T * idx[i]] * v[i];
+        sc[t + (size_t)T * j] = sg * s;
+      }
+      DFM_SYNC();
+    } else {
+      double lam = G[order[j] + (size_t)n * order[j]];
+      double sig = sqrt(lam > 0 ? lam : 0.0);
+      // right singular vector (up to scale): w = Xb' u
+      for (int i = DFM_TID; i < nb; i += DFM_NT) {
+        const double* col = X + (size_t)idx[i] * T;
+        double s = 0.0;
+        for (int t = 0; t < T; ++t) s += col[t] * v[t];
+        vtmp[i] = s;
+      }
+      DFM_SYNC();
+      if (DFM_TID == 0) {
+        double best = 0.0, sg = 1.0;
+        for (int i = 0; i < nb; ++i) if (fabs(vtmp[i]) > best) { best = fabs(vtmp[i]); sg = (vtmp[i] < 0) ? -1.0 : 1.0; }
+        red[36] = sg;
+      }
+      DFM_SYNC();
+      double sg = red[36];
+      for (int t = DFM_TID; t < T; t += DFM_NT) sc[t + (size_t)T * j] = sg * sig * v[t];
+      DFM_SYNC();
+    }
+  }
+}
+
+// ---------------------------------------------------------------- K3 ALS sweep  (:352-370)
+// out (r x r) = M'M over rows whose first entry is not NaN.  M is nrow x r, ld nrow.  grid (B).
+__global__ void k_gram_small(const double* __restrict__ Mall, int nrow, int r, double* __restrict__ out,
+                             const AlsState* st) {
+  int b = DFM_BX;
+  if (st && st[b].done) return;
+  const double* M = Mall + (size_t)b * nrow * r;
+  double* o = out + (size_t)b * r * r;
+  for (int e = DFM_TID; e < r * r; e += DFM_NT) {
+    int a = e % r, c = e / r;
+    if (a < c) continue;
+    double s = 0.0;
+    for (int t = 0; t < nrow; ++t) { double m0 = M[t]; if (!is_nan(m0)) s += M[t + (size_t)nrow * a] * M[t + (size_t)nrow * c]; }
+    o[a + r * c] = s; o[c + r * a] = s;
+  }
+}
+
+// Lambda-step (:355-362): one block per series.  mode 0: write Lam (NaN if < nt_min obs), apply the
+// :factor constraint (:1125-1141);  mode 1: R2 of the per-series regression (:372-380);
+// mode 2: EM initialisation: Lam and R_i = ssr_i / T_i.
+// FtF = F'F over ALL rows (used only by the constraint, which passes the full f: :360).
+__global__ void k_als_lambda(const double* __restrict__ Xs, const double* __restrict__ Fall, int T, int N, int r,
+                             int nt_min, int mode, double* __restrict__ Lam, double* __restrict__ out2,
+                             const double* __restrict__ FtF, int n_constr, const int* __restrict__ c_index,
+                             const double* __restrict__ c_R, const double* __restrict__ c_r,
+                             const double* __restrict__ xstd, AlsState* st) {
+  DFM_SMEM(sm);
+  int i = DFM_BX, b = DFM_BY;
+  if (st && st[b].done && mode == 0) return;
+  const double* x = Xs + ((size_t)b * N + i) * T;
+  const double* F = Fall + (size_t)b * T * r;
+  int np = r * (r + 1) / 2;
+  double* A = sm;                 // packed np
+  double* c = A + np;             // r
+  double* sc = c + r;             // [0]=cnt [1]=sxx [2]=sx
+  double* wk = sc + 4;            // constraint workspace
+  int nwork = np + r + 3;
+  for (int e = DFM_TID; e < nwork; e += DFM_NT) {
+    double s = 0.0;
+    if (e < np) {
+      int a = 0; while ((a + 1) * (a + 2) / 2 <= e) ++a;
+      int cc = e - a * (a + 1) / 2;
+      const double* fa = F + (size_t)T * a; const double* fc = F + (size_t)T * cc;
+      for (int t = 0; t < T; ++t) if (!is_nan(x[t])) s += fa[t] * fc[t];
+      A[e] = s;
+    } else if (e < np + r) {
+      const double* fa = F + (size_t)T * (e - np);
+      for (int t = 0; t < T; ++t) { double v = x[t]; if (!is_nan(v)) s += v * fa[t]; }
+      c[e - np] = s;
+    } else if (e == np + r) {
+      for (int t = 0; t < T; ++t) if (!is_nan(x[t])) s += 1.0;
+      sc[0] = s;
+    } else if (e == np + r + 1) {
+      for (int t = 0; t < T; ++t) { double v = x[t]; if (!is_nan(v)) s += v * v; }
+      sc[1] = s;
+    } else {
+      for (int t = 0; t < T; ++t) { double v = x[t]; if (!is_nan(v)) s += v; }
+      sc[2] = s;
+    }
+  }
+  DFM_SYNC();
+  if (DFM_TID != 0) return;
+  double cnt = sc[0];
+  double* lam = Lam ? Lam + (size_t)b * N * r : nullptr;
+  bool ok = (mode == 2) ? (cnt > r) : (cnt >= nt_min);
+  if (!ok) {
+    if (mode != 1 && lam) for (int a = 0; a < r; ++a) lam[i + (size_t)N * a] = DFM_NAN;
+    if (mode != 0 && out2) out2[(size_t)b * N + i] = DFM_NAN;
+    return;
+  }
+  double cty[64];                 // copy of rhs (r <= 64 enforced by the host)
+  for (int a = 0; a < r; ++a) cty[a] = c[a];
+  int bad = chol_solve_packed(A, c, r, 1);
+  if (bad) {
+    if (st) st[b].status = 3;
+    if (mode != 1 && lam) for (int a = 0; a < r; ++a) lam[i + (size_t)N * a] = DFM_NAN;
+    if (mode != 0 && out2) out2[(size_t)b * N + i] = DFM_NAN;
+    return;
+  }
+  if (mode == 0 && n_constr > 0) {
+    // rows of the stacked constraint that belong to this series
+    int nc = 0;
+    for (int q = 0; q < n_constr; ++q) if (c_index[q] == i) ++nc;
+    if (nc > 0) {
+      // tmp = (F'F)^-1 R'  (r x nc), S = R tmp (nc x nc), b -= tmp S^-1 (R b - r_std)
+      double* Gp = wk;                       // packed F'F
+      double* tmp = Gp + np;                 // r x nc
+      double* S = tmp + r * nc;              // packed nc
+      double* res = S + nc * (nc + 1) / 2;   // nc
+      const double* ftf = FtF + (size_t)b * r * r;
+      for (int a = 0; a < r; ++a) for (int cc = 0; cc <= a; ++cc) Gp[pidx(a, cc)] = ftf[a + r * cc];
+      int col = 0; bool first = true;
+      for (int q = 0; q < n_constr; ++q) {
+        if (c_index[q] != i) continue;
+        for (int a = 0; a < r; ++a) tmp[a + r * col] = c_R[q + (size_t)n_constr * a];
+        if (first) { if (chol_solve_packed(Gp, tmp + r * col, r, 1)) { st[b].status = 3; return; } first = false; }
+        else chol_resolve_packed(Gp, tmp + r * col, r, 1);
+        double rb = 0.0;
+        for (int a = 0; a < r; ++a) rb += c_R[q + (size_t)n_constr * a] * c[a];
+        res[col] = rb - c_r[q] / xstd[(size_t)b * N + c_index[q]];   // r_std (:1182-1186)
+        ++col;
+      }
+      int row = 0;
+      for (int q = 0; q < n_constr; ++q) {
+        if (c_index[q] != i) continue;
+        for (int cc = 0; cc <= row; ++cc) {
+          double s = 0.0;
+          for (int a = 0; a < r; ++a) s += c_R[q + (size_t)n_constr * a] * tmp[a + r * cc];
+          S[pidx(row, cc)] = s;
+        }
+        ++row;
+      }
+      if (chol_solve_packed(S, res, nc, 1)) { st[b].status = 3; return; }
+      for (int a = 0; a < r; ++a) { double s = 0.0; for (int cc = 0; cc < nc; ++cc) s += tmp[a + r * cc] * res[cc]; c[a] -= s; }
+    }
+  }
+  if (mode != 1 && lam) for (int a = 0; a < r; ++a) lam[i + (size_t)N * a] = c[a];
+  if (mode != 0 && out2) {
+    double bc = 0.0;
+    for (int a = 0; a < r; ++a) bc += c[a] * cty[a];
+    double ssr = sc[1] - bc;
+    if (mode == 1) { double tss = sc[1] - sc[2] * sc[2] / cnt; out2[(size_t)b * N + i] = 1.0 - ssr / tss; }
+    else out2[(size_t)b * N + i] = ssr / cnt;
+  }
+}
+
+// F-step (:364-366): one THREAD per period t; per-thread packed normal equations in shared memory.
+// A_t = Lam'Lam - sum_{i missing at t} lam_i lam_i'  (series with NaN Lam are excluded everywhere).
+// grid (ceil(T/NT), B); shared: (np + r) * NT + 40 doubles.
+__global__ void k_als_factor(const double* __restrict__ Xs, const double* __restrict__ LamAll,
+                             const double* __restrict__ LtLall, int T, int N, int r, double* __restrict__ Fnew,
+                             double* __restrict__ ssr_part, AlsState* st) {
+  DFM_SMEM(sm);
+  int b = DFM_BY;
+  if (st[b].done) return;
+  int np = r * (r + 1) / 2;
+  int nt = DFM_NT;
+  double* A = sm + DFM_TID;                 // element e at A[e*nt]
+  double* c = sm + (size_t)np * nt + DFM_TID;
+  double* red = sm + (size_t)(np + r) * nt;
+  const double* X = Xs + (size_t)b * T * N;
+  const double* Lam = LamAll + (size_t)b * N * r;
+  const double* LtL = LtLall + (size_t)b * r * r;
+  double* F = Fnew + (size_t)b * T * r;
+  double ssr = 0.0;
+  for (int t = DFM_BX * nt + DFM_TID; t < T; t += DFM_GX * nt) {
+    for (int a = 0; a < r; ++a) { c[a * nt] = 0.0; for (int cc = 0; cc <= a; ++cc) A[pidx(a, cc) * nt] = LtL[a + r * cc]; }
+    int nobs = 0;
+    for (int i = 0; i < N; ++i) {
+      double l0 = Lam[i];
+      if (is_nan(l0)) continue;
+      double x = X[t + (size_t)T * i];
+      if (!is_nan(x)) { ++nobs; for (int a = 0; a < r; ++a) c[a * nt] += x * Lam[i + (size_t)N * a]; }
+      else for (int a = 0; a < r; ++a) { double la = Lam[i + (size_t)N * a]; for (int cc = 0; cc <= a; ++cc) A[pidx(a, cc) * nt] -= la * Lam[i + (size_t)N * cc]; }
+    }
+    int bad = (nobs < r) ? 1 : chol_solve_packed(A, c, r, nt);
+    if (bad) { st[b].status = (nobs < r) ? 2 : 3; for (int a = 0; a < r; ++a) c[a * nt] = DFM_NAN; }
+    for (int a = 0; a < r; ++a) F[t + (size_t)T * a] = c[a * nt];
+    if (!bad)
+      for (int i = 0; i < N; ++i) {
+        double l0 = Lam[i];
+        if (is_nan(l0)) continue;
+        double x = X[t + (size_t)T * i];
+        if (is_nan(x)) continue;
+        double e = x;
+        for (int a = 0; a < r; ++a) e -= Lam[i + (size_t)N * a] * c[a * nt];
+        ssr += e * e;
+      }
+  }
+  ssr = block_sum(ssr, red);
+  if (DFM_TID == 0) ssr_part[(size_t)b * DFM_GX + DFM_BX] = ssr;
+}
+
+// SSR total + convergence test (:366-368).  grid (B), 1 thread.
+__global__ void k_als_check(AlsState* st, const double* ssr_part, int nblk, double tol, int T, int N,
+                            long long max_iter) {
+  if (DFM_TID != 0) return;
+  int b = DFM_BX;
+  if (st[b].done) return;
+  double s = 0.0;
+  for (int j = 0; j < nblk; ++j) s += ssr_part[(size_t)b * nblk + j];
+  st[b].ssr_old = st[b].ssr;
+  st[b].ssr = s;
+  st[b].iters += 1;
+  double diff = fabs(st[b].ssr_old - s);
+  if (!(diff >= tol * (double)T * (double)N)) st[b].done = 1;          // `diff >= tol*T*ns || break`
+  else if ((long long)st[b].iters >= max_iter) { st[b].done = 1; if (st[b].status == 0) st[b].status = 4; }
+  if (st[b].status == 2 || st[b].status == 3) st[b].done = 1;
+}
+
+// number of panels not yet done -> *out (device int).  grid (1), 1 block.
+__global__ void k_count_active(const AlsState* st, int B, int* out) {
+  DFM_SMEM(sm);
+  double n = 0.0;
+  for (int b = DFM_TID; b < B; b += DFM_NT) n += st[b].done ? 0.0 : 1.0;
+  n = block_sum(n, sm);
+  if (DFM_TID == 0) *out = (int)n;
+}
+
+// ---------------------------------------------------------------- a9 loadings + AR  (:391-415, :295-311)
+// One block per series.  data T x ns raw units, F T x r.  Regressors [F 1] (:399).
+// scratch: T doubles per block for the gap-free residual vector.
+__global__ void k_loading(const double* __restrict__ dataAll, const double* __restrict__ Fall, int T, int ns, int r,
+                          int nt_min, int n_uarlag, double* __restrict__ lambda, double* __restrict__ r2out,
+                          double* __restrict__ uar_coef, double* __restrict__ uar_ser, double* __restrict__ scratch,
+                          int n_constr, const int* __restrict__ c_index, const double* __restrict__ c_R,
+                          const double* __restrict__ c_r, int* __restrict__ status) {
+  DFM_SMEM(sm);
+  int s_ = DFM_BX, b = DFM_BY;
+  const double* y = dataAll + ((size_t)b * ns + s_) * T;
+  const double* F = Fall + (size_t)b * T * r;
+  double* u = scratch + ((size_t)b * ns + s_) * T;
+  int K = r + 1, np = K * (K + 1) / 2;
+  double* A = sm;               // packed K
+  double* c = A + np;           // K
+  double* sc = c + K;           // cnt, syy, sy
+  double* wk = sc + 4;
+  int nwork = np + K + 3;
+  for (int e = DFM_TID; e < nwork; e += DFM_NT) {
+    double s = 0.0;
+    if (e < np) {
+      int a = 0; while ((a + 1) * (a + 2) / 2 <= e) ++a;
+      int cc = e - a * (a + 1) / 2;
+      for (int t = 0; t < T; ++t) if (!is_nan(y[t])) {
+        double za = (a < r) ? F[t + (size_t)T * a] : 1.0, zc = (cc < r) ? F[t + (size_t)T * cc] : 1.0;
+        s += za * zc;
+      }
+      A[e] = s;
+    } else if (e < np + K) {
+      int a = e - np;
+      for (int t = 0; t < T; ++t) { double v = y[t]; if (!is_nan(v)) s += v * ((a < r) ? F[t + (size_t)T * a] : 1.0); }
+      c[a] = s;
+    } else if (e == np + K) { for (int t = 0; t < T; ++t) if (!is_nan(y[t])) s += 1.0; sc[0] = s; }
+    else if (e == np + K + 1) { for (int t = 0; t < T; ++t) { double v = y[t]; if (!is_nan(v)) s += v * v; } sc[1] = s; }
+    else { for (int t = 0; t < T; ++t) { double v = y[t]; if (!is_nan(v)) s += v; } sc[2] = s; }
+  }
+  DFM_SYNC();
+  if (DFM_TID != 0) return;
+  size_t o = (size_t)b * ns + s_;
+  double* lam = lambda + (size_t)b * ns * r;
+  double* ac = uar_coef + (size_t)b * ns * n_uarlag;
+  int cnt = (int)sc[0];
+  if (cnt < nt_min) {            // reference leaves these undefined (SURVEY 'bugs'): NaN
+    for (int a = 0; a < r; ++a) lam[s_ + (size_t)ns * a] = DFM_NAN;
+    r2out[o] = DFM_NAN; uar_ser[o] = DFM_NAN;
+    for (int l = 0; l < n_uarlag; ++l) ac[s_ + (size_t)ns * l] = DFM_NAN;
+    return;
+  }
+  bool constrained = false;
+  for (int q = 0; q < n_constr; ++q) if (c_index[q] == s_) constrained = true;
+  if (chol_solve_packed(A, c, K, 1)) { status[b] = 3; r2out[o] = DFM_NAN; return; }
+  if (constrained) {             // :loading constraint: R_tmp = [R 0], r unstandardized (:1147-1148)
+    int nc = 0;
+    for (int q = 0; q < n_constr; ++q) if (c_index[q] == s_) ++nc;
+    double* tmp = wk;            // K x nc
+    double* S = tmp + K * nc;
+    double* res = S + nc * (nc + 1) / 2;
+    int col = 0;
+    for (int q = 0; q < n_constr; ++q) {
+      if (c_index[q] != s_) continue;
+      for (int a = 0; a < r; ++a) tmp[a + K * col] = c_R[q + (size_t)n_constr * a];
+      tmp[r + K * col] = 0.0;
+      chol_resolve_packed(A, tmp + K * col, K, 1);
+      double rb = 0.0;
+      for (int a = 0; a < r; ++a) rb += c_R[q + (size_t)n_constr * a] * c[a];
+      res[col] = rb - c_r[q];
+      ++col;
+    }
+    int row = 0;
+    for (int q = 0; q < n_constr; ++q) {
+      if (c_index[q] != s_) continue;
+      for (int cc = 0; cc <= row; ++cc) {
+        double s = 0.0;
+        for (int a = 0; a < r; ++a) s += c_R[q + (size_t)n_constr * a] * tmp[a + K * cc];
+        S[pidx(row, cc)] = s;
+      }
+      ++row;
+    }
+    if (chol_solve_packed(S, res, nc, 1)) { status[b] = 3; return; }
+    for (int a = 0; a < K; ++a) { double s = 0.0; for (int cc = 0; cc < nc; ++cc) s += tmp[a + K * cc] * res[cc]; c[a] -= s; }
+  }
+  for (int a = 0; a < r; ++a) lam[s_ + (size_t)ns * a] = c[a];
+  // gap-free residuals (:400), R2 (:404 via compute_r2 :565-569)
+  int n = 0; double ssr = 0.0;
+  for (int t = 0; t < T; ++t) {
+    double v = y[t];
+    if (is_nan(v)) continue;
+    double e = v - c[r];
+    for (int a = 0; a < r; ++a) e -= c[a] * F[t + (size_t)T * a];
+    u[n++] = e; ssr += e * e;
+  }
+  double tss = sc[1] - sc[2] * sc[2] / cnt;
+  double R2 = 1.0 - ssr / tss;
+  r2out[o] = R2;
+  if (!(R2 < 0.9999)) {          // :405-409
+    for (int l = 0; l < n_uarlag; ++l) ac[s_ + (size_t)ns * l] = 0.0;
+    uar_ser[o] = 0.0;
+    return;
+  }
+  // uar (:305-311): regress u[j] on u[j-1..j-L], j = L..n-1; ser = sqrt(ssr/(n - L))
+  int L = n_uarlag, npl = L * (L + 1) / 2;
+  double* AA = wk; double* cc2 = AA + npl;
+  for (int e = 0; e < npl + L; ++e) AA[e] = 0.0;
+  for (int j = L; j < n; ++j)
+    for (int a = 0; a < L; ++a) {
+      double ua = u[j - 1 - a];
+      cc2[a] += ua * u[j];
+      for (int q = 0; q <= a; ++q) AA[pidx(a, q)] += ua * u[j - 1 - q];
+    }
+  if (n - L < L || chol_solve_packed(AA, cc2, L, 1)) { status[b] = 3; uar_ser[o] = DFM_NAN; return; }
+  double ssr2 = 0.0;
+  for (int j = L; j < n; ++j) { double e = u[j]; for (int a = 0; a < L; ++a) e -= cc2[a] * u[j - 1 - a]; ssr2 += e * e; }
+  for (int l = 0; l < L; ++l) ac[s_ + (size_t)ns * l] = cc2[l];
+  uar_ser[o] = sqrt(ssr2 / (double)(n - L));
+}
+
+// ---------------------------------------------------------------- a10 factor VAR (:444-492)
+// grid (B), one block.  Regressors [1, y_{t-1}, ..., y_{t-p}] (const first, :451).  dof_mode 0:
+// seps = e'e/(T_used - K) (:460-461); dof_mode 1: e'e/T_used (EM initialisation).
+// shared: K*K + K*r + 64 doubles.
+__global__ void k_var(const double* __restrict__ Fall, int T, int r, int p, int withconst, int dof_mode,
+                      double* __restrict__ betahat, double* __restrict__ resid, double* __restrict__ seps,
+                      double* __restrict__ Mo, double* __restrict__ Qo, double* __restrict__ Go, double* __restrict__ Ao,
+                      int* __restrict__ status) {
+  DFM_SMEM(sm);
+  int b = DFM_BX;
+  const double* F = Fall + (size_t)b * T * r;
+  int k = r * p, K = k + (withconst ? 1 : 0), Tu = T - p;
+  double* ZZ = sm;                 // K x K
+  double* ZY = ZZ + K * K;         // K x r  -> beta
+  double* Se = ZY + K * r;         // r x r
+  int* info = (int*)(Se + r * r);
+  if (DFM_TID == 0) *info = 0;
+  if (Tu <= K) { if (DFM_TID == 0) status[b] = 2; return; }
+  // regressor j at time t (t = p..T-1): j==0&&const -> 1 ; else lag l = (j-c)/r + 1, var = (j-c)%r
+#define ZREG(t, j) ((withconst && (j) == 0) ? 1.0 : F[((t) - (((j) - (withconst ? 1 : 0)) / r + 1)) + (size_t)T * (((j) - (withconst ? 1 : 0)) % r)])
+  for (int e = DFM_TID; e < K * K; e += DFM_NT) {
+    int a = e % K, c = e / K;
+    if (a < c) continue;
+    double s = 0.0;
+    for (int t = p; t < T; ++t) s += ZREG(t, a) * ZREG(t, c);
+    ZZ[a + K * c] = s; ZZ[c + K * a] = s;
+  }
+  for (int e = DFM_TID; e < K * r; e += DFM_NT) {
+    int a = e % K, c = e / K;
+    double s = 0.0;
+    for (int t = p; t < T; ++t) s += ZREG(t, a) * F[t + (size_t)T * c];
+    ZY[a + K * c] = s;
+  }
+  DFM_SYNC();
+  bm_chol(ZZ, K, K, info);
+  bm_trsm_lower(ZZ, K, K, ZY, K, r);
+  bm_trsm_lowerT(ZZ, K, K, ZY, K, r);          // ZY = betahat (K x r)
+  if (*info) { if (DFM_TID == 0) status[b] = 3; return; }
+  // residuals -> global (needed for seps); rows < p are NaN (:464 leaves them missing)
+  double* res = resid + (size_t)b * T * r;
+  for (int e = DFM_TID; e < T * r; e += DFM_NT) {
+    int t = e % T, c = e / T;
+    double v = DFM_NAN;
+    if (t >= p) { v = F[t + (size_t)T * c]; for (int a = 0; a < K; ++a) v -= ZREG(t, a) * ZY[a + K * c]; }
+    res[t + (size_t)T * c] = v;
+  }
+  DFM_SYNC();
+#undef ZREG
+  double ndf = dof_mode ? (double)Tu : (double)(Tu - K);
+  for (int e = DFM_TID; e < r * r; e += DFM_NT) {
+    int a = e % r, c = e / r;
+    double s = 0.0;
+    for (int t = p; t < T; ++t) s += res[t + (size_t)T * a] * res[t + (size_t)T * c];
+    Se[a + r * c] = s / ndf;
+  }
+  DFM_SYNC();
+  if (betahat) for (int e = DFM_TID; e < K * r; e += DFM_NT) betahat[(size_t)b * K * r + e] = ZY[e];
+  if (seps) for (int e = DFM_TID; e < r * r; e += DFM_NT) seps[(size_t)b * r * r + e] = Se[e];
+  // companion matrices (:477-492)
+  int c0 = withconst ? 1 : 0;
+  if (Mo) for (int e = DFM_TID; e < k * k; e += DFM_NT) {
+    int i = e % k, j = e / k;
+    double v = 0.0;
+    if (i < r) v = ZY[(c0 + j) + K * i];            // b = betahat[2:end,:]'
+    else if (j == i - r) v = 1.0;
+    Mo[(size_t)b * k * k + e] = v;
+  }
+  if (Ao) for (int e = DFM_TID; e < r * k; e += DFM_NT) { int i = e % r, j = e / r; Ao[(size_t)b * r * k + e] = ZY[(c0 + j) + K * i]; }
+  if (Qo) for (int e = DFM_TID; e < r * k; e += DFM_NT) { int i = e % r, j = e / r; Qo[(size_t)b * r * k + e] = (i == j) ? 1.0 : 0.0; }
+  DFM_SYNC();
+  if (Go) {
+    bm_chol(Se, r, r, info);                           // lower factor = cholesky(seps).U'
+    if (*info && DFM_TID == 0) status[b] = 3;
+    for (int e = DFM_TID; e < k * r; e += DFM_NT) { int i = e % k, j = e / k; Go[(size_t)b * k * r + e] = (i < r) ? Se[i + r * j] : 0.0; }
+  }
+}
+
+// ---------------------------------------------------------------- a11 IRF (:793-816)
+// grid (n_shock, B), one block per shock; shared 2k doubles.
+__global__ void k_irf(const double* __restrict__ Mall, const double* __restrict__ Qall, const double* __restrict__ Gall,
+                      int k, int r, int H, int n_shock, const int* __restrict__ shock_ids, double* __restrict__ irf) {
+  DFM_SMEM(sm);
+  int j = DFM_BX, b = DFM_BY;
+  const double* M = Mall + (size_t)b * k * k; const double* Q = Qall + (size_t)b * r * k;
+  const double* G = Gall + (size_t)b * k * r;
+  double* x = sm; double* x2 = sm + k;
+  double* out = irf + ((size_t)b * n_shock + j) * r * H;
+  for (int i = DFM_TID; i < k; i += DFM_NT) x[i] = G[i + (size_t)k * shock_ids[j]];
+  DFM_SYNC();
+  for (int h = 0; h < H; ++h) {
+    for (int i = DFM_TID; i < r; i += DFM_NT) { double s = 0.0; for (int l = 0; l < k; ++l) s += Q[i + (size_t)r * l] * x[l]; out[i + (size_t)r * h] = s; }
+    for (int i = DFM_TID; i < k; i += DFM_NT) { double s = 0.0; for (int l = 0; l < k; ++l) s += M[i + (size_t)k * l] * x[l]; x2[i] = s; }
+    DFM_SYNC();
+    for (int i = DFM_TID; i < k; i += DFM_NT) x[i] = x2[i];
+    DFM_SYNC();
+  }
+}
+
+}  // namespace dfm

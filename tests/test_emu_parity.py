@@ -1,0 +1,35 @@
+"""CPU-only: run the parity checks against the HOST-EMULATION build of the kernel source
+(tests/emu/libdfm_emu.so = the same .cu/.cuh files compiled by g++ with one logical thread per
+block).  This validates kernel index/algebra logic and the C-ABI host orchestration without a GPU;
+the real CUDA parity tests are tests/test_gpu_parity.py (-m gpu)."""
+import os
+import sys
+
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "emu"))
+import build_emu  # noqa: E402
+import parity_checks as P  # noqa: E402
+from dynamic_factor_models_b200 import Library  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def lib():
+    L = Library(build_emu.build())
+    yield L
+    L.close()
+
+
+def test_standardize(lib): P.check_standardize(lib)
+def test_pca(lib): P.check_pca(lib)
+def test_estimate_factor_same_init(lib): P.check_estimate_factor_same_init(lib)
+def test_estimate_factor_c1(lib, panels): P.check_estimate_factor_c1(lib, panels)
+def test_constraint(lib, panels): P.check_constraint(lib, panels)
+def test_full_nonparametric_c1(lib, panels): P.check_full_nonparametric_c1(lib, panels)
+def test_var_irf(lib): P.check_var_irf(lib)
+def test_em_p1_balanced(lib): P.check_em(lib, p=1, miss=0.0)
+def test_em_p2_missing(lib): P.check_em(lib, p=2, miss=0.12)
+def test_em_convergence_rule(lib): P.check_em_convergence_rule(lib)
+def test_em_batch(lib): P.check_em_batch(lib)
+def test_als_batch(lib): P.check_als_batch(lib)
+def test_parametric_c1(lib, panels): P.check_parametric_c1(lib, panels, iters=2)
