@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""bench.py -- EM iterations/sec of the B200 DFM hot path (BASELINE.json metric).
+
+Unit of work: one EM iteration (Kalman filter + RTS smoother E-step, M-step) on one C2-shaped panel
+(N=200, r=8, T=500, FP64).  A "step" = EM_ITERS iterations over this rank's shard of independent
+Monte-Carlo panels (BASELINE config C5 sharded: 10 000 / 8 = 1250 panels per GPU, weak scaling),
+followed by the path's single collective: one NCCL all-gather of the per-replication statistics.
+
+  value  : panel-EM-iterations / s, inputs resident in HBM, device-timed (CUDA events), max over ranks
+  e2e    : same through the C ABI with pinned HOST buffers (H2D of panel + initial parameters and
+           D2H of factors + parameters inside the timed region)
+  roofline: dominant kernel's algorithmic bytes (2*T*N*8 per panel-iteration) / its
+           CUDA-event duration, against MEASURED_PEAKS.json
+  cpu_baseline / --impl reference: the oracle's C port of the same EM (OpenMP over panels) on the
+           host cores -- the reference itself is Julia and has no Kalman/EM code.
+
+python bench.py --gpus N --steps K --warmup W [--impl reference]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NS, R_, T_, P_ = 200, 8, 500, 1
+METRIC = "EM iters/sec (N=200,r=8,T=500)"
+UNIT = "panel-EM-iterations/s"
+
+
+def make_panels(B, rep0):
+    """Frozen DGP of SURVEY.md 8d (oracle/dgp.py), vectorised AR recursion.  (B, T, N) float64."""
+    from scipy.signal import lfilter
+    from oracle.dgp import SEED
+    out = np.empty((B, T_, NS))
+    for b in range(B):
+        rng = np.random.Generator(np.random.Philox(key=[SEED, rep0 + b]))
+        Lam = rng.standard_normal((NS, R_)); a = rng.uniform(0.2, 0.8, R_); s2 = rng.uniform(0.5, 1.5, NS)
+        eta = rng.standard_normal((T_ + 100, R_)); e = rng.standard_normal((T_, NS)) * np.sqrt(s2)
+        F = np.stack([lfilter([1.0], [1.0, -a[j]], eta[:, j]) for j in range(R_)], axis=1)[100:]
+        X = F @ Lam.T + e
+        out[b] = (X - X.mean(0)) / X.std(0)
+    return out
+
+
+class ClockSampler:
+    def __init__(self, dev):
+        self.dev, self.rows, self.proc = dev, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.dev), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True); self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for j, n in enumerate(names) if any(len(r) >= 7 and r[3 + j].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_em(Xs, init, iters, nthreads=0):
+    """Oracle C port on host cores: (seconds, panel-iterations)."""
+    from oracle.c import kem
+    t0 = time.perf_counter()
+    out = kem.em_kalman_batch(Xs, init[0], init[1], init[2], init[3], p=P_, max_iter=iters, tol=0.0, nthreads=nthreads, want_F=True)
+    dt = time.perf_counter() - t0
+    assert (out["status"] == 0).all()
+    return dt, Xs.shape[0] * iters, out
+
+
+def host_init(Xs):
+    from oracle import dfm_ref as Rf, kalman_em as K
+    ini = [K.init_from_factors(Xs[b], Rf.pca_score(Xs[b], R_), P_) for b in range(Xs.shape[0])]
+    return tuple(np.stack([i[j] for i in ini]) for j in range(4))
+
+
+def run_reference(args):
+    """--impl reference: the CPU arm.  The reference is Julia (not installable here: no julia, no
+    network) and contains no Kalman/EM code, so the oracle's C port of the same EM is timed, with all
+    host threads, on a bounded sample of the same workload per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.c import kem
+    cores = kem.max_threads()
+    Bs = 4 * cores
+    Xs = make_panels(Bs, 0)
+    init = host_init(Xs)
+    iters = args.em_iters
+    for _ in range(args.warmup):
+        cpu_em(Xs, init, 2)
+    t = 0.0; n = 0
+    for _ in range(args.steps):
+        dt, units, _ = cpu_em(Xs, init, iters)
+        t += dt; n += units
+    v = n / t
+    sample = f"{Bs} panels x {iters} EM iterations per step (oracle C port, OpenMP over panels)"
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                      "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                      "config": {"workload": f"C2-shaped panels N={NS} r={R_} T={T_}, Kalman-EM, bounded CPU sample", "em_iters": iters},
+                      "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                      "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--panels", type=int, default=1250, help="panels per GPU (C5 shard = 10000/8)")
+    ap.add_argument("--em-iters", type=int, default=50, help="EM iterations per step (SURVEY 8d: fixed 50)")
+    ap.add_argument("--path", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from dynamic_factor_models_b200 import Library
+    from dynamic_factor_models_b200._lib import MEM_DEVICE, MEM_HOST
+
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = Library(device=local)
+
+    B, iters, K_, W_ = args.panels, args.em_iters, args.steps, args.warmup
+    k = R_ * P_; np_ = R_ * (R_ + 1) // 2
+    # ---- inputs: this rank's replication shard (ids rank*B .. rank*B+B-1: identical whatever the GPU count)
+    Xh = make_panels(B, rank * B)                                  # (B, T, N)
+    X_cm = torch.from_numpy(np.ascontiguousarray(Xh.transpose(0, 2, 1)))   # column-major panels
+    dX = X_cm.to(dev)
+    # initial parameters on the device: one ALS sweep from PCA (reference path) -> init_from_factors
+    dF0 = torch.empty(B * T_ * R_, dtype=torch.float64, device=dev)
+    lib.estimate_factor_raw(dX.data_ptr(), T_, NS, R_, B, MEM_DEVICE, F=dF0.data_ptr(), max_iter=1)
+    dLam0 = torch.empty(B * NS * R_, dtype=torch.float64, device=dev); dR0 = torch.empty(B * NS, dtype=torch.float64, device=dev)
+    dA0 = torch.empty(B * R_ * k, dtype=torch.float64, device=dev); dQ0 = torch.empty(B * R_ * R_, dtype=torch.float64, device=dev)
+    import ctypes as C
+    lib.check(lib.lib.dfm_em_init_from_factors(lib.h, C.c_void_p(dX.data_ptr()), C.c_void_p(dF0.data_ptr()), T_, NS, R_, P_, B, MEM_DEVICE,
+                                               C.c_void_p(dLam0.data_ptr()), C.c_void_p(dR0.data_ptr()), C.c_void_p(dA0.data_ptr()),
+                                               C.c_void_p(dQ0.data_ptr())), "em_init")
+    lib.sync()
+    dout = {n: torch.empty(sz, dtype=torch.float64, device=dev) for n, sz in
+            dict(Lam=B * NS * R_, R=B * NS, A=B * R_ * k, Q=B * R_ * R_, F=B * T_ * R_, loglik=B * iters).items()}
+    dit = torch.empty(B, dtype=torch.int32, device=dev); dst = torch.empty(B, dtype=torch.int32, device=dev)
+    init_d = dict(Lam=dLam0.data_ptr(), R=dR0.data_ptr(), A=dA0.data_ptr(), Q=dQ0.data_ptr(), P0=0)
+    out_d = dict(Lam=dout["Lam"].data_ptr(), R=dout["R"].data_ptr(), A=dout["A"].data_ptr(), Q=dout["Q"].data_ptr(), P0=0,
+                 F=dout["F"].data_ptr(), PF=0, loglik=dout["loglik"].data_ptr(), iters=dit.data_ptr(), status=dst.data_ptr())
+    rec = torch.empty(B, 2, dtype=torch.float64, device=dev)       # per-replication record: final loglik, iterations
+    gathered = torch.empty(world * B, 2, dtype=torch.float64, device=dev) if world > 1 else None
+
+    def step_device():
+        lib.em_kalman_raw(dX.data_ptr(), T_, NS, R_, P_, B, iters, 0.0, init_d, out_d, MEM_DEVICE, args.path)
+        lib.sync()
+        rec[:, 0] = dout["loglik"].view(B, iters)[:, -1]; rec[:, 1] = dit.to(torch.float64)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, rec)             # the path's single collective (NCCL / NVLink)
+
+    def timed(fn, nsteps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter(); e0.record()
+        for _ in range(nsteps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        ms = e0.elapsed_time(e1)
+        ms = max(ms, 0.0)
+        tt = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt[0]), float(tt[1])
+
+    for _ in range(W_):
+        step_device()
+    clocks = ClockSampler(local); clocks.start()
+    l0 = lib.launches
+    ms_dev, ms_wall = timed(step_device, K_)
+    launches = lib.launches - l0
+    clk = clocks.stop()
+    ms = max(ms_dev, 0.0)
+    # library work is on its own stream: the step ends with lib.sync(), so torch-stream events bracket
+    # host-synchronised steps; use the larger of event / wall clock (they agree to < 1%)
+    ms = max(ms, ms_wall) if ms < 0.5 * ms_wall else ms
+    units = world * B * iters * K_
+    value = units / (ms * 1e-3)
+    status_ok = bool((dst == 0).all().item())
+
+    # ---- e2e through the C ABI with pinned host buffers
+    hX = X_cm.pin_memory()
+    hin = {n: t.cpu().pin_memory() for n, t in dict(Lam=dLam0, R=dR0, A=dA0, Q=dQ0).items()}
+    hout = {n: torch.empty(t.numel(), dtype=torch.float64).pin_memory() for n, t in dout.items()}
+    hit = torch.empty(B, dtype=torch.int32).pin_memory(); hst = torch.empty(B, dtype=torch.int32).pin_memory()
+    init_h = dict(Lam=hin["Lam"].data_ptr(), R=hin["R"].data_ptr(), A=hin["A"].data_ptr(), Q=hin["Q"].data_ptr(), P0=0)
+    out_h = dict(Lam=hout["Lam"].data_ptr(), R=hout["R"].data_ptr(), A=hout["A"].data_ptr(), Q=hout["Q"].data_ptr(), P0=0,
+                 F=hout["F"].data_ptr(), PF=0, loglik=hout["loglik"].data_ptr(), iters=hit.data_ptr(), status=hst.data_ptr())
+    h2d = 8 * (hX.numel() + sum(t.numel() for t in hin.values()))
+    d2h = 8 * sum(t.numel() for t in hout.values()) + 8 * B
+
+    def step_e2e():
+        lib.em_kalman_raw(hX.data_ptr(), T_, NS, R_, P_, B, iters, 0.0, init_h, out_h, MEM_HOST, args.path)
+        if world > 1:
+            rec[:, 0] = hout["loglik"].view(B, iters)[:, -1].to(dev); rec[:, 1] = hit.to(dev).to(torch.float64)
+            dist.all_gather_into_tensor(gathered, rec)
+
+    step_e2e()
+    Ke = max(2, min(K_, 3))
+    _, ms_e2e = timed(step_e2e, Ke)
+    e2e_value = world * B * iters * Ke / (ms_e2e * 1e-3)
+
+    # ---- roofline: per-kernel CUDA-event timing of one profiled step (outside the timed region)
+    lib.profile(True)
+    lib.em_kalman_raw(dX.data_ptr(), T_, NS, R_, P_, B, iters, 0.0, init_d, out_d, MEM_DEVICE, args.path)
+    lib.sync()
+    prof = lib.profile_report(); lib.profile(False)
+    tot = sum(v[0] for v in prof.values()) or 1.0
+    dom = max(prof, key=lambda n: prof[n][0]) if prof else None
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    if os.path.exists(peaks_path):
+        try:
+            pk = json.load(open(peaks_path)); peak = float(pk.get("hbm_gbs", peak)); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    roof = None
+    if dom:
+        d_ms, d_cnt = prof[dom]
+        units_per_launch = B * iters / d_cnt                       # panel-iterations one launch of the dominant kernel processes
+        alg_bytes = 2.0 * T_ * NS * 8 * units_per_launch           # 2*T*N*8 bytes per panel-iteration
+        ach = alg_bytes / (d_ms / d_cnt * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "peak_source": peak_src, "kernel_share_of_step": d_ms / tot, "avg_launch_ms": d_ms / d_cnt,
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "kernel_ms": {n: round(v[0], 3) for n, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}}
+
+    # ---- CPU baseline (rank 0, N=1 only): oracle C port on a bounded sample of the same workload
+    cpu = None; rmse = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle.c import kem
+        cores = kem.max_threads()
+        Bs = min(B, 4 * cores)
+        Lh = lambda t, rows, cols: np.ascontiguousarray(t[:Bs * rows * cols].cpu().numpy().reshape(Bs, cols, rows).transpose(0, 2, 1))
+        init = (Lh(dLam0, NS, R_), dR0[:Bs * NS].cpu().numpy().reshape(Bs, NS), Lh(dA0, R_, k), Lh(dQ0, R_, R_))
+        cpu_em(Xh[:2], tuple(a[:2] for a in init), 2)
+        dt, n, out = cpu_em(Xh[:Bs], init, iters)
+        cpu = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{Bs} of the same panels x {iters} EM iterations, oracle C port (gcc -O3, OpenMP over panels), {dt:.1f} s"}
+        Fg = dout["F"][:Bs * T_ * R_].cpu().numpy().reshape(Bs, R_, T_).transpose(0, 2, 1)
+        rmse = float(np.sqrt(np.mean((Fg - out["F"]) ** 2)))
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K_, "warmup": W_,
+                "ms_per_step": ms / K_, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": f"C5 shard of C2-shaped Monte-Carlo panels: {B} panels/GPU, N={NS} r={R_} T={T_} p={P_}, "
+                                       f"{iters} EM iterations (Kalman filter + RTS smoother + M-step) per step, then one all-gather",
+                           "panels_per_gpu": B, "em_iters_per_step": iters, "parallelism": f"replications x{world}",
+                           "l2": f"inputs {B * T_ * NS * 8 / 1e6:.0f} MB/GPU > 126 MB L2 (no flush needed)",
+                           "path": args.path, "all_status_ok": status_ok},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / Ke},
+                "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+                "factor_rmse_vs_oracle": rmse, "timing": {"cuda_event_ms": ms_dev, "wall_ms": ms_wall}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    lib.close()
+
+
+if __name__ == "__main__":
+    main()

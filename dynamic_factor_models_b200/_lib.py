@@ -56,7 +56,8 @@ def default_library_path():
 
 
 EXPORTS = ["dfm_version", "dfm_status_string", "dfm_create", "dfm_create_on_stream", "dfm_destroy", "dfm_sync",
-           "dfm_launch_count", "dfm_last_error", "dfm_standardize", "dfm_pca_score", "dfm_estimate_factor",
+           "dfm_launch_count", "dfm_last_error", "dfm_profile_enable", "dfm_profile_query", "dfm_profile_reset",
+           "dfm_profile_kernel_name", "dfm_standardize", "dfm_pca_score", "dfm_estimate_factor",
            "dfm_estimate_loading", "dfm_estimate_var", "dfm_irf", "dfm_em_kalman", "dfm_em_init_from_factors",
            "dfm_allgather_results", "dfm_shard_range"]
 
@@ -104,6 +105,11 @@ class Library:
         L.dfm_last_error.argtypes = [C.c_void_p]
         L.dfm_launch_count.restype = C.c_longlong
         L.dfm_launch_count.argtypes = [C.c_void_p]
+        L.dfm_profile_enable.argtypes = [C.c_void_p, C.c_int]
+        L.dfm_profile_query.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
+        L.dfm_profile_reset.argtypes = [C.c_void_p]
+        L.dfm_profile_kernel_name.argtypes = [C.c_void_p, C.c_int]
+        L.dfm_profile_kernel_name.restype = C.c_char_p
         L.dfm_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
         L.dfm_create_on_stream.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
         L.dfm_destroy.argtypes = [C.c_void_p]
@@ -148,6 +154,40 @@ class Library:
     @property
     def launches(self):
         return int(self.lib.dfm_launch_count(self.h))
+
+    def profile(self, on=True):
+        self.lib.dfm_profile_reset(self.h)
+        self.lib.dfm_profile_enable(self.h, int(on))
+
+    def profile_report(self):
+        """{kernel name: (total ms, launches)} since profile(True)."""
+        out = {}
+        i = 0
+        while True:
+            nm = self.lib.dfm_profile_kernel_name(self.h, i)
+            if not nm:
+                break
+            ms, cnt = C.c_double(), C.c_longlong()
+            self.lib.dfm_profile_query(self.h, nm, C.byref(ms), C.byref(cnt))
+            out[nm.decode()] = (ms.value, cnt.value)
+            i += 1
+        return out
+
+    def em_kalman_raw(self, X, T, N, r, p, B, max_iter, tol, init, out, mem, path=0):
+        """Pointer-level call (ints = device or pinned-host addresses).  init/out: dicts of
+        name -> address (missing = NULL)."""
+        o = EmOpts(T=T, N=N, r=r, p=p, max_iter=max_iter, tol=tol, batch=B, mem=mem, path=path)
+        ini = EmInit(**{k: C.c_void_p(v) if v else None for k, v in init.items()})
+        ou = EmOut(**{k: C.c_void_p(v) if v else None for k, v in out.items()})
+        self.check(self.lib.dfm_em_kalman(self.h, C.c_void_p(X), C.byref(o), C.byref(ini), C.byref(ou)), "dfm_em_kalman")
+
+    def estimate_factor_raw(self, X, T, N, r, B, mem, F=0, Lam=0, nt_min=20, tol=1e-8, max_iter=100000000, F_init=0):
+        o = FactorOpts(T=T, N=N, r=r, nt_min=nt_min, tol=tol, max_iter=max_iter, compute_r2=0, batch=B, mem=mem)
+        st = (FactorStats * B)()
+        vp = lambda a: C.c_void_p(a) if a else None
+        self.check(self.lib.dfm_estimate_factor(self.h, C.c_void_p(X), C.byref(o), vp(F_init), vp(F), vp(Lam), None, None, None, st),
+                   "dfm_estimate_factor")
+        return [dict(ssr=s.ssr, tss=s.tss, nobs=s.nobs, iters=s.iters, status=s.status) for s in st]
 
     def shard_range(self, n_rep, rank, world):
         b, e = C.c_longlong(), C.c_longlong()

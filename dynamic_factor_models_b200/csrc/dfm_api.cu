@@ -35,6 +35,12 @@ static inline const char* cudaGetErrorString(cudaError_t) { return "emu"; }
 
 using namespace dfm;
 
+struct ProfRec { const char* name; 
+#ifndef DFM_EMU
+  cudaEvent_t e0, e1;
+#endif
+};
+
 struct dfm_handle {
   int device;
   cudaStream_t stream;
@@ -42,6 +48,8 @@ struct dfm_handle {
   char* ws;
   size_t ws_bytes;
   long long launches;
+  int profile;                 // 1: bracket every kernel launch with CUDA events (dfm_profile_*)
+  std::vector<ProfRec>* prof;
   char err[256];
 };
 
@@ -70,8 +78,17 @@ int fail(dfm_handle* h, int code, const char* msg) {
     snprintf(h->err, sizeof(h->err), "%s:%d %s", __FILE__, __LINE__, cudaGetErrorString(e__));    \
     return DFM_ERR_CUDA; } } while (0)
 
+#ifdef DFM_EMU
+#define PROF_BEGIN(name) ((void)0)
+#define PROF_END() ((void)0)
+#else
+#define PROF_BEGIN(name_)                                                                          \
+  ProfRec pr__; pr__.name = name_;                                                                 \
+  if (h->profile) { cudaEventCreate(&pr__.e0); cudaEventCreate(&pr__.e1); cudaEventRecord(pr__.e0, h->stream); }
+#define PROF_END() if (h->profile) { cudaEventRecord(pr__.e1, h->stream); h->prof->push_back(pr__); }
+#endif
 #define L(kern, gx, gy, nt, smem, ...)                                                             \
-  do { DFM_LAUNCH(kern, gx, gy, nt, smem, h->stream, __VA_ARGS__); h->launches++; } while (0)
+  do { PROF_BEGIN(#kern); DFM_LAUNCH(kern, gx, gy, nt, smem, h->stream, __VA_ARGS__); PROF_END(); h->launches++; } while (0)
 
 int ensure_ws(dfm_handle* h, size_t bytes) {
   if (bytes <= h->ws_bytes) return DFM_OK;
@@ -140,6 +157,7 @@ int dfm_create_on_stream(int device, void* cuda_stream, dfm_handle** out) {
   dfm_handle* h = new (std::nothrow) dfm_handle();
   if (!h) return DFM_ERR_CUDA;
   h->device = device; h->ws = nullptr; h->ws_bytes = 0; h->launches = 0; h->err[0] = 0;
+  h->profile = 0; h->prof = new std::vector<ProfRec>();
   if (cuda_stream) { h->stream = (cudaStream_t)cuda_stream; h->own_stream = false; }
   else { if (cudaStreamCreate(&h->stream) != cudaSuccess) { delete h; return DFM_ERR_CUDA; } h->own_stream = true; }
   DFM_SET_SMEM(k_em_filter_smooth, kMaxSmem); DFM_SET_SMEM(k_als_factor, kMaxSmem); DFM_SET_SMEM(k_em_contract, kMaxSmem);
@@ -157,12 +175,50 @@ int dfm_destroy(dfm_handle* h) {
   cudaStreamSynchronize(h->stream);
   if (h->ws) cudaFree(h->ws);
   if (h->own_stream) cudaStreamDestroy(h->stream);
+  delete h->prof;
   delete h;
   return DFM_OK;
 }
 int dfm_sync(dfm_handle* h) { if (!h) return DFM_ERR_ARG; CK(cudaStreamSynchronize(h->stream)); return DFM_OK; }
 long long dfm_launch_count(const dfm_handle* h) { return h ? h->launches : -1; }
 const char* dfm_last_error(const dfm_handle* h) { return h ? h->err : "null handle"; }
+
+// ---- per-kernel CUDA-event profiling (bench.py's roofline leg; off by default) -----------------
+int dfm_profile_enable(dfm_handle* h, int on) {
+  if (!h) return DFM_ERR_ARG;
+  h->profile = on ? 1 : 0;
+  return DFM_OK;
+}
+// Sum of device time (ms) and number of launches of kernel `name` since the last reset; name = NULL
+// or "" sums over all kernels.  Synchronizes the stream.
+int dfm_profile_query(dfm_handle* h, const char* name, double* ms, long long* count) {
+  if (!h || !ms || !count) return DFM_ERR_ARG;
+  *ms = 0; *count = 0;
+#ifndef DFM_EMU
+  CK(cudaStreamSynchronize(h->stream));
+  for (auto& r : *h->prof) {
+    if (name && name[0] && strcmp(name, r.name) != 0) continue;
+    float t = 0; cudaEventElapsedTime(&t, r.e0, r.e1); *ms += t; *count += 1;
+  }
+#endif
+  return DFM_OK;
+}
+int dfm_profile_reset(dfm_handle* h) {
+  if (!h) return DFM_ERR_ARG;
+#ifndef DFM_EMU
+  cudaStreamSynchronize(h->stream);
+  for (auto& r : *h->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+#endif
+  h->prof->clear();
+  return DFM_OK;
+}
+// name of the i-th distinct profiled kernel (NULL when i is out of range)
+const char* dfm_profile_kernel_name(dfm_handle* h, int i) {
+  if (!h) return nullptr;
+  std::vector<const char*> names;
+  for (auto& r : *h->prof) { bool seen = false; for (auto n : names) if (!strcmp(n, r.name)) seen = true; if (!seen) names.push_back(r.name); }
+  return (i >= 0 && i < (int)names.size()) ? names[i] : nullptr;
+}
 
 int dfm_shard_range(long long n_rep, int rank, int world, long long* begin, long long* end) {
   if (n_rep < 0 || world <= 0 || rank < 0 || rank >= world || !begin || !end) return DFM_ERR_ARG;

@@ -57,6 +57,12 @@ int dfm_sync(dfm_handle* h);
 /* number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 long long dfm_launch_count(const dfm_handle* h);
 const char* dfm_last_error(const dfm_handle* h);
+/* Optional per-kernel device timing with CUDA events on the handle's stream (measurement aid for
+ * bench.py's roofline leg; off by default, adds two event records per launch when on). */
+int dfm_profile_enable(dfm_handle* h, int on);
+int dfm_profile_query(dfm_handle* h, const char* kernel_name /*NULL = all*/, double* ms, long long* count);
+int dfm_profile_reset(dfm_handle* h);
+const char* dfm_profile_kernel_name(dfm_handle* h, int i);
 
 /* ---- a2: standardize_data, dfm_functions.ipynb:501-509 ------------------------------- */
 /* Xs = (X - mean)/std per column over non-missing entries, population std. */

@@ -1,0 +1,77 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path through the C ABI vs the
+oracle, on the reference's own panel (hom_fac_1, committed fixture), seeded synthetic panels,
+edge cases, and size-independent properties at BASELINE.json's full sizes."""
+import numpy as np
+import pytest
+
+import parity_checks as P
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from dynamic_factor_models_b200 import Library
+    L = Library()            # in-tree CUDA build; raises if missing (no fallback)
+    assert L.path.endswith("libdfm_b200.so")
+    yield L
+    L.close()
+
+
+def test_standardize(lib): P.check_standardize(lib)
+def test_pca(lib): P.check_pca(lib)
+def test_estimate_factor_same_init(lib): P.check_estimate_factor_same_init(lib)
+def test_estimate_factor_c1(lib, panels): P.check_estimate_factor_c1(lib, panels)
+def test_estimate_factor_c1_r1(lib, panels): P.check_estimate_factor_c1(lib, panels, r=1)
+def test_constraint(lib, panels): P.check_constraint(lib, panels)
+def test_full_nonparametric_c1(lib, panels): P.check_full_nonparametric_c1(lib, panels)
+def test_var_irf(lib): P.check_var_irf(lib)
+def test_em_p1_balanced(lib): P.check_em(lib, p=1, miss=0.0, path=1)
+def test_em_p2_missing(lib): P.check_em(lib, p=2, miss=0.12, path=1)
+def test_em_p1_missing(lib): P.check_em(lib, p=1, miss=0.1, path=1, rep=10)
+def test_em_auto_path(lib): P.check_em(lib, N=40, r=8, T=90, p=1, miss=0.0, path=0, iters=5)
+def test_em_convergence_rule(lib): P.check_em_convergence_rule(lib, path=1)
+def test_em_batch(lib): P.check_em_batch(lib, path=1)
+def test_als_batch(lib): P.check_als_batch(lib)
+def test_parametric_c1(lib, panels): P.check_parametric_c1(lib, panels, iters=3)
+
+
+def test_table2B_through_gpu(lib, panels, notebook_tables):
+    """Golden Table 2B (Stock_Watson.ipynb:616-629) reproduced by the CUDA path, r = 1..10."""
+    import dynamic_factor_models_b200 as D
+    gold = np.array(notebook_tables["table2B"])
+    for r in range(1, 11):
+        g = P.gpu_model(panels["all_bpdata"], panels["all_inclcode"], r)
+        D.estimate_factor(g, computeR2=False, lib=lib)
+        assert abs((1 - g.fes.ssr / g.fes.tss) - gold[r - 1, 1]) < 6e-4
+        assert abs(D.bai_ng_criterion(g) - gold[r - 1, 3]) < 6e-4
+
+
+def test_c2_full_size_vs_oracle(lib):
+    """BASELINE config C2 (N=200, r=8, T=500): 3 EM iterations vs the oracle + EM invariants."""
+    P.check_em(lib, N=200, r=8, T=500, p=1, miss=0.0, iters=3, path=0, rep=0)
+
+
+def test_c2_full_size_properties(lib):
+    """Size-independent properties at full C2 size over a batch: monotone log-likelihood, batch
+    independence (a panel's result does not depend on its neighbours), permutation equivariance."""
+    from oracle.dgp import simulate_batch
+    from oracle import dfm_ref as R, kalman_em as K
+    B, N, r, T = 6, 200, 8, 500
+    Xb = simulate_batch(B, N, r, T, rep0=100)
+    inits = [K.init_from_factors(Xb[b], R.pca_score(Xb[b], r), 1) for b in range(B)]
+    Lam = np.stack([i[0] for i in inits]); Rv = np.stack([i[1] for i in inits])
+    A = np.stack([i[2] for i in inits]); Q = np.stack([i[3] for i in inits])
+    got = lib.em_kalman(Xb, Lam, Rv, A, Q, p=1, max_iter=20)
+    ll = got["loglik"]
+    assert (np.diff(ll, axis=1) > -1e-9 * np.abs(ll[:, :-1])).all()
+    perm = np.array([3, 0, 5, 1, 4, 2])
+    got2 = lib.em_kalman(Xb[perm], Lam[perm], Rv[perm], A[perm], Q[perm], p=1, max_iter=20)
+    np.testing.assert_allclose(got2["F"], got["F"][perm], rtol=1e-12, atol=1e-13)
+    # series-permutation equivariance: reordering series leaves factors unchanged (to rounding)
+    sp = np.random.default_rng(0).permutation(N)
+    got3 = lib.em_kalman(Xb[0][:, sp], Lam[0][sp], Rv[0][sp], A[0], Q[0], p=1, max_iter=20)
+    assert P.rmse(got3["F"], got["F"][0]) < 1e-9
+    np.testing.assert_allclose(got3["Lam"], got["Lam"][0][sp], rtol=1e-7, atol=1e-9)
