@@ -5,6 +5,7 @@
 #include "dfm_common.cuh"
 #include "dfm_kernels_np.cuh"
 #include "dfm_kernels_em.cuh"
+#include "dfm_kernels_fused.cuh"
 #include <algorithm>
 #include <new>
 #include <vector>
@@ -129,6 +130,46 @@ int tpt_threads(int ws_doubles) {
 }
 
 }  // namespace
+
+// any NaN in the panel / parameters?  (the fused path handles balanced panels only)
+namespace dfm {
+__global__ void k_em_scan_fused(const double* __restrict__ X, const double* __restrict__ Lam, const double* __restrict__ R,
+                                int T, int N, int r, int* flag) {
+  int i = DFM_BX, b = DFM_BY;
+  const double* x = X + ((size_t)b * N + i) * T;
+  int bad = 0;
+  for (int t = DFM_TID; t < T; t += DFM_NT) if (is_nan(x[t])) bad = 1;
+  if (DFM_TID == 0) { for (int a = 0; a < r; ++a) if (is_nan(Lam[(size_t)b * N * r + i + (size_t)N * a])) bad = 1; if (is_nan(R[(size_t)b * N + i])) bad = 1; }
+  if (bad) *flag = 1;
+}
+}  // namespace dfm
+
+template <int RT>
+static int launch_fused(dfm_handle* h, const FusedArgs& fa, int B, int T, int N, double** scratch_out, Arena* arena, bool dry) {
+  size_t smem = fused_smem_doubles<RT>(T, N) * 8;
+  int grid = B;
+#ifndef DFM_EMU
+  if (!dry) {
+    DFM_SET_SMEM(k_em_fused<RT>, smem);
+    int dev = 0, nsm = 148, occ = 1;
+    cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_em_fused<RT>, 128, smem);
+    if (occ < 1) occ = 1;
+    grid = std::min(B, nsm * occ);
+  } else grid = std::min(B, 148 * 8);
+#endif
+  double* scr = arena->get<double>((size_t)(dry ? std::min(B, 148 * 8) : std::min(B, 148 * 8)) * T * FUSED_SCR(RT));
+  if (dry) return DFM_OK;
+  FusedArgs a2 = fa; a2.scratch = scr;
+  L(k_em_fused<RT>, grid, 1, 128, smem, a2);
+  (void)scratch_out;
+  return DFM_OK;
+}
+
+static bool fused_shape_ok(int T, int N, int r, int p) {
+  if (p != 1 || r < 1 || r > 8 || T < 3) return false;
+  return ((size_t)T * FZ + (size_t)N * r + 3 * (size_t)N + 30 * (size_t)r * r + 128) * 8 <= kMaxSmem;
+}
 
 extern "C" {
 
@@ -487,13 +528,6 @@ int dfm_em_init_from_factors(dfm_handle* h, const double* Xs, const double* F, i
 }
 
 // ------------------------------------------------------------------------------------ a'
-#ifndef DFM_EMU
-int dfm_em_kalman_fused(dfm_handle* h, const double* dX, const dfm_em_opts* o, double* dLam, double* dR, double* dA,
-                        double* dQ, const double* dP0, double* dFs, double* dPsF, double* dll, int* diters, int* dstatus,
-                        long long* launches);   // dfm_fast.cu
-int dfm_em_fused_supported(const dfm_em_opts* o);
-#endif
-
 int dfm_em_kalman(dfm_handle* h, const double* X, const dfm_em_opts* o, const dfm_em_init* init, const dfm_em_out* out) {
   if (!h || !X || !o || !init || !out || !init->Lam || !init->R || !init->A || !init->Q)
     return fail(h, DFM_ERR_ARG, "dfm_em_kalman: null argument");
@@ -506,11 +540,9 @@ int dfm_em_kalman(dfm_handle* h, const double* X, const dfm_em_opts* o, const df
   size_t B = batch, TN = (size_t)T * N; int k = r * p, kk = k * k, rr = r * r, rk = r * k, np = r * (r + 1) / 2;
   int ntC = tpt_threads(np + r);
   int nblkC = (T + ntC - 1) / ntC;
-  bool fused = false;
-#ifndef DFM_EMU
-  fused = (o->path == 2) || (o->path == 0 && dfm_em_fused_supported(o));
-  if (o->path == 2 && !dfm_em_fused_supported(o)) return fail(h, DFM_ERR_UNSUPPORTED, "dfm_em_kalman: fused path does not support this shape");
-#endif
+  const bool fused_ok = fused_shape_ok(T, N, r, p);
+  if (o->path == 2 && !fused_ok) return fail(h, DFM_ERR_UNSUPPORTED, "dfm_em_kalman: fused path needs p = 1, r <= 8 and a panel that fits shared memory");
+  bool fused = fused_ok && o->path != 1;
   for (int pass = 0; pass < 2; ++pass) {
     Arena a(pass ? h->ws : nullptr);
     double* dXb = mem == DFM_MEM_HOST ? a.get<double>(B * TN) : nullptr;
@@ -523,7 +555,19 @@ int dfm_em_kalman(dfm_handle* h, const double* X, const dfm_em_opts* o, const df
     double *dAn = nullptr, *dQn = nullptr, *dW = nullptr, *dlogR = nullptr, *dC = nullptr, *dBt = nullptr, *dqt = nullptr,
            *dslr = nullptr, *dCt = nullptr, *dzp = nullptr, *dzf = nullptr, *dPp = nullptr, *dPf = nullptr, *dSff = nullptr;
     int* dnt = nullptr;
-    if (!fused) {
+    int* dflag = a.get<int>(4);
+    Arena fa_arena(nullptr);
+    size_t fused_off = a.off;
+    if (fused_ok && o->path != 1) {      // scratch of the fused kernel (superset allocation: the path is chosen after the scan)
+      FusedArgs dummy{}; Arena tmpa(nullptr);
+      switch (r) {
+#define DFM_CASE(RT) case RT: launch_fused<RT>(h, dummy, batch, T, N, nullptr, &a, true); break;
+        DFM_CASE(1) DFM_CASE(2) DFM_CASE(3) DFM_CASE(4) DFM_CASE(5) DFM_CASE(6) DFM_CASE(7) DFM_CASE(8)
+#undef DFM_CASE
+      }
+    }
+    (void)fa_arena; (void)fused_off;
+    {
       dAn = a.get<double>(B * rk); dQn = a.get<double>(B * rr); dW = a.get<double>(B * N * r); dlogR = a.get<double>(B * N);
       dC = a.get<double>(B * rr); dBt = a.get<double>(B * T * r); dqt = a.get<double>(B * T); dslr = a.get<double>(B * T);
       dnt = a.get<int>(B * T); dCt = a.get<double>(B * T * np); dzp = a.get<double>(B * T * k); dzf = a.get<double>(B * T * k);
@@ -542,11 +586,29 @@ int dfm_em_kalman(dfm_handle* h, const double* X, const dfm_em_opts* o, const df
       long long n = (long long)B * mi;
       L(k_fill, (int)std::min<long long>((n + 255) / 256, 1024), 1, 256, 0, dll, n, DFM_NAN);
     }
+    if (fused) {                          // balanced panel, all series in the model?
+      CK(cudaMemsetAsync(dflag, 0, sizeof(int), h->stream));
+      L(k_em_scan_fused, N, batch, 64, 0, x, dL, dR, T, N, r, dflag);
+      int hflag = 0;
+      CK(cudaMemcpyAsync(&hflag, dflag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      if (hflag) {
+        if (o->path == 2) return fail(h, DFM_ERR_UNSUPPORTED, "dfm_em_kalman: fused path needs a balanced panel (no NaN)");
+        fused = false;
+      }
+    }
     if (fused) {
-#ifndef DFM_EMU
-      rc = dfm_em_kalman_fused(h, x, o, dL, dR, dA, dQ, dP0, dFs, dPsF, dll, dit, dstat, &h->launches);
-      if (rc) return fail(h, rc, "dfm_em_kalman: fused path failed");
-#endif
+      FusedArgs fa{};
+      fa.X = x; fa.Lam = dL; fa.R = dR; fa.A = dA; fa.Q = dQ; fa.P0 = dP0; fa.Fs = dFs; fa.PsF = dPsF; fa.loglik = dll;
+      fa.iters = dit; fa.status = dstat; fa.B = batch; fa.T = T; fa.N = N; fa.max_iter = mi; fa.tol = o->tol;
+      // re-derive the scratch pointer: it was the first allocation after dflag in this pass
+      Arena a2(h->ws); a2.off = fused_off;
+      switch (r) {
+#define DFM_CASE(RT) case RT: rc = launch_fused<RT>(h, fa, batch, T, N, nullptr, &a2, false); break;
+        DFM_CASE(1) DFM_CASE(2) DFM_CASE(3) DFM_CASE(4) DFM_CASE(5) DFM_CASE(6) DFM_CASE(7) DFM_CASE(8)
+#undef DFM_CASE
+      }
+      if (rc) return rc;
     } else {
       L(k_em_state_init, batch, 1, 1, 0, st);
       L(k_em_scan, N, batch, 64, 0, x, dL, T, N, r, st);

@@ -2,7 +2,7 @@
 // state-space EM, row a' of SURVEY.md section 8.  No reference code exists for this path
 // (dfm_functions.ipynb:23 is an empty placeholder); the spec is oracle/kalman_em.py.
 // One EM iteration = k_em_prep -> k_em_contract -> k_em_filter_smooth -> k_em_mstep_series.
-// The fused small-k fast path lives in dfm_fast.cu; this file is also the path the host-emulation
+// The fused small-k fast path lives in dfm_kernels_fused.cuh; this file is also the path the host-emulation
 // tests exercise.
 #pragma once
 #include "dfm_common.cuh"

@@ -1,0 +1,576 @@
+// dfm_kernels_fused.cuh -- FUSED per-panel EM kernel: the whole EM loop (E-step Kalman filter + RTS
+// smoother, M-step) of one panel runs inside one CTA; one launch covers all panels and all
+// iterations.  Row a' of SURVEY.md section 8, fast path for p = 1, r <= 8, balanced panels (k = r).
+//
+//  * panel reads: exactly two streaming passes per EM iteration (E-step contraction
+//    b_t = Lam' R^-1 x_t and M-step contraction S_xf = X' E[f]), straight from HBM into FP64
+//    tensor-core fragments: mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4) -- tcgen05 has no FP64 kind and
+//    the 1e-5 parity bar needs FP64;
+//  * Lam, 1/R and the T x r state buffer Z (b_t -> f_t|t -> f_t|T in place) live in shared memory;
+//  * the covariance recursion of a balanced panel is data independent and time invariant: warp 0
+//    runs it explicitly only until P_{t|t-1} stops changing (relative 1e-14; a handful of steps at
+//    N = 200), forward and backward, and closes the moment sums in closed form over the frozen
+//    range (validated in tools/proto_fused.py against the oracle);
+//  * the mean recursions are two T-step r x r matvec chains on r lanes of warp 0.
+// The serial logic is written phase-style (loops over DFM_LANE + DFM_WSYNC) so that the host
+// emulation harness (tests/emu) executes the very same source; only the two DMMA loops have an
+// #ifdef DFM_EMU plain-loop twin.
+#pragma once
+#include "dfm_common.cuh"
+
+#ifdef DFM_EMU
+#define DFM_LANE 0
+#define DFM_WSZ 1
+#define DFM_WARP 0
+#define DFM_NWARP 1
+#define DFM_WSYNC() ((void)0)
+#else
+#define DFM_LANE ((int)(threadIdx.x & 31))
+#define DFM_WSZ 32
+#define DFM_WARP ((int)(threadIdx.x >> 5))
+#define DFM_NWARP ((int)(blockDim.x >> 5))
+#define DFM_WSYNC() __syncwarp()
+#endif
+
+namespace dfm {
+
+#define FZ 8   // padded row stride of Z (= DMMA tile width)
+
+struct FusedArgs {
+  const double* X;      // [B][N][T] column-major panels
+  double* Lam;          // [B][N*r] column-major (in: init, out: final)
+  double* R;            // [B][N]
+  double* A;            // [B][r*r] column-major
+  double* Q;            // [B][r*r]
+  const double* P0;     // [B][r*r]
+  double* Fs;           // [B][T*r] column-major  (out)
+  double* PsF;          // [B][T*np] packed        (out)
+  double* loglik;       // [B][max_iter]           (pre-filled with NaN)
+  int* iters; int* status;
+  double* scratch;      // [gridDim.x][T * FUSED_SCR]
+  int B, T, N, max_iter;
+  double tol;
+};
+#define FUSED_SCR(R_) (5 * (R_) * (R_) + 1)
+
+__device__ __forceinline__ double w_max(double v) {
+#ifndef DFM_EMU
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+#endif
+  return v;
+}
+
+// ---- warp-0 small dense ops on row-major R x R matrices in shared memory ------------------------
+template <int R>
+__device__ __forceinline__ void w_gemm(double* C, const double* A, bool ta, const double* B, bool tb) {
+  for (int e = DFM_LANE; e < R * R; e += DFM_WSZ) {
+    int i = e / R, j = e % R;
+    double s = 0.0;
+#pragma unroll
+    for (int l = 0; l < R; ++l) s += (ta ? A[l * R + i] : A[i * R + l]) * (tb ? B[j * R + l] : B[l * R + j]);
+    C[e] = s;
+  }
+  DFM_WSYNC();
+}
+template <int R>
+__device__ __forceinline__ void w_sym(double* A) {
+  for (int e = DFM_LANE; e < R * R; e += DFM_WSZ) {
+    int i = e / R, j = e % R;
+    if (i > j) { double v = 0.5 * (A[i * R + j] + A[j * R + i]); A[i * R + j] = v; A[j * R + i] = v; }
+  }
+  DFM_WSYNC();
+}
+// Gauss-Jordan inverse (no pivoting; SPD input) + log det.  Ai <- A^-1.  tmp: 2R doubles.
+template <int R>
+__device__ __forceinline__ double w_inv(double* Ai, const double* A, double* tmp, int* bad) {
+  for (int e = DFM_LANE; e < R * R; e += DFM_WSZ) Ai[e] = A[e];
+  DFM_WSYNC();
+  double ld = 0.0;
+  for (int p = 0; p < R; ++p) {
+    for (int e = DFM_LANE; e < R; e += DFM_WSZ) { tmp[e] = Ai[p * R + e]; tmp[R + e] = Ai[e * R + p]; }
+    DFM_WSYNC();
+    double piv = tmp[p];
+    if (!(piv > 0.0)) { *bad = 1; piv = 1.0; }
+    ld += log(piv);
+    double d = 1.0 / piv;
+    for (int e = DFM_LANE; e < R * R; e += DFM_WSZ) {
+      int i = e / R, j = e % R;
+      double v;
+      if (i == p && j == p) v = d;
+      else if (i == p) v = tmp[j] * d;
+      else if (j == p) v = -tmp[R + i] * d;
+      else v = Ai[e] - tmp[R + i] * tmp[j] * d;
+      Ai[e] = v;
+    }
+    DFM_WSYNC();
+  }
+  return ld;
+}
+
+// Serial constant-coefficient recursion on warp 0:  Z[t] <- Cf Z[t - dir] + Z[t]  for t = t0, t0+dir, ..
+// up to (excluding) t1.  R lanes own one state component each (coefficient row in registers); all
+// 32 lanes execute the same __syncwarp sequence.
+template <int R>
+__device__ __forceinline__ void w_recur(double* Z, const double* Cf, double* tmp, int t0, int t1, int dir) {
+#ifdef DFM_EMU
+  for (int t = t0; t != t1; t += dir) {
+    if ((dir > 0 && t >= t1) || (dir < 0 && t <= t1)) break;
+    for (int i = 0; i < R; ++i) { double s = Z[t * FZ + i]; for (int j = 0; j < R; ++j) s += Cf[i * R + j] * Z[(t - dir) * FZ + j]; tmp[i] = s; }
+    for (int i = 0; i < R; ++i) Z[t * FZ + i] = tmp[i];
+  }
+#else
+  (void)tmp;
+  const int i = threadIdx.x & 31;
+  const bool act = i < R;
+  double cf[R];
+#pragma unroll
+  for (int j = 0; j < R; ++j) cf[j] = act ? Cf[i * R + j] : 0.0;
+  if ((dir > 0 && t0 >= t1) || (dir < 0 && t0 <= t1)) return;
+  for (int t = t0; t != t1; t += dir) {
+    double s0 = 0.0, s1 = 0.0;
+    if (act) {
+      const double* zp = Z + (t - dir) * FZ;
+      s0 = Z[t * FZ + i];
+#pragma unroll
+      for (int j = 0; j < R; j += 2) { s0 += cf[j] * zp[j]; if (j + 1 < R) s1 += cf[j + 1] * zp[j + 1]; }
+      Z[t * FZ + i] = s0 + s1;
+    }
+    __syncwarp();
+  }
+#endif
+}
+
+// ================================================================================================
+#ifdef DFM_EMU
+#define DFM_FUSED_BOUNDS
+#else
+#define DFM_FUSED_BOUNDS __launch_bounds__(128, 3)
+#endif
+template <int R>
+__global__ void DFM_FUSED_BOUNDS k_em_fused(FusedArgs a) {
+  DFM_SMEM(sm);
+  constexpr int RR = R * R, NP = R * (R + 1) / 2;
+  const int T = a.T, N = a.N;
+  // ---- shared layout
+  double* Z = sm;                          // [T][FZ]
+  double* Lam = Z + (size_t)T * FZ;        // [N][R] row-major
+  double* rinv = Lam + (size_t)N * R;      // [N]
+  double* Rv = rinv + N;                   // [N]
+  double* sxx = Rv + N;                    // [N]
+  double* mats = sxx + N;
+  double* M = mats;            double* Q = M + RR;        double* C = Q + RR;        double* Pp = C + RR;
+  double* Pi = Pp + RR;        double* Pf = Pi + RR;      double* Wm = Pf + RR;      double* G = Wm + RR;
+  double* Phi = G + RR;        double* Jm = Phi + RR;     double* Pn = Jm + RR;      double* T1 = Pn + RR;
+  double* T2 = T1 + RR;        double* Ps = T2 + RR;      double* Psn = Ps + RR;     double* SPall = Psn + RR;
+  double* SP00 = SPall + RR;   double* SPff2 = SP00 + RR; double* SP11 = SPff2 + RR; double* Sm = SP11 + RR;
+  double* S11m = Sm + RR;      double* Pfinf = S11m + RR; double* Phinf = Pfinf + RR; double* Jinf = Phinf + RR;
+  double* Winf = Jinf + RR;    double* Ppinf = Winf + RR; double* IJM = Ppinf + RR;  double* Pfprev = IJM + RR;
+  double* tmp = Pfprev + RR;               // 2R
+  double* red = tmp + 2 * R;               // 40
+  double* scal = red + 40;                 // 8: [0]=slr [1]=ld_inf [2]=qsum
+  int* ctl = (int*)(scal + 8);             // [0]=nE [1]=tb [2]=bad [3]=frozen
+  double* scr = a.scratch + (size_t)DFM_BX * T * FUSED_SCR(R);
+  // per explicit step t: scr[t*SCR + {0:Pf, RR:Phi, 2RR:J, 3RR:W, 4RR:Ps, 5RR: ld}]
+  const double eps = 1e-14;
+
+  for (int b = DFM_BX; b < a.B; b += DFM_GX) {
+    const double* X = a.X + (size_t)b * T * N;
+    // ---- load parameters (global column-major -> shared row-major)
+    for (int e = DFM_TID; e < N * R; e += DFM_NT) { int i = e % N, c = e / N; Lam[i * R + c] = a.Lam[(size_t)b * N * R + e]; }
+    for (int e = DFM_TID; e < N; e += DFM_NT) Rv[e] = a.R[(size_t)b * N + e];
+    for (int e = DFM_TID; e < RR; e += DFM_NT) {
+      int i = e / R, j = e % R;
+      M[e] = a.A[(size_t)b * RR + i + R * j]; Q[e] = a.Q[(size_t)b * RR + i + R * j];
+    }
+    if (DFM_TID == 0) ctl[2] = 0;
+    DFM_SYNC();
+    int it = 0, status = 0;
+    double ll_prev = 0.0;
+    for (; it < a.max_iter; ++it) {
+      // ---------------------------------------------------------------- P0: prep
+      double slr_p = 0.0;
+      for (int i = DFM_TID; i < N; i += DFM_NT) { double rv = Rv[i]; rinv[i] = 1.0 / rv; slr_p += log(rv); if (!(rv > 0.0)) ctl[2] = 1; }
+      slr_p = block_sum(slr_p, red);
+      if (DFM_TID == 0) scal[0] = slr_p;
+      for (int e = DFM_TID; e < RR; e += DFM_NT) {
+        int i = e / R, j = e % R;
+        double s = 0.0;
+        for (int n = 0; n < N; ++n) s += Lam[n * R + i] * rinv[n] * Lam[n * R + j];
+        C[e] = s;
+      }
+      DFM_SYNC();
+      // ---------------------------------------------------------------- P1: E-step contraction (panel pass 1)
+      double qacc = 0.0;
+#ifdef DFM_EMU
+      for (int t = 0; t < T; ++t) {
+        for (int c = 0; c < FZ; ++c) Z[t * FZ + c] = 0.0;
+        for (int n = 0; n < N; ++n) {
+          double x = X[(size_t)n * T + t], xr = x * rinv[n];
+          qacc += x * xr;
+          for (int c = 0; c < R; ++c) Z[t * FZ + c] += xr * Lam[n * R + c];
+        }
+      }
+#else
+      {
+        const int lane = DFM_LANE, lr = lane >> 2, lc = lane & 3;
+        const int nrb = (T + 7) / 8;
+        for (int rb = DFM_WARP; rb < nrb; rb += DFM_NWARP) {
+          int t = rb * 8 + lr;
+          bool tok = t < T;
+          double d0 = 0.0, d1 = 0.0;
+          const double* xp = X + (tok ? t : 0);
+          for (int i0 = 0; i0 < N; i0 += 40) {
+            double av[10];
+#pragma unroll
+            for (int u = 0; u < 10; ++u) {
+              int n = i0 + 4 * u + lc;
+              av[u] = (tok && n < N) ? __ldg(xp + (size_t)n * T) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 10; ++u) {
+              int n = i0 + 4 * u + lc;
+              if (i0 + 4 * u < N) {
+                double ri = (n < N) ? rinv[n] : 0.0;
+                double ar = av[u] * ri;
+                qacc += av[u] * ar;
+                double bv = (n < N && lr < R) ? Lam[n * R + lr] : 0.0;
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                             : "+d"(d0), "+d"(d1) : "d"(ar), "d"(bv));
+              }
+            }
+          }
+          if (tok) { Z[t * FZ + 2 * lc] = d0; Z[t * FZ + 2 * lc + 1] = d1; }
+        }
+      }
+#endif
+      qacc = block_sum(qacc, red);
+      if (DFM_TID == 0) scal[2] = qacc;
+      DFM_SYNC();
+      // ---------------------------------------------------------------- P2: covariance chain (warp 0, data independent)
+      if (DFM_WARP == 0) {
+        int* bad = &ctl[2];
+        // forward
+        for (int e = DFM_LANE; e < RR; e += DFM_WSZ) { int i = e / R, j = e % R; Pp[e] = a.P0[(size_t)b * RR + i + R * j]; }
+        DFM_WSYNC();
+        int nE = T, frozen_at = -1, t = 0;
+        while (t < T) {
+          double ldp = w_inv<R>(Pi, Pp, tmp, bad);
+          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) Wm[e] = Pi[e] + C[e];
+          DFM_WSYNC();
+          double ldw = w_inv<R>(Pf, Wm, tmp, bad);
+          w_gemm<R>(G, Pf, false, Pi, false);
+          w_gemm<R>(Phi, G, false, M, false);
+          if (t >= 1) { w_gemm<R>(T1, Pfprev, false, M, true); w_gemm<R>(Jm, T1, false, Pi, false); }   // J_{t-1}
+          w_gemm<R>(T1, M, false, Pf, false);
+          w_gemm<R>(Pn, T1, false, M, true);
+          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) Pn[e] += Q[e];
+          DFM_WSYNC();
+          w_sym<R>(Pn);
+          double* s_ = scr + (size_t)t * FUSED_SCR(R);
+          double dmax = 0.0, pmax = 0.0;
+          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) {
+            s_[e] = Pf[e]; s_[RR + e] = Phi[e]; s_[3 * RR + e] = Wm[e];
+            if (t >= 1) (s_ - FUSED_SCR(R))[2 * RR + e] = Jm[e];
+            dmax = fmax(dmax, fabs(Pn[e] - Pp[e])); pmax = fmax(pmax, fabs(Pp[e]));
+            Pfprev[e] = Pf[e];
+          }
+          if (DFM_LANE == 0) s_[5 * RR] = ldp + ldw;
+          dmax = w_max(dmax); pmax = w_max(pmax);
+          DFM_WSYNC();
+          if (frozen_at >= 0 && t == frozen_at + 1) {
+            nE = t + 1;
+            for (int e = DFM_LANE; e < RR; e += DFM_WSZ) { Pfinf[e] = Pf[e]; Phinf[e] = Phi[e]; Winf[e] = Wm[e]; }
+            if (DFM_LANE == 0) scal[1] = ldp + ldw;
+            DFM_WSYNC();
+            w_gemm<R>(T1, Pf, false, M, true);
+            w_gemm<R>(Jinf, T1, false, Pi, false);                 // J_inf = Pf_inf M' Pi_inf
+            break;
+          }
+          if (frozen_at < 0 && dmax <= eps * pmax) frozen_at = t;
+          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) Pp[e] = Pn[e];
+          DFM_WSYNC();
+          ++t;
+        }
+        const int frozen = nE < T;
+        // backward covariance chain + covariance parts of the moment sums
+        for (int e = DFM_LANE; e < RR; e += DFM_WSZ) {
+          double v = frozen ? Pfinf[e] : (scr + (size_t)(T - 1) * FUSED_SCR(R))[e];
+          Psn[e] = v; SPall[e] = v; SPff2[e] = v; SP00[e] = 0.0; SP11[e] = 0.0;
+          (scr + (size_t)(T - 1) * FUSED_SCR(R))[4 * RR + e] = v;
+        }
+        DFM_WSYNC();
+        const int lo = frozen ? nE - 1 : T;
+        int tb = -1;                        // frozen smoothed range is [lo, tb)
+        t = T - 2;
+        while (t >= 0) {
+          const double* pf_t = (t < nE) ? scr + (size_t)t * FUSED_SCR(R) : Pfinf;
+          const double* j_t = (t < nE - 1) ? scr + (size_t)t * FUSED_SCR(R) + 2 * RR : Jinf;
+          // Pp_{t+1} = M Pf_t M' + Q (recomputed: cheaper than storing)
+          w_gemm<R>(T1, M, false, pf_t, false);
+          w_gemm<R>(T2, T1, false, M, true);
+          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) T2[e] = Psn[e] - (T2[e] + Q[e]);
+          DFM_WSYNC();
+          w_sym<R>(T2);                                           // D = Ps_{t+1} - Pp_{t+1}
+          w_gemm<R>(T1, j_t, false, T2, false);
+          w_gemm<R>(Ps, T1, false, j_t, true);
+          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) Ps[e] += pf_t[e];
+          DFM_WSYNC();
+          w_sym<R>(Ps);
+          w_gemm<R>(T1, Psn, false, j_t, true);                    // Ps_{t+1} J_t'
+          double dmax = 0.0, pmax = 0.0;
+          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) {
+            SP11[e] += T1[e]; SPall[e] += Ps[e]; SP00[e] += Ps[e];
+            if (t >= 1) SPff2[e] += Ps[e];
+            (scr + (size_t)t * FUSED_SCR(R))[4 * RR + e] = Ps[e];
+            dmax = fmax(dmax, fabs(Ps[e] - Psn[e])); pmax = fmax(pmax, fabs(Ps[e]));
+          }
+          dmax = w_max(dmax); pmax = w_max(pmax);
+          DFM_WSYNC();
+          bool conv = frozen && t > lo && dmax <= eps * pmax;
+          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) Psn[e] = Ps[e];
+          DFM_WSYNC();
+          if (conv) {
+            tb = t;
+            double cnt = (double)(t - lo);
+            w_gemm<R>(T1, Ps, false, Jinf, true);
+            for (int e = DFM_LANE; e < RR; e += DFM_WSZ) {
+              SPall[e] += cnt * Ps[e]; SP00[e] += cnt * Ps[e];
+              SPff2[e] += ((lo >= 1) ? cnt : cnt - 1.0) * Ps[e];
+              SP11[e] += cnt * T1[e];
+              Ppinf[e] = Ps[e];                                  // Ps_inf (smoothed covariance of the frozen range)
+            }
+            DFM_WSYNC();
+            t = lo - 1;
+          } else --t;
+        }
+        if (DFM_LANE == 0) { ctl[0] = nE; ctl[1] = tb; ctl[3] = frozen; }
+        // I - J_inf M  (for the parallel pre-pass of the backward mean recursion)
+        if (frozen) {
+          w_gemm<R>(IJM, Jinf, false, M, false);
+          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) { int i = e / R, j = e % R; IJM[e] = ((i == j) ? 1.0 : 0.0) - IJM[e]; }
+        }
+        DFM_WSYNC();
+      }
+      DFM_SYNC();
+      const int nE = ctl[0], frozen = ctl[3];
+      // ---------------------------------------------------------------- P3: forward means
+      // parallel pre-pass over the frozen range: Z[t] <- Pf_inf b_t
+      for (int t = nE + DFM_TID; t < T; t += DFM_NT) {
+        double bb[R], u[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) bb[j] = Z[t * FZ + j];
+#pragma unroll
+        for (int i = 0; i < R; ++i) { double s = 0.0;
+#pragma unroll
+          for (int j = 0; j < R; ++j) s += Pfinf[i * R + j] * bb[j]; u[i] = s; }
+#pragma unroll
+        for (int i = 0; i < R; ++i) Z[t * FZ + i] = u[i];
+      }
+      DFM_SYNC();
+      if (DFM_WARP == 0) {
+        // explicit steps
+        for (int t = 0; t < nE; ++t) {
+          const double* s_ = scr + (size_t)t * FUSED_SCR(R);
+          for (int i = DFM_LANE; i < R; i += DFM_WSZ) {
+            double s = 0.0;
+            for (int j = 0; j < R; ++j) s += s_[i * R + j] * Z[t * FZ + j];                 // Pf_t b_t
+            if (t >= 1) for (int j = 0; j < R; ++j) s += s_[RR + i * R + j] * Z[(t - 1) * FZ + j];   // Phi_t zf_{t-1}
+            tmp[i] = s;
+          }
+          DFM_WSYNC();
+          for (int i = DFM_LANE; i < R; i += DFM_WSZ) Z[t * FZ + i] = tmp[i];
+          DFM_WSYNC();
+        }
+        // frozen steps: z_t = Phi_inf z_{t-1} + u_t   (R lanes, coefficient row in registers)
+        w_recur<R>(Z, Phinf, tmp, (nE > 0 ? nE : 1), T, +1);
+      }
+      DFM_SYNC();
+      // ---------------------------------------------------------------- P4: log-likelihood (parallel over t)
+      double llp = 0.0;
+      for (int t = DFM_TID; t < T; t += DFM_NT) {
+        const double* Wt = (t < nE) ? scr + (size_t)t * FUSED_SCR(R) + 3 * RR : Winf;
+        double ldt = (t < nE) ? (scr + (size_t)t * FUSED_SCR(R))[5 * RR] : scal[1];
+        double zp[R], d[R];
+#pragma unroll
+        for (int i = 0; i < R; ++i) { double s = 0.0; if (t >= 1) {
+#pragma unroll
+            for (int j = 0; j < R; ++j) s += M[i * R + j] * Z[(t - 1) * FZ + j]; }
+          zp[i] = s; d[i] = Z[t * FZ + i] - s; }
+        double quad = 0.0;
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+          double cz = 0.0, g = 0.0;
+#pragma unroll
+          for (int j = 0; j < R; ++j) { cz += C[i * R + j] * zp[j]; g += Wt[i * R + j] * d[j]; }
+          quad -= zp[i] * cz + 2.0 * zp[i] * g + g * d[i];
+        }
+        llp += -0.5 * ((double)N * 1.8378770664093454835606594728112 + scal[0] + ldt + quad);
+      }
+      llp = block_sum(llp, red);
+      const double ll = llp - 0.5 * scal[2];
+      // ---------------------------------------------------------------- P5: backward means
+      if (frozen) {
+        int lo = nE - 1;
+        for (int t = lo + DFM_TID; t < T - 1; t += DFM_NT) {       // Z[t] <- (I - J_inf M) zf_t
+          double zz[R], v[R];
+#pragma unroll
+          for (int j = 0; j < R; ++j) zz[j] = Z[t * FZ + j];
+#pragma unroll
+          for (int i = 0; i < R; ++i) { double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < R; ++j) s += IJM[i * R + j] * zz[j]; v[i] = s; }
+#pragma unroll
+          for (int i = 0; i < R; ++i) Z[t * FZ + i] = v[i];
+        }
+      }
+      DFM_SYNC();
+      if (DFM_WARP == 0) {
+        const int lo = frozen ? nE - 1 : T;
+        // frozen range: z_t = J_inf z_{t+1} + v_t
+        w_recur<R>(Z, Jinf, tmp, T - 2, lo - 1, -1);
+        // explicit range: zs_t = zf_t + J_t (zs_{t+1} - M zf_t)
+        for (int t = (lo - 1 < T - 2 ? lo - 1 : T - 2); t >= 0; --t) {
+          const double* j_t = scr + (size_t)t * FUSED_SCR(R) + 2 * RR;
+          for (int i = DFM_LANE; i < R; i += DFM_WSZ) { double s = Z[(t + 1) * FZ + i]; for (int j = 0; j < R; ++j) s -= M[i * R + j] * Z[t * FZ + j]; tmp[i] = s; }
+          DFM_WSYNC();
+          for (int i = DFM_LANE; i < R; i += DFM_WSZ) { double s = Z[t * FZ + i]; for (int j = 0; j < R; ++j) s += j_t[i * R + j] * tmp[j]; tmp[R + i] = s; }
+          DFM_WSYNC();
+          for (int i = DFM_LANE; i < R; i += DFM_WSZ) Z[t * FZ + i] = tmp[R + i];
+          DFM_WSYNC();
+        }
+      }
+      DFM_SYNC();
+      // ---------------------------------------------------------------- P7: mean parts of the moment sums
+      for (int e = DFM_TID; e < 2 * RR; e += DFM_NT) {
+        int which = e / RR, ee = e % RR, i = ee / R, j = ee % R;
+        double s = 0.0;
+        if (which == 0) { for (int t = 0; t < T; ++t) s += Z[t * FZ + i] * Z[t * FZ + j]; Sm[ee] = s; }
+        else { for (int t = 1; t < T; ++t) s += Z[t * FZ + i] * Z[(t - 1) * FZ + j]; S11m[ee] = s; }
+      }
+      DFM_SYNC();
+      // ---------------------------------------------------------------- P8: M-step contraction (panel pass 2)
+#ifdef DFM_EMU
+      for (int n = 0; n < N; ++n) {
+        double s2 = 0.0, acc[R];
+        for (int c = 0; c < R; ++c) acc[c] = 0.0;
+        for (int t = 0; t < T; ++t) { double x = X[(size_t)n * T + t]; s2 += x * x; for (int c = 0; c < R; ++c) acc[c] += x * Z[t * FZ + c]; }
+        for (int c = 0; c < R; ++c) Lam[n * R + c] = acc[c];
+        sxx[n] = s2;
+      }
+#else
+      {
+        const int lane = DFM_LANE, lr = lane >> 2, lc = lane & 3;
+        const int nsb = (N + 7) / 8;
+        for (int sb = DFM_WARP; sb < nsb; sb += DFM_NWARP) {
+          int n = sb * 8 + lr;
+          bool nok = n < N;
+          const double* xp = X + (size_t)(nok ? n : 0) * T;
+          double d0 = 0.0, d1 = 0.0, s2 = 0.0;
+          for (int t0 = 0; t0 < T; t0 += 40) {
+            double av[10];
+#pragma unroll
+            for (int u = 0; u < 10; ++u) { int t = t0 + 4 * u + lc; av[u] = (nok && t < T) ? __ldg(xp + t) : 0.0; }
+#pragma unroll
+            for (int u = 0; u < 10; ++u) {
+              int t = t0 + 4 * u + lc;
+              if (t0 + 4 * u < T) {
+                s2 += av[u] * av[u];
+                double bv = (t < T) ? Z[t * FZ + lr] : 0.0;
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                             : "+d"(d0), "+d"(d1) : "d"(av[u]), "d"(bv));
+              }
+            }
+          }
+          s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+          if (nok) {
+            if (2 * lc < R) Lam[n * R + 2 * lc] = d0;
+            if (2 * lc + 1 < R) Lam[n * R + 2 * lc + 1] = d1;
+            if (lc == 0) sxx[n] = s2;
+          }
+        }
+      }
+#endif
+      DFM_SYNC();
+      // ---------------------------------------------------------------- P9: M-step solves
+      if (DFM_WARP == 0) {
+        int* bad = &ctl[2];
+        // measurement: S = SffAll;  Lam_i = S^-1 Sxf_i
+        for (int e = DFM_LANE; e < RR; e += DFM_WSZ) T1[e] = Sm[e] + SPall[e];
+        DFM_WSYNC();
+        w_sym<R>(T1);
+        w_inv<R>(G, T1, tmp, bad);                                 // G = S^-1, T1 = S
+        // transition: A = S11 S00^-1 ; Q = (Sff2 - A S11') / (T-1)
+        for (int e = DFM_LANE; e < RR; e += DFM_WSZ) {
+          int i = e / R, j = e % R;
+          Pp[e] = Sm[e] - Z[(T - 1) * FZ + i] * Z[(T - 1) * FZ + j] + SP00[e];        // S00
+          Pi[e] = Sm[e] - Z[0 * FZ + i] * Z[0 * FZ + j] + SPff2[e];                    // Sff2
+          Pf[e] = S11m[e] + SP11[e];                                                    // S11
+        }
+        DFM_WSYNC();
+        w_sym<R>(Pp);
+        w_inv<R>(Wm, Pp, tmp, bad);
+        w_gemm<R>(Phi, Pf, false, Wm, false);                      // A_new
+        w_gemm<R>(Pn, Phi, false, Pf, true);                       // A S11'
+        for (int e = DFM_LANE; e < RR; e += DFM_WSZ) Pn[e] = (Pi[e] - Pn[e]) / (double)(T - 1);
+        DFM_WSYNC();
+        w_sym<R>(Pn);                                              // Q_new
+      }
+      DFM_SYNC();
+      for (int n = DFM_TID; n < N; n += DFM_NT) {
+        double sx[R], lam[R];
+#pragma unroll
+        for (int c = 0; c < R; ++c) sx[c] = Lam[n * R + c];
+        double q1 = 0.0, q2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < R; ++i) { double s = 0.0;
+#pragma unroll
+          for (int j = 0; j < R; ++j) s += G[i * R + j] * sx[j]; lam[i] = s; q1 += s * sx[i]; }
+#pragma unroll
+        for (int i = 0; i < R; ++i) { double s = 0.0;
+#pragma unroll
+          for (int j = 0; j < R; ++j) s += T1[i * R + j] * lam[j]; q2 += lam[i] * s; }
+#pragma unroll
+        for (int c = 0; c < R; ++c) Lam[n * R + c] = lam[c];
+        Rv[n] = (sxx[n] - 2.0 * q1 + q2) / (double)T;
+      }
+      DFM_SYNC();
+      for (int e = DFM_TID; e < RR; e += DFM_NT) { M[e] = Phi[e]; Q[e] = Pn[e]; }
+      if (DFM_TID == 0) a.loglik[(size_t)b * a.max_iter + it] = ll;
+      DFM_SYNC();
+      if (ctl[2] || !(ll == ll)) { status = 3; ++it; break; }
+      bool conv = (it >= 1) && fabs(ll - ll_prev) <= a.tol * 0.5 * (fabs(ll) + fabs(ll_prev));
+      ll_prev = ll;
+      if (conv) { ++it; break; }
+    }
+    // ---- outputs
+    for (int e = DFM_TID; e < N * R; e += DFM_NT) { int i = e % N, c = e / N; a.Lam[(size_t)b * N * R + e] = Lam[i * R + c]; }
+    for (int e = DFM_TID; e < N; e += DFM_NT) a.R[(size_t)b * N + e] = Rv[e];
+    for (int e = DFM_TID; e < RR; e += DFM_NT) {
+      int i = e % R, j = e / R;                                   // column-major out
+      a.A[(size_t)b * RR + e] = M[i * R + j]; a.Q[(size_t)b * RR + e] = Q[i * R + j];
+    }
+    for (int e = DFM_TID; e < T * R; e += DFM_NT) { int t = e % T, c = e / T; a.Fs[(size_t)b * T * R + e] = Z[t * FZ + c]; }
+    {
+      const int nE = ctl[0], tb = ctl[1], frozen = ctl[3];
+      const int lo = frozen ? nE - 1 : T;
+      for (int e = DFM_TID; e < T * NP; e += DFM_NT) {
+        int t = e % T, pe = e / T;
+        int i = 0; while ((i + 1) * (i + 2) / 2 <= pe) ++i;
+        int j = pe - i * (i + 1) / 2;
+        bool in_frozen = frozen && tb >= 0 && t >= lo && t < tb;
+        double v = in_frozen ? Ppinf[i * R + j] : (scr + (size_t)t * FUSED_SCR(R))[4 * RR + i * R + j];
+        a.PsF[(size_t)b * T * NP + e] = v;
+      }
+    }
+    if (DFM_TID == 0) { a.iters[b] = it > a.max_iter ? a.max_iter : it; a.status[b] = status; }
+    DFM_SYNC();
+  }
+}
+
+template <int R>
+inline size_t fused_smem_doubles(int T, int N) {
+  return (size_t)T * FZ + (size_t)N * R + 3 * (size_t)N + 30 * (size_t)R * R + 2 * R + 40 + 8 + 8;
+}
+
+}  // namespace dfm

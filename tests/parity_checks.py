@@ -220,6 +220,20 @@ def check_em_batch(lib, B=3, N=16, r=2, T=40, p=1, path=0):
         assert rmse(got["F"][b], ref["F"]) < 1e-8
 
 
+def check_em_batch_balanced(lib, B=5, N=16, r=2, T=40, path=0):
+    Xb = np.stack([simulate_panel(N, r, T, rep=40 + b)[0] for b in range(B)])
+    inits = [K.init_from_factors(Xb[b], R.pca_score(Xb[b], r), 1) for b in range(B)]
+    Lam = np.stack([i[0] for i in inits]); Rv = np.stack([i[1] for i in inits])
+    A = np.stack([i[2] for i in inits]); Q = np.stack([i[3] for i in inits])
+    got = lib.em_kalman(Xb, Lam, Rv, A, Q, p=1, max_iter=4, path=path)
+    for b in range(B):
+        ref = K.em_kalman(Xb[b], Lam[b], Rv[b], A[b], Q[b], p=1, max_iter=4)
+        assert rmse(got["F"][b], ref["F"]) < 1e-8
+        np.testing.assert_allclose(got["loglik"][b], ref["loglik"], rtol=1e-10)
+        np.testing.assert_allclose(got["PF"][b], ref["PsF"], rtol=1e-7, atol=1e-10)
+        np.testing.assert_allclose(got["Lam"][b], ref["Lam"], rtol=1e-7, atol=1e-9)
+
+
 def check_als_batch(lib, B=3, N=20, r=2, T=50):
     Xb = np.stack([simulate_panel(N, r, T, rep=30 + b, standardize=False)[0] for b in range(B)])
     Xb[:, 5:9, 3:8] = np.nan; Xb[1, 20:30, 0] = np.nan

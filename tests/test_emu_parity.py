@@ -33,3 +33,17 @@ def test_em_convergence_rule(lib): P.check_em_convergence_rule(lib)
 def test_em_batch(lib): P.check_em_batch(lib)
 def test_als_batch(lib): P.check_als_batch(lib)
 def test_parametric_c1(lib, panels): P.check_parametric_c1(lib, panels, iters=2)
+
+
+# ---- fused per-panel EM kernel (path=2): same source under emulation (DMMA loops have a plain twin)
+def test_fused_em_r3(lib): P.check_em(lib, p=1, miss=0.0, path=2)
+def test_fused_em_r8(lib): P.check_em(lib, N=40, r=8, T=90, p=1, miss=0.0, path=2, iters=5)
+def test_fused_em_r1(lib): P.check_em(lib, N=12, r=1, T=50, p=1, miss=0.0, path=2, iters=4)
+def test_fused_em_convergence_rule(lib): P.check_em_convergence_rule(lib, path=2)
+def test_fused_em_batch(lib): P.check_em_batch_balanced(lib, path=2)
+def test_fused_rejects_missing(lib):
+    import numpy as np
+    from dynamic_factor_models_b200 import DFMError
+    with pytest.raises(DFMError):
+        P.check_em(lib, p=1, miss=0.1, path=2)
+    P.check_em(lib, p=1, miss=0.1, path=0)       # auto falls back to the general path
