@@ -168,7 +168,7 @@ static int launch_fused(dfm_handle* h, const FusedArgs& fa, int B, int T, int N,
 
 static bool fused_shape_ok(int T, int N, int r, int p) {
   if (p != 1 || r < 1 || r > 8 || T < 3) return false;
-  return ((size_t)T * FZ + (size_t)N * r + 3 * (size_t)N + 30 * (size_t)r * r + 128) * 8 <= kMaxSmem;
+  return ((size_t)T * FZ + (size_t)N * r + 3 * (size_t)N + 31 * (size_t)r * r + 66 * (size_t)r + 128) * 8 <= kMaxSmem;
 }
 
 extern "C" {

@@ -85,13 +85,13 @@ template <int R>
 __device__ __forceinline__ double w_inv(double* Ai, const double* A, double* tmp, int* bad) {
   for (int e = DFM_LANE; e < R * R; e += DFM_WSZ) Ai[e] = A[e];
   DFM_WSYNC();
-  double ld = 0.0;
+  double pp = 1.0;
   for (int p = 0; p < R; ++p) {
     for (int e = DFM_LANE; e < R; e += DFM_WSZ) { tmp[e] = Ai[p * R + e]; tmp[R + e] = Ai[e * R + p]; }
     DFM_WSYNC();
     double piv = tmp[p];
     if (!(piv > 0.0)) { *bad = 1; piv = 1.0; }
-    ld += log(piv);
+    pp *= piv;                              // det = product of pivots (R <= 8: no over/underflow concern)
     double d = 1.0 / piv;
     for (int e = DFM_LANE; e < R * R; e += DFM_WSZ) {
       int i = e / R, j = e % R;
@@ -104,40 +104,116 @@ __device__ __forceinline__ double w_inv(double* Ai, const double* A, double* tmp
     }
     DFM_WSYNC();
   }
-  return ld;
+  return log(pp);
 }
 
-// Serial constant-coefficient recursion on warp 0:  Z[t] <- Cf Z[t - dir] + Z[t]  for t = t0, t0+dir, ..
-// up to (excluding) t1.  R lanes own one state component each (coefficient row in registers); all
-// 32 lanes execute the same __syncwarp sequence.
+// Constant-coefficient linear recursion  Z[t] <- Cf Z[t - dir] + Z[t],  t = t0, t0+dir, ... (n steps),
+// parallel in time over the whole CTA: the n steps are cut into chunks of Lc (a power of two)
+// owned by 8-lane groups (lane = state component, coefficient row in registers);
+//   pass 1  every chunk runs the recursion from a zero state (chunk 0 from the true state),
+//   bound   one group propagates the true chunk-end states with Cf^Lc (pw, by repeated squaring),
+//   pass 2  every chunk adds Cf^(s+1) * (true state entering the chunk).
+// Exact up to rounding (linear recurrence).  Called by ALL threads; ends with a block barrier.
+// smem: pw, pw2 [R*R], bnd [(chunks+1) * R].  Requires blockDim = 128 (16 groups) on the GPU.
 template <int R>
-__device__ __forceinline__ void w_recur(double* Z, const double* Cf, double* tmp, int t0, int t1, int dir) {
+__device__ __forceinline__ void blk_recur(double* Z, const double* Cf, double* pw, double* pw2, double* bnd, int t0, int n, int dir) {
+  if (n <= 0) return;
+  // chunk length: odd (=> the 4 groups of a warp hit 2 bank groups instead of 1) and <= 16 chunks
+  int Lc = 1;
+  while (Lc * 16 < n) Lc <<= 1;
+  if (Lc > 1) Lc += 1;
+  const int nch = (n + Lc - 1) / Lc;
+  // pw = Cf^Lc by binary exponentiation (warp 0; a handful of r x r products); bnd[0..R*R) is scratch
+  if (DFM_WARP == 0 && nch > 1) {
+    double* base = bnd + 64 * R;                                  // R*R scratch beyond the boundary vectors
+    for (int e = DFM_LANE; e < R * R; e += DFM_WSZ) { int i = e / R, j = e % R; pw[e] = (i == j) ? 1.0 : 0.0; base[e] = Cf[e]; }
+    DFM_WSYNC();
+    for (int ex = Lc; ex > 0; ex >>= 1) {
+      if (ex & 1) { w_gemm<R>(pw2, pw, false, base, false); for (int e = DFM_LANE; e < R * R; e += DFM_WSZ) pw[e] = pw2[e]; DFM_WSYNC(); }
+      if (ex > 1) { w_gemm<R>(pw2, base, false, base, false); for (int e = DFM_LANE; e < R * R; e += DFM_WSZ) base[e] = pw2[e]; DFM_WSYNC(); }
+    }
+  }
+  // ---- pass 1
 #ifdef DFM_EMU
-  for (int t = t0; t != t1; t += dir) {
-    if ((dir > 0 && t >= t1) || (dir < 0 && t <= t1)) break;
-    for (int i = 0; i < R; ++i) { double s = Z[t * FZ + i]; for (int j = 0; j < R; ++j) s += Cf[i * R + j] * Z[(t - dir) * FZ + j]; tmp[i] = s; }
-    for (int i = 0; i < R; ++i) Z[t * FZ + i] = tmp[i];
+  for (int g = 0; g < nch; ++g) {
+    const int s0 = g * Lc, len = (n - s0 < Lc) ? n - s0 : Lc;
+    for (int s = 0; s < len; ++s) {
+      int t = t0 + dir * (s0 + s);
+      if (g > 0 && s == 0) continue;                        // zero incoming state
+      double nz[R];
+      for (int i = 0; i < R; ++i) { double a = Z[t * FZ + i]; for (int j = 0; j < R; ++j) a += Cf[i * R + j] * Z[(t - dir) * FZ + j]; nz[i] = a; }
+      for (int i = 0; i < R; ++i) Z[t * FZ + i] = nz[i];
+    }
   }
 #else
-  (void)tmp;
-  const int i = threadIdx.x & 31;
-  const bool act = i < R;
+  const int g = threadIdx.x >> 3, gl = threadIdx.x & 7;           // blockDim = 128: 16 groups >= nch
+  const int s0 = g * Lc;
+  const int len = (g < nch) ? ((n - s0 < Lc) ? n - s0 : Lc) : 0;
+  const bool act = gl < R && len > 0;
   double cf[R];
 #pragma unroll
-  for (int j = 0; j < R; ++j) cf[j] = act ? Cf[i * R + j] : 0.0;
-  if ((dir > 0 && t0 >= t1) || (dir < 0 && t0 <= t1)) return;
-  for (int t = t0; t != t1; t += dir) {
-    double s0 = 0.0, s1 = 0.0;
-    if (act) {
+  for (int j = 0; j < R; ++j) cf[j] = (gl < R) ? Cf[gl * R + j] : 0.0;
+  for (int s = 0; s < Lc; ++s) {
+    if (act && s < len && !(g > 0 && s == 0)) {
+      const int t = t0 + dir * (s0 + s);
       const double* zp = Z + (t - dir) * FZ;
-      s0 = Z[t * FZ + i];
+      double a0 = Z[t * FZ + gl], a1 = 0.0;
 #pragma unroll
-      for (int j = 0; j < R; j += 2) { s0 += cf[j] * zp[j]; if (j + 1 < R) s1 += cf[j + 1] * zp[j + 1]; }
-      Z[t * FZ + i] = s0 + s1;
+      for (int j = 0; j < R; j += 2) { a0 += cf[j] * zp[j]; if (j + 1 < R) a1 += cf[j + 1] * zp[j + 1]; }
+      Z[t * FZ + gl] = a0 + a1;
     }
     __syncwarp();
   }
 #endif
+  DFM_SYNC();
+  if (nch > 1) {
+    // ---- boundary propagation: bnd[g] = true state entering chunk g (g >= 1)
+    if (DFM_WARP == 0) {
+      for (int gg = 1; gg < nch; ++gg) {
+        const int tend = t0 + dir * (gg * Lc - 1);            // last step of chunk gg-1
+        for (int i = DFM_LANE; i < R; i += DFM_WSZ) {
+          double a = Z[tend * FZ + i];
+          if (gg > 1) for (int j = 0; j < R; ++j) a += pw[i * R + j] * bnd[(gg - 1) * R + j];
+          bnd[gg * R + i] = a;
+        }
+        DFM_WSYNC();
+      }
+    }
+    DFM_SYNC();
+    // ---- pass 2: add Cf^(s+1) bnd[g]
+#ifdef DFM_EMU
+    for (int g = 1; g < nch; ++g) {
+      const int s0 = g * Lc, len = (n - s0 < Lc) ? n - s0 : Lc;
+      double c[R], c2[R];
+      for (int i = 0; i < R; ++i) c[i] = bnd[g * R + i];
+      for (int s = 0; s < len; ++s) {
+        int t = t0 + dir * (s0 + s);
+        for (int i = 0; i < R; ++i) { double a = 0.0; for (int j = 0; j < R; ++j) a += Cf[i * R + j] * c[j]; c2[i] = a; }
+        for (int i = 0; i < R; ++i) { c[i] = c2[i]; Z[t * FZ + i] += c[i]; }
+      }
+    }
+#else
+    {
+      const bool act2 = act && g > 0;
+      double* cb = bnd + (size_t)(17 + 2 * g) * R;               // per-group ping-pong vector [2][R]
+      if (act2) cb[gl] = bnd[g * R + gl];
+      __syncwarp();
+      for (int s = 0; s < Lc; ++s) {
+        if (act2) {
+          const double* cp = cb + (s & 1) * R;
+          double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+          for (int j = 0; j < R; j += 2) { a0 += cf[j] * cp[j]; if (j + 1 < R) a1 += cf[j + 1] * cp[j + 1]; }
+          a0 += a1;
+          cb[((s + 1) & 1) * R + gl] = a0;
+          if (s < len) Z[(t0 + dir * (s0 + s)) * FZ + gl] += a0;
+        }
+        __syncwarp();
+      }
+    }
+#endif
+    DFM_SYNC();
+  }
 }
 
 // ================================================================================================
@@ -169,6 +245,7 @@ __global__ void DFM_FUSED_BOUNDS k_em_fused(FusedArgs a) {
   double* red = tmp + 2 * R;               // 40
   double* scal = red + 40;                 // 8: [0]=slr [1]=ld_inf [2]=qsum
   int* ctl = (int*)(scal + 8);             // [0]=nE [1]=tb [2]=bad [3]=frozen
+  double* bnd = scal + 16;                 // [0,17R) chunk-boundary states, [17R,49R) per-group ping-pong vectors, [64R, 64R+RR) scratch
   double* scr = a.scratch + (size_t)DFM_BX * T * FUSED_SCR(R);
   // per explicit step t: scr[t*SCR + {0:Pf, RR:Phi, 2RR:J, 3RR:W, 4RR:Ps, 5RR: ld}]
   const double eps = 1e-14;
@@ -381,10 +458,10 @@ __global__ void DFM_FUSED_BOUNDS k_em_fused(FusedArgs a) {
           for (int i = DFM_LANE; i < R; i += DFM_WSZ) Z[t * FZ + i] = tmp[i];
           DFM_WSYNC();
         }
-        // frozen steps: z_t = Phi_inf z_{t-1} + u_t   (R lanes, coefficient row in registers)
-        w_recur<R>(Z, Phinf, tmp, (nE > 0 ? nE : 1), T, +1);
       }
       DFM_SYNC();
+      // frozen steps: z_t = Phi_inf z_{t-1} + u_t, parallel in time over the CTA
+      if (frozen) blk_recur<R>(Z, Phinf, T1, T2, bnd, (nE > 0 ? nE : 1), T - (nE > 0 ? nE : 1), +1);
       // ---------------------------------------------------------------- P4: log-likelihood (parallel over t)
       double llp = 0.0;
       for (int t = DFM_TID; t < T; t += DFM_NT) {
@@ -424,10 +501,10 @@ __global__ void DFM_FUSED_BOUNDS k_em_fused(FusedArgs a) {
         }
       }
       DFM_SYNC();
+      // frozen range: z_t = J_inf z_{t+1} + v_t, parallel in time over the CTA
+      if (frozen) blk_recur<R>(Z, Jinf, T1, T2, bnd, T - 2, (T - 2) - (nE - 1) + 1, -1);
       if (DFM_WARP == 0) {
         const int lo = frozen ? nE - 1 : T;
-        // frozen range: z_t = J_inf z_{t+1} + v_t
-        w_recur<R>(Z, Jinf, tmp, T - 2, lo - 1, -1);
         // explicit range: zs_t = zf_t + J_t (zs_{t+1} - M zf_t)
         for (int t = (lo - 1 < T - 2 ? lo - 1 : T - 2); t >= 0; --t) {
           const double* j_t = scr + (size_t)t * FUSED_SCR(R) + 2 * RR;
@@ -570,7 +647,7 @@ __global__ void DFM_FUSED_BOUNDS k_em_fused(FusedArgs a) {
 
 template <int R>
 inline size_t fused_smem_doubles(int T, int N) {
-  return (size_t)T * FZ + (size_t)N * R + 3 * (size_t)N + 30 * (size_t)R * R + 2 * R + 40 + 8 + 8;
+  return (size_t)T * FZ + (size_t)N * R + 3 * (size_t)N + 30 * (size_t)R * R + 2 * R + 40 + 8 + 8 + 64 * R + (size_t)R * R + 8;
 }
 
 }  // namespace dfm
