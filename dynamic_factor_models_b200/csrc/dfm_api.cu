@@ -6,6 +6,7 @@
 #include "dfm_kernels_np.cuh"
 #include "dfm_kernels_em.cuh"
 #include "dfm_kernels_fused.cuh"
+#include "dfm_kernels_fused2.cuh"
 #include <algorithm>
 #include <new>
 #include <vector>
@@ -166,9 +167,35 @@ static int launch_fused(dfm_handle* h, const FusedArgs& fa, int B, int T, int N,
   return DFM_OK;
 }
 
+template <int RT>
+static int launch_fused2(dfm_handle* h, const FusedArgs& fa, int B, int T, int N, Arena* arena, bool dry) {
+  size_t smem = fused2_smem_doubles<RT>(T, N) * 8;
+  int grid = std::min(B, 148 * 8);
+  double* scr = arena->get<double>((size_t)std::min(B, 148 * 8) * T * FUSED_SCR(RT));
+  if (dry) return DFM_OK;
+#ifndef DFM_EMU
+  DFM_SET_SMEM(k_em_fused2<RT>, smem);
+  int dev = 0, nsm = 148, occ = 1;
+  cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_em_fused2<RT>, 256, smem);
+  if (occ < 1) occ = 1;
+  grid = std::min(B, nsm * occ);
+#endif
+  FusedArgs a2 = fa; a2.scratch = scr;
+  L(k_em_fused2<RT>, grid, 1, 256, smem, a2);
+  return DFM_OK;
+}
+
+static bool fused2_shape_ok(int T, int N, int r, int p) {
+  if (p != 1 || r < 1 || r > 8 || T < 4 || (T & 1)) return false;
+  size_t need = ((size_t)FZ * pad4mod16(T) + (size_t)r * pad4mod16(N) + 3 * (size_t)N + 31 * (size_t)r * r + 99 * (size_t)r +
+                 2 * F2_NCW * 72 + (size_t)F2_S * 8 * F2_TS + 90) * 8;
+  return need <= 113 * 1024;          // two CTAs per SM
+}
+
 static bool fused_shape_ok(int T, int N, int r, int p) {
   if (p != 1 || r < 1 || r > 8 || T < 3) return false;
-  return ((size_t)T * FZ + (size_t)N * r + 3 * (size_t)N + 31 * (size_t)r * r + 66 * (size_t)r + 128) * 8 <= kMaxSmem;
+  return ((size_t)FZ * pad4mod16(T) + (size_t)r * pad4mod16(N) + 3 * (size_t)N + 31 * (size_t)r * r + 66 * (size_t)r + 128) * 8 <= kMaxSmem;
 }
 
 extern "C" {
@@ -542,7 +569,10 @@ int dfm_em_kalman(dfm_handle* h, const double* X, const dfm_em_opts* o, const df
   int nblkC = (T + ntC - 1) / ntC;
   const bool fused_ok = fused_shape_ok(T, N, r, p);
   if (o->path == 2 && !fused_ok) return fail(h, DFM_ERR_UNSUPPORTED, "dfm_em_kalman: fused path needs p = 1, r <= 8 and a panel that fits shared memory");
-  bool fused = fused_ok && o->path != 1;
+  const bool fused2_ok = fused2_shape_ok(T, N, r, p);
+  if (o->path == 3 && !fused2_ok) return fail(h, DFM_ERR_UNSUPPORTED, "dfm_em_kalman: TMA fused path needs p = 1, r <= 8, even T and a panel that fits shared memory");
+  bool fused = (fused_ok || fused2_ok) && o->path != 1;
+  const bool use2 = fused2_ok && (o->path == 0 || o->path == 3);
   for (int pass = 0; pass < 2; ++pass) {
     Arena a(pass ? h->ws : nullptr);
     double* dXb = mem == DFM_MEM_HOST ? a.get<double>(B * TN) : nullptr;
@@ -558,7 +588,8 @@ int dfm_em_kalman(dfm_handle* h, const double* X, const dfm_em_opts* o, const df
     int* dflag = a.get<int>(4);
     Arena fa_arena(nullptr);
     size_t fused_off = a.off;
-    if (fused_ok && o->path != 1) {      // scratch of the fused kernel (superset allocation: the path is chosen after the scan)
+    if (fused && !(fused_ok || fused2_ok)) fused = false;
+    if ((fused_ok || fused2_ok) && o->path != 1) {      // scratch of the fused kernel (superset allocation: the path is chosen after the scan)
       FusedArgs dummy{}; Arena tmpa(nullptr);
       switch (r) {
 #define DFM_CASE(RT) case RT: launch_fused<RT>(h, dummy, batch, T, N, nullptr, &a, true); break;
@@ -593,7 +624,7 @@ int dfm_em_kalman(dfm_handle* h, const double* X, const dfm_em_opts* o, const df
       CK(cudaMemcpyAsync(&hflag, dflag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
       CK(cudaStreamSynchronize(h->stream));
       if (hflag) {
-        if (o->path == 2) return fail(h, DFM_ERR_UNSUPPORTED, "dfm_em_kalman: fused path needs a balanced panel (no NaN)");
+        if (o->path == 2 || o->path == 3) return fail(h, DFM_ERR_UNSUPPORTED, "dfm_em_kalman: fused path needs a balanced panel (no NaN)");
         fused = false;
       }
     }
@@ -601,14 +632,45 @@ int dfm_em_kalman(dfm_handle* h, const double* X, const dfm_em_opts* o, const df
       FusedArgs fa{};
       fa.X = x; fa.Lam = dL; fa.R = dR; fa.A = dA; fa.Q = dQ; fa.P0 = dP0; fa.Fs = dFs; fa.PsF = dPsF; fa.loglik = dll;
       fa.iters = dit; fa.status = dstat; fa.B = batch; fa.T = T; fa.N = N; fa.max_iter = mi; fa.tol = o->tol;
+      fa.phase_cycles = nullptr;
+#ifndef DFM_EMU
+      if (getenv("DFM_FUSED_PHASES")) {            // diagnostics: per-phase clock64 totals printed to stderr
+        static long long* dph = nullptr;
+        if (!dph) cudaMalloc((void**)&dph, 148 * 8 * 16 * sizeof(long long));
+        cudaMemsetAsync(dph, 0, 148 * 8 * 16 * sizeof(long long), h->stream);
+        fa.phase_cycles = dph;
+      }
+#endif
       // re-derive the scratch pointer: it was the first allocation after dflag in this pass
       Arena a2(h->ws); a2.off = fused_off;
+      if (use2) {
+        switch (r) {
+#define DFM_CASE2(RT) case RT: rc = launch_fused2<RT>(h, fa, batch, T, N, &a2, false); break;
+          DFM_CASE2(1) DFM_CASE2(2) DFM_CASE2(3) DFM_CASE2(4) DFM_CASE2(5) DFM_CASE2(6) DFM_CASE2(7) DFM_CASE2(8)
+#undef DFM_CASE2
+        }
+      } else
       switch (r) {
 #define DFM_CASE(RT) case RT: rc = launch_fused<RT>(h, fa, batch, T, N, nullptr, &a2, false); break;
         DFM_CASE(1) DFM_CASE(2) DFM_CASE(3) DFM_CASE(4) DFM_CASE(5) DFM_CASE(6) DFM_CASE(7) DFM_CASE(8)
 #undef DFM_CASE
       }
       if (rc) return rc;
+#ifndef DFM_EMU
+      if (fa.phase_cycles) {
+        std::vector<long long> hp(148 * 8 * 16);
+        cudaStreamSynchronize(h->stream);
+        cudaMemcpy(hp.data(), fa.phase_cycles, hp.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        double tot[16] = {0}; int nb = 0;
+        for (int g = 0; g < 148 * 8; ++g) { double s_ = 0; for (int k_ = 0; k_ < 12; ++k_) s_ += hp[(size_t)g * 16 + k_]; if (s_ > 0) { ++nb; for (int k_ = 0; k_ < 16; ++k_) tot[k_] += hp[(size_t)g * 16 + k_]; } }
+        const char* nm[12] = {"loop/params", "P0 prep", "P1 E-contract", "P2 cov chain", "P3 fwd means", "P4 loglik", "P5 bwd means", "P7 sums", "P8 M-contract", "P9 solves", "iter close", "outputs"};
+        // tick k measures the phase that ENDS at tick k: tick0 ends loop/param load, tick1 ends P0, ...
+        double all = 0; for (int k_ = 0; k_ < 12; ++k_) all += tot[k_];
+        fprintf(stderr, "[dfm fused chain] forward loop %.0f cyc/CTA, backward loop %.0f cyc/CTA\n", tot[12] / (nb ? nb : 1), tot[13] / (nb ? nb : 1));
+        fprintf(stderr, "[dfm fused phases] %d CTAs, mean cycles per CTA: %.0f\n", nb, all / (nb ? nb : 1));
+        for (int k_ = 0; k_ < 12; ++k_) fprintf(stderr, "  %-14s %6.2f%%  %12.0f cyc/CTA\n", nm[k_], 100.0 * tot[k_] / all, tot[k_] / (nb ? nb : 1));
+      }
+#endif
     } else {
       L(k_em_state_init, batch, 1, 1, 0, st);
       L(k_em_scan, N, batch, 64, 0, x, dL, T, N, r, st);

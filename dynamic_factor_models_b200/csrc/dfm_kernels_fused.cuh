@@ -34,7 +34,13 @@
 
 namespace dfm {
 
-#define FZ 8   // padded row stride of Z (= DMMA tile width)
+#define FZ 8   // number of state components kept in Z (= DMMA tile width)
+// Z and Lam are stored COMPONENT-major with a leading dimension == 4 (mod 16) doubles: conflict-free
+// for thread-per-period row access, for the 8-lane recursion groups and (per half-warp) for the DMMA
+// B-fragments.
+#define ZI(t_, i_) ((i_) * Tp + (t_))
+#define LI(n_, c_) ((c_) * Np + (n_))
+__host__ __device__ inline int pad4mod16(int x) { return x + ((4 - x % 16) + 16) % 16; }
 
 struct FusedArgs {
   const double* X;      // [B][N][T] column-major panels
@@ -50,7 +56,13 @@ struct FusedArgs {
   double* scratch;      // [gridDim.x][T * FUSED_SCR]
   int B, T, N, max_iter;
   double tol;
+  long long* phase_cycles;   // optional [gridDim.x][16] per-phase clock64() totals (diagnostics; NULL = off)
 };
+#ifdef DFM_EMU
+#define DFM_TICK(k_) ((void)0)
+#else
+#define DFM_TICK(k_) do { if (a.phase_cycles && threadIdx.x == 0) { long long now_ = clock64(); a.phase_cycles[(size_t)blockIdx.x * 16 + (k_)] += now_ - tick_; tick_ = now_; } } while (0)
+#endif
 #define FUSED_SCR(R_) (5 * (R_) * (R_) + 1)
 
 __device__ __forceinline__ double w_max(double v) {
@@ -61,8 +73,34 @@ __device__ __forceinline__ double w_max(double v) {
 }
 
 // ---- warp-0 small dense ops on row-major R x R matrices in shared memory ------------------------
+// NOT inlined on the GPU: the chain calls them ~100 times per EM iteration; inlined + unrolled they
+// made one chain step ~40 KB of straight-line code executed by a single warp, i.e. instruction-cache
+// misses all the way (measured: 48K cycles per step in the kernel vs 15K in isolation).
+#ifdef DFM_EMU
+#define DFM_HELPER inline
+#else
+#define DFM_HELPER __device__ __noinline__
+#endif
 template <int R>
-__device__ __forceinline__ void w_gemm(double* C, const double* A, bool ta, const double* B, bool tb) {
+DFM_HELPER void w_gemm(double* C, const double* A, bool ta, const double* B, bool tb) {
+#ifndef DFM_EMU
+  if (R == 8) {
+    // 8x8x8 product on the FP64 tensor path: two DMMA.8x8x4 with fragments straight from shared memory
+    const int lane = threadIdx.x & 31, lr = lane >> 2, lc = lane & 3;
+    double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+    for (int kc = 0; kc < 2; ++kc) {
+      const int kk = 4 * kc + lc;
+      const double av = ta ? A[kk * 8 + lr] : A[lr * 8 + kk];      // A-fragment: op(A)[lr][kk]
+      const double bv = tb ? B[lr * 8 + kk] : B[kk * 8 + lr];      // B-fragment: op(B)[kk][lr]
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                   : "+d"(d0), "+d"(d1) : "d"(av), "d"(bv));
+    }
+    C[lr * 8 + 2 * lc] = d0; C[lr * 8 + 2 * lc + 1] = d1;
+    __syncwarp();
+    return;
+  }
+#endif
   for (int e = DFM_LANE; e < R * R; e += DFM_WSZ) {
     int i = e / R, j = e % R;
     double s = 0.0;
@@ -73,7 +111,17 @@ __device__ __forceinline__ void w_gemm(double* C, const double* A, bool ta, cons
   DFM_WSYNC();
 }
 template <int R>
-__device__ __forceinline__ void w_sym(double* A) {
+DFM_HELPER void w_sym(double* A) {
+#ifndef DFM_EMU
+  if (R == 8) {                 // every lane: read its two elements and their transposes, then write
+    const int lane = threadIdx.x & 31, i = lane >> 2, j0 = 2 * (lane & 3);
+    const double v0 = 0.5 * (A[i * 8 + j0] + A[j0 * 8 + i]), v1 = 0.5 * (A[i * 8 + j0 + 1] + A[(j0 + 1) * 8 + i]);
+    __syncwarp();
+    A[i * 8 + j0] = v0; A[i * 8 + j0 + 1] = v1;
+    __syncwarp();
+    return;
+  }
+#endif
   for (int e = DFM_LANE; e < R * R; e += DFM_WSZ) {
     int i = e / R, j = e % R;
     if (i > j) { double v = 0.5 * (A[i * R + j] + A[j * R + i]); A[i * R + j] = v; A[j * R + i] = v; }
@@ -82,7 +130,35 @@ __device__ __forceinline__ void w_sym(double* A) {
 }
 // Gauss-Jordan inverse (no pivoting; SPD input) + log det.  Ai <- A^-1.  tmp: 2R doubles.
 template <int R>
-__device__ __forceinline__ double w_inv(double* Ai, const double* A, double* tmp, int* bad) {
+DFM_HELPER double w_inv(double* Ai, const double* A, double* tmp, int* bad) {
+#ifndef DFM_EMU
+  if (R == 8) {
+    // register version: lane owns elements (i, j0) and (i, j0+1), i = lane/4, j0 = 2 (lane%4); per
+    // pivot four double shuffles (pivot, its row for my columns, its column for my row) -- no shared
+    // memory round trips, ~8x faster than the generic version below (tools/bench_chain.cu)
+    const int lane = threadIdx.x & 31, i = lane >> 2, q = lane & 3, j0 = 2 * q;
+    double x0 = A[i * 8 + j0], x1 = A[i * 8 + j0 + 1];
+    double pp = 1.0;
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      const double sel = (p & 1) ? x1 : x0;                               // my element in column-pair slot p&1
+      double piv = __shfl_sync(0xffffffffu, sel, p * 4 + (p >> 1));       // a[p][p]
+      const double rp0 = __shfl_sync(0xffffffffu, x0, p * 4 + q);         // a[p][j0]
+      const double rp1 = __shfl_sync(0xffffffffu, x1, p * 4 + q);         // a[p][j0+1]
+      const double cp = __shfl_sync(0xffffffffu, sel, (lane & ~3) + (p >> 1));   // a[i][p]
+      if (!(piv > 0.0)) { *bad = 1; piv = 1.0; }
+      pp *= piv;
+      const double d = 1.0 / piv, cd = cp * d;
+      const bool ip = (i == p);
+      x0 = ip ? ((j0 == p) ? d : rp0 * d) : ((j0 == p) ? -cd : x0 - cd * rp0);
+      x1 = ip ? ((j0 + 1 == p) ? d : rp1 * d) : ((j0 + 1 == p) ? -cd : x1 - cd * rp1);
+    }
+    Ai[i * 8 + j0] = x0; Ai[i * 8 + j0 + 1] = x1;
+    __syncwarp();
+    (void)tmp;
+    return log(pp);
+  }
+#endif
   for (int e = DFM_LANE; e < R * R; e += DFM_WSZ) Ai[e] = A[e];
   DFM_WSYNC();
   double pp = 1.0;
@@ -116,16 +192,17 @@ __device__ __forceinline__ double w_inv(double* Ai, const double* A, double* tmp
 // Exact up to rounding (linear recurrence).  Called by ALL threads; ends with a block barrier.
 // smem: pw, pw2 [R*R], bnd [(chunks+1) * R].  Requires blockDim = 128 (16 groups) on the GPU.
 template <int R>
-__device__ __forceinline__ void blk_recur(double* Z, const double* Cf, double* pw, double* pw2, double* bnd, int t0, int n, int dir) {
+__device__ __forceinline__ void blk_recur(double* Z, int Tp, const double* Cf, double* pw, double* pw2, double* bnd, int t0, int n, int dir, int ng) {
   if (n <= 0) return;
-  // chunk length: odd (=> the 4 groups of a warp hit 2 bank groups instead of 1) and <= 16 chunks
+  // ng = number of 8-lane groups of the CTA (blockDim / 8).  chunk length: odd (=> the 4 groups of a
+  // warp hit different banks) and at most ng chunks.  bnd: [(3 ng + 1) R + R R] doubles.
   int Lc = 1;
-  while (Lc * 16 < n) Lc <<= 1;
+  while (Lc * ng < n) Lc <<= 1;
   if (Lc > 1) Lc += 1;
   const int nch = (n + Lc - 1) / Lc;
   // pw = Cf^Lc by binary exponentiation (warp 0; a handful of r x r products); bnd[0..R*R) is scratch
   if (DFM_WARP == 0 && nch > 1) {
-    double* base = bnd + 64 * R;                                  // R*R scratch beyond the boundary vectors
+    double* base = bnd + (size_t)(3 * ng + 1) * R;                // R*R scratch beyond the boundary + ping-pong vectors
     for (int e = DFM_LANE; e < R * R; e += DFM_WSZ) { int i = e / R, j = e % R; pw[e] = (i == j) ? 1.0 : 0.0; base[e] = Cf[e]; }
     DFM_WSYNC();
     for (int ex = Lc; ex > 0; ex >>= 1) {
@@ -141,12 +218,12 @@ __device__ __forceinline__ void blk_recur(double* Z, const double* Cf, double* p
       int t = t0 + dir * (s0 + s);
       if (g > 0 && s == 0) continue;                        // zero incoming state
       double nz[R];
-      for (int i = 0; i < R; ++i) { double a = Z[t * FZ + i]; for (int j = 0; j < R; ++j) a += Cf[i * R + j] * Z[(t - dir) * FZ + j]; nz[i] = a; }
-      for (int i = 0; i < R; ++i) Z[t * FZ + i] = nz[i];
+      for (int i = 0; i < R; ++i) { double a = Z[ZI(t, i)]; for (int j = 0; j < R; ++j) a += Cf[i * R + j] * Z[ZI(t - dir, j)]; nz[i] = a; }
+      for (int i = 0; i < R; ++i) Z[ZI(t, i)] = nz[i];
     }
   }
 #else
-  const int g = threadIdx.x >> 3, gl = threadIdx.x & 7;           // blockDim = 128: 16 groups >= nch
+  const int g = threadIdx.x >> 3, gl = threadIdx.x & 7;           // ng groups >= nch
   const int s0 = g * Lc;
   const int len = (g < nch) ? ((n - s0 < Lc) ? n - s0 : Lc) : 0;
   const bool act = gl < R && len > 0;
@@ -156,11 +233,11 @@ __device__ __forceinline__ void blk_recur(double* Z, const double* Cf, double* p
   for (int s = 0; s < Lc; ++s) {
     if (act && s < len && !(g > 0 && s == 0)) {
       const int t = t0 + dir * (s0 + s);
-      const double* zp = Z + (t - dir) * FZ;
-      double a0 = Z[t * FZ + gl], a1 = 0.0;
+      const double* zp = Z + (t - dir);
+      double a0 = Z[ZI(t, gl)], a1 = 0.0;
 #pragma unroll
-      for (int j = 0; j < R; j += 2) { a0 += cf[j] * zp[j]; if (j + 1 < R) a1 += cf[j + 1] * zp[j + 1]; }
-      Z[t * FZ + gl] = a0 + a1;
+      for (int j = 0; j < R; j += 2) { a0 += cf[j] * zp[j * Tp]; if (j + 1 < R) a1 += cf[j + 1] * zp[(j + 1) * Tp]; }
+      Z[ZI(t, gl)] = a0 + a1;
     }
     __syncwarp();
   }
@@ -172,7 +249,7 @@ __device__ __forceinline__ void blk_recur(double* Z, const double* Cf, double* p
       for (int gg = 1; gg < nch; ++gg) {
         const int tend = t0 + dir * (gg * Lc - 1);            // last step of chunk gg-1
         for (int i = DFM_LANE; i < R; i += DFM_WSZ) {
-          double a = Z[tend * FZ + i];
+          double a = Z[ZI(tend, i)];
           if (gg > 1) for (int j = 0; j < R; ++j) a += pw[i * R + j] * bnd[(gg - 1) * R + j];
           bnd[gg * R + i] = a;
         }
@@ -189,13 +266,13 @@ __device__ __forceinline__ void blk_recur(double* Z, const double* Cf, double* p
       for (int s = 0; s < len; ++s) {
         int t = t0 + dir * (s0 + s);
         for (int i = 0; i < R; ++i) { double a = 0.0; for (int j = 0; j < R; ++j) a += Cf[i * R + j] * c[j]; c2[i] = a; }
-        for (int i = 0; i < R; ++i) { c[i] = c2[i]; Z[t * FZ + i] += c[i]; }
+        for (int i = 0; i < R; ++i) { c[i] = c2[i]; Z[ZI(t, i)] += c[i]; }
       }
     }
 #else
     {
       const bool act2 = act && g > 0;
-      double* cb = bnd + (size_t)(17 + 2 * g) * R;               // per-group ping-pong vector [2][R]
+      double* cb = bnd + (size_t)(ng + 1 + 2 * g) * R;           // per-group ping-pong vector [2][R]
       if (act2) cb[gl] = bnd[g * R + gl];
       __syncwarp();
       for (int s = 0; s < Lc; ++s) {
@@ -206,7 +283,7 @@ __device__ __forceinline__ void blk_recur(double* Z, const double* Cf, double* p
           for (int j = 0; j < R; j += 2) { a0 += cf[j] * cp[j]; if (j + 1 < R) a1 += cf[j + 1] * cp[j + 1]; }
           a0 += a1;
           cb[((s + 1) & 1) * R + gl] = a0;
-          if (s < len) Z[(t0 + dir * (s0 + s)) * FZ + gl] += a0;
+          if (s < len) Z[ZI(t0 + dir * (s0 + s), gl)] += a0;
         }
         __syncwarp();
       }
@@ -228,9 +305,10 @@ __global__ void DFM_FUSED_BOUNDS k_em_fused(FusedArgs a) {
   constexpr int RR = R * R, NP = R * (R + 1) / 2;
   const int T = a.T, N = a.N;
   // ---- shared layout
-  double* Z = sm;                          // [T][FZ]
-  double* Lam = Z + (size_t)T * FZ;        // [N][R] row-major
-  double* rinv = Lam + (size_t)N * R;      // [N]
+  const int Tp = pad4mod16(T), Np = pad4mod16(N);
+  double* Z = sm;                          // [FZ][Tp] component-major
+  double* Lam = Z + (size_t)FZ * Tp;       // [R][Np] component-major
+  double* rinv = Lam + (size_t)R * Np;     // [N]
   double* Rv = rinv + N;                   // [N]
   double* sxx = Rv + N;                    // [N]
   double* mats = sxx + N;
@@ -249,11 +327,14 @@ __global__ void DFM_FUSED_BOUNDS k_em_fused(FusedArgs a) {
   double* scr = a.scratch + (size_t)DFM_BX * T * FUSED_SCR(R);
   // per explicit step t: scr[t*SCR + {0:Pf, RR:Phi, 2RR:J, 3RR:W, 4RR:Ps, 5RR: ld}]
   const double eps = 1e-14;
+#ifndef DFM_EMU
+  long long tick_ = clock64();
+#endif
 
   for (int b = DFM_BX; b < a.B; b += DFM_GX) {
     const double* X = a.X + (size_t)b * T * N;
     // ---- load parameters (global column-major -> shared row-major)
-    for (int e = DFM_TID; e < N * R; e += DFM_NT) { int i = e % N, c = e / N; Lam[i * R + c] = a.Lam[(size_t)b * N * R + e]; }
+    for (int e = DFM_TID; e < N * R; e += DFM_NT) { int i = e % N, c = e / N; Lam[LI(i, c)] = a.Lam[(size_t)b * N * R + e]; }
     for (int e = DFM_TID; e < N; e += DFM_NT) Rv[e] = a.R[(size_t)b * N + e];
     for (int e = DFM_TID; e < RR; e += DFM_NT) {
       int i = e / R, j = e % R;
@@ -264,6 +345,7 @@ __global__ void DFM_FUSED_BOUNDS k_em_fused(FusedArgs a) {
     int it = 0, status = 0;
     double ll_prev = 0.0;
     for (; it < a.max_iter; ++it) {
+      DFM_TICK(0);
       // ---------------------------------------------------------------- P0: prep
       double slr_p = 0.0;
       for (int i = DFM_TID; i < N; i += DFM_NT) { double rv = Rv[i]; rinv[i] = 1.0 / rv; slr_p += log(rv); if (!(rv > 0.0)) ctl[2] = 1; }
@@ -272,57 +354,64 @@ __global__ void DFM_FUSED_BOUNDS k_em_fused(FusedArgs a) {
       for (int e = DFM_TID; e < RR; e += DFM_NT) {
         int i = e / R, j = e % R;
         double s = 0.0;
-        for (int n = 0; n < N; ++n) s += Lam[n * R + i] * rinv[n] * Lam[n * R + j];
+        for (int n = 0; n < N; ++n) s += Lam[LI(n, i)] * rinv[n] * Lam[LI(n, j)];
         C[e] = s;
       }
       DFM_SYNC();
+      DFM_TICK(1);
       // ---------------------------------------------------------------- P1: E-step contraction (panel pass 1)
       double qacc = 0.0;
 #ifdef DFM_EMU
       for (int t = 0; t < T; ++t) {
-        for (int c = 0; c < FZ; ++c) Z[t * FZ + c] = 0.0;
+        for (int c = 0; c < FZ; ++c) Z[ZI(t, c)] = 0.0;
         for (int n = 0; n < N; ++n) {
           double x = X[(size_t)n * T + t], xr = x * rinv[n];
           qacc += x * xr;
-          for (int c = 0; c < R; ++c) Z[t * FZ + c] += xr * Lam[n * R + c];
+          for (int c = 0; c < R; ++c) Z[ZI(t, c)] += xr * Lam[LI(n, c)];
         }
       }
 #else
       {
+        // flattened (row-block, 40-series batch) loop, software pipelined: the loads of batch q+1 are
+        // in flight while the 10 DMMAs of batch q issue (two register buffers of 10 doubles)
         const int lane = DFM_LANE, lr = lane >> 2, lc = lane & 3;
-        const int nrb = (T + 7) / 8;
-        for (int rb = DFM_WARP; rb < nrb; rb += DFM_NWARP) {
-          int t = rb * 8 + lr;
-          bool tok = t < T;
-          double d0 = 0.0, d1 = 0.0;
-          const double* xp = X + (tok ? t : 0);
-          for (int i0 = 0; i0 < N; i0 += 40) {
-            double av[10];
-#pragma unroll
-            for (int u = 0; u < 10; ++u) {
-              int n = i0 + 4 * u + lc;
-              av[u] = (tok && n < N) ? __ldg(xp + (size_t)n * T) : 0.0;
-            }
-#pragma unroll
-            for (int u = 0; u < 10; ++u) {
-              int n = i0 + 4 * u + lc;
-              if (i0 + 4 * u < N) {
-                double ri = (n < N) ? rinv[n] : 0.0;
-                double ar = av[u] * ri;
-                qacc += av[u] * ar;
-                double bv = (n < N && lr < R) ? Lam[n * R + lr] : 0.0;
-                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                             : "+d"(d0), "+d"(d1) : "d"(ar), "d"(bv));
-              }
-            }
-          }
-          if (tok) { Z[t * FZ + 2 * lc] = d0; Z[t * FZ + 2 * lc + 1] = d1; }
+        const int nrb = (T + 7) / 8, nbt = (N + 39) / 40;
+        const int my_rb = (nrb - DFM_WARP + DFM_NWARP - 1) / DFM_NWARP;      // row blocks of this warp
+        const int nq = my_rb * nbt;
+        double bufA[10], bufB[10];
+        double d0 = 0.0, d1 = 0.0;
+#define DFM_E_LOAD(buf, q_)                                                                         \
+        { const int rb_ = DFM_WARP + DFM_NWARP * ((q_) / nbt), i0_ = ((q_) % nbt) * 40;             \
+          const int t_ = rb_ * 8 + lr; const bool tok_ = t_ < T; const double* xp_ = X + (tok_ ? t_ : 0); \
+          _Pragma("unroll") for (int u = 0; u < 10; ++u) { const int n_ = i0_ + 4 * u + lc;          \
+            buf[u] = (tok_ && n_ < N) ? __ldg(xp_ + (size_t)n_ * T) : 0.0; } }
+#define DFM_E_USE(buf, q_)                                                                          \
+        { const int rb_ = DFM_WARP + DFM_NWARP * ((q_) / nbt), bt_ = (q_) % nbt, i0_ = bt_ * 40;     \
+          _Pragma("unroll") for (int u = 0; u < 10; ++u) { const int n_ = i0_ + 4 * u + lc;          \
+            if (i0_ + 4 * u < N) {                                                                   \
+              const double ri_ = (n_ < N) ? rinv[n_] : 0.0; const double ar_ = buf[u] * ri_;         \
+              qacc += buf[u] * ar_;                                                                  \
+              const double bv_ = (n_ < N && lr < R) ? Lam[LI(n_, lr)] : 0.0;                        \
+              asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" \
+                           : "+d"(d0), "+d"(d1) : "d"(ar_), "d"(bv_)); } }                           \
+          if (bt_ == nbt - 1) { const int t_ = rb_ * 8 + lr;                                         \
+            if (t_ < T) { Z[ZI(t_, 2 * lc)] = d0; Z[ZI(t_, 2 * lc + 1)] = d1; }                  \
+            d0 = 0.0; d1 = 0.0; } }
+        if (nq > 0) DFM_E_LOAD(bufA, 0);
+        for (int q = 0; q < nq; q += 2) {
+          if (q + 1 < nq) DFM_E_LOAD(bufB, q + 1);
+          DFM_E_USE(bufA, q);
+          if (q + 2 < nq) DFM_E_LOAD(bufA, q + 2);
+          if (q + 1 < nq) DFM_E_USE(bufB, q + 1);
         }
+#undef DFM_E_LOAD
+#undef DFM_E_USE
       }
 #endif
       qacc = block_sum(qacc, red);
       if (DFM_TID == 0) scal[2] = qacc;
       DFM_SYNC();
+      DFM_TICK(2);
       // ---------------------------------------------------------------- P2: covariance chain (warp 0, data independent)
       if (DFM_WARP == 0) {
         int* bad = &ctl[2];
@@ -421,6 +510,9 @@ __global__ void DFM_FUSED_BOUNDS k_em_fused(FusedArgs a) {
           } else --t;
         }
         if (DFM_LANE == 0) { ctl[0] = nE; ctl[1] = tb; ctl[3] = frozen; }
+#ifdef DFM_EMU
+        if (getenv("DFM_DEBUG_CHAIN")) printf("[chain] b=%d it=%d nE=%d frozen=%d tb=%d (T=%d)\n", b, it, nE, frozen, tb, T);
+#endif
         // I - J_inf M  (for the parallel pre-pass of the backward mean recursion)
         if (frozen) {
           w_gemm<R>(IJM, Jinf, false, M, false);
@@ -430,18 +522,25 @@ __global__ void DFM_FUSED_BOUNDS k_em_fused(FusedArgs a) {
       }
       DFM_SYNC();
       const int nE = ctl[0], frozen = ctl[3];
+#ifndef DFM_EMU
+      if (a.phase_cycles && threadIdx.x == 0) {      // diagnostics: chain lengths
+        a.phase_cycles[(size_t)blockIdx.x * 16 + 12] += nE; a.phase_cycles[(size_t)blockIdx.x * 16 + 13] += (ctl[1] < 0 ? T - 1 : T - 1 - ctl[1]);
+        a.phase_cycles[(size_t)blockIdx.x * 16 + 14] += 1; a.phase_cycles[(size_t)blockIdx.x * 16 + 15] += frozen;
+      }
+#endif
+      DFM_TICK(3);
       // ---------------------------------------------------------------- P3: forward means
       // parallel pre-pass over the frozen range: Z[t] <- Pf_inf b_t
       for (int t = nE + DFM_TID; t < T; t += DFM_NT) {
         double bb[R], u[R];
 #pragma unroll
-        for (int j = 0; j < R; ++j) bb[j] = Z[t * FZ + j];
+        for (int j = 0; j < R; ++j) bb[j] = Z[ZI(t, j)];
 #pragma unroll
         for (int i = 0; i < R; ++i) { double s = 0.0;
 #pragma unroll
           for (int j = 0; j < R; ++j) s += Pfinf[i * R + j] * bb[j]; u[i] = s; }
 #pragma unroll
-        for (int i = 0; i < R; ++i) Z[t * FZ + i] = u[i];
+        for (int i = 0; i < R; ++i) Z[ZI(t, i)] = u[i];
       }
       DFM_SYNC();
       if (DFM_WARP == 0) {
@@ -450,18 +549,19 @@ __global__ void DFM_FUSED_BOUNDS k_em_fused(FusedArgs a) {
           const double* s_ = scr + (size_t)t * FUSED_SCR(R);
           for (int i = DFM_LANE; i < R; i += DFM_WSZ) {
             double s = 0.0;
-            for (int j = 0; j < R; ++j) s += s_[i * R + j] * Z[t * FZ + j];                 // Pf_t b_t
-            if (t >= 1) for (int j = 0; j < R; ++j) s += s_[RR + i * R + j] * Z[(t - 1) * FZ + j];   // Phi_t zf_{t-1}
+            for (int j = 0; j < R; ++j) s += s_[i * R + j] * Z[ZI(t, j)];                 // Pf_t b_t
+            if (t >= 1) for (int j = 0; j < R; ++j) s += s_[RR + i * R + j] * Z[ZI(t - 1, j)];   // Phi_t zf_{t-1}
             tmp[i] = s;
           }
           DFM_WSYNC();
-          for (int i = DFM_LANE; i < R; i += DFM_WSZ) Z[t * FZ + i] = tmp[i];
+          for (int i = DFM_LANE; i < R; i += DFM_WSZ) Z[ZI(t, i)] = tmp[i];
           DFM_WSYNC();
         }
       }
       DFM_SYNC();
       // frozen steps: z_t = Phi_inf z_{t-1} + u_t, parallel in time over the CTA
-      if (frozen) blk_recur<R>(Z, Phinf, T1, T2, bnd, (nE > 0 ? nE : 1), T - (nE > 0 ? nE : 1), +1);
+      if (frozen) blk_recur<R>(Z, Tp, Phinf, T1, T2, bnd, (nE > 0 ? nE : 1), T - (nE > 0 ? nE : 1), +1, 16);
+      DFM_TICK(4);
       // ---------------------------------------------------------------- P4: log-likelihood (parallel over t)
       double llp = 0.0;
       for (int t = DFM_TID; t < T; t += DFM_NT) {
@@ -471,8 +571,8 @@ __global__ void DFM_FUSED_BOUNDS k_em_fused(FusedArgs a) {
 #pragma unroll
         for (int i = 0; i < R; ++i) { double s = 0.0; if (t >= 1) {
 #pragma unroll
-            for (int j = 0; j < R; ++j) s += M[i * R + j] * Z[(t - 1) * FZ + j]; }
-          zp[i] = s; d[i] = Z[t * FZ + i] - s; }
+            for (int j = 0; j < R; ++j) s += M[i * R + j] * Z[ZI(t - 1, j)]; }
+          zp[i] = s; d[i] = Z[ZI(t, i)] - s; }
         double quad = 0.0;
 #pragma unroll
         for (int i = 0; i < R; ++i) {
@@ -485,90 +585,97 @@ __global__ void DFM_FUSED_BOUNDS k_em_fused(FusedArgs a) {
       }
       llp = block_sum(llp, red);
       const double ll = llp - 0.5 * scal[2];
+      DFM_TICK(5);
       // ---------------------------------------------------------------- P5: backward means
       if (frozen) {
         int lo = nE - 1;
         for (int t = lo + DFM_TID; t < T - 1; t += DFM_NT) {       // Z[t] <- (I - J_inf M) zf_t
           double zz[R], v[R];
 #pragma unroll
-          for (int j = 0; j < R; ++j) zz[j] = Z[t * FZ + j];
+          for (int j = 0; j < R; ++j) zz[j] = Z[ZI(t, j)];
 #pragma unroll
           for (int i = 0; i < R; ++i) { double s = 0.0;
 #pragma unroll
             for (int j = 0; j < R; ++j) s += IJM[i * R + j] * zz[j]; v[i] = s; }
 #pragma unroll
-          for (int i = 0; i < R; ++i) Z[t * FZ + i] = v[i];
+          for (int i = 0; i < R; ++i) Z[ZI(t, i)] = v[i];
         }
       }
       DFM_SYNC();
       // frozen range: z_t = J_inf z_{t+1} + v_t, parallel in time over the CTA
-      if (frozen) blk_recur<R>(Z, Jinf, T1, T2, bnd, T - 2, (T - 2) - (nE - 1) + 1, -1);
+      if (frozen) blk_recur<R>(Z, Tp, Jinf, T1, T2, bnd, T - 2, (T - 2) - (nE - 1) + 1, -1, 16);
       if (DFM_WARP == 0) {
         const int lo = frozen ? nE - 1 : T;
         // explicit range: zs_t = zf_t + J_t (zs_{t+1} - M zf_t)
         for (int t = (lo - 1 < T - 2 ? lo - 1 : T - 2); t >= 0; --t) {
           const double* j_t = scr + (size_t)t * FUSED_SCR(R) + 2 * RR;
-          for (int i = DFM_LANE; i < R; i += DFM_WSZ) { double s = Z[(t + 1) * FZ + i]; for (int j = 0; j < R; ++j) s -= M[i * R + j] * Z[t * FZ + j]; tmp[i] = s; }
+          for (int i = DFM_LANE; i < R; i += DFM_WSZ) { double s = Z[ZI(t + 1, i)]; for (int j = 0; j < R; ++j) s -= M[i * R + j] * Z[ZI(t, j)]; tmp[i] = s; }
           DFM_WSYNC();
-          for (int i = DFM_LANE; i < R; i += DFM_WSZ) { double s = Z[t * FZ + i]; for (int j = 0; j < R; ++j) s += j_t[i * R + j] * tmp[j]; tmp[R + i] = s; }
+          for (int i = DFM_LANE; i < R; i += DFM_WSZ) { double s = Z[ZI(t, i)]; for (int j = 0; j < R; ++j) s += j_t[i * R + j] * tmp[j]; tmp[R + i] = s; }
           DFM_WSYNC();
-          for (int i = DFM_LANE; i < R; i += DFM_WSZ) Z[t * FZ + i] = tmp[R + i];
+          for (int i = DFM_LANE; i < R; i += DFM_WSZ) Z[ZI(t, i)] = tmp[R + i];
           DFM_WSYNC();
         }
       }
       DFM_SYNC();
+      DFM_TICK(6);
       // ---------------------------------------------------------------- P7: mean parts of the moment sums
       for (int e = DFM_TID; e < 2 * RR; e += DFM_NT) {
         int which = e / RR, ee = e % RR, i = ee / R, j = ee % R;
         double s = 0.0;
-        if (which == 0) { for (int t = 0; t < T; ++t) s += Z[t * FZ + i] * Z[t * FZ + j]; Sm[ee] = s; }
-        else { for (int t = 1; t < T; ++t) s += Z[t * FZ + i] * Z[(t - 1) * FZ + j]; S11m[ee] = s; }
+        if (which == 0) { for (int t = 0; t < T; ++t) s += Z[ZI(t, i)] * Z[ZI(t, j)]; Sm[ee] = s; }
+        else { for (int t = 1; t < T; ++t) s += Z[ZI(t, i)] * Z[ZI(t - 1, j)]; S11m[ee] = s; }
       }
       DFM_SYNC();
+      DFM_TICK(7);
       // ---------------------------------------------------------------- P8: M-step contraction (panel pass 2)
 #ifdef DFM_EMU
       for (int n = 0; n < N; ++n) {
         double s2 = 0.0, acc[R];
         for (int c = 0; c < R; ++c) acc[c] = 0.0;
-        for (int t = 0; t < T; ++t) { double x = X[(size_t)n * T + t]; s2 += x * x; for (int c = 0; c < R; ++c) acc[c] += x * Z[t * FZ + c]; }
-        for (int c = 0; c < R; ++c) Lam[n * R + c] = acc[c];
+        for (int t = 0; t < T; ++t) { double x = X[(size_t)n * T + t]; s2 += x * x; for (int c = 0; c < R; ++c) acc[c] += x * Z[ZI(t, c)]; }
+        for (int c = 0; c < R; ++c) Lam[LI(n, c)] = acc[c];
         sxx[n] = s2;
       }
 #else
       {
         const int lane = DFM_LANE, lr = lane >> 2, lc = lane & 3;
-        const int nsb = (N + 7) / 8;
-        for (int sb = DFM_WARP; sb < nsb; sb += DFM_NWARP) {
-          int n = sb * 8 + lr;
-          bool nok = n < N;
-          const double* xp = X + (size_t)(nok ? n : 0) * T;
-          double d0 = 0.0, d1 = 0.0, s2 = 0.0;
-          for (int t0 = 0; t0 < T; t0 += 40) {
-            double av[10];
-#pragma unroll
-            for (int u = 0; u < 10; ++u) { int t = t0 + 4 * u + lc; av[u] = (nok && t < T) ? __ldg(xp + t) : 0.0; }
-#pragma unroll
-            for (int u = 0; u < 10; ++u) {
-              int t = t0 + 4 * u + lc;
-              if (t0 + 4 * u < T) {
-                s2 += av[u] * av[u];
-                double bv = (t < T) ? Z[t * FZ + lr] : 0.0;
-                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                             : "+d"(d0), "+d"(d1) : "d"(av[u]), "d"(bv));
-              }
-            }
-          }
-          s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
-          s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
-          if (nok) {
-            if (2 * lc < R) Lam[n * R + 2 * lc] = d0;
-            if (2 * lc + 1 < R) Lam[n * R + 2 * lc + 1] = d1;
-            if (lc == 0) sxx[n] = s2;
-          }
+        const int nsb = (N + 7) / 8, nbt = (T + 39) / 40;
+        const int my_sb = (nsb - DFM_WARP + DFM_NWARP - 1) / DFM_NWARP;
+        const int nq = my_sb * nbt;
+        double bufA[10], bufB[10];
+        double d0 = 0.0, d1 = 0.0, s2 = 0.0;
+#define DFM_M_LOAD(buf, q_)                                                                         \
+        { const int sb_ = DFM_WARP + DFM_NWARP * ((q_) / nbt), t0_ = ((q_) % nbt) * 40;              \
+          const int n_ = sb_ * 8 + lr; const bool nok_ = n_ < N; const double* xp_ = X + (size_t)(nok_ ? n_ : 0) * T; \
+          _Pragma("unroll") for (int u = 0; u < 10; ++u) { const int t_ = t0_ + 4 * u + lc;          \
+            buf[u] = (nok_ && t_ < T) ? __ldg(xp_ + t_) : 0.0; } }
+#define DFM_M_USE(buf, q_)                                                                          \
+        { const int sb_ = DFM_WARP + DFM_NWARP * ((q_) / nbt), bt_ = (q_) % nbt, t0_ = bt_ * 40;     \
+          _Pragma("unroll") for (int u = 0; u < 10; ++u) { const int t_ = t0_ + 4 * u + lc;          \
+            if (t0_ + 4 * u < T) {                                                                   \
+              s2 += buf[u] * buf[u];                                                                 \
+              const double bv_ = (t_ < T) ? Z[ZI(t_, lr)] : 0.0;                                   \
+              asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" \
+                           : "+d"(d0), "+d"(d1) : "d"(buf[u]), "d"(bv_)); } }                        \
+          if (bt_ == nbt - 1) { const int n_ = sb_ * 8 + lr;                                         \
+            s2 += __shfl_xor_sync(0xffffffffu, s2, 1); s2 += __shfl_xor_sync(0xffffffffu, s2, 2);    \
+            if (n_ < N) { if (2 * lc < R) Lam[LI(n_, 2 * lc)] = d0; if (2 * lc + 1 < R) Lam[LI(n_, 2 * lc + 1)] = d1; \
+                          if (lc == 0) sxx[n_] = s2; }                                               \
+            d0 = 0.0; d1 = 0.0; s2 = 0.0; } }
+        if (nq > 0) DFM_M_LOAD(bufA, 0);
+        for (int q = 0; q < nq; q += 2) {
+          if (q + 1 < nq) DFM_M_LOAD(bufB, q + 1);
+          DFM_M_USE(bufA, q);
+          if (q + 2 < nq) DFM_M_LOAD(bufA, q + 2);
+          if (q + 1 < nq) DFM_M_USE(bufB, q + 1);
         }
+#undef DFM_M_LOAD
+#undef DFM_M_USE
       }
 #endif
       DFM_SYNC();
+      DFM_TICK(8);
       // ---------------------------------------------------------------- P9: M-step solves
       if (DFM_WARP == 0) {
         int* bad = &ctl[2];
@@ -580,8 +687,8 @@ __global__ void DFM_FUSED_BOUNDS k_em_fused(FusedArgs a) {
         // transition: A = S11 S00^-1 ; Q = (Sff2 - A S11') / (T-1)
         for (int e = DFM_LANE; e < RR; e += DFM_WSZ) {
           int i = e / R, j = e % R;
-          Pp[e] = Sm[e] - Z[(T - 1) * FZ + i] * Z[(T - 1) * FZ + j] + SP00[e];        // S00
-          Pi[e] = Sm[e] - Z[0 * FZ + i] * Z[0 * FZ + j] + SPff2[e];                    // Sff2
+          Pp[e] = Sm[e] - Z[ZI(T - 1, i)] * Z[ZI(T - 1, j)] + SP00[e];        // S00
+          Pi[e] = Sm[e] - Z[ZI(0, i)] * Z[ZI(0, j)] + SPff2[e];                    // Sff2
           Pf[e] = S11m[e] + SP11[e];                                                    // S11
         }
         DFM_WSYNC();
@@ -597,7 +704,7 @@ __global__ void DFM_FUSED_BOUNDS k_em_fused(FusedArgs a) {
       for (int n = DFM_TID; n < N; n += DFM_NT) {
         double sx[R], lam[R];
 #pragma unroll
-        for (int c = 0; c < R; ++c) sx[c] = Lam[n * R + c];
+        for (int c = 0; c < R; ++c) sx[c] = Lam[LI(n, c)];
         double q1 = 0.0, q2 = 0.0;
 #pragma unroll
         for (int i = 0; i < R; ++i) { double s = 0.0;
@@ -608,11 +715,12 @@ __global__ void DFM_FUSED_BOUNDS k_em_fused(FusedArgs a) {
 #pragma unroll
           for (int j = 0; j < R; ++j) s += T1[i * R + j] * lam[j]; q2 += lam[i] * s; }
 #pragma unroll
-        for (int c = 0; c < R; ++c) Lam[n * R + c] = lam[c];
+        for (int c = 0; c < R; ++c) Lam[LI(n, c)] = lam[c];
         Rv[n] = (sxx[n] - 2.0 * q1 + q2) / (double)T;
       }
       DFM_SYNC();
       for (int e = DFM_TID; e < RR; e += DFM_NT) { M[e] = Phi[e]; Q[e] = Pn[e]; }
+      DFM_TICK(9);
       if (DFM_TID == 0) a.loglik[(size_t)b * a.max_iter + it] = ll;
       DFM_SYNC();
       if (ctl[2] || !(ll == ll)) { status = 3; ++it; break; }
@@ -620,14 +728,15 @@ __global__ void DFM_FUSED_BOUNDS k_em_fused(FusedArgs a) {
       ll_prev = ll;
       if (conv) { ++it; break; }
     }
+    DFM_TICK(10);
     // ---- outputs
-    for (int e = DFM_TID; e < N * R; e += DFM_NT) { int i = e % N, c = e / N; a.Lam[(size_t)b * N * R + e] = Lam[i * R + c]; }
+    for (int e = DFM_TID; e < N * R; e += DFM_NT) { int i = e % N, c = e / N; a.Lam[(size_t)b * N * R + e] = Lam[LI(i, c)]; }
     for (int e = DFM_TID; e < N; e += DFM_NT) a.R[(size_t)b * N + e] = Rv[e];
     for (int e = DFM_TID; e < RR; e += DFM_NT) {
       int i = e % R, j = e / R;                                   // column-major out
       a.A[(size_t)b * RR + e] = M[i * R + j]; a.Q[(size_t)b * RR + e] = Q[i * R + j];
     }
-    for (int e = DFM_TID; e < T * R; e += DFM_NT) { int t = e % T, c = e / T; a.Fs[(size_t)b * T * R + e] = Z[t * FZ + c]; }
+    for (int e = DFM_TID; e < T * R; e += DFM_NT) { int t = e % T, c = e / T; a.Fs[(size_t)b * T * R + e] = Z[ZI(t, c)]; }
     {
       const int nE = ctl[0], tb = ctl[1], frozen = ctl[3];
       const int lo = frozen ? nE - 1 : T;
@@ -642,12 +751,13 @@ __global__ void DFM_FUSED_BOUNDS k_em_fused(FusedArgs a) {
     }
     if (DFM_TID == 0) { a.iters[b] = it > a.max_iter ? a.max_iter : it; a.status[b] = status; }
     DFM_SYNC();
+    DFM_TICK(11);
   }
 }
 
 template <int R>
 inline size_t fused_smem_doubles(int T, int N) {
-  return (size_t)T * FZ + (size_t)N * R + 3 * (size_t)N + 30 * (size_t)R * R + 2 * R + 40 + 8 + 8 + 64 * R + (size_t)R * R + 8;
+  return (size_t)FZ * pad4mod16(T) + (size_t)R * pad4mod16(N) + 3 * (size_t)N + 30 * (size_t)R * R + 2 * R + 40 + 8 + 8 + 64 * R + (size_t)R * R + 8;
 }
 
 }  // namespace dfm

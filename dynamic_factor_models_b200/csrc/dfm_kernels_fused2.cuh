@@ -1,0 +1,582 @@
+// dfm_kernels_fused2.cuh -- TMA-fed variant of the fused per-panel EM kernel (see dfm_kernels_fused.cuh
+// for the algorithm).  Differences:
+//  * 256 threads: warp 0 = TMA producer during the two panel passes, warps 1..7 = DMMA consumers;
+//  * both passes stream the column-major panel as CONTIGUOUS column runs with cp.async.bulk
+//    (SASS UBLKCP) into a 5-stage shared-memory ring guarded by mbarriers (full/empty).  Measured
+//    with tools/bench_stream.cu at this occupancy: LDG-to-fragment patterns 2.5-3.5 TB/s, bulk ring
+//    6.3-6.8 TB/s;
+//  * E pass = rank-8 updates Z[t-chunk] += X' (Lam/R) accumulated in shared memory, M pass = S_xf
+//    partial tiles per consumer warp + deterministic cross-warp reduction per series block;
+//  * the ring is idle between the passes and doubles as storage for the explicit covariance steps
+//    (no dependent global-memory round trips on the serial path).
+// Requires T even (16-byte aligned column runs); otherwise dfm_em_kalman uses k_em_fused.
+#pragma once
+#include "dfm_kernels_fused.cuh"
+
+namespace dfm {
+
+#define F2_S 5          // ring stages
+#define F2_TC 96        // periods per stage (12 DMMA row blocks / 24 k-chunks per stage)
+#define F2_TS 100       // row stride in the ring (== 4 mod 16: conflict-free fragments)
+#define F2_NCW 6        // consumer warps (warps 1..6; warp 0 = producer, warp 7 idles during the passes)
+#define F2_NEXS(R_) ((F2_S * 8 * F2_TS) / FUSED_SCR(R_))
+
+#ifndef DFM_EMU
+__device__ __forceinline__ uint32_t f2_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void f2_mbar_init(uint64_t* bar, int cnt) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(f2_smem_u32(bar)), "r"(cnt)); }
+__device__ __forceinline__ void f2_mbar_expect(uint64_t* bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(f2_smem_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void f2_mbar_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(f2_smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ void f2_mbar_wait(uint64_t* bar, uint32_t phase) {
+  asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(f2_smem_u32(bar)), "r"(phase) : "memory");
+}
+__device__ __forceinline__ void f2_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(f2_smem_u32(dst)), "l"(src), "r"(bytes), "r"(f2_smem_u32(bar)) : "memory");
+}
+#endif
+
+#ifdef DFM_EMU
+#define DFM_FUSED2_BOUNDS
+#else
+#define DFM_FUSED2_BOUNDS __launch_bounds__(256, 2)
+#endif
+template <int R>
+__global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a) {
+  DFM_SMEM(sm);
+  constexpr int RR = R * R, NP = R * (R + 1) / 2;
+  const int T = a.T, N = a.N;
+  // ---- shared layout
+  const int Tp = pad4mod16(T), Np = pad4mod16(N);
+  double* Z = sm;                          // [FZ][Tp] component-major
+  double* Lam = Z + (size_t)FZ * Tp;       // [R][Np] component-major
+  double* rinv = Lam + (size_t)R * Np;     // [N]
+  double* Rv = rinv + N;                   // [N]
+  double* sxx = Rv + N;                    // [N]
+  double* mats = sxx + N;
+  double* M = mats;            double* Q = M + RR;        double* C = Q + RR;        double* Pp = C + RR;
+  double* Pi = Pp + RR;        double* Pf = Pi + RR;      double* Wm = Pf + RR;      double* G = Wm + RR;
+  double* Phi = G + RR;        double* Jm = Phi + RR;     double* Pn = Jm + RR;      double* T1 = Pn + RR;
+  double* T2 = T1 + RR;        double* Ps = T2 + RR;      double* Psn = Ps + RR;     double* SPall = Psn + RR;
+  double* SP00 = SPall + RR;   double* SPff2 = SP00 + RR; double* SP11 = SPff2 + RR; double* Sm = SP11 + RR;
+  double* S11m = Sm + RR;      double* Pfinf = S11m + RR; double* Phinf = Pfinf + RR; double* Jinf = Phinf + RR;
+  double* Winf = Jinf + RR;    double* Ppinf = Winf + RR; double* IJM = Ppinf + RR;  double* Pfprev = IJM + RR;
+  double* tmp = Pfprev + RR;               // 2R
+  double* red = tmp + 2 * R;               // 40
+  double* scal = red + 40;                 // 8: [0]=slr [1]=ld_inf [2]=qsum
+  int* ctl = (int*)(scal + 8);             // [0]=nE [1]=tb [2]=bad [3]=frozen
+  double* bnd = scal + 16;                 // (3*32+1) R + RR: blk_recur workspace for 32 groups
+  double* part = bnd + (size_t)97 * R + RR;          // [2][F2_NCW][72] M-pass partial accumulators
+  double* ring = part + 2 * F2_NCW * 72;             // F2_S stages x 8 x F2_TS
+  ring += ((ring - sm) & 1);                         // bulk copies need 16-byte aligned destinations
+  double* gscr = a.scratch + (size_t)DFM_BX * T * FUSED_SCR(R);
+  // per explicit step t: SCRP(t)[{0:Pf, RR:Phi, 2RR:J, 3RR:W, 4RR:Ps, 5RR: ld}]; the first F2_NEXS(R)
+  // steps live in the (idle between the two passes) ring, the rest in global scratch
+#define SCRP(t_) (((t_) < F2_NEXS(R)) ? (ring + (size_t)(t_) * FUSED_SCR(R)) : (gscr + (size_t)(t_) * FUSED_SCR(R)))
+#define GPS(t_) (gscr + (size_t)(t_) * FUSED_SCR(R) + 4 * RR)      // smoothed covariances: always global (read at output time only)
+#ifndef DFM_EMU
+  __shared__ uint64_t fullb[F2_S], emptyb[F2_S];
+  if (threadIdx.x == 0) { for (int s_ = 0; s_ < F2_S; ++s_) { f2_mbar_init(&fullb[s_], 1); f2_mbar_init(&emptyb[s_], F2_NCW); } }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  int rs_ = 0; uint32_t rph_ = 0; bool rwrap_ = false;   // ring position of this thread: stage, parity, "ring has wrapped"
+#define F2_ADVANCE() do { if (++rs_ == F2_S) { rs_ = 0; rph_ ^= 1; rwrap_ = true; } } while (0)
+#endif
+  const double eps = 1e-14;
+#ifndef DFM_EMU
+  long long tick_ = clock64();
+#endif
+
+  for (int b = DFM_BX; b < a.B; b += DFM_GX) {
+    const double* X = a.X + (size_t)b * T * N;
+    // ---- load parameters (global column-major -> shared row-major)
+    for (int e = DFM_TID; e < N * R; e += DFM_NT) { int i = e % N, c = e / N; Lam[LI(i, c)] = a.Lam[(size_t)b * N * R + e]; }
+    for (int e = DFM_TID; e < N; e += DFM_NT) Rv[e] = a.R[(size_t)b * N + e];
+    for (int e = DFM_TID; e < RR; e += DFM_NT) {
+      int i = e / R, j = e % R;
+      M[e] = a.A[(size_t)b * RR + i + R * j]; Q[e] = a.Q[(size_t)b * RR + i + R * j];
+    }
+    if (DFM_TID == 0) ctl[2] = 0;
+    DFM_SYNC();
+    int it = 0, status = 0;
+    double ll_prev = 0.0;
+    for (; it < a.max_iter; ++it) {
+      DFM_TICK(0);
+      // ---------------------------------------------------------------- P0: prep
+      double slr_p = 0.0;
+      for (int i = DFM_TID; i < N; i += DFM_NT) { double rv = Rv[i]; rinv[i] = 1.0 / rv; slr_p += log(rv); if (!(rv > 0.0)) ctl[2] = 1; }
+      slr_p = block_sum(slr_p, red);
+      if (DFM_TID == 0) scal[0] = slr_p;
+      for (int e = DFM_TID; e < RR; e += DFM_NT) {
+        int i = e / R, j = e % R;
+        double s = 0.0;
+        for (int n = 0; n < N; ++n) s += Lam[LI(n, i)] * rinv[n] * Lam[LI(n, j)];
+        C[e] = s;
+      }
+      DFM_SYNC();
+      DFM_TICK(1);
+      // ---------------------------------------------------------------- P1: E-step contraction (panel pass 1)
+      double qacc = 0.0;
+#ifdef DFM_EMU
+      for (int t = 0; t < T; ++t) {
+        for (int c = 0; c < FZ; ++c) Z[ZI(t, c)] = 0.0;
+        for (int n = 0; n < N; ++n) {
+          double x = X[(size_t)n * T + t], xr = x * rinv[n];
+          qacc += x * xr;
+          for (int c = 0; c < R; ++c) Z[ZI(t, c)] += xr * Lam[LI(n, c)];
+        }
+      }
+#else
+      {
+        // TMA pass.  Item q = (period chunk c, series block sb), sb fastest: a stage = 8 series x
+        // (<= F2_TC periods) of CONTIGUOUS column runs copied by cp.async.bulk (UBLKCP) into the ring.
+        // Each consumer warp owns two 8-period row blocks of the chunk and keeps their 8x8 DMMA
+        // accumulators in registers across all series blocks; Z is written once per chunk.
+        const int nsb = (N + 7) / 8, nck = (T + F2_TC - 1) / F2_TC;
+        const long long nitems = (long long)nsb * nck;
+        if (DFM_WARP == 0) {
+          // producer warp: lane 0 arms the stage barrier, lanes 0..7 issue one row copy each (a single
+          // thread can only issue a bulk copy every ~100 cycles: measured with tools/bench_stream.cu)
+          const int lane = DFM_LANE;
+          for (int c = 0; c < nck; ++c) {
+            const int len = (T - c * F2_TC < F2_TC) ? T - c * F2_TC : F2_TC;
+            for (int sb = 0; sb < nsb; ++sb) {
+              if (rwrap_) f2_mbar_wait(&emptyb[rs_], rph_ ^ 1);
+              const int rows = (N - sb * 8 < 8) ? N - sb * 8 : 8;
+              if (lane == 0) f2_mbar_expect(&fullb[rs_], (uint32_t)(rows * len * 8));
+              __syncwarp();
+              if (lane < rows)
+                f2_bulk_g2s(ring + (size_t)rs_ * 8 * F2_TS + lane * F2_TS, X + (size_t)(sb * 8 + lane) * T + c * F2_TC, (uint32_t)(len * 8), &fullb[rs_]);
+              F2_ADVANCE();
+            }
+          }
+        } else if (DFM_WARP <= F2_NCW) {
+          const int cw = DFM_WARP - 1, lane = DFM_LANE, lr = lane >> 2, lc = lane & 3;
+          for (int c = 0; c < nck; ++c) {
+            const int len = (T - c * F2_TC < F2_TC) ? T - c * F2_TC : F2_TC;
+            const int tl0 = cw * 8 + lr, tl1 = (cw + F2_NCW) * 8 + lr;       // F2_TC / 8 = 2 * F2_NCW row blocks
+            const bool v0 = tl0 < len, v1 = tl1 < len;
+            double d00 = 0.0, d01 = 0.0, d10 = 0.0, d11 = 0.0;
+            for (int sb = 0; sb < nsb; ++sb) {
+              f2_mbar_wait(&fullb[rs_], rph_);
+              const double* tile = ring + (size_t)rs_ * 8 * F2_TS;
+#pragma unroll
+              for (int kc = 0; kc < 2; ++kc) {
+                const int n = sb * 8 + kc * 4 + lc;
+                const bool nok = n < N;
+                const double rn = nok ? rinv[n] : 0.0;
+                const double lam = (nok && lr < R) ? Lam[LI(n, lr)] : 0.0;
+                const double a0 = (nok && v0) ? tile[(kc * 4 + lc) * F2_TS + tl0] : 0.0;
+                const double a1 = (nok && v1) ? tile[(kc * 4 + lc) * F2_TS + tl1] : 0.0;
+                const double ar0 = a0 * rn, ar1 = a1 * rn;
+                qacc += a0 * ar0 + a1 * ar1;
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                             : "+d"(d00), "+d"(d01) : "d"(ar0), "d"(lam));
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                             : "+d"(d10), "+d"(d11) : "d"(ar1), "d"(lam));
+              }
+              __syncwarp();
+              if (lane == 0) f2_mbar_arrive(&emptyb[rs_]);
+              F2_ADVANCE();
+            }
+            if (v0) { const int t = c * F2_TC + tl0; Z[ZI(t, 2 * lc)] = d00; Z[ZI(t, 2 * lc + 1)] = d01; }
+            if (v1) { const int t = c * F2_TC + tl1; Z[ZI(t, 2 * lc)] = d10; Z[ZI(t, 2 * lc + 1)] = d11; }
+          }
+        }
+        else { for (long long q = 0; q < nitems; ++q) F2_ADVANCE(); }      // idle warps keep the ring position in step
+      }
+#endif
+      qacc = block_sum(qacc, red);
+      if (DFM_TID == 0) scal[2] = qacc;
+      DFM_SYNC();
+      DFM_TICK(2);
+      // ---------------------------------------------------------------- P2: covariance chain (warp 0, data independent)
+      if (DFM_WARP == 0) {
+        int* bad = &ctl[2];
+        // forward
+        for (int e = DFM_LANE; e < RR; e += DFM_WSZ) { int i = e / R, j = e % R; Pp[e] = a.P0[(size_t)b * RR + i + R * j]; }
+        DFM_WSYNC();
+        int nE = T, frozen_at = -1, t = 0;
+#ifndef DFM_EMU
+        long long c0_ = clock64();
+#endif
+        while (t < T) {
+          double ldp = w_inv<R>(Pi, Pp, tmp, bad);
+          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) Wm[e] = Pi[e] + C[e];
+          DFM_WSYNC();
+          double ldw = w_inv<R>(Pf, Wm, tmp, bad);
+          w_gemm<R>(G, Pf, false, Pi, false);
+          w_gemm<R>(Phi, G, false, M, false);
+          if (t >= 1) { w_gemm<R>(T1, Pfprev, false, M, true); w_gemm<R>(Jm, T1, false, Pi, false); }   // J_{t-1}
+          w_gemm<R>(T1, M, false, Pf, false);
+          w_gemm<R>(Pn, T1, false, M, true);
+          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) Pn[e] += Q[e];
+          DFM_WSYNC();
+          w_sym<R>(Pn);
+          double* s_ = SCRP(t);
+          double dmax = 0.0, pmax = 0.0;
+          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) {
+            s_[e] = Pf[e]; s_[RR + e] = Phi[e]; s_[3 * RR + e] = Wm[e];
+            if (t >= 1) SCRP(t - 1)[2 * RR + e] = Jm[e];
+            dmax = fmax(dmax, fabs(Pn[e] - Pp[e])); pmax = fmax(pmax, fabs(Pp[e]));
+            Pfprev[e] = Pf[e];
+          }
+          if (DFM_LANE == 0) s_[5 * RR] = ldp + ldw;
+          dmax = w_max(dmax); pmax = w_max(pmax);
+          DFM_WSYNC();
+          if (frozen_at >= 0 && t == frozen_at + 1) {
+            nE = t + 1;
+            for (int e = DFM_LANE; e < RR; e += DFM_WSZ) { Pfinf[e] = Pf[e]; Phinf[e] = Phi[e]; Winf[e] = Wm[e]; }
+            if (DFM_LANE == 0) scal[1] = ldp + ldw;
+            DFM_WSYNC();
+            w_gemm<R>(T1, Pf, false, M, true);
+            w_gemm<R>(Jinf, T1, false, Pi, false);                 // J_inf = Pf_inf M' Pi_inf
+            break;
+          }
+          if (frozen_at < 0 && dmax <= eps * pmax) frozen_at = t;
+          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) Pp[e] = Pn[e];
+          DFM_WSYNC();
+          ++t;
+        }
+        const int frozen = nE < T;
+#ifndef DFM_EMU
+        long long c1_ = clock64();
+#endif
+        // backward covariance chain + covariance parts of the moment sums
+        for (int e = DFM_LANE; e < RR; e += DFM_WSZ) {
+          double v = frozen ? Pfinf[e] : (SCRP(T - 1))[e];
+          Psn[e] = v; SPall[e] = v; SPff2[e] = v; SP00[e] = 0.0; SP11[e] = 0.0;
+          GPS(T - 1)[e] = v;
+        }
+        DFM_WSYNC();
+        const int lo = frozen ? nE - 1 : T;
+        int tb = -1;                        // frozen smoothed range is [lo, tb)
+        t = T - 2;
+        while (t >= 0) {
+          const double* pf_t = (t < nE) ? SCRP(t) : Pfinf;
+          const double* j_t = (t < nE - 1) ? SCRP(t) + 2 * RR : Jinf;
+          // Pp_{t+1} = M Pf_t M' + Q (recomputed: cheaper than storing)
+          w_gemm<R>(T1, M, false, pf_t, false);
+          w_gemm<R>(T2, T1, false, M, true);
+          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) T2[e] = Psn[e] - (T2[e] + Q[e]);
+          DFM_WSYNC();
+          w_sym<R>(T2);                                           // D = Ps_{t+1} - Pp_{t+1}
+          w_gemm<R>(T1, j_t, false, T2, false);
+          w_gemm<R>(Ps, T1, false, j_t, true);
+          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) Ps[e] += pf_t[e];
+          DFM_WSYNC();
+          w_sym<R>(Ps);
+          w_gemm<R>(T1, Psn, false, j_t, true);                    // Ps_{t+1} J_t'
+          double dmax = 0.0, pmax = 0.0;
+          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) {
+            SP11[e] += T1[e]; SPall[e] += Ps[e]; SP00[e] += Ps[e];
+            if (t >= 1) SPff2[e] += Ps[e];
+            GPS(t)[e] = Ps[e];
+            dmax = fmax(dmax, fabs(Ps[e] - Psn[e])); pmax = fmax(pmax, fabs(Ps[e]));
+          }
+          dmax = w_max(dmax); pmax = w_max(pmax);
+          DFM_WSYNC();
+          bool conv = frozen && t > lo && dmax <= eps * pmax;
+          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) Psn[e] = Ps[e];
+          DFM_WSYNC();
+          if (conv) {
+            tb = t;
+            double cnt = (double)(t - lo);
+            w_gemm<R>(T1, Ps, false, Jinf, true);
+            for (int e = DFM_LANE; e < RR; e += DFM_WSZ) {
+              SPall[e] += cnt * Ps[e]; SP00[e] += cnt * Ps[e];
+              SPff2[e] += ((lo >= 1) ? cnt : cnt - 1.0) * Ps[e];
+              SP11[e] += cnt * T1[e];
+              Ppinf[e] = Ps[e];                                  // Ps_inf (smoothed covariance of the frozen range)
+            }
+            DFM_WSYNC();
+            t = lo - 1;
+          } else --t;
+        }
+        if (DFM_LANE == 0) { ctl[0] = nE; ctl[1] = tb; ctl[3] = frozen; }
+#ifndef DFM_EMU
+        if (a.phase_cycles && threadIdx.x == 0) { long long c2_ = clock64(); a.phase_cycles[(size_t)blockIdx.x * 16 + 12] += c1_ - c0_; a.phase_cycles[(size_t)blockIdx.x * 16 + 13] += c2_ - c1_; }
+#endif
+#ifdef DFM_EMU
+        if (getenv("DFM_DEBUG_CHAIN")) printf("[chain] b=%d it=%d nE=%d frozen=%d tb=%d (T=%d)\n", b, it, nE, frozen, tb, T);
+#endif
+        // I - J_inf M  (for the parallel pre-pass of the backward mean recursion)
+        if (frozen) {
+          w_gemm<R>(IJM, Jinf, false, M, false);
+          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) { int i = e / R, j = e % R; IJM[e] = ((i == j) ? 1.0 : 0.0) - IJM[e]; }
+        }
+        DFM_WSYNC();
+      }
+      DFM_SYNC();
+      const int nE = ctl[0], frozen = ctl[3];
+      DFM_TICK(3);
+      // ---------------------------------------------------------------- P3: forward means
+      // parallel pre-pass over the frozen range: Z[t] <- Pf_inf b_t
+      for (int t = nE + DFM_TID; t < T; t += DFM_NT) {
+        double bb[R], u[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) bb[j] = Z[ZI(t, j)];
+#pragma unroll
+        for (int i = 0; i < R; ++i) { double s = 0.0;
+#pragma unroll
+          for (int j = 0; j < R; ++j) s += Pfinf[i * R + j] * bb[j]; u[i] = s; }
+#pragma unroll
+        for (int i = 0; i < R; ++i) Z[ZI(t, i)] = u[i];
+      }
+      DFM_SYNC();
+      if (DFM_WARP == 0) {
+        // explicit steps
+        for (int t = 0; t < nE; ++t) {
+          const double* s_ = SCRP(t);
+          for (int i = DFM_LANE; i < R; i += DFM_WSZ) {
+            double s = 0.0;
+            for (int j = 0; j < R; ++j) s += s_[i * R + j] * Z[ZI(t, j)];                 // Pf_t b_t
+            if (t >= 1) for (int j = 0; j < R; ++j) s += s_[RR + i * R + j] * Z[ZI(t - 1, j)];   // Phi_t zf_{t-1}
+            tmp[i] = s;
+          }
+          DFM_WSYNC();
+          for (int i = DFM_LANE; i < R; i += DFM_WSZ) Z[ZI(t, i)] = tmp[i];
+          DFM_WSYNC();
+        }
+      }
+      DFM_SYNC();
+      // frozen steps: z_t = Phi_inf z_{t-1} + u_t, parallel in time over the CTA
+      if (frozen) blk_recur<R>(Z, Tp, Phinf, T1, T2, bnd, (nE > 0 ? nE : 1), T - (nE > 0 ? nE : 1), +1, 32);
+      DFM_TICK(4);
+      // ---------------------------------------------------------------- P4: log-likelihood (parallel over t)
+      double llp = 0.0;
+      for (int t = DFM_TID; t < T; t += DFM_NT) {
+        const double* Wt = (t < nE) ? SCRP(t) + 3 * RR : Winf;
+        double ldt = (t < nE) ? (SCRP(t))[5 * RR] : scal[1];
+        double zp[R], d[R];
+#pragma unroll
+        for (int i = 0; i < R; ++i) { double s = 0.0; if (t >= 1) {
+#pragma unroll
+            for (int j = 0; j < R; ++j) s += M[i * R + j] * Z[ZI(t - 1, j)]; }
+          zp[i] = s; d[i] = Z[ZI(t, i)] - s; }
+        double quad = 0.0;
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+          double cz = 0.0, g = 0.0;
+#pragma unroll
+          for (int j = 0; j < R; ++j) { cz += C[i * R + j] * zp[j]; g += Wt[i * R + j] * d[j]; }
+          quad -= zp[i] * cz + 2.0 * zp[i] * g + g * d[i];
+        }
+        llp += -0.5 * ((double)N * 1.8378770664093454835606594728112 + scal[0] + ldt + quad);
+      }
+      llp = block_sum(llp, red);
+      const double ll = llp - 0.5 * scal[2];
+      DFM_TICK(5);
+      // ---------------------------------------------------------------- P5: backward means
+      if (frozen) {
+        int lo = nE - 1;
+        for (int t = lo + DFM_TID; t < T - 1; t += DFM_NT) {       // Z[t] <- (I - J_inf M) zf_t
+          double zz[R], v[R];
+#pragma unroll
+          for (int j = 0; j < R; ++j) zz[j] = Z[ZI(t, j)];
+#pragma unroll
+          for (int i = 0; i < R; ++i) { double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < R; ++j) s += IJM[i * R + j] * zz[j]; v[i] = s; }
+#pragma unroll
+          for (int i = 0; i < R; ++i) Z[ZI(t, i)] = v[i];
+        }
+      }
+      DFM_SYNC();
+      // frozen range: z_t = J_inf z_{t+1} + v_t, parallel in time over the CTA
+      if (frozen) blk_recur<R>(Z, Tp, Jinf, T1, T2, bnd, T - 2, (T - 2) - (nE - 1) + 1, -1, 32);
+      if (DFM_WARP == 0) {
+        const int lo = frozen ? nE - 1 : T;
+        // explicit range: zs_t = zf_t + J_t (zs_{t+1} - M zf_t)
+        for (int t = (lo - 1 < T - 2 ? lo - 1 : T - 2); t >= 0; --t) {
+          const double* j_t = SCRP(t) + 2 * RR;
+          for (int i = DFM_LANE; i < R; i += DFM_WSZ) { double s = Z[ZI(t + 1, i)]; for (int j = 0; j < R; ++j) s -= M[i * R + j] * Z[ZI(t, j)]; tmp[i] = s; }
+          DFM_WSYNC();
+          for (int i = DFM_LANE; i < R; i += DFM_WSZ) { double s = Z[ZI(t, i)]; for (int j = 0; j < R; ++j) s += j_t[i * R + j] * tmp[j]; tmp[R + i] = s; }
+          DFM_WSYNC();
+          for (int i = DFM_LANE; i < R; i += DFM_WSZ) Z[ZI(t, i)] = tmp[R + i];
+          DFM_WSYNC();
+        }
+      }
+      DFM_SYNC();
+      DFM_TICK(6);
+      // ---------------------------------------------------------------- P7: mean parts of the moment sums
+      for (int e = DFM_TID; e < 2 * RR; e += DFM_NT) {
+        int which = e / RR, ee = e % RR, i = ee / R, j = ee % R;
+        double s = 0.0;
+        if (which == 0) { for (int t = 0; t < T; ++t) s += Z[ZI(t, i)] * Z[ZI(t, j)]; Sm[ee] = s; }
+        else { for (int t = 1; t < T; ++t) s += Z[ZI(t, i)] * Z[ZI(t - 1, j)]; S11m[ee] = s; }
+      }
+      DFM_SYNC();
+      DFM_TICK(7);
+      // ---------------------------------------------------------------- P8: M-step contraction (panel pass 2)
+#ifdef DFM_EMU
+      for (int n = 0; n < N; ++n) {
+        double s2 = 0.0, acc[R];
+        for (int c = 0; c < R; ++c) acc[c] = 0.0;
+        for (int t = 0; t < T; ++t) { double x = X[(size_t)n * T + t]; s2 += x * x; for (int c = 0; c < R; ++c) acc[c] += x * Z[ZI(t, c)]; }
+        for (int c = 0; c < R; ++c) Lam[LI(n, c)] = acc[c];
+        sxx[n] = s2;
+      }
+#else
+      {
+        // the ring held explicit-step scratch written with ordinary stores: order them before the
+        // async-proxy writes of the bulk copies
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        const int nsb = (N + 7) / 8, nck = (T + F2_TC - 1) / F2_TC;
+        const long long nitems = (long long)nsb * nck;
+        if (DFM_WARP == 0) {
+          const int lane = DFM_LANE;
+          for (int sb = 0; sb < nsb; ++sb) {
+            const int rows = (N - sb * 8 < 8) ? N - sb * 8 : 8;
+            for (int c = 0; c < nck; ++c) {
+              const int len = (T - c * F2_TC < F2_TC) ? T - c * F2_TC : F2_TC;
+              if (rwrap_) f2_mbar_wait(&emptyb[rs_], rph_ ^ 1);
+              if (lane == 0) f2_mbar_expect(&fullb[rs_], (uint32_t)(rows * len * 8));
+              __syncwarp();
+              if (lane < rows)
+                f2_bulk_g2s(ring + (size_t)rs_ * 8 * F2_TS + lane * F2_TS, X + (size_t)(sb * 8 + lane) * T + c * F2_TC, (uint32_t)(len * 8), &fullb[rs_]);
+              F2_ADVANCE();
+            }
+          }
+        } else if (DFM_WARP <= F2_NCW) {
+          const int cw = DFM_WARP - 1, lane = DFM_LANE, lr = lane >> 2, lc = lane & 3;
+          double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0, s2 = 0.0;       // two independent accumulator pairs
+          for (int sb = 0; sb < nsb; ++sb)
+          for (int c = 0; c < nck; ++c) {
+            f2_mbar_wait(&fullb[rs_], rph_);
+            const double* tile = ring + (size_t)rs_ * 8 * F2_TS;
+            const int len = (T - c * F2_TC < F2_TC) ? T - c * F2_TC : F2_TC;
+            const bool nok = sb * 8 + lr < N;
+            const double* zc = Z + (size_t)lr * Tp + c * F2_TC;
+#pragma unroll
+            for (int j = 0; j < 4; j += 2) {                           // k-chunks cw, cw+6, cw+12, cw+18 (F2_TC/4 = 4 * F2_NCW)
+              const int tla = (cw + j * F2_NCW) * 4 + lc, tlb = (cw + (j + 1) * F2_NCW) * 4 + lc;
+              const double ava = (nok && tla < len) ? tile[lr * F2_TS + tla] : 0.0;
+              const double avb = (nok && tlb < len) ? tile[lr * F2_TS + tlb] : 0.0;
+              const double bva = (tla < len) ? zc[tla] : 0.0;
+              const double bvb = (tlb < len) ? zc[tlb] : 0.0;
+              s2 += ava * ava + avb * avb;
+              asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                           : "+d"(d0), "+d"(d1) : "d"(ava), "d"(bva));
+              asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                           : "+d"(e0), "+d"(e1) : "d"(avb), "d"(bvb));
+            }
+            __syncwarp();
+            if (lane == 0) f2_mbar_arrive(&emptyb[rs_]);
+            F2_ADVANCE();
+            if (c == nck - 1) {
+              // series block complete: deterministic cross-warp reduction of the F2_NCW partial tiles
+              s2 += __shfl_xor_sync(0xffffffffu, s2, 1); s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+              double* pb = part + (size_t)(sb & 1) * F2_NCW * 72 + cw * 72;
+              pb[2 * lane] = d0 + e0; pb[2 * lane + 1] = d1 + e1;
+              if (lc == 0) pb[64 + lr] = s2;
+              asm volatile("bar.sync 1, %0;" ::"n"(F2_NCW * 32) : "memory");
+              const int ct = cw * 32 + lane;                          // 0 .. F2_NCW*32-1
+              if (ct < 72) {
+                const double* pp_ = part + (size_t)(sb & 1) * F2_NCW * 72 + ct;
+                double tot_ = 0.0;
+#pragma unroll
+                for (int w_ = 0; w_ < F2_NCW; ++w_) tot_ += pp_[w_ * 72];
+                if (ct < 64) {
+                  const int l_ = ct >> 1, h_ = ct & 1, row = l_ >> 2, col = 2 * (l_ & 3) + h_, n = sb * 8 + row;
+                  if (n < N && col < R) Lam[LI(n, col)] = tot_;
+                } else { const int n = sb * 8 + (ct - 64); if (n < N) sxx[n] = tot_; }
+              }
+              d0 = 0.0; d1 = 0.0; e0 = 0.0; e1 = 0.0; s2 = 0.0;
+            }
+          }
+        }
+        else { for (long long q = 0; q < nitems; ++q) F2_ADVANCE(); }
+      }
+#endif
+      DFM_SYNC();
+      DFM_TICK(8);
+      // ---------------------------------------------------------------- P9: M-step solves
+      if (DFM_WARP == 0) {
+        int* bad = &ctl[2];
+        // measurement: S = SffAll;  Lam_i = S^-1 Sxf_i
+        for (int e = DFM_LANE; e < RR; e += DFM_WSZ) T1[e] = Sm[e] + SPall[e];
+        DFM_WSYNC();
+        w_sym<R>(T1);
+        w_inv<R>(G, T1, tmp, bad);                                 // G = S^-1, T1 = S
+        // transition: A = S11 S00^-1 ; Q = (Sff2 - A S11') / (T-1)
+        for (int e = DFM_LANE; e < RR; e += DFM_WSZ) {
+          int i = e / R, j = e % R;
+          Pp[e] = Sm[e] - Z[ZI(T - 1, i)] * Z[ZI(T - 1, j)] + SP00[e];        // S00
+          Pi[e] = Sm[e] - Z[ZI(0, i)] * Z[ZI(0, j)] + SPff2[e];                    // Sff2
+          Pf[e] = S11m[e] + SP11[e];                                                    // S11
+        }
+        DFM_WSYNC();
+        w_sym<R>(Pp);
+        w_inv<R>(Wm, Pp, tmp, bad);
+        w_gemm<R>(Phi, Pf, false, Wm, false);                      // A_new
+        w_gemm<R>(Pn, Phi, false, Pf, true);                       // A S11'
+        for (int e = DFM_LANE; e < RR; e += DFM_WSZ) Pn[e] = (Pi[e] - Pn[e]) / (double)(T - 1);
+        DFM_WSYNC();
+        w_sym<R>(Pn);                                              // Q_new
+      }
+      DFM_SYNC();
+      for (int n = DFM_TID; n < N; n += DFM_NT) {
+        double sx[R], lam[R];
+#pragma unroll
+        for (int c = 0; c < R; ++c) sx[c] = Lam[LI(n, c)];
+        double q1 = 0.0, q2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < R; ++i) { double s = 0.0;
+#pragma unroll
+          for (int j = 0; j < R; ++j) s += G[i * R + j] * sx[j]; lam[i] = s; q1 += s * sx[i]; }
+#pragma unroll
+        for (int i = 0; i < R; ++i) { double s = 0.0;
+#pragma unroll
+          for (int j = 0; j < R; ++j) s += T1[i * R + j] * lam[j]; q2 += lam[i] * s; }
+#pragma unroll
+        for (int c = 0; c < R; ++c) Lam[LI(n, c)] = lam[c];
+        Rv[n] = (sxx[n] - 2.0 * q1 + q2) / (double)T;
+      }
+      DFM_SYNC();
+      for (int e = DFM_TID; e < RR; e += DFM_NT) { M[e] = Phi[e]; Q[e] = Pn[e]; }
+      DFM_TICK(9);
+      if (DFM_TID == 0) a.loglik[(size_t)b * a.max_iter + it] = ll;
+      DFM_SYNC();
+      if (ctl[2] || !(ll == ll)) { status = 3; ++it; break; }
+      bool conv = (it >= 1) && fabs(ll - ll_prev) <= a.tol * 0.5 * (fabs(ll) + fabs(ll_prev));
+      ll_prev = ll;
+      if (conv) { ++it; break; }
+    }
+    DFM_TICK(10);
+    // ---- outputs
+    for (int e = DFM_TID; e < N * R; e += DFM_NT) { int i = e % N, c = e / N; a.Lam[(size_t)b * N * R + e] = Lam[LI(i, c)]; }
+    for (int e = DFM_TID; e < N; e += DFM_NT) a.R[(size_t)b * N + e] = Rv[e];
+    for (int e = DFM_TID; e < RR; e += DFM_NT) {
+      int i = e % R, j = e / R;                                   // column-major out
+      a.A[(size_t)b * RR + e] = M[i * R + j]; a.Q[(size_t)b * RR + e] = Q[i * R + j];
+    }
+    for (int e = DFM_TID; e < T * R; e += DFM_NT) { int t = e % T, c = e / T; a.Fs[(size_t)b * T * R + e] = Z[ZI(t, c)]; }
+    {
+      const int nE = ctl[0], tb = ctl[1], frozen = ctl[3];
+      const int lo = frozen ? nE - 1 : T;
+      for (int e = DFM_TID; e < T * NP; e += DFM_NT) {
+        int t = e % T, pe = e / T;
+        int i = 0; while ((i + 1) * (i + 2) / 2 <= pe) ++i;
+        int j = pe - i * (i + 1) / 2;
+        bool in_frozen = frozen && tb >= 0 && t >= lo && t < tb;
+        double v = in_frozen ? Ppinf[i * R + j] : GPS(t)[i * R + j];
+        a.PsF[(size_t)b * T * NP + e] = v;
+      }
+    }
+    if (DFM_TID == 0) { a.iters[b] = it > a.max_iter ? a.max_iter : it; a.status[b] = status; }
+    DFM_SYNC();
+    DFM_TICK(11);
+  }
+}
+
+#undef SCRP
+#undef GPS
+#undef F2_ADVANCE
+template <int R>
+inline size_t fused2_smem_doubles(int T, int N) {
+  return (size_t)FZ * pad4mod16(T) + (size_t)R * pad4mod16(N) + 3 * (size_t)N + 30 * (size_t)R * R + 2 * R + 40 + 8 + 8 +
+         (size_t)97 * R + (size_t)R * R + 2 * F2_NCW * 72 + (size_t)F2_S * 8 * F2_TS + 10;
+}
+
+}  // namespace dfm

@@ -145,7 +145,7 @@ typedef struct {
   double tol;               /* stop after iteration j>=2 when |ll_j-ll_{j-1}| <= tol*(|ll_j|+|ll_{j-1}|)/2 ; 0 = run max_iter */
   int batch;
   int mem;
-  int path;                 /* 0 = auto, 1 = general multi-kernel path, 2 = fused per-panel path (small k) */
+  int path;                 /* 0 = auto, 1 = general multi-kernel path, 2 = fused per-panel kernel (LDG->DMMA), 3 = fused per-panel kernel with TMA bulk-copy ring (needs even T) */
 } dfm_em_opts;
 
 typedef struct {            /* initial parameters; all column-major, per panel back to back */

@@ -47,3 +47,11 @@ def test_fused_rejects_missing(lib):
     with pytest.raises(DFMError):
         P.check_em(lib, p=1, miss=0.1, path=2)
     P.check_em(lib, p=1, miss=0.1, path=0)       # auto falls back to the general path
+
+
+# ---- TMA-fed fused kernel (path=3): emulation exercises its serial logic + 32-group scan + ring-scratch indexing
+def test_fused2_em_r3(lib): P.check_em(lib, p=1, miss=0.0, path=3)
+def test_fused2_em_r8(lib): P.check_em(lib, N=40, r=8, T=90, p=1, miss=0.0, path=3, iters=5)
+def test_fused2_em_r1(lib): P.check_em(lib, N=12, r=1, T=50, p=1, miss=0.0, path=3, iters=4)
+def test_fused2_em_convergence_rule(lib): P.check_em_convergence_rule(lib, path=3)
+def test_fused2_em_batch(lib): P.check_em_batch_balanced(lib, path=3)

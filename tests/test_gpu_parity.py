@@ -102,3 +102,30 @@ def test_fused_rejects_missing(lib):
     with pytest.raises(DFMError):
         P.check_em(lib, p=1, miss=0.1, path=2)
     P.check_em(lib, p=1, miss=0.1, path=0)
+
+
+# ---- TMA-fed fused kernel (cp.async.bulk ring + mbarriers + DMMA), path=3
+def test_fused2_em_r3(lib): P.check_em(lib, p=1, miss=0.0, path=3)
+def test_fused2_em_r8(lib): P.check_em(lib, N=40, r=8, T=90, p=1, miss=0.0, path=3, iters=5)
+def test_fused2_em_r1(lib): P.check_em(lib, N=12, r=1, T=50, p=1, miss=0.0, path=3, iters=4)
+def test_fused2_em_r5_ragged(lib): P.check_em(lib, N=37, r=5, T=102, p=1, miss=0.0, path=3, iters=4)   # N % 8 != 0, short chunks
+def test_fused2_em_long(lib): P.check_em(lib, N=24, r=4, T=300, p=1, miss=0.0, path=3, iters=3)        # several ring wraps, 3 period chunks
+def test_fused2_em_convergence_rule(lib): P.check_em_convergence_rule(lib, path=3)
+def test_fused2_em_batch(lib): P.check_em_batch_balanced(lib, B=7, path=3)
+def test_fused2_matches_general_c2(lib):
+    from oracle.dgp import simulate_panel
+    from oracle import dfm_ref as R, kalman_em as K
+    X, _ = simulate_panel(200, 8, 500, rep=3)
+    Lam, Rv, A, Q = K.init_from_factors(X, R.pca_score(X, 8), 1)
+    g1 = lib.em_kalman(X, Lam, Rv, A, Q, p=1, max_iter=10, path=1)
+    g2 = lib.em_kalman(X, Lam, Rv, A, Q, p=1, max_iter=10, path=3)
+    np.testing.assert_allclose(g2["loglik"], g1["loglik"], rtol=1e-11)
+    assert P.rmse(g2["F"], g1["F"]) < 1e-9
+    np.testing.assert_allclose(g2["PF"], g1["PF"], rtol=1e-7, atol=1e-11)
+    np.testing.assert_allclose(g2["Lam"], g1["Lam"], rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(g2["A"], g1["A"], rtol=1e-6, atol=1e-9)
+def test_fused2_odd_T_falls_back(lib):
+    from dynamic_factor_models_b200 import DFMError
+    with pytest.raises(DFMError):
+        P.check_em(lib, N=20, r=3, T=71, p=1, path=3)
+    P.check_em(lib, N=20, r=3, T=71, p=1, path=0)
