@@ -70,6 +70,7 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a) {
   double* gscr = a.scratch + (size_t)DFM_BX * T * FUSED_SCR(R);
   // per explicit step t: SCRP(t)[{0:Pf, RR:Phi, 2RR:J, 3RR:W, 4RR:Ps, 5RR: ld}]; the first F2_NEXS(R)
   // steps live in the (idle between the two passes) ring, the rest in global scratch
+#define GSC(t_) (gscr + (size_t)(t_) * FUSED_SCR(R))
 #define SCRP(t_) (((t_) < F2_NEXS(R)) ? (ring + (size_t)(t_) * FUSED_SCR(R)) : (gscr + (size_t)(t_) * FUSED_SCR(R)))
 #define GPS(t_) (gscr + (size_t)(t_) * FUSED_SCR(R) + 4 * RR)      // smoothed covariances: always global (read at output time only)
 #ifndef DFM_EMU
@@ -181,15 +182,9 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a) {
             if (v1) { const int t = c * F2_TC + tl1; Z[ZI(t, 2 * lc)] = d10; Z[ZI(t, 2 * lc + 1)] = d11; }
           }
         }
-        else { for (long long q = 0; q < nitems; ++q) F2_ADVANCE(); }      // idle warps keep the ring position in step
-      }
-#endif
-      qacc = block_sum(qacc, red);
-      if (DFM_TID == 0) scal[2] = qacc;
-      DFM_SYNC();
-      DFM_TICK(2);
-      // ---------------------------------------------------------------- P2: covariance chain (warp 0, data independent)
-      if (DFM_WARP == 0) {
+        else {
+          for (long long q = 0; q < nitems; ++q) F2_ADVANCE();             // keep the ring position in step
+        {   // ---- covariance chain (data independent), on the chain warp, concurrently with the E pass
         int* bad = &ctl[2];
         // forward
         for (int e = DFM_LANE; e < RR; e += DFM_WSZ) { int i = e / R, j = e % R; Pp[e] = a.P0[(size_t)b * RR + i + R * j]; }
@@ -211,11 +206,11 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a) {
           for (int e = DFM_LANE; e < RR; e += DFM_WSZ) Pn[e] += Q[e];
           DFM_WSYNC();
           w_sym<R>(Pn);
-          double* s_ = SCRP(t);
+          double* s_ = GSC(t);
           double dmax = 0.0, pmax = 0.0;
           for (int e = DFM_LANE; e < RR; e += DFM_WSZ) {
             s_[e] = Pf[e]; s_[RR + e] = Phi[e]; s_[3 * RR + e] = Wm[e];
-            if (t >= 1) SCRP(t - 1)[2 * RR + e] = Jm[e];
+            if (t >= 1) GSC(t - 1)[2 * RR + e] = Jm[e];
             dmax = fmax(dmax, fabs(Pn[e] - Pp[e])); pmax = fmax(pmax, fabs(Pp[e]));
             Pfprev[e] = Pf[e];
           }
@@ -242,7 +237,7 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a) {
 #endif
         // backward covariance chain + covariance parts of the moment sums
         for (int e = DFM_LANE; e < RR; e += DFM_WSZ) {
-          double v = frozen ? Pfinf[e] : (SCRP(T - 1))[e];
+          double v = frozen ? Pfinf[e] : (GSC(T - 1))[e];
           Psn[e] = v; SPall[e] = v; SPff2[e] = v; SP00[e] = 0.0; SP11[e] = 0.0;
           GPS(T - 1)[e] = v;
         }
@@ -251,8 +246,8 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a) {
         int tb = -1;                        // frozen smoothed range is [lo, tb)
         t = T - 2;
         while (t >= 0) {
-          const double* pf_t = (t < nE) ? SCRP(t) : Pfinf;
-          const double* j_t = (t < nE - 1) ? SCRP(t) + 2 * RR : Jinf;
+          const double* pf_t = (t < nE) ? GSC(t) : Pfinf;
+          const double* j_t = (t < nE - 1) ? GSC(t) + 2 * RR : Jinf;
           // Pp_{t+1} = M Pf_t M' + Q (recomputed: cheaper than storing)
           w_gemm<R>(T1, M, false, pf_t, false);
           w_gemm<R>(T2, T1, false, M, true);
@@ -305,6 +300,136 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a) {
         }
         DFM_WSYNC();
       }
+        }
+      }
+#endif
+#ifdef DFM_EMU
+        {   // ---- covariance chain (data independent), on the chain warp, concurrently with the E pass
+        int* bad = &ctl[2];
+        // forward
+        for (int e = DFM_LANE; e < RR; e += DFM_WSZ) { int i = e / R, j = e % R; Pp[e] = a.P0[(size_t)b * RR + i + R * j]; }
+        DFM_WSYNC();
+        int nE = T, frozen_at = -1, t = 0;
+#ifndef DFM_EMU
+        long long c0_ = clock64();
+#endif
+        while (t < T) {
+          double ldp = w_inv<R>(Pi, Pp, tmp, bad);
+          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) Wm[e] = Pi[e] + C[e];
+          DFM_WSYNC();
+          double ldw = w_inv<R>(Pf, Wm, tmp, bad);
+          w_gemm<R>(G, Pf, false, Pi, false);
+          w_gemm<R>(Phi, G, false, M, false);
+          if (t >= 1) { w_gemm<R>(T1, Pfprev, false, M, true); w_gemm<R>(Jm, T1, false, Pi, false); }   // J_{t-1}
+          w_gemm<R>(T1, M, false, Pf, false);
+          w_gemm<R>(Pn, T1, false, M, true);
+          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) Pn[e] += Q[e];
+          DFM_WSYNC();
+          w_sym<R>(Pn);
+          double* s_ = GSC(t);
+          double dmax = 0.0, pmax = 0.0;
+          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) {
+            s_[e] = Pf[e]; s_[RR + e] = Phi[e]; s_[3 * RR + e] = Wm[e];
+            if (t >= 1) GSC(t - 1)[2 * RR + e] = Jm[e];
+            dmax = fmax(dmax, fabs(Pn[e] - Pp[e])); pmax = fmax(pmax, fabs(Pp[e]));
+            Pfprev[e] = Pf[e];
+          }
+          if (DFM_LANE == 0) s_[5 * RR] = ldp + ldw;
+          dmax = w_max(dmax); pmax = w_max(pmax);
+          DFM_WSYNC();
+          if (frozen_at >= 0 && t == frozen_at + 1) {
+            nE = t + 1;
+            for (int e = DFM_LANE; e < RR; e += DFM_WSZ) { Pfinf[e] = Pf[e]; Phinf[e] = Phi[e]; Winf[e] = Wm[e]; }
+            if (DFM_LANE == 0) scal[1] = ldp + ldw;
+            DFM_WSYNC();
+            w_gemm<R>(T1, Pf, false, M, true);
+            w_gemm<R>(Jinf, T1, false, Pi, false);                 // J_inf = Pf_inf M' Pi_inf
+            break;
+          }
+          if (frozen_at < 0 && dmax <= eps * pmax) frozen_at = t;
+          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) Pp[e] = Pn[e];
+          DFM_WSYNC();
+          ++t;
+        }
+        const int frozen = nE < T;
+#ifndef DFM_EMU
+        long long c1_ = clock64();
+#endif
+        // backward covariance chain + covariance parts of the moment sums
+        for (int e = DFM_LANE; e < RR; e += DFM_WSZ) {
+          double v = frozen ? Pfinf[e] : (GSC(T - 1))[e];
+          Psn[e] = v; SPall[e] = v; SPff2[e] = v; SP00[e] = 0.0; SP11[e] = 0.0;
+          GPS(T - 1)[e] = v;
+        }
+        DFM_WSYNC();
+        const int lo = frozen ? nE - 1 : T;
+        int tb = -1;                        // frozen smoothed range is [lo, tb)
+        t = T - 2;
+        while (t >= 0) {
+          const double* pf_t = (t < nE) ? GSC(t) : Pfinf;
+          const double* j_t = (t < nE - 1) ? GSC(t) + 2 * RR : Jinf;
+          // Pp_{t+1} = M Pf_t M' + Q (recomputed: cheaper than storing)
+          w_gemm<R>(T1, M, false, pf_t, false);
+          w_gemm<R>(T2, T1, false, M, true);
+          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) T2[e] = Psn[e] - (T2[e] + Q[e]);
+          DFM_WSYNC();
+          w_sym<R>(T2);                                           // D = Ps_{t+1} - Pp_{t+1}
+          w_gemm<R>(T1, j_t, false, T2, false);
+          w_gemm<R>(Ps, T1, false, j_t, true);
+          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) Ps[e] += pf_t[e];
+          DFM_WSYNC();
+          w_sym<R>(Ps);
+          w_gemm<R>(T1, Psn, false, j_t, true);                    // Ps_{t+1} J_t'
+          double dmax = 0.0, pmax = 0.0;
+          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) {
+            SP11[e] += T1[e]; SPall[e] += Ps[e]; SP00[e] += Ps[e];
+            if (t >= 1) SPff2[e] += Ps[e];
+            GPS(t)[e] = Ps[e];
+            dmax = fmax(dmax, fabs(Ps[e] - Psn[e])); pmax = fmax(pmax, fabs(Ps[e]));
+          }
+          dmax = w_max(dmax); pmax = w_max(pmax);
+          DFM_WSYNC();
+          bool conv = frozen && t > lo && dmax <= eps * pmax;
+          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) Psn[e] = Ps[e];
+          DFM_WSYNC();
+          if (conv) {
+            tb = t;
+            double cnt = (double)(t - lo);
+            w_gemm<R>(T1, Ps, false, Jinf, true);
+            for (int e = DFM_LANE; e < RR; e += DFM_WSZ) {
+              SPall[e] += cnt * Ps[e]; SP00[e] += cnt * Ps[e];
+              SPff2[e] += ((lo >= 1) ? cnt : cnt - 1.0) * Ps[e];
+              SP11[e] += cnt * T1[e];
+              Ppinf[e] = Ps[e];                                  // Ps_inf (smoothed covariance of the frozen range)
+            }
+            DFM_WSYNC();
+            t = lo - 1;
+          } else --t;
+        }
+        if (DFM_LANE == 0) { ctl[0] = nE; ctl[1] = tb; ctl[3] = frozen; }
+#ifndef DFM_EMU
+        if (a.phase_cycles && threadIdx.x == 0) { long long c2_ = clock64(); a.phase_cycles[(size_t)blockIdx.x * 16 + 12] += c1_ - c0_; a.phase_cycles[(size_t)blockIdx.x * 16 + 13] += c2_ - c1_; }
+#endif
+#ifdef DFM_EMU
+        if (getenv("DFM_DEBUG_CHAIN")) printf("[chain] b=%d it=%d nE=%d frozen=%d tb=%d (T=%d)\n", b, it, nE, frozen, tb, T);
+#endif
+        // I - J_inf M  (for the parallel pre-pass of the backward mean recursion)
+        if (frozen) {
+          w_gemm<R>(IJM, Jinf, false, M, false);
+          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) { int i = e / R, j = e % R; IJM[e] = ((i == j) ? 1.0 : 0.0) - IJM[e]; }
+        }
+        DFM_WSYNC();
+      }
+#endif
+      DFM_SYNC();
+      {   // explicit covariance steps: global scratch -> (now idle) ring, one cooperative copy
+        const int ncp = (ctl[0] < F2_NEXS(R)) ? ctl[0] : F2_NEXS(R);
+        for (int e = DFM_TID; e < ncp * FUSED_SCR(R); e += DFM_NT) ring[e] = gscr[e];
+      }
+      qacc = block_sum(qacc, red);
+      if (DFM_TID == 0) scal[2] = qacc;
+      DFM_SYNC();
+      DFM_TICK(2);
       DFM_SYNC();
       const int nE = ctl[0], frozen = ctl[3];
       DFM_TICK(3);
@@ -571,6 +696,7 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a) {
 }
 
 #undef SCRP
+#undef GSC
 #undef GPS
 #undef F2_ADVANCE
 template <int R>
