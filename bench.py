@@ -259,7 +259,12 @@ def main():
         units_per_launch = B * iters / d_cnt                       # panel-iterations one launch of the dominant kernel processes
         alg_bytes = 2.0 * T_ * NS * 8 * units_per_launch           # 2*T*N*8 bytes per panel-iteration
         ach = alg_bytes / (d_ms / d_cnt * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+        traffic = None; traffic_src = None
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tp) and "fused2" in dom:
+            tj = json.load(open(tp)); traffic = tj["dram_bytes_per_panel_iteration"] * units_per_launch; traffic_src = tj["source"]
+        roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                "traffic_source": traffic_src,
                 "peak_source": peak_src, "kernel_share_of_step": d_ms / tot, "avg_launch_ms": d_ms / d_cnt,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "kernel_ms": {n: round(v[0], 3) for n, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}}

@@ -1,0 +1,52 @@
+"""GPU: replication-level drivers (configs C4 / C5 in miniature) vs the oracle."""
+import numpy as np
+import pytest
+
+import parity_checks as P
+from oracle import dfm_ref as R, kalman_em as K
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from dynamic_factor_models_b200 import Library
+    L = Library()
+    yield L
+    L.close()
+
+
+def test_monte_carlo_em_matches_oracle(lib):
+    from dynamic_factor_models_b200 import replicate
+    n_rep, N, r, T, iters = 6, 40, 3, 120, 8
+    rec = replicate.monte_carlo_em(lib, n_rep, N, r, T, em_iters=iters)
+    assert rec.shape == (n_rep, 4) and (rec[:, 2] == 0).all() and (rec[:, 1] == iters).all()
+    for b in (0, n_rep - 1):
+        X = replicate.simulate_panel(N, r, T, rep=b)
+        m = R.DFMModel(X, np.ones(N, int), 20, 40, 1, T, 0, r, 1e-8, 4, 1)
+        R.estimate_factor(m, max_iter=1, computeR2=False)
+        Lam, Rv, A, Q = K.init_from_factors(m.xs, m.factor, 1)
+        ref = K.em_kalman(m.xs, Lam, Rv, A, Q, p=1, max_iter=iters)
+        np.testing.assert_allclose(rec[b, 0], ref["loglik"][-1], rtol=1e-9)
+        np.testing.assert_allclose(rec[b, 3], 1 - m.fes.ssr / m.fes.tss, rtol=1e-9)
+
+
+def test_bootstrap_irf_c1(lib, panels):
+    """C4 in miniature: 4 bootstrap replications of the hom_fac_1 model; one replication is
+    re-estimated with the oracle pipeline and compared."""
+    import dynamic_factor_models_b200 as D
+    from dynamic_factor_models_b200 import replicate
+    g = P.gpu_model(panels["all_bpdata"], panels["all_inclcode"], 4)
+    D.estimate(g, lib=lib)
+    irfs, bands = replicate.bootstrap_irf(lib, g, 4, H=8)
+    assert irfs.shape == (4, 4, 8, 4) and np.isfinite(irfs).all()
+    assert (bands[5] <= bands[95] + 1e-12).all()
+    # oracle re-estimation of replication 2
+    Xs = replicate.bootstrap_panels(g, [2])[0]
+    full = np.full_like(panels["all_bpdata"], np.nan); full[2:224] = Xs
+    m = P.ref_model(full, panels["all_inclcode"], 4)
+    R.estimate_factor(m, computeR2=False); R.estimate_var(m.factor_var_model)
+    F0 = g.factor[2:224]
+    s = np.sign((m.factor[2:224] * F0).sum(0)); s[s == 0] = 1
+    ref = R.impulse_response(m.factor_var_model, [0, 1, 2, 3], 8) * s[:, None, None] * s[None, None, :]
+    np.testing.assert_allclose(irfs[2], ref, rtol=1e-5, atol=1e-8)
