@@ -104,16 +104,16 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle.c import kem
-    cores = kem.max_threads()
+    cores = os.cpu_count() or kem.max_threads()        # all host threads (torchrun pins OMP_NUM_THREADS=1: override)
     Bs = 4 * cores
     Xs = make_panels(Bs, 0)
     init = host_init(Xs)
     iters = args.em_iters
     for _ in range(args.warmup):
-        cpu_em(Xs, init, 2)
+        cpu_em(Xs, init, 2, nthreads=cores)
     t = 0.0; n = 0
     for _ in range(args.steps):
-        dt, units, _ = cpu_em(Xs, init, iters)
+        dt, units, _ = cpu_em(Xs, init, iters, nthreads=cores)
         t += dt; n += units
     v = n / t
     sample = f"{Bs} panels x {iters} EM iterations per step (oracle C port, OpenMP over panels)"
@@ -150,7 +150,12 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL may print a version banner on stdout: keep stdout clean for the single JSON line
+        sys.stdout.flush(); saved_fd = os.dup(1); os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush(); os.dup2(saved_fd, 1); os.close(saved_fd)
     lib = Library(device=local)
 
     B, iters, K_, W_ = args.panels, args.em_iters, args.steps, args.warmup
@@ -273,12 +278,12 @@ def main():
     cpu = None; rmse = None
     if rank == 0 and world == 1 and not args.no_cpu:
         from oracle.c import kem
-        cores = kem.max_threads()
+        cores = os.cpu_count() or kem.max_threads()
         Bs = min(B, 4 * cores)
         Lh = lambda t, rows, cols: np.ascontiguousarray(t[:Bs * rows * cols].cpu().numpy().reshape(Bs, cols, rows).transpose(0, 2, 1))
         init = (Lh(dLam0, NS, R_), dR0[:Bs * NS].cpu().numpy().reshape(Bs, NS), Lh(dA0, R_, k), Lh(dQ0, R_, R_))
-        cpu_em(Xh[:2], tuple(a[:2] for a in init), 2)
-        dt, n, out = cpu_em(Xh[:Bs], init, iters)
+        cpu_em(Xh[:2], tuple(a[:2] for a in init), 2, nthreads=cores)
+        dt, n, out = cpu_em(Xh[:Bs], init, iters, nthreads=cores)
         cpu = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{Bs} of the same panels x {iters} EM iterations, oracle C port (gcc -O3, OpenMP over panels), {dt:.1f} s"}
         Fg = dout["F"][:Bs * T_ * R_].cpu().numpy().reshape(Bs, R_, T_).transpose(0, 2, 1)
