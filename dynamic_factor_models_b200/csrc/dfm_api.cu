@@ -230,7 +230,7 @@ int dfm_create_on_stream(int device, void* cuda_stream, dfm_handle** out) {
   else { if (cudaStreamCreate(&h->stream) != cudaSuccess) { delete h; return DFM_ERR_CUDA; } h->own_stream = true; }
   DFM_SET_SMEM(k_em_filter_smooth, kMaxSmem); DFM_SET_SMEM(k_als_factor, kMaxSmem); DFM_SET_SMEM(k_em_contract, kMaxSmem);
   DFM_SET_SMEM(k_lyapunov, kMaxSmem); DFM_SET_SMEM(k_var, kMaxSmem); DFM_SET_SMEM(k_pca_finish, kMaxSmem);
-  DFM_SET_SMEM(k_jacobi, kMaxSmem); DFM_SET_SMEM(k_loading, kMaxSmem); DFM_SET_SMEM(k_als_lambda, kMaxSmem);
+  DFM_SET_SMEM(k_jacobi, kMaxSmem); DFM_SET_SMEM(k_subspace_eig, kMaxSmem); DFM_SET_SMEM(k_loading, kMaxSmem); DFM_SET_SMEM(k_als_lambda, kMaxSmem);
   if (cudaGetLastError() != cudaSuccess) { delete h; return DFM_ERR_CUDA; }
   *out = h;
   return DFM_OK;
@@ -316,22 +316,29 @@ int dfm_standardize(dfm_handle* h, const double* X, int T, int N, int batch, int
 }
 
 // ------------------------------------------------------------------------------------ PCA helper
-// device-side PCA of the balanced columns of dXs into dF.  nmax = min(N,T) <= 256.
+// device-side PCA of the balanced columns of dXs into dF.  min(N,T) <= 64: direct Jacobi on the Gram
+// matrix; larger: block subspace iteration with Rayleigh-Ritz (Ysub = scratch nmax x PCA_MMAX per panel).
+#define PCA_MMAX 64
+static int pca_block(int r) { return std::min(PCA_MMAX, std::max(2 * r, r + 16)); }
 static int run_pca(dfm_handle* h, const double* dXs, int T, int N, int r, int batch, const int* col_n /*null = all cols*/,
-                   int* bal_idx, int* nbal, double* G, double* V, double* dF, int* status, AlsState* st) {
+                   int* bal_idx, int* nbal, double* G, double* V, double* Ysub, double* dF, int* status, AlsState* st) {
   int nmax = std::min(N, T);
   if (col_n) L(k_balanced_cols, batch, 1, 1, 0, col_n, T, N, bal_idx, nbal);
   else L(k_all_cols, batch, 1, 128, 0, N, bal_idx, nbal);
   int gx = (int)std::min<long long>(((long long)nmax * nmax + 255) / 256, 4096);
   L(k_gram, gx, batch, 256, 0, dXs, T, N, bal_idx, nbal, G, nmax);
-  L(k_jacobi, batch, 1, 256, (size_t)(nmax + 2 + 48) * 8, G, V, nbal, T, nmax, 60, (int*)nullptr);
+  if (nmax <= 64) L(k_jacobi, batch, 1, 256, (size_t)(nmax + 2 + 48) * 8, G, V, nbal, T, nmax, 60, (int*)nullptr);
+  else {
+    int m = std::min(nmax, pca_block(r));
+    L(k_subspace_eig, batch, 1, 256, (size_t)(3 * m * m + 2 * m + 64) * 8, G, V, Ysub, nbal, T, nmax, r, m, 500, 1e-13, (int*)nullptr);
+  }
   L(k_pca_finish, batch, 1, 128, (size_t)(r / 2 + 2 + 48 + N) * 8, dXs, T, N, bal_idx, nbal, G, V, nmax, r, dF, status, st);
   return DFM_OK;
 }
 
 int dfm_pca_score(dfm_handle* h, const double* X, int T, int N, int r, int batch, int mem, double* score) {
   if (!h || !X || !score || T <= 0 || N <= 0 || r <= 0 || batch <= 0 || r > std::min(T, N)) return fail(h, DFM_ERR_ARG, "dfm_pca_score: bad argument");
-  if (std::min(N, T) > 256) return fail(h, DFM_ERR_UNSUPPORTED, "dfm_pca_score: min(T,N) > 256 not supported yet");
+  if (r > 48) return fail(h, DFM_ERR_UNSUPPORTED, "dfm_pca_score: r > 48");
   CK(cudaSetDevice(h->device));
   size_t B = batch, TN = (size_t)T * N; int nmax = std::min(N, T);
   for (int pass = 0; pass < 2; ++pass) {
@@ -340,10 +347,11 @@ int dfm_pca_score(dfm_handle* h, const double* X, int T, int N, int r, int batch
     double* dF = mem == DFM_MEM_HOST ? a.get<double>(B * T * r) : score;
     int* bal = a.get<int>(B * N); int* nbal = a.get<int>(B); int* status = a.get<int>(B);
     double* G = a.get<double>(B * nmax * nmax); double* V = a.get<double>(B * nmax * nmax);
+    double* Ysub = a.get<double>(B * nmax * PCA_MMAX);
     if (!pass) { int rc = ensure_ws(h, a.off); if (rc) return rc; continue; }
     const double* x; int rc = stage_in(h, X, dX, B * TN, mem, &x); if (rc) return rc;
     CK(cudaMemsetAsync(status, 0, B * sizeof(int), h->stream));
-    rc = run_pca(h, x, T, N, r, batch, nullptr, bal, nbal, G, V, dF, status, nullptr); if (rc) return rc;
+    rc = run_pca(h, x, T, N, r, batch, nullptr, bal, nbal, G, V, Ysub, dF, status, nullptr); if (rc) return rc;
     if (mem == DFM_MEM_HOST) { rc = copy_out(h, score, dF, B * T * r, mem); if (rc) return rc; }
   }
   return finish(h, mem);
@@ -357,7 +365,7 @@ int dfm_estimate_factor(dfm_handle* h, const double* X, const dfm_factor_opts* o
   if (T <= 1 || N <= 0 || r <= 0 || batch <= 0 || r > 64 || r > N || r > T || o->max_iter < 1 || o->n_constr < 0 ||
       (o->n_constr > 0 && (!o->constr_index || !o->constr_R || !o->constr_r)) || o->n_constr > 64)
     return fail(h, DFM_ERR_ARG, "dfm_estimate_factor: bad shape/options");
-  if (!F_init && std::min(N, T) > 256) return fail(h, DFM_ERR_UNSUPPORTED, "PCA init: min(T,N) > 256 not supported yet (pass F_init)");
+  if (!F_init && r > 48) return fail(h, DFM_ERR_UNSUPPORTED, "PCA init: r > 48 (pass F_init)");
   CK(cudaSetDevice(h->device));
   size_t B = batch, TN = (size_t)T * N; int nmax = std::min(N, T), np = r * (r + 1) / 2, nc = o->n_constr;
   int ntF = tpt_threads(np + r);
@@ -370,6 +378,7 @@ int dfm_estimate_factor(dfm_handle* h, const double* X, const dfm_factor_opts* o
     int* cn = a.get<int>(B * N); AlsState* st = a.get<AlsState>(B);
     int* bal = a.get<int>(B * N); int* nbal = a.get<int>(B); int* active = a.get<int>(4);
     double* G = F_init ? nullptr : a.get<double>(B * nmax * nmax); double* V = F_init ? nullptr : a.get<double>(B * nmax * nmax);
+    double* Ysub = F_init ? nullptr : a.get<double>(B * nmax * PCA_MMAX);
     double* dF = a.get<double>(B * T * r); double* dLam = a.get<double>(B * N * r); double* dR2 = a.get<double>(B * N);
     double* FtF = a.get<double>(B * r * r); double* LtL = a.get<double>(B * r * r); double* ssrp = a.get<double>(B * nblk);
     int* cidx = a.get<int>(nc + 1); double* cR = a.get<double>((size_t)nc * r + 1); double* cr = a.get<double>(nc + 1);
@@ -384,7 +393,7 @@ int dfm_estimate_factor(dfm_handle* h, const double* X, const dfm_factor_opts* o
     L(k_als_init_state, batch, 1, 128, 48 * 8, st, css, cn, N);                        // :342-343
     if (F_init) { const double* fi; rc = stage_in(h, F_init, dF, B * T * r, mem, &fi); if (rc) return rc;
                   if (fi != dF) CK(cudaMemcpyAsync(dF, fi, B * T * r * sizeof(double), cudaMemcpyDeviceToDevice, h->stream)); }
-    else { rc = run_pca(h, dXs, T, N, r, batch, cn, bal, nbal, G, V, dF, nullptr, st); if (rc) return rc; }   // :345-348
+    else { rc = run_pca(h, dXs, T, N, r, batch, cn, bal, nbal, G, V, Ysub, dF, nullptr, st); if (rc) return rc; }   // :345-348
     size_t smL = (size_t)(2 * np + 2 * r + 8 + (size_t)r * nc + (size_t)nc * (nc + 1) / 2 + nc) * 8;
     size_t smF = ((size_t)(np + r) * ntF + 48) * 8;
     long long it = 0;

@@ -97,20 +97,12 @@ __global__ void k_gram(const double* __restrict__ Xs, int T, int N, const int* _
   }
 }
 
-// Cyclic Jacobi eigen-solver with round-robin parallel ordering.  grid (B), one block per panel.
-// G (n x n, destroyed: diagonal = eigenvalues), V (n x n eigenvectors in columns).
-__global__ void k_jacobi(double* __restrict__ Gall, double* __restrict__ Vall, const int* __restrict__ nbal,
-                         int T, int nmax, int max_sweeps, int* __restrict__ sweeps_out) {
-  DFM_SMEM(sm);
-  int b = DFM_BX;
-  int nb = nbal[b];
-  int n = (nb <= T) ? nb : T;
-  double* G = Gall + (size_t)b * nmax * nmax;
-  double* V = Vall + (size_t)b * nmax * nmax;
+// Cyclic Jacobi eigen-solver core (round-robin parallel ordering) on an n x n symmetric matrix G with
+// leading dimension n (shared or global memory).  G is destroyed (diagonal = eigenvalues); V (n x n,
+// ld n) receives the eigenvectors in its columns.  cs: n+2 doubles, red: 40 doubles of shared scratch.
+// Block-cooperative; returns the number of sweeps.
+__device__ inline int jacobi_core(double* G, double* V, int n, double* cs, double* red, int max_sweeps) {
   int m = (n + 1) & ~1;                  // even number of players
-  double* cs = sm;                       // [m/2][2]
-  double* red = sm + m;                  // 33
-  int* flag = (int*)(red + 40);
   for (int e = DFM_TID; e < n * n; e += DFM_NT) { int i = e % n, j = e / n; V[i + (size_t)n * j] = (i == j) ? 1.0 : 0.0; }
   DFM_SYNC();
   int sweep = 0;
@@ -174,8 +166,129 @@ __global__ void k_jacobi(double* __restrict__ Gall, double* __restrict__ Vall, c
       DFM_SYNC();
     }
   }
-  if (DFM_TID == 0 && sweeps_out) sweeps_out[b] = sweep;
-  (void)flag;
+  return sweep;
+}
+
+// Direct Jacobi on the Gram matrix (small n).  grid (B), one block per panel.
+__global__ void k_jacobi(double* __restrict__ Gall, double* __restrict__ Vall, const int* __restrict__ nbal,
+                         int T, int nmax, int max_sweeps, int* __restrict__ sweeps_out) {
+  DFM_SMEM(sm);
+  int b = DFM_BX;
+  int nb = nbal[b];
+  int n = (nb <= T) ? nb : T;
+  double* G = Gall + (size_t)b * nmax * nmax;
+  double* V = Vall + (size_t)b * nmax * nmax;
+  int m = (n + 1) & ~1;
+  int sw = jacobi_core(G, V, n, sm, sm + m + 2, max_sweeps);
+  if (DFM_TID == 0 && sweeps_out) sweeps_out[b] = sw;
+}
+
+// Top-m eigenpairs of the Gram matrix by block subspace iteration with Rayleigh-Ritz (n > 64):
+//   V <- orth(G V) (CholQR2), H = V'GV (m x m), Jacobi on H in shared memory, V <- V W,
+// until the residuals ||G v_i - theta_i v_i|| of the leading r pairs drop below tol * theta_1.
+// Results are left in the layout k_pca_finish expects: eigenvalues on the diagonal of G (entries
+// m..n-1 set to -1e300), Ritz vectors in the first m columns of V (ld n).  grid (B), one block.
+// Y: global scratch n x m per panel.  shared: 3 m^2 + m + 64 doubles.
+__global__ void k_subspace_eig(double* __restrict__ Gall, double* __restrict__ Vall, double* __restrict__ Yall,
+                               const int* __restrict__ nbal, int T, int nmax, int r, int mmax, int maxit, double tol,
+                               int* __restrict__ iters_out) {
+  DFM_SMEM(sm);
+  int b = DFM_BX;
+  int nb = nbal[b];
+  int n = (nb <= T) ? nb : T;
+  int m = (mmax < n) ? mmax : n;
+  double* G = Gall + (size_t)b * nmax * nmax;
+  double* V = Vall + (size_t)b * nmax * nmax;           // n x m in the first m columns
+  double* Y = Yall + (size_t)b * nmax * mmax;           // n x m
+  double* H = sm; double* W = H + m * m; double* S = W + m * m; double* cs = S + m * m; double* red = cs + m + 2;
+  int* info = (int*)(red + 40);
+  double* theta = red + 44;                              // m
+  if (DFM_TID == 0) *info = 0;
+  // deterministic start: V[i][j] = hash-based pseudo-random in (-1, 1)
+  for (int e = DFM_TID; e < n * m; e += DFM_NT) {
+    unsigned h = (unsigned)e * 2654435761u + 12345u; h ^= h >> 15; h *= 2246822519u; h ^= h >> 13; h *= 3266489917u; h ^= h >> 16;
+    V[e] = (double)(h & 0xffffff) / 8388608.0 - 1.0;
+  }
+  DFM_SYNC();
+  int it = 0;
+  double res = 1.0;
+  for (; it < maxit; ++it) {
+    // ---- orthonormalise V (CholQR, twice): S = V'V = L L', V <- V L^-T
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int e = DFM_TID; e < m * m; e += DFM_NT) {
+        int a = e % m, c = e / m;
+        if (a < c) continue;
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) s += V[i + (size_t)n * a] * V[i + (size_t)n * c];
+        S[a + m * c] = s; S[c + m * a] = s;
+      }
+      DFM_SYNC();
+      bm_chol(S, m, m, info);
+      for (int i = DFM_TID; i < n; i += DFM_NT) {        // row i: x L' = v  (forward substitution over columns)
+        for (int c = 0; c < m; ++c) {
+          double s = V[i + (size_t)n * c];
+          for (int l = 0; l < c; ++l) s -= S[c + m * l] * V[i + (size_t)n * l];
+          V[i + (size_t)n * c] = s / S[c + m * c];
+        }
+      }
+      DFM_SYNC();
+    }
+    // ---- Y = G V
+    for (int e = DFM_TID; e < n * m; e += DFM_NT) {
+      int i = e % n, j = e / n;
+      double s = 0.0;
+      for (int l = 0; l < n; ++l) s += G[i + (size_t)n * l] * V[l + (size_t)n * j];
+      Y[e] = s;
+    }
+    DFM_SYNC();
+    // ---- Rayleigh-Ritz: H = V'Y, eigen-decomposition in shared memory, rotate V and Y
+    for (int e = DFM_TID; e < m * m; e += DFM_NT) {
+      int a = e % m, c = e / m;
+      if (a < c) continue;
+      double s = 0.0;
+      for (int i = 0; i < n; ++i) s += V[i + (size_t)n * a] * Y[i + (size_t)n * c];
+      H[a + m * c] = s; H[c + m * a] = s;
+    }
+    DFM_SYNC();
+    jacobi_core(H, W, m, cs, red, 40);
+    // order the Ritz values (descending) -> theta, permutation kept in cs (as doubles)
+    if (DFM_TID == 0) {
+      for (int j = 0; j < m; ++j) {
+        int best = -1; double bv = -1e300;
+        for (int i = 0; i < m; ++i) { bool used = false; for (int l = 0; l < j; ++l) if ((int)cs[l] == i) used = true;
+          if (!used && H[i + m * i] > bv) { bv = H[i + m * i]; best = i; } }
+        cs[j] = (double)best; theta[j] = bv;
+      }
+    }
+    DFM_SYNC();
+    // V <- V W[:, perm], Y <- Y W[:, perm]   (row by row, m x m product per row, in place via registers is too
+    // big: use S as per-thread-row staging is not possible either -> two passes through S rows in chunks)
+    for (int i = DFM_TID; i < n; i += DFM_NT) {
+      // rotate row i of V then of Y using a small local buffer in registers (m <= 64)
+      double rowv[64];
+      for (int c = 0; c < m; ++c) rowv[c] = V[i + (size_t)n * c];
+      for (int j = 0; j < m; ++j) { int pj = (int)cs[j]; double s = 0.0; for (int c = 0; c < m; ++c) s += rowv[c] * W[c + m * pj]; V[i + (size_t)n * j] = s; }
+      for (int c = 0; c < m; ++c) rowv[c] = Y[i + (size_t)n * c];
+      for (int j = 0; j < m; ++j) { int pj = (int)cs[j]; double s = 0.0; for (int c = 0; c < m; ++c) s += rowv[c] * W[c + m * pj]; Y[i + (size_t)n * j] = s; }
+    }
+    DFM_SYNC();
+    // ---- residuals of the leading r pairs
+    double rmax = 0.0;
+    for (int j = 0; j < r; ++j) {
+      double s = 0.0;
+      for (int i = DFM_TID; i < n; i += DFM_NT) { double d = Y[i + (size_t)n * j] - theta[j] * V[i + (size_t)n * j]; s += d * d; }
+      s = block_sum(s, red);
+      rmax = fmax(rmax, sqrt(s));
+    }
+    res = rmax / fabs(theta[0]);
+    if (res <= tol) { ++it; break; }
+    // next iterate: V <- Y (= G V, to be orthonormalised)
+    for (int e = DFM_TID; e < n * m; e += DFM_NT) V[e] = Y[e];
+    DFM_SYNC();
+  }
+  // ---- leave results where k_pca_finish looks for them
+  for (int i = DFM_TID; i < n; i += DFM_NT) G[i + (size_t)n * i] = (i < m) ? theta[i] : -1e300;
+  if (DFM_TID == 0 && iters_out) iters_out[b] = (res <= tol) ? it : -it;
 }
 
 // Pick the r largest eigenpairs and form scores.  grid (B), one block.

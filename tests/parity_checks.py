@@ -38,8 +38,8 @@ def check_standardize(lib, rng=None):
     assert (np.isnan(gxs) == np.isnan(xs)).all()
 
 
-def check_pca(lib, T=60, N=25, r=4):
-    for (t, n) in ((T, N), (N, T)):          # both Gram modes (X'X and XX')
+def check_pca(lib, T=60, N=25, r=4, sizes=None):
+    for (t, n) in (sizes or ((T, N), (N, T))):          # both Gram modes (X'X and XX')
         X, _ = simulate_panel(n, r, t, rep=2)
         ref = R.pca_score(X, r)
         got = lib.pca_score(X, r)

@@ -22,6 +22,7 @@ def lib():
 
 def test_standardize(lib): P.check_standardize(lib)
 def test_pca(lib): P.check_pca(lib)
+def test_pca_subspace(lib): P.check_pca(lib, r=5, sizes=((150, 90), (80, 130)))     # min(T,N) > 64 -> subspace iteration
 def test_estimate_factor_same_init(lib): P.check_estimate_factor_same_init(lib)
 def test_estimate_factor_c1(lib, panels): P.check_estimate_factor_c1(lib, panels)
 def test_constraint(lib, panels): P.check_constraint(lib, panels)

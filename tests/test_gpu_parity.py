@@ -129,3 +129,27 @@ def test_fused2_odd_T_falls_back(lib):
     with pytest.raises(DFMError):
         P.check_em(lib, N=20, r=3, T=71, p=1, path=3)
     P.check_em(lib, N=20, r=3, T=71, p=1, path=0)
+
+
+def test_pca_subspace(lib): P.check_pca(lib, r=5, sizes=((150, 90), (80, 130), (300, 200)))
+
+
+def test_c3_full_size(lib):
+    """BASELINE config C3 (N=2000, r=20, T=2000): PCA by subspace iteration vs LAPACK SVD, one ALS sweep
+    and two EM iterations of the general path vs the oracle's C port."""
+    from oracle.dgp import simulate_panel
+    from oracle.c import kem
+    from oracle import dfm_ref as R, kalman_em as K
+    N, r, T = 2000, 20, 2000
+    X, _ = simulate_panel(N, r, T, rep=0)
+    ref = R.pca_score(X, r)
+    got = lib.pca_score(X, r)
+    got, _ = P.sign_align(got, ref)
+    assert P.rmse(got, ref) < 1e-8 * np.abs(ref).max()
+    out = lib.estimate_factor(X, r, max_iter=1, compute_r2=False, F_init=ref)
+    assert out["stats"]["status"] in (0, 4)
+    Lam, Rv, A, Q = lib.em_init_from_factors(X, out["F"], 1)
+    em = lib.em_kalman(X, Lam, Rv, A, Q, p=1, max_iter=2, want_PF=False)
+    cref = kem.em_kalman_batch(X[None], Lam[None], Rv[None], A[None], Q[None], p=1, max_iter=2)
+    np.testing.assert_allclose(em["loglik"], cref["loglik"][0], rtol=1e-9)
+    assert P.rmse(em["F"], cref["F"][0]) < 1e-8
