@@ -186,6 +186,27 @@ static int launch_fused2(dfm_handle* h, const FusedArgs& fa, int B, int T, int N
   return DFM_OK;
 }
 
+template <int RT>
+static int launch_als_fused2(dfm_handle* h, const AlsFusedArgs& fa, int B, int T, int N) {
+  size_t smem = als_fused2_smem_doubles<RT>(T, N) * 8;
+  int grid = std::min(B, 148 * 8);
+#ifndef DFM_EMU
+  DFM_SET_SMEM(k_als_fused2<RT>, smem);
+  int dev = 0, nsm = 148, occ = 1;
+  cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_als_fused2<RT>, 256, smem);
+  if (occ < 1) occ = 1;
+  grid = std::min(B, nsm * occ);
+#endif
+  L(k_als_fused2<RT>, grid, 1, 256, smem, fa);
+  return DFM_OK;
+}
+static bool als_fused2_shape_ok(int T, int N, int r) {
+  if (r < 1 || r > 8 || T < 4 || (T & 1)) return false;
+  return ((size_t)FZ * pad4mod16(T) + (size_t)r * pad4mod16(N) + (size_t)N + 4 * (size_t)r * r + 2 * r + 48 +
+          2 * F2_NCW * 72 + (size_t)F2_S * 8 * F2_TS + 16) * 8 <= 113 * 1024;
+}
+
 static bool fused2_shape_ok(int T, int N, int r, int p) {
   if (p != 1 || r < 1 || r > 8 || T < 4 || (T & 1)) return false;
   size_t need = ((size_t)FZ * pad4mod16(T) + (size_t)r * pad4mod16(N) + 3 * (size_t)N + 31 * (size_t)r * r + 99 * (size_t)r +
@@ -398,6 +419,24 @@ int dfm_estimate_factor(dfm_handle* h, const double* X, const dfm_factor_opts* o
     size_t smF = ((size_t)(np + r) * ntF + 48) * 8;
     long long it = 0;
     int h_active = batch;
+    // balanced panels without constraints: all sweeps in ONE fused launch (TMA ring + DMMA passes)
+    if (nc == 0 && als_fused2_shape_ok(T, N, r) && o->nt_min <= T && !getenv("DFM_ALS_GENERAL")) {
+      std::vector<AlsState> hs(B);
+      CK(cudaMemcpyAsync(hs.data(), st, B * sizeof(AlsState), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      bool balanced = true;
+      for (size_t b = 0; b < B; ++b) if (hs[b].nobs != (long long)T * N || hs[b].status != 0) balanced = false;
+      if (balanced) {
+        AlsFusedArgs fa{}; fa.Xs = dXs; fa.F = dF; fa.Lam = dLam; fa.st = st; fa.B = batch; fa.T = T; fa.N = N; fa.tol = o->tol; fa.max_iter = o->max_iter;
+        switch (r) {
+#define DFM_CASEA(RT) case RT: rc = launch_als_fused2<RT>(h, fa, batch, T, N); break;
+          DFM_CASEA(1) DFM_CASEA(2) DFM_CASEA(3) DFM_CASEA(4) DFM_CASEA(5) DFM_CASEA(6) DFM_CASEA(7) DFM_CASEA(8)
+#undef DFM_CASEA
+        }
+        if (rc) return rc;
+        h_active = 0;
+      }
+    }
     while (it < o->max_iter && h_active > 0) {                                       // :352
       if (nc > 0) L(k_gram_small, batch, 1, 128, 0, dF, T, r, FtF, st);
       L(k_als_lambda, N, batch, 64, smL, dXs, dF, T, N, r, o->nt_min, 0, dLam, (double*)nullptr, FtF, nc, cidx, cR, cr, ds, st);   // :355-362

@@ -34,6 +34,134 @@ __device__ __forceinline__ void f2_bulk_g2s(void* dst, const void* src, uint32_t
 }
 #endif
 
+
+#ifndef DFM_EMU
+// Position in the ring (every thread keeps its own copy; all copies advance in lock step).
+struct F2Ring {
+  double* ring; uint64_t* full; uint64_t* empty;
+  int rs; uint32_t rph; bool wrap;
+  __device__ __forceinline__ void advance() { if (++rs == F2_S) { rs = 0; rph ^= 1; wrap = true; } }
+  __device__ __forceinline__ void skip(long long n) { for (long long q = 0; q < n; ++q) advance(); }
+};
+
+// Producer side of one pass (all 32 lanes of warp 0).  Items (c, sb): c_outer selects the loop order.
+__device__ __forceinline__ void f2_produce(F2Ring& rg, const double* X, int T, int N, bool c_outer) {
+  const int lane = threadIdx.x & 31;
+  const int nsb = (N + 7) / 8, nck = (T + F2_TC - 1) / F2_TC;
+  const int n_out = c_outer ? nck : nsb, n_in = c_outer ? nsb : nck;
+  for (int o = 0; o < n_out; ++o)
+    for (int i = 0; i < n_in; ++i) {
+      const int c = c_outer ? o : i, sb = c_outer ? i : o;
+      const int len = (T - c * F2_TC < F2_TC) ? T - c * F2_TC : F2_TC;
+      const int rows = (N - sb * 8 < 8) ? N - sb * 8 : 8;
+      if (rg.wrap) f2_mbar_wait(&rg.empty[rg.rs], rg.rph ^ 1);
+      if (lane == 0) f2_mbar_expect(&rg.full[rg.rs], (uint32_t)(rows * len * 8));
+      __syncwarp();
+      // lanes 0..7 issue one contiguous column run each: a single thread can only issue a bulk copy
+      // every ~100 cycles (tools/bench_stream.cu)
+      if (lane < rows)
+        f2_bulk_g2s(rg.ring + (size_t)rg.rs * 8 * F2_TS + lane * F2_TS, X + (size_t)(sb * 8 + lane) * T + c * F2_TC, (uint32_t)(len * 8), &rg.full[rg.rs]);
+      rg.advance();
+    }
+}
+
+// E pass, consumer warp cw (0..F2_NCW-1):  Z[t][:] = sum_n x[t,n] w_n Lam[n][:]  (w = rinv or 1), returns this
+// thread's share of sum x^2 w.  Period-chunk outer / series-block inner; each warp keeps the 8x8 DMMA
+// accumulators of its two row blocks in registers across all series blocks.
+template <int R>
+__device__ __forceinline__ double f2_consume_E(F2Ring& rg, int cw, int T, int N, int Tp, int Np, double* Z, const double* Lam,
+                                               const double* rinv) {
+  const int lane = threadIdx.x & 31, lr = lane >> 2, lc = lane & 3;
+  const int nsb = (N + 7) / 8, nck = (T + F2_TC - 1) / F2_TC;
+  double qacc = 0.0;
+  for (int c = 0; c < nck; ++c) {
+    const int len = (T - c * F2_TC < F2_TC) ? T - c * F2_TC : F2_TC;
+    const int tl0 = cw * 8 + lr, tl1 = (cw + F2_NCW) * 8 + lr;       // F2_TC / 8 = 2 * F2_NCW row blocks
+    const bool v0 = tl0 < len, v1 = tl1 < len;
+    double d00 = 0.0, d01 = 0.0, d10 = 0.0, d11 = 0.0;
+    for (int sb = 0; sb < nsb; ++sb) {
+      f2_mbar_wait(&rg.full[rg.rs], rg.rph);
+      const double* tile = rg.ring + (size_t)rg.rs * 8 * F2_TS;
+#pragma unroll
+      for (int kc = 0; kc < 2; ++kc) {
+        const int n = sb * 8 + kc * 4 + lc;
+        const bool nok = n < N;
+        const double rn = nok ? (rinv ? rinv[n] : 1.0) : 0.0;
+        const double lam = (nok && lr < R) ? Lam[LI(n, lr)] : 0.0;
+        const double a0 = (nok && v0) ? tile[(kc * 4 + lc) * F2_TS + tl0] : 0.0;
+        const double a1 = (nok && v1) ? tile[(kc * 4 + lc) * F2_TS + tl1] : 0.0;
+        const double ar0 = a0 * rn, ar1 = a1 * rn;
+        qacc += a0 * ar0 + a1 * ar1;
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                     : "+d"(d00), "+d"(d01) : "d"(ar0), "d"(lam));
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                     : "+d"(d10), "+d"(d11) : "d"(ar1), "d"(lam));
+      }
+      __syncwarp();
+      if (lane == 0) f2_mbar_arrive(&rg.empty[rg.rs]);
+      rg.advance();
+    }
+    if (v0) { const int t = c * F2_TC + tl0; Z[ZI(t, 2 * lc)] = d00; Z[ZI(t, 2 * lc + 1)] = d01; }
+    if (v1) { const int t = c * F2_TC + tl1; Z[ZI(t, 2 * lc)] = d10; Z[ZI(t, 2 * lc + 1)] = d11; }
+  }
+  return qacc;
+}
+
+// M pass, consumer warp cw:  Lam[n][:] <- sum_t x[t,n] Z[t][:]  (S_xf) and sxx[n] <- sum_t x[t,n]^2.
+// Series-block outer / period-chunk inner; two accumulator pairs per warp; deterministic cross-warp
+// reduction of the F2_NCW partial tiles at the end of every series block (named barrier 1).
+template <int R>
+__device__ __forceinline__ void f2_consume_M(F2Ring& rg, int cw, int T, int N, int Tp, int Np, const double* Z, double* Lam,
+                                             double* sxx, double* part) {
+  const int lane = threadIdx.x & 31, lr = lane >> 2, lc = lane & 3;
+  const int nsb = (N + 7) / 8, nck = (T + F2_TC - 1) / F2_TC;
+  double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0, s2 = 0.0;
+  for (int sb = 0; sb < nsb; ++sb)
+    for (int c = 0; c < nck; ++c) {
+      f2_mbar_wait(&rg.full[rg.rs], rg.rph);
+      const double* tile = rg.ring + (size_t)rg.rs * 8 * F2_TS;
+      const int len = (T - c * F2_TC < F2_TC) ? T - c * F2_TC : F2_TC;
+      const bool nok = sb * 8 + lr < N;
+      const double* zc = Z + (size_t)lr * Tp + c * F2_TC;
+#pragma unroll
+      for (int j = 0; j < 4; j += 2) {                           // k-chunks cw, cw+6, cw+12, cw+18 (F2_TC/4 = 4 * F2_NCW)
+        const int tla = (cw + j * F2_NCW) * 4 + lc, tlb = (cw + (j + 1) * F2_NCW) * 4 + lc;
+        const double ava = (nok && tla < len) ? tile[lr * F2_TS + tla] : 0.0;
+        const double avb = (nok && tlb < len) ? tile[lr * F2_TS + tlb] : 0.0;
+        const double bva = (tla < len) ? zc[tla] : 0.0;
+        const double bvb = (tlb < len) ? zc[tlb] : 0.0;
+        s2 += ava * ava + avb * avb;
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                     : "+d"(d0), "+d"(d1) : "d"(ava), "d"(bva));
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                     : "+d"(e0), "+d"(e1) : "d"(avb), "d"(bvb));
+      }
+      __syncwarp();
+      if (lane == 0) f2_mbar_arrive(&rg.empty[rg.rs]);
+      rg.advance();
+      if (c == nck - 1) {
+        s2 += __shfl_xor_sync(0xffffffffu, s2, 1); s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+        double* pb = part + (size_t)(sb & 1) * F2_NCW * 72 + cw * 72;
+        pb[2 * lane] = d0 + e0; pb[2 * lane + 1] = d1 + e1;
+        if (lc == 0) pb[64 + lr] = s2;
+        asm volatile("bar.sync 1, %0;" ::"n"(F2_NCW * 32) : "memory");
+        const int ct = cw * 32 + lane;                          // 0 .. F2_NCW*32-1
+        if (ct < 72) {
+          const double* pp_ = part + (size_t)(sb & 1) * F2_NCW * 72 + ct;
+          double tot_ = 0.0;
+#pragma unroll
+          for (int w_ = 0; w_ < F2_NCW; ++w_) tot_ += pp_[w_ * 72];
+          if (ct < 64) {
+            const int l_ = ct >> 1, h_ = ct & 1, row = l_ >> 2, col = 2 * (l_ & 3) + h_, n = sb * 8 + row;
+            if (n < N && col < R) Lam[LI(n, col)] = tot_;
+          } else { const int n = sb * 8 + (ct - 64); if (n < N) sxx[n] = tot_; }
+        }
+        d0 = 0.0; d1 = 0.0; e0 = 0.0; e1 = 0.0; s2 = 0.0;
+      }
+    }
+}
+#endif  // !DFM_EMU
+
 #ifdef DFM_EMU
 #define DFM_FUSED2_BOUNDS
 #else
@@ -78,8 +206,7 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a) {
   if (threadIdx.x == 0) { for (int s_ = 0; s_ < F2_S; ++s_) { f2_mbar_init(&fullb[s_], 1); f2_mbar_init(&emptyb[s_], F2_NCW); } }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
-  int rs_ = 0; uint32_t rph_ = 0; bool rwrap_ = false;   // ring position of this thread: stage, parity, "ring has wrapped"
-#define F2_ADVANCE() do { if (++rs_ == F2_S) { rs_ = 0; rph_ ^= 1; rwrap_ = true; } } while (0)
+  F2Ring rg; rg.ring = ring; rg.full = fullb; rg.empty = emptyb; rg.rs = 0; rg.rph = 0; rg.wrap = false;
 #endif
   const double eps = 1e-14;
 #ifndef DFM_EMU
@@ -127,63 +254,13 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a) {
       }
 #else
       {
-        // TMA pass.  Item q = (period chunk c, series block sb), sb fastest: a stage = 8 series x
-        // (<= F2_TC periods) of CONTIGUOUS column runs copied by cp.async.bulk (UBLKCP) into the ring.
-        // Each consumer warp owns two 8-period row blocks of the chunk and keeps their 8x8 DMMA
-        // accumulators in registers across all series blocks; Z is written once per chunk.
-        const int nsb = (N + 7) / 8, nck = (T + F2_TC - 1) / F2_TC;
-        const long long nitems = (long long)nsb * nck;
-        if (DFM_WARP == 0) {
-          // producer warp: lane 0 arms the stage barrier, lanes 0..7 issue one row copy each (a single
-          // thread can only issue a bulk copy every ~100 cycles: measured with tools/bench_stream.cu)
-          const int lane = DFM_LANE;
-          for (int c = 0; c < nck; ++c) {
-            const int len = (T - c * F2_TC < F2_TC) ? T - c * F2_TC : F2_TC;
-            for (int sb = 0; sb < nsb; ++sb) {
-              if (rwrap_) f2_mbar_wait(&emptyb[rs_], rph_ ^ 1);
-              const int rows = (N - sb * 8 < 8) ? N - sb * 8 : 8;
-              if (lane == 0) f2_mbar_expect(&fullb[rs_], (uint32_t)(rows * len * 8));
-              __syncwarp();
-              if (lane < rows)
-                f2_bulk_g2s(ring + (size_t)rs_ * 8 * F2_TS + lane * F2_TS, X + (size_t)(sb * 8 + lane) * T + c * F2_TC, (uint32_t)(len * 8), &fullb[rs_]);
-              F2_ADVANCE();
-            }
-          }
-        } else if (DFM_WARP <= F2_NCW) {
-          const int cw = DFM_WARP - 1, lane = DFM_LANE, lr = lane >> 2, lc = lane & 3;
-          for (int c = 0; c < nck; ++c) {
-            const int len = (T - c * F2_TC < F2_TC) ? T - c * F2_TC : F2_TC;
-            const int tl0 = cw * 8 + lr, tl1 = (cw + F2_NCW) * 8 + lr;       // F2_TC / 8 = 2 * F2_NCW row blocks
-            const bool v0 = tl0 < len, v1 = tl1 < len;
-            double d00 = 0.0, d01 = 0.0, d10 = 0.0, d11 = 0.0;
-            for (int sb = 0; sb < nsb; ++sb) {
-              f2_mbar_wait(&fullb[rs_], rph_);
-              const double* tile = ring + (size_t)rs_ * 8 * F2_TS;
-#pragma unroll
-              for (int kc = 0; kc < 2; ++kc) {
-                const int n = sb * 8 + kc * 4 + lc;
-                const bool nok = n < N;
-                const double rn = nok ? rinv[n] : 0.0;
-                const double lam = (nok && lr < R) ? Lam[LI(n, lr)] : 0.0;
-                const double a0 = (nok && v0) ? tile[(kc * 4 + lc) * F2_TS + tl0] : 0.0;
-                const double a1 = (nok && v1) ? tile[(kc * 4 + lc) * F2_TS + tl1] : 0.0;
-                const double ar0 = a0 * rn, ar1 = a1 * rn;
-                qacc += a0 * ar0 + a1 * ar1;
-                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                             : "+d"(d00), "+d"(d01) : "d"(ar0), "d"(lam));
-                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                             : "+d"(d10), "+d"(d11) : "d"(ar1), "d"(lam));
-              }
-              __syncwarp();
-              if (lane == 0) f2_mbar_arrive(&emptyb[rs_]);
-              F2_ADVANCE();
-            }
-            if (v0) { const int t = c * F2_TC + tl0; Z[ZI(t, 2 * lc)] = d00; Z[ZI(t, 2 * lc + 1)] = d01; }
-            if (v1) { const int t = c * F2_TC + tl1; Z[ZI(t, 2 * lc)] = d10; Z[ZI(t, 2 * lc + 1)] = d11; }
-          }
-        }
+        // TMA pass (see f2_produce / f2_consume_E): warp 0 produces, warps 1..6 consume, warp 7 runs the
+        // data-independent covariance chain concurrently
+        const long long nitems = (long long)((N + 7) / 8) * ((T + F2_TC - 1) / F2_TC);
+        if (DFM_WARP == 0) f2_produce(rg, X, T, N, /*c_outer=*/true);
+        else if (DFM_WARP <= F2_NCW) qacc += f2_consume_E<R>(rg, DFM_WARP - 1, T, N, Tp, Np, Z, Lam, rinv);
         else {
-          for (long long q = 0; q < nitems; ++q) F2_ADVANCE();             // keep the ring position in step
+          rg.skip(nitems);                                                   // keep the ring position in step
         {   // ---- covariance chain (data independent), on the chain warp, concurrently with the E pass
         int* bad = &ctl[2];
         // forward
@@ -547,71 +624,10 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a) {
         // async-proxy writes of the bulk copies
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
-        const int nsb = (N + 7) / 8, nck = (T + F2_TC - 1) / F2_TC;
-        const long long nitems = (long long)nsb * nck;
-        if (DFM_WARP == 0) {
-          const int lane = DFM_LANE;
-          for (int sb = 0; sb < nsb; ++sb) {
-            const int rows = (N - sb * 8 < 8) ? N - sb * 8 : 8;
-            for (int c = 0; c < nck; ++c) {
-              const int len = (T - c * F2_TC < F2_TC) ? T - c * F2_TC : F2_TC;
-              if (rwrap_) f2_mbar_wait(&emptyb[rs_], rph_ ^ 1);
-              if (lane == 0) f2_mbar_expect(&fullb[rs_], (uint32_t)(rows * len * 8));
-              __syncwarp();
-              if (lane < rows)
-                f2_bulk_g2s(ring + (size_t)rs_ * 8 * F2_TS + lane * F2_TS, X + (size_t)(sb * 8 + lane) * T + c * F2_TC, (uint32_t)(len * 8), &fullb[rs_]);
-              F2_ADVANCE();
-            }
-          }
-        } else if (DFM_WARP <= F2_NCW) {
-          const int cw = DFM_WARP - 1, lane = DFM_LANE, lr = lane >> 2, lc = lane & 3;
-          double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0, s2 = 0.0;       // two independent accumulator pairs
-          for (int sb = 0; sb < nsb; ++sb)
-          for (int c = 0; c < nck; ++c) {
-            f2_mbar_wait(&fullb[rs_], rph_);
-            const double* tile = ring + (size_t)rs_ * 8 * F2_TS;
-            const int len = (T - c * F2_TC < F2_TC) ? T - c * F2_TC : F2_TC;
-            const bool nok = sb * 8 + lr < N;
-            const double* zc = Z + (size_t)lr * Tp + c * F2_TC;
-#pragma unroll
-            for (int j = 0; j < 4; j += 2) {                           // k-chunks cw, cw+6, cw+12, cw+18 (F2_TC/4 = 4 * F2_NCW)
-              const int tla = (cw + j * F2_NCW) * 4 + lc, tlb = (cw + (j + 1) * F2_NCW) * 4 + lc;
-              const double ava = (nok && tla < len) ? tile[lr * F2_TS + tla] : 0.0;
-              const double avb = (nok && tlb < len) ? tile[lr * F2_TS + tlb] : 0.0;
-              const double bva = (tla < len) ? zc[tla] : 0.0;
-              const double bvb = (tlb < len) ? zc[tlb] : 0.0;
-              s2 += ava * ava + avb * avb;
-              asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                           : "+d"(d0), "+d"(d1) : "d"(ava), "d"(bva));
-              asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                           : "+d"(e0), "+d"(e1) : "d"(avb), "d"(bvb));
-            }
-            __syncwarp();
-            if (lane == 0) f2_mbar_arrive(&emptyb[rs_]);
-            F2_ADVANCE();
-            if (c == nck - 1) {
-              // series block complete: deterministic cross-warp reduction of the F2_NCW partial tiles
-              s2 += __shfl_xor_sync(0xffffffffu, s2, 1); s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
-              double* pb = part + (size_t)(sb & 1) * F2_NCW * 72 + cw * 72;
-              pb[2 * lane] = d0 + e0; pb[2 * lane + 1] = d1 + e1;
-              if (lc == 0) pb[64 + lr] = s2;
-              asm volatile("bar.sync 1, %0;" ::"n"(F2_NCW * 32) : "memory");
-              const int ct = cw * 32 + lane;                          // 0 .. F2_NCW*32-1
-              if (ct < 72) {
-                const double* pp_ = part + (size_t)(sb & 1) * F2_NCW * 72 + ct;
-                double tot_ = 0.0;
-#pragma unroll
-                for (int w_ = 0; w_ < F2_NCW; ++w_) tot_ += pp_[w_ * 72];
-                if (ct < 64) {
-                  const int l_ = ct >> 1, h_ = ct & 1, row = l_ >> 2, col = 2 * (l_ & 3) + h_, n = sb * 8 + row;
-                  if (n < N && col < R) Lam[LI(n, col)] = tot_;
-                } else { const int n = sb * 8 + (ct - 64); if (n < N) sxx[n] = tot_; }
-              }
-              d0 = 0.0; d1 = 0.0; e0 = 0.0; e1 = 0.0; s2 = 0.0;
-            }
-          }
-        }
-        else { for (long long q = 0; q < nitems; ++q) F2_ADVANCE(); }
+        const long long nitems = (long long)((N + 7) / 8) * ((T + F2_TC - 1) / F2_TC);
+        if (DFM_WARP == 0) f2_produce(rg, X, T, N, /*c_outer=*/false);
+        else if (DFM_WARP <= F2_NCW) f2_consume_M<R>(rg, DFM_WARP - 1, T, N, Tp, Np, Z, Lam, sxx, part);
+        else rg.skip(nitems);
       }
 #endif
       DFM_SYNC();
@@ -698,7 +714,147 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a) {
 #undef SCRP
 #undef GSC
 #undef GPS
-#undef F2_ADVANCE
+// ================================================================================================
+// Fused ALS kernel: the reference's least-squares "EM" (estimate_factor!, dfm_functions.ipynb:352-370)
+// for BALANCED panels without constraints, one CTA per panel, all sweeps in one launch, on the same
+// TMA ring + DMMA passes as k_em_fused2:
+//   Lambda-step (:355-362):  Lam = (X'F)(F'F)^-1        = M pass + r x r inverse
+//   F-step      (:364-365):  F   = (X Lam)(Lam'Lam)^-1  = E pass (unit weights) + r x r inverse
+//   SSR         (:366):      sum x^2 - sum_t b_t'(Lam'Lam)^-1 b_t,  b_t = Lam'x_t   (no third pass)
+//   stop        (:367-368):  |dSSR| < tol T N
+// Panels with missing data / constraints / odd T use the general kernels (k_als_lambda, k_als_factor).
+struct AlsFusedArgs {
+  const double* Xs;     // [B][N][T] standardised, no NaN
+  double* F;            // [B][T*r] column-major: in = starting factors, out = final factors
+  double* Lam;          // [B][N*r] column-major out
+  AlsState* st;         // tss / nobs already set; ssr, iters, done, status written here
+  int B, T, N;
+  double tol;
+  long long max_iter;
+};
+
+template <int R>
+__global__ void DFM_FUSED2_BOUNDS k_als_fused2(AlsFusedArgs a) {
+  DFM_SMEM(sm);
+  constexpr int RR = R * R;
+  const int T = a.T, N = a.N;
+  const int Tp = pad4mod16(T), Np = pad4mod16(N);
+  double* Z = sm;                          // [FZ][Tp]
+  double* Lam = Z + (size_t)FZ * Tp;       // [R][Np]
+  double* sxx = Lam + (size_t)R * Np;      // [N]
+  double* FtF = sxx + N;  double* Gi = FtF + RR;  double* LtL = Gi + RR;  double* Hi = LtL + RR;
+  double* tmp = Hi + RR;                   // 2R
+  double* red = tmp + 2 * R;               // 40
+  int* ctl = (int*)(red + 40);             // [0] = bad
+  double* part = red + 48;                 // 2 * F2_NCW * 72
+  double* ring = part + 2 * F2_NCW * 72;
+  ring += ((ring - sm) & 1);
+#ifndef DFM_EMU
+  __shared__ uint64_t fullb[F2_S], emptyb[F2_S];
+  if (threadIdx.x == 0) { for (int s_ = 0; s_ < F2_S; ++s_) { f2_mbar_init(&fullb[s_], 1); f2_mbar_init(&emptyb[s_], F2_NCW); } }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  F2Ring rg; rg.ring = ring; rg.full = fullb; rg.empty = emptyb; rg.rs = 0; rg.rph = 0; rg.wrap = false;
+  const long long nitems = (long long)((N + 7) / 8) * ((T + F2_TC - 1) / F2_TC);
+#endif
+  for (int b = DFM_BX; b < a.B; b += DFM_GX) {
+    const double* X = a.Xs + (size_t)b * T * N;
+    for (int e = DFM_TID; e < FZ * Tp; e += DFM_NT) Z[e] = 0.0;
+    DFM_SYNC();
+    for (int e = DFM_TID; e < T * R; e += DFM_NT) { int t = e % T, c = e / T; Z[ZI(t, c)] = a.F[(size_t)b * T * R + e]; }
+    if (DFM_TID == 0) ctl[0] = 0;
+    DFM_SYNC();
+    double ssr = 0.0, ssr_old = 0.0;
+    long long it = 0;
+    int status = 0;
+    while (it < a.max_iter) {
+      // ---------------- Lambda-step
+      for (int e = DFM_TID; e < RR; e += DFM_NT) {
+        int i = e / R, j = e % R; double s = 0.0;
+        for (int t = 0; t < T; ++t) s += Z[ZI(t, i)] * Z[ZI(t, j)];
+        FtF[e] = s;
+      }
+      DFM_SYNC();
+      if (DFM_WARP == 0) w_inv<R>(Gi, FtF, tmp, &ctl[0]);
+#ifdef DFM_EMU
+      for (int n = 0; n < N; ++n) {
+        double s2 = 0.0, acc[R];
+        for (int c = 0; c < R; ++c) acc[c] = 0.0;
+        for (int t = 0; t < T; ++t) { double x = X[(size_t)n * T + t]; s2 += x * x; for (int c = 0; c < R; ++c) acc[c] += x * Z[ZI(t, c)]; }
+        for (int c = 0; c < R; ++c) Lam[LI(n, c)] = acc[c];
+        sxx[n] = s2;
+      }
+#else
+      if (DFM_WARP == 0) f2_produce(rg, X, T, N, /*c_outer=*/false);
+      else if (DFM_WARP <= F2_NCW) f2_consume_M<R>(rg, DFM_WARP - 1, T, N, Tp, Np, Z, Lam, sxx, part);
+      else rg.skip(nitems);
+#endif
+      DFM_SYNC();
+      for (int n = DFM_TID; n < N; n += DFM_NT) {             // Lam_n = (F'F)^-1 S_xf,n
+        double sx[R], lam[R];
+#pragma unroll
+        for (int c = 0; c < R; ++c) sx[c] = Lam[LI(n, c)];
+#pragma unroll
+        for (int i = 0; i < R; ++i) { double s = 0.0;
+#pragma unroll
+          for (int j = 0; j < R; ++j) s += Gi[i * R + j] * sx[j]; lam[i] = s; }
+#pragma unroll
+        for (int c = 0; c < R; ++c) Lam[LI(n, c)] = lam[c];
+      }
+      DFM_SYNC();
+      // ---------------- F-step
+      for (int e = DFM_TID; e < RR; e += DFM_NT) {
+        int i = e / R, j = e % R; double s = 0.0;
+        for (int n = 0; n < N; ++n) s += Lam[LI(n, i)] * Lam[LI(n, j)];
+        LtL[e] = s;
+      }
+      DFM_SYNC();
+      if (DFM_WARP == 0) w_inv<R>(Hi, LtL, tmp, &ctl[0]);
+      double tssp = 0.0;
+#ifdef DFM_EMU
+      for (int t = 0; t < T; ++t) {
+        for (int c = 0; c < FZ; ++c) Z[ZI(t, c)] = 0.0;
+        for (int n = 0; n < N; ++n) { double x = X[(size_t)n * T + t]; tssp += x * x; for (int c = 0; c < R; ++c) Z[ZI(t, c)] += x * Lam[LI(n, c)]; }
+      }
+#else
+      if (DFM_WARP == 0) f2_produce(rg, X, T, N, /*c_outer=*/true);
+      else if (DFM_WARP <= F2_NCW) tssp += f2_consume_E<R>(rg, DFM_WARP - 1, T, N, Tp, Np, Z, Lam, nullptr);
+      else rg.skip(nitems);
+#endif
+      DFM_SYNC();
+      double bf = 0.0;
+      for (int t = DFM_TID; t < T; t += DFM_NT) {              // f_t = (Lam'Lam)^-1 b_t ; b_t'f_t
+        double bb[R], f[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) bb[j] = Z[ZI(t, j)];
+#pragma unroll
+        for (int i = 0; i < R; ++i) { double s = 0.0;
+#pragma unroll
+          for (int j = 0; j < R; ++j) s += Hi[i * R + j] * bb[j]; f[i] = s; bf += s * bb[i]; }
+#pragma unroll
+        for (int i = 0; i < R; ++i) Z[ZI(t, i)] = f[i];
+      }
+      bf = block_sum(bf, red);
+      tssp = block_sum(tssp, red);
+      ssr_old = ssr; ssr = tssp - bf;
+      ++it;
+      if (ctl[0]) { status = 3; break; }
+      if (!(fabs(ssr_old - ssr) >= a.tol * (double)T * (double)N)) break;            // :367-368
+      if (it >= a.max_iter) { status = 4; break; }
+    }
+    for (int e = DFM_TID; e < T * R; e += DFM_NT) { int t = e % T, c = e / T; a.F[(size_t)b * T * R + e] = Z[ZI(t, c)]; }
+    for (int e = DFM_TID; e < N * R; e += DFM_NT) { int i = e % N, c = e / N; a.Lam[(size_t)b * N * R + e] = Lam[LI(i, c)]; }
+    if (DFM_TID == 0) { a.st[b].ssr_old = ssr_old; a.st[b].ssr = ssr; a.st[b].iters = (int)it; a.st[b].done = 1; a.st[b].status = status; }
+    DFM_SYNC();
+  }
+}
+
+template <int R>
+inline size_t als_fused2_smem_doubles(int T, int N) {
+  return (size_t)FZ * pad4mod16(T) + (size_t)R * pad4mod16(N) + (size_t)N + 4 * (size_t)R * R + 2 * R + 48 +
+         2 * F2_NCW * 72 + (size_t)F2_S * 8 * F2_TS + 10;
+}
+
 template <int R>
 inline size_t fused2_smem_doubles(int T, int N) {
   return (size_t)FZ * pad4mod16(T) + (size_t)R * pad4mod16(N) + 3 * (size_t)N + 30 * (size_t)R * R + 2 * R + 40 + 8 + 8 +

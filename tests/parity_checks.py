@@ -234,6 +234,35 @@ def check_em_batch_balanced(lib, B=5, N=16, r=2, T=40, path=0):
         np.testing.assert_allclose(got["Lam"][b], ref["Lam"], rtol=1e-7, atol=1e-9)
 
 
+def check_als_balanced(lib, N=30, r=3, T=80, B=4):
+    """Balanced panels -> fused ALS kernel (one launch for all sweeps): vs the oracle, from a perturbed
+    start so that several sweeps are needed; also PCA start, iteration cap and batch."""
+    rng = np.random.default_rng(3)
+    Xb = np.stack([simulate_panel(N, r, T, rep=60 + b, standardize=False)[0] * (1 + 0.3 * b) + b for b in range(B)])
+    f0s = []
+    for b in range(B):
+        xs, _ = R.standardize_data(Xb[b])
+        f0s.append(R.pca_score(xs, r) @ (np.eye(r) + 0.3 * rng.standard_normal((r, r))) + 0.5 * rng.standard_normal((T, r)))
+    f0s = np.stack(f0s)
+    for max_iter in (1, 4, 100000):
+        got = lib.estimate_factor(Xb, r, nt_min=20, tol=1e-8, max_iter=max_iter, F_init=f0s)
+        for b in range(B):
+            m = R.DFMModel(Xb[b], np.ones(N, int), 20, 40, 1, T, 0, r, 1e-8, 4, 2)
+            R.estimate_factor(m, max_iter=max_iter, f_init=f0s[b])
+            assert got["stats"][b]["iters"] == m.fes.iters, (max_iter, b, got["stats"][b]["iters"], m.fes.iters)
+            np.testing.assert_allclose(got["F"][b], m.factor, rtol=1e-8, atol=1e-9)
+            np.testing.assert_allclose(got["Lam"][b], m.lambda_est, rtol=1e-8, atol=1e-9)
+            np.testing.assert_allclose(got["stats"][b]["ssr"], m.fes.ssr, rtol=1e-9)
+            np.testing.assert_allclose(got["stats"][b]["tss"], m.fes.tss, rtol=1e-12)
+            np.testing.assert_allclose(got["R2"][b], m.fes.R2, rtol=1e-7, atol=1e-9)
+    # PCA start (sign-aligned)
+    got = lib.estimate_factor(Xb[0], r, nt_min=20, tol=1e-8)
+    m = R.DFMModel(Xb[0], np.ones(N, int), 20, 40, 1, T, 0, r, 1e-8, 4, 2); R.estimate_factor(m)
+    assert got["stats"]["iters"] == m.fes.iters
+    F, _ = sign_align(got["F"], m.factor)
+    assert rmse(F, m.factor) < 1e-8
+
+
 def check_als_batch(lib, B=3, N=20, r=2, T=50):
     Xb = np.stack([simulate_panel(N, r, T, rep=30 + b, standardize=False)[0] for b in range(B)])
     Xb[:, 5:9, 3:8] = np.nan; Xb[1, 20:30, 0] = np.nan

@@ -33,6 +33,8 @@ def test_em_p2_missing(lib): P.check_em(lib, p=2, miss=0.12)
 def test_em_convergence_rule(lib): P.check_em_convergence_rule(lib)
 def test_em_batch(lib): P.check_em_batch(lib)
 def test_als_batch(lib): P.check_als_batch(lib)
+def test_als_balanced_fused(lib): P.check_als_balanced(lib)
+def test_als_balanced_fused_r8(lib): P.check_als_balanced(lib, N=48, r=8, T=120, B=2)
 def test_parametric_c1(lib, panels): P.check_parametric_c1(lib, panels, iters=2)
 
 

@@ -35,6 +35,8 @@ def test_em_auto_path(lib): P.check_em(lib, N=40, r=8, T=90, p=1, miss=0.0, path
 def test_em_convergence_rule(lib): P.check_em_convergence_rule(lib, path=1)
 def test_em_batch(lib): P.check_em_batch(lib, path=1)
 def test_als_batch(lib): P.check_als_batch(lib)
+def test_als_balanced_fused(lib): P.check_als_balanced(lib)
+def test_als_balanced_fused_r8(lib): P.check_als_balanced(lib, N=48, r=8, T=120, B=2)
 def test_parametric_c1(lib, panels): P.check_parametric_c1(lib, panels, iters=3)
 
 
