@@ -156,7 +156,7 @@ def main():
         dist.barrier()
         torch.cuda.synchronize()
         sys.stdout.flush(); os.dup2(saved_fd, 1); os.close(saved_fd)
-    lib = Library(device=local)
+    lib = Library(path=os.environ.get("DFM_BENCH_LIB"), device=local)      # DFM_BENCH_LIB: dev-only A/B of kernel variants
 
     B, iters, K_, W_ = args.panels, args.em_iters, args.steps, args.warmup
     k = R_ * P_; np_ = R_ * (R_ + 1) // 2

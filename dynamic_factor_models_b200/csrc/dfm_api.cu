@@ -145,6 +145,32 @@ __global__ void k_em_scan_fused(const double* __restrict__ X, const double* __re
 }
 }  // namespace dfm
 
+// [T, rows] FP64 view of a batch of column-major panels with the fused kernels' F2_TS x 8 box
+static int make_panel_tmap(dfm_handle* h, const double* X, int T, long long rows, CUtensorMap* out) {
+#ifdef DFM_EMU
+  (void)h; (void)X; (void)T; (void)rows; memset(out, 0, sizeof(*out));
+  return DFM_OK;
+#else
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr; cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p)
+      return fail(h, DFM_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+    fn = (encode_fn)p;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)T, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)T * 8};
+  cuuint32_t box[2] = {F2_TS, 8}, es[2] = {1, 1};
+  CUresult rc = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)X, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) { snprintf(h->err, sizeof(h->err), "cuTensorMapEncodeTiled failed (%d)", (int)rc); return DFM_ERR_CUDA; }
+  return DFM_OK;
+#endif
+}
+
 template <int RT>
 static int launch_fused(dfm_handle* h, const FusedArgs& fa, int B, int T, int N, double** scratch_out, Arena* arena, bool dry) {
   size_t smem = fused_smem_doubles<RT>(T, N) * 8;
@@ -182,7 +208,8 @@ static int launch_fused2(dfm_handle* h, const FusedArgs& fa, int B, int T, int N
   grid = std::min(B, nsm * occ);
 #endif
   FusedArgs a2 = fa; a2.scratch = scr;
-  L(k_em_fused2<RT>, grid, 1, 256, smem, a2);
+  CUtensorMap tm; int rc_ = make_panel_tmap(h, fa.X, T, (long long)B * N, &tm); if (rc_) return rc_;
+  L(k_em_fused2<RT>, grid, 1, 256, smem, a2, tm);
   return DFM_OK;
 }
 
@@ -198,19 +225,20 @@ static int launch_als_fused2(dfm_handle* h, const AlsFusedArgs& fa, int B, int T
   if (occ < 1) occ = 1;
   grid = std::min(B, nsm * occ);
 #endif
-  L(k_als_fused2<RT>, grid, 1, 256, smem, fa);
+  CUtensorMap tm; int rc_ = make_panel_tmap(h, fa.Xs, T, (long long)B * N, &tm); if (rc_) return rc_;
+  L(k_als_fused2<RT>, grid, 1, 256, smem, fa, tm);
   return DFM_OK;
 }
 static bool als_fused2_shape_ok(int T, int N, int r) {
   if (r < 1 || r > 8 || T < 4 || (T & 1)) return false;
   return ((size_t)FZ * pad4mod16(T) + (size_t)r * pad4mod16(N) + (size_t)N + 4 * (size_t)r * r + 2 * r + 48 +
-          2 * F2_NCW * 72 + (size_t)F2_S * 8 * F2_TS + 16) * 8 <= 113 * 1024;
+          2 * F2_NCW * 72 + (size_t)F2_S * 8 * F2_TS + 32) * 8 <= 113 * 1024;
 }
 
 static bool fused2_shape_ok(int T, int N, int r, int p) {
   if (p != 1 || r < 1 || r > 8 || T < 4 || (T & 1)) return false;
-  size_t need = ((size_t)FZ * pad4mod16(T) + (size_t)r * pad4mod16(N) + 3 * (size_t)N + 31 * (size_t)r * r + 99 * (size_t)r +
-                 2 * F2_NCW * 72 + (size_t)F2_S * 8 * F2_TS + 90) * 8;
+  size_t need = ((size_t)FZ * pad4mod16(T) + (size_t)r * pad4mod16(N) + 3 * (size_t)N + 30 * (size_t)r * r + 2 * (size_t)r +
+                 std::max((size_t)97 * r + (size_t)r * r, (size_t)2 * F2_NCW * 72) + (size_t)F2_S * 8 * F2_TS + 106) * 8;
   return need <= 113 * 1024;          // two CTAs per SM
 }
 

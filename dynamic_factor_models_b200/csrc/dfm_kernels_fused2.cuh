@@ -11,13 +11,27 @@
 //    (no dependent global-memory round trips on the serial path).
 // Requires T even (16-byte aligned column runs); otherwise dfm_em_kalman uses k_em_fused.
 #pragma once
+#include <algorithm>
 #include "dfm_kernels_fused.cuh"
+#ifdef DFM_EMU
+struct CUtensorMap { char opaque[128]; };
+#define DFM_GRID_CONSTANT
+#else
+#include <cuda.h>          // CUtensorMap (types only; the encoder is fetched with cudaGetDriverEntryPoint)
+#define DFM_GRID_CONSTANT __grid_constant__
+#endif
 
 namespace dfm {
 
-#define F2_S 5          // ring stages
+#ifndef F2_S
+#define F2_S 6          // ring stages
+#endif
 #define F2_TC 96        // periods per stage (12 DMMA row blocks / 24 k-chunks per stage)
 #define F2_TS 100       // row stride in the ring (== 4 mod 16: conflict-free fragments)
+#ifndef F2_PF
+#define F2_PF 0
+#endif
+// F2_PF: L2 prefetch distance (stages), 0 = off:        // L2 prefetch distance (stages)
 #define F2_NCW 6        // consumer warps (warps 1..6; warp 0 = producer, warp 7 idles during the passes)
 #define F2_NEXS(R_) ((F2_S * 8 * F2_TS) / FUSED_SCR(R_))
 
@@ -28,6 +42,14 @@ __device__ __forceinline__ void f2_mbar_expect(uint64_t* bar, uint32_t bytes) { 
 __device__ __forceinline__ void f2_mbar_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(f2_smem_u32(bar)) : "memory"); }
 __device__ __forceinline__ void f2_mbar_wait(uint64_t* bar, uint32_t phase) {
   asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(f2_smem_u32(bar)), "r"(phase) : "memory");
+}
+__device__ __forceinline__ void f2_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+// one 2-D tensor-map copy (SASS UTMALDG): box F2_TS periods x 8 series of the [T, B*N] view of the batch
+__device__ __forceinline__ void f2_tma_2d(void* dst, const CUtensorMap* tmap, int x, int y, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(f2_smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(x), "r"(y), "r"(f2_smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void f2_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(f2_smem_u32(dst)), "l"(src), "r"(bytes), "r"(f2_smem_u32(bar)) : "memory");
@@ -44,23 +66,25 @@ struct F2Ring {
   __device__ __forceinline__ void skip(long long n) { for (long long q = 0; q < n; ++q) advance(); }
 };
 
-// Producer side of one pass (all 32 lanes of warp 0).  Items (c, sb): c_outer selects the loop order.
-__device__ __forceinline__ void f2_produce(F2Ring& rg, const double* X, int T, int N, bool c_outer) {
+// Producer side of one pass (warp 0).  Items (c, sb): c_outer selects the loop order.  ONE request per
+// stage: a 2-D tensor-map copy of the box [F2_TS periods x 8 series] at (c*F2_TC, row0 + sb*8) of the
+// [T, B*N] view of the batch (column runs of 800 B; the box is 4 periods wider than the chunk so that the
+// dense row pitch in shared memory is == 4 mod 16, i.e. conflict-free; rows/periods beyond the tensor are
+// zero-filled, rows of the next panel are masked by the consumers).  Eight 1-D bulk copies per stage were
+// issue-bound (~115 cycles per request, serialised over the lanes of a warp: tools/bench_stream.cu).
+__device__ __forceinline__ void f2_produce(F2Ring& rg, const CUtensorMap* tmap, int row0, int T, int N, bool c_outer) {
   const int lane = threadIdx.x & 31;
   const int nsb = (N + 7) / 8, nck = (T + F2_TC - 1) / F2_TC;
   const int n_out = c_outer ? nck : nsb, n_in = c_outer ? nsb : nck;
   for (int o = 0; o < n_out; ++o)
     for (int i = 0; i < n_in; ++i) {
       const int c = c_outer ? o : i, sb = c_outer ? i : o;
-      const int len = (T - c * F2_TC < F2_TC) ? T - c * F2_TC : F2_TC;
-      const int rows = (N - sb * 8 < 8) ? N - sb * 8 : 8;
       if (rg.wrap) f2_mbar_wait(&rg.empty[rg.rs], rg.rph ^ 1);
-      if (lane == 0) f2_mbar_expect(&rg.full[rg.rs], (uint32_t)(rows * len * 8));
+      if (lane == 0) {
+        f2_mbar_expect(&rg.full[rg.rs], (uint32_t)(8 * F2_TS * 8));
+        f2_tma_2d(rg.ring + (size_t)rg.rs * 8 * F2_TS, tmap, c * F2_TC, row0 + sb * 8, &rg.full[rg.rs]);
+      }
       __syncwarp();
-      // lanes 0..7 issue one contiguous column run each: a single thread can only issue a bulk copy
-      // every ~100 cycles (tools/bench_stream.cu)
-      if (lane < rows)
-        f2_bulk_g2s(rg.ring + (size_t)rg.rs * 8 * F2_TS + lane * F2_TS, X + (size_t)(sb * 8 + lane) * T + c * F2_TC, (uint32_t)(len * 8), &rg.full[rg.rs]);
       rg.advance();
     }
 }
@@ -168,7 +192,7 @@ __device__ __forceinline__ void f2_consume_M(F2Ring& rg, int cw, int T, int N, i
 #define DFM_FUSED2_BOUNDS __launch_bounds__(256, 2)
 #endif
 template <int R>
-__global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a) {
+__global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTANT CUtensorMap tmap) {
   DFM_SMEM(sm);
   constexpr int RR = R * R, NP = R * (R + 1) / 2;
   const int T = a.T, N = a.N;
@@ -192,9 +216,12 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a) {
   double* scal = red + 40;                 // 8: [0]=slr [1]=ld_inf [2]=qsum
   int* ctl = (int*)(scal + 8);             // [0]=nE [1]=tb [2]=bad [3]=frozen
   double* bnd = scal + 16;                 // (3*32+1) R + RR: blk_recur workspace for 32 groups
-  double* part = bnd + (size_t)97 * R + RR;          // [2][F2_NCW][72] M-pass partial accumulators
-  double* ring = part + 2 * F2_NCW * 72;             // F2_S stages x 8 x F2_TS
-  ring += ((ring - sm) & 1);                         // bulk copies need 16-byte aligned destinations
+  double* part = bnd;                                // [2][F2_NCW][72] M-pass partial accumulators: ALIASES the scan
+                                                     // workspace (used only inside the M pass / only in P3, P5)
+  double* ring = bnd + (((size_t)97 * R + RR > 2 * F2_NCW * 72) ? (size_t)97 * R + RR : 2 * F2_NCW * 72);   // F2_S stages x 8 x F2_TS
+#ifndef DFM_EMU
+  ring += ((128u - (f2_smem_u32(ring) & 127u)) & 127u) / 8;      // tensor-map copies need 128-byte aligned destinations
+#endif
   double* gscr = a.scratch + (size_t)DFM_BX * T * FUSED_SCR(R);
   // per explicit step t: SCRP(t)[{0:Pf, RR:Phi, 2RR:J, 3RR:W, 4RR:Ps, 5RR: ld}]; the first F2_NEXS(R)
   // steps live in the (idle between the two passes) ring, the rest in global scratch
@@ -257,7 +284,7 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a) {
         // TMA pass (see f2_produce / f2_consume_E): warp 0 produces, warps 1..6 consume, warp 7 runs the
         // data-independent covariance chain concurrently
         const long long nitems = (long long)((N + 7) / 8) * ((T + F2_TC - 1) / F2_TC);
-        if (DFM_WARP == 0) f2_produce(rg, X, T, N, /*c_outer=*/true);
+        if (DFM_WARP == 0) f2_produce(rg, &tmap, b * N, T, N, /*c_outer=*/true);
         else if (DFM_WARP <= F2_NCW) qacc += f2_consume_E<R>(rg, DFM_WARP - 1, T, N, Tp, Np, Z, Lam, rinv);
         else {
           rg.skip(nitems);                                                   // keep the ring position in step
@@ -625,7 +652,7 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
         const long long nitems = (long long)((N + 7) / 8) * ((T + F2_TC - 1) / F2_TC);
-        if (DFM_WARP == 0) f2_produce(rg, X, T, N, /*c_outer=*/false);
+        if (DFM_WARP == 0) f2_produce(rg, &tmap, b * N, T, N, /*c_outer=*/false);
         else if (DFM_WARP <= F2_NCW) f2_consume_M<R>(rg, DFM_WARP - 1, T, N, Tp, Np, Z, Lam, sxx, part);
         else rg.skip(nitems);
       }
@@ -734,7 +761,7 @@ struct AlsFusedArgs {
 };
 
 template <int R>
-__global__ void DFM_FUSED2_BOUNDS k_als_fused2(AlsFusedArgs a) {
+__global__ void DFM_FUSED2_BOUNDS k_als_fused2(AlsFusedArgs a, const DFM_GRID_CONSTANT CUtensorMap tmap) {
   DFM_SMEM(sm);
   constexpr int RR = R * R;
   const int T = a.T, N = a.N;
@@ -748,8 +775,8 @@ __global__ void DFM_FUSED2_BOUNDS k_als_fused2(AlsFusedArgs a) {
   int* ctl = (int*)(red + 40);             // [0] = bad
   double* part = red + 48;                 // 2 * F2_NCW * 72
   double* ring = part + 2 * F2_NCW * 72;
-  ring += ((ring - sm) & 1);
 #ifndef DFM_EMU
+  ring += ((128u - (f2_smem_u32(ring) & 127u)) & 127u) / 8;
   __shared__ uint64_t fullb[F2_S], emptyb[F2_S];
   if (threadIdx.x == 0) { for (int s_ = 0; s_ < F2_S; ++s_) { f2_mbar_init(&fullb[s_], 1); f2_mbar_init(&emptyb[s_], F2_NCW); } }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -785,7 +812,7 @@ __global__ void DFM_FUSED2_BOUNDS k_als_fused2(AlsFusedArgs a) {
         sxx[n] = s2;
       }
 #else
-      if (DFM_WARP == 0) f2_produce(rg, X, T, N, /*c_outer=*/false);
+      if (DFM_WARP == 0) f2_produce(rg, &tmap, b * N, T, N, /*c_outer=*/false);
       else if (DFM_WARP <= F2_NCW) f2_consume_M<R>(rg, DFM_WARP - 1, T, N, Tp, Np, Z, Lam, sxx, part);
       else rg.skip(nitems);
 #endif
@@ -817,7 +844,7 @@ __global__ void DFM_FUSED2_BOUNDS k_als_fused2(AlsFusedArgs a) {
         for (int n = 0; n < N; ++n) { double x = X[(size_t)n * T + t]; tssp += x * x; for (int c = 0; c < R; ++c) Z[ZI(t, c)] += x * Lam[LI(n, c)]; }
       }
 #else
-      if (DFM_WARP == 0) f2_produce(rg, X, T, N, /*c_outer=*/true);
+      if (DFM_WARP == 0) f2_produce(rg, &tmap, b * N, T, N, /*c_outer=*/true);
       else if (DFM_WARP <= F2_NCW) tssp += f2_consume_E<R>(rg, DFM_WARP - 1, T, N, Tp, Np, Z, Lam, nullptr);
       else rg.skip(nitems);
 #endif
@@ -852,13 +879,13 @@ __global__ void DFM_FUSED2_BOUNDS k_als_fused2(AlsFusedArgs a) {
 template <int R>
 inline size_t als_fused2_smem_doubles(int T, int N) {
   return (size_t)FZ * pad4mod16(T) + (size_t)R * pad4mod16(N) + (size_t)N + 4 * (size_t)R * R + 2 * R + 48 +
-         2 * F2_NCW * 72 + (size_t)F2_S * 8 * F2_TS + 10;
+         2 * F2_NCW * 72 + (size_t)F2_S * 8 * F2_TS + 26;
 }
 
 template <int R>
 inline size_t fused2_smem_doubles(int T, int N) {
   return (size_t)FZ * pad4mod16(T) + (size_t)R * pad4mod16(N) + 3 * (size_t)N + 30 * (size_t)R * R + 2 * R + 40 + 8 + 8 +
-         (size_t)97 * R + (size_t)R * R + 2 * F2_NCW * 72 + (size_t)F2_S * 8 * F2_TS + 10;
+         std::max((size_t)97 * R + (size_t)R * R, (size_t)2 * F2_NCW * 72) + (size_t)F2_S * 8 * F2_TS + 26;
 }
 
 }  // namespace dfm

@@ -168,6 +168,58 @@ __global__ void __launch_bounds__(128, 3) k_m_tma(const double* __restrict__ Xal
   if (acc == 1.2345) out[0] = acc;
 }
 
+
+// ---- producer-issue experiment: 256 threads; the 8 row copies of a stage are issued by
+//   MODE 0: lane 0 of warp 0 (serial)   MODE 1: lanes 0..7 of warp 0   MODE 2: lane 0 of warps 0..NPW-1 (rows strided)
+template <int S, int MODE, int NPW>
+__global__ void __launch_bounds__(256, 2) k_m_tma2(const double* __restrict__ Xall, int B, double* out) {
+  extern __shared__ __align__(128) double sm[];
+  double* ring = sm; double* zb = sm + S * 8 * TS;
+  __shared__ uint64_t full[S], empty[S];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, lr = lane >> 2, lc = lane & 3;
+  constexpr int NPROD = (MODE == 2) ? NPW : 1;
+  constexpr int NCONS = 8 - NPROD;
+  if (threadIdx.x == 0) { for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCONS); } }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  const int per_panel = (N / 8) * (T / TC);
+  long long nitems = 0;
+  for (int b = blockIdx.x; b < B; b += gridDim.x) nitems += per_panel;
+  double acc = 0;
+  if (w < NPROD) {
+    long long it = 0;
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+      const double* X = Xall + (size_t)b * T * N;
+      for (int item = 0; item < per_panel; ++item, ++it) {
+        int s = it % S; uint32_t ph = (it / S) & 1;
+        if (it >= S) mbar_wait(&empty[s], ph ^ 1);
+        int sb = item / (T / TC), c = item % (T / TC);
+        if (w == 0 && lane == 0) mbar_expect(&full[s], 8 * TC * 8);
+        __syncwarp();
+        if (MODE == 0) { if (lane == 0) for (int r = 0; r < 8; ++r) bulk_g2s(ring + (size_t)s * 8 * TS + r * TS, X + (size_t)(sb * 8 + r) * T + c * TC, TC * 8, &full[s]); }
+        else if (MODE == 1) { if (lane < 8) bulk_g2s(ring + (size_t)s * 8 * TS + lane * TS, X + (size_t)(sb * 8 + lane) * T + c * TC, TC * 8, &full[s]); }
+        else { if (lane == 0) for (int r = w; r < 8; r += NPROD) bulk_g2s(ring + (size_t)s * 8 * TS + r * TS, X + (size_t)(sb * 8 + r) * T + c * TC, TC * 8, &full[s]); }
+      }
+    }
+  } else {
+    const int cw = w - NPROD;
+    double d0 = 0, d1 = 0, e0 = 0, e1 = 0;
+    for (long long it = 0; it < nitems; ++it) {
+      int s = it % S; uint32_t ph = (it / S) & 1;
+      mbar_wait(&full[s], ph);
+      const double* tile = ring + (size_t)s * 8 * TS;
+      for (int kc = cw; kc < TC / 4; kc += 2 * NCONS) {
+        dmma(d0, d1, tile[lr * TS + kc * 4 + lc], zb[(kc * 4 + lc) * 8 + lr]);
+        if (kc + NCONS < TC / 4) dmma(e0, e1, tile[lr * TS + (kc + NCONS) * 4 + lc], zb[((kc + NCONS) * 4 + lc) * 8 + lr]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+    }
+    acc = d0 + d1 + e0 + e1;
+  }
+  if (acc == 1.2345) out[0] = acc;
+}
+
 template <typename F>
 void run(const char* name, F launch, double bytes) {
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -202,5 +254,16 @@ int main() {
   run("E ldg8 U=25 grid296", [&] { k_e<25, false><<<296, 128, smem>>>(X, B, out); }, bytes);
   run("M TMA S=8 grid296", [&] { k_m_tma<8><<<296, 128, smem>>>(X, B, out); }, bytes);
   run("copy 16B U=8 grid296", [&] { k_copy<8><<<296, 128, smem>>>(X, B, out); }, bytes);
+  {
+    const int smem2 = 110 * 1024;
+#define SET2(k) CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2))
+    SET2((k_m_tma2<5, 0, 1>)); SET2((k_m_tma2<5, 1, 1>)); SET2((k_m_tma2<5, 2, 2>)); SET2((k_m_tma2<5, 2, 4>)); SET2((k_m_tma2<10, 1, 1>)); SET2((k_m_tma2<10, 2, 4>));
+    run("256thr 2/SM S=5  1 lane x 8 copies", [&] { k_m_tma2<5, 0, 1><<<296, 256, smem2>>>(X, B, out); }, bytes);
+    run("256thr 2/SM S=5  8 lanes of one warp", [&] { k_m_tma2<5, 1, 1><<<296, 256, smem2>>>(X, B, out); }, bytes);
+    run("256thr 2/SM S=5  lane0 of 2 warps", [&] { k_m_tma2<5, 2, 2><<<296, 256, smem2>>>(X, B, out); }, bytes);
+    run("256thr 2/SM S=5  lane0 of 4 warps", [&] { k_m_tma2<5, 2, 4><<<296, 256, smem2>>>(X, B, out); }, bytes);
+    run("256thr 2/SM S=10 8 lanes of one warp", [&] { k_m_tma2<10, 1, 1><<<296, 256, smem2>>>(X, B, out); }, bytes);
+    run("256thr 2/SM S=10 lane0 of 4 warps", [&] { k_m_tma2<10, 2, 4><<<296, 256, smem2>>>(X, B, out); }, bytes);
+  }
   return 0;
 }
