@@ -260,11 +260,18 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
       for (int i = DFM_TID; i < N; i += DFM_NT) { double rv = Rv[i]; rinv[i] = 1.0 / rv; slr_p += log(rv); if (!(rv > 0.0)) ctl[2] = 1; }
       slr_p = block_sum(slr_p, red);
       if (DFM_TID == 0) scal[0] = slr_p;
-      for (int e = DFM_TID; e < RR; e += DFM_NT) {
-        int i = e / R, j = e % R;
-        double s = 0.0;
-        for (int n = 0; n < N; ++n) s += Lam[LI(n, i)] * rinv[n] * Lam[LI(n, j)];
-        C[e] = s;
+      DFM_SYNC();
+      {   // C = Lam' R^-1 Lam: RR outputs x (NT / RR) slices of the series range, combined in fixed order
+        const int nsl = (DFM_NT >= 4 * RR) ? 4 : 1;
+        for (int e = DFM_TID; e < nsl * RR; e += DFM_NT) {
+          int sl = e / RR, ee = e % RR, i = ee / R, j = ee % R;
+          int n0 = (int)((long long)N * sl / nsl), n1 = (int)((long long)N * (sl + 1) / nsl);
+          double s = 0.0;
+          for (int n = n0; n < n1; ++n) s += Lam[LI(n, i)] * rinv[n] * Lam[LI(n, j)];
+          T1[sl * RR + ee] = s;                    // T1, T2, Ps, Psn are contiguous scratch matrices
+        }
+        DFM_SYNC();
+        for (int e = DFM_TID; e < RR; e += DFM_NT) { double s = 0.0; for (int sl = 0; sl < nsl; ++sl) s += T1[sl * RR + e]; C[e] = s; }
       }
       DFM_SYNC();
       DFM_TICK(1);
@@ -627,14 +634,6 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
       }
       DFM_SYNC();
       DFM_TICK(6);
-      // ---------------------------------------------------------------- P7: mean parts of the moment sums
-      for (int e = DFM_TID; e < 2 * RR; e += DFM_NT) {
-        int which = e / RR, ee = e % RR, i = ee / R, j = ee % R;
-        double s = 0.0;
-        if (which == 0) { for (int t = 0; t < T; ++t) s += Z[ZI(t, i)] * Z[ZI(t, j)]; Sm[ee] = s; }
-        else { for (int t = 1; t < T; ++t) s += Z[ZI(t, i)] * Z[ZI(t - 1, j)]; S11m[ee] = s; }
-      }
-      DFM_SYNC();
       DFM_TICK(7);
       // ---------------------------------------------------------------- P8: M-step contraction (panel pass 2)
 #ifdef DFM_EMU
@@ -654,14 +653,22 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
         const long long nitems = (long long)((N + 7) / 8) * ((T + F2_TC - 1) / F2_TC);
         if (DFM_WARP == 0) f2_produce(rg, &tmap, b * N, T, N, /*c_outer=*/false);
         else if (DFM_WARP <= F2_NCW) f2_consume_M<R>(rg, DFM_WARP - 1, T, N, Tp, Np, Z, Lam, sxx, part);
-        else rg.skip(nitems);
-      }
-#endif
-      DFM_SYNC();
-      DFM_TICK(8);
-      // ---------------------------------------------------------------- P9: M-step solves
-      if (DFM_WARP == 0) {
+        else {
+          rg.skip(nitems);
+        {   // ---- moment sums + M-step r x r solves (all inputs are ready before the M pass): on the idle
+            // warp, concurrently with the pass
         int* bad = &ctl[2];
+        // mean parts of the moment sums (needs only the smoothed means in Z)
+        for (int e = DFM_LANE; e < 2 * RR; e += DFM_WSZ) {
+          int which = e / RR, ee = e % RR, i = ee / R, j = ee % R;
+          double s0 = 0.0, s1 = 0.0;
+          if (which == 0) { for (int t = 0; t + 1 < T; t += 2) { s0 += Z[ZI(t, i)] * Z[ZI(t, j)]; s1 += Z[ZI(t + 1, i)] * Z[ZI(t + 1, j)]; }
+                            if (T & 1) s0 += Z[ZI(T - 1, i)] * Z[ZI(T - 1, j)]; Sm[ee] = s0 + s1; }
+          else { for (int t = 1; t + 1 < T; t += 2) { s0 += Z[ZI(t, i)] * Z[ZI(t - 1, j)]; s1 += Z[ZI(t + 1, i)] * Z[ZI(t, j)]; }
+                 if (!(T & 1)) s0 += Z[ZI(T - 1, i)] * Z[ZI(T - 2, j)]; S11m[ee] = s0 + s1; }
+        }
+        DFM_WSYNC();
+
         // measurement: S = SffAll;  Lam_i = S^-1 Sxf_i
         for (int e = DFM_LANE; e < RR; e += DFM_WSZ) T1[e] = Sm[e] + SPall[e];
         DFM_WSYNC();
@@ -683,6 +690,49 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
         DFM_WSYNC();
         w_sym<R>(Pn);                                              // Q_new
       }
+        }
+      }
+#endif
+#ifdef DFM_EMU
+        {   // ---- moment sums + M-step r x r solves (all inputs are ready before the M pass): on the idle
+            // warp, concurrently with the pass
+        int* bad = &ctl[2];
+        // mean parts of the moment sums (needs only the smoothed means in Z)
+        for (int e = DFM_LANE; e < 2 * RR; e += DFM_WSZ) {
+          int which = e / RR, ee = e % RR, i = ee / R, j = ee % R;
+          double s0 = 0.0, s1 = 0.0;
+          if (which == 0) { for (int t = 0; t + 1 < T; t += 2) { s0 += Z[ZI(t, i)] * Z[ZI(t, j)]; s1 += Z[ZI(t + 1, i)] * Z[ZI(t + 1, j)]; }
+                            if (T & 1) s0 += Z[ZI(T - 1, i)] * Z[ZI(T - 1, j)]; Sm[ee] = s0 + s1; }
+          else { for (int t = 1; t + 1 < T; t += 2) { s0 += Z[ZI(t, i)] * Z[ZI(t - 1, j)]; s1 += Z[ZI(t + 1, i)] * Z[ZI(t, j)]; }
+                 if (!(T & 1)) s0 += Z[ZI(T - 1, i)] * Z[ZI(T - 2, j)]; S11m[ee] = s0 + s1; }
+        }
+        DFM_WSYNC();
+
+        // measurement: S = SffAll;  Lam_i = S^-1 Sxf_i
+        for (int e = DFM_LANE; e < RR; e += DFM_WSZ) T1[e] = Sm[e] + SPall[e];
+        DFM_WSYNC();
+        w_sym<R>(T1);
+        w_inv<R>(G, T1, tmp, bad);                                 // G = S^-1, T1 = S
+        // transition: A = S11 S00^-1 ; Q = (Sff2 - A S11') / (T-1)
+        for (int e = DFM_LANE; e < RR; e += DFM_WSZ) {
+          int i = e / R, j = e % R;
+          Pp[e] = Sm[e] - Z[ZI(T - 1, i)] * Z[ZI(T - 1, j)] + SP00[e];        // S00
+          Pi[e] = Sm[e] - Z[ZI(0, i)] * Z[ZI(0, j)] + SPff2[e];                    // Sff2
+          Pf[e] = S11m[e] + SP11[e];                                                    // S11
+        }
+        DFM_WSYNC();
+        w_sym<R>(Pp);
+        w_inv<R>(Wm, Pp, tmp, bad);
+        w_gemm<R>(Phi, Pf, false, Wm, false);                      // A_new
+        w_gemm<R>(Pn, Phi, false, Pf, true);                       // A S11'
+        for (int e = DFM_LANE; e < RR; e += DFM_WSZ) Pn[e] = (Pi[e] - Pn[e]) / (double)(T - 1);
+        DFM_WSYNC();
+        w_sym<R>(Pn);                                              // Q_new
+      }
+#endif
+      DFM_SYNC();
+      DFM_TICK(8);
+      // ---------------------------------------------------------------- P9: M-step solves
       DFM_SYNC();
       for (int n = DFM_TID; n < N; n += DFM_NT) {
         double sx[R], lam[R];
