@@ -46,6 +46,7 @@ struct ProfRec { const char* name;
 struct dfm_handle {
   int device;
   cudaStream_t stream;
+  cudaStream_t copy_stream;    // second stream: H2D/D2H of chunk k+1 / k-1 overlap the kernels of chunk k
   bool own_stream;
   char* ws;
   size_t ws_bytes;
@@ -193,6 +194,33 @@ static int launch_fused(dfm_handle* h, const FusedArgs& fa, int B, int T, int N,
   return DFM_OK;
 }
 
+// General multi-kernel EM path on device-resident data (any r, p, missing data).
+static int run_em_general(dfm_handle* h, const double* x, const dfm_em_opts* o, double* dL, double* dR, double* dA, double* dQ, double* dP0,
+                          double* dAn, double* dQn, double* dW, double* dlogR, double* dC, double* dBt, double* dqt, double* dslr, int* dnt,
+                          double* dCt, double* dzp, double* dzf, double* dPp, double* dPf, double* dFs, double* dPsF, double* dSff, double* dll,
+                          EmState* st, int* dit, int* dstat, int* active, int ntC, int nblkC, size_t smFS) {
+  int T = o->T, N = o->N, r = o->r, p = o->p, batch = o->batch, mi = o->max_iter;
+  int np = r * (r + 1) / 2;
+  L(k_em_state_init, batch, 1, 1, 0, st);
+  L(k_em_scan, N, batch, 64, 0, x, dL, T, N, r, st);
+  L(k_em_prep, batch, 1, 128, 0, dL, dR, N, r, p, dW, dlogR, dC, dA, dAn, dQ, dQn, st, mi, 0);
+  int h_active = batch;
+  for (int it = 0; it < mi && h_active > 0; ++it) {
+    L(k_em_contract, nblkC, batch, ntC, ((size_t)(np + r) * ntC + 8) * 8, x, dL, dW, dR, dlogR, dC, T, N, r, dBt, dqt, dslr, dnt, dCt, st);
+    L(k_em_filter_smooth, batch, 1, 128, smFS, dA, dQ, dP0, dC, dBt, dqt, dslr, dnt, dCt, T, r, p, dzp, dzf, dPp, dPf,
+      dFs, dPsF, dSff, dAn, dQn, dll, mi, o->tol, st);
+    L(k_em_mstep_series, N, batch, 64, (size_t)(2 * np + r + 8) * 8, x, dFs, dPsF, dSff, T, N, r, dL, dR, st);
+    L(k_em_prep, batch, 1, 128, 0, dL, dR, N, r, p, dW, dlogR, dC, dA, dAn, dQ, dQn, st, mi, 1);
+    if (o->tol > 0 && ((it & 3) == 3)) {
+      L(k_em_count_active, 1, 1, 128, 48 * 8, st, batch, active);
+      CK(cudaMemcpyAsync(&h_active, active, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+    }
+  }
+  L(k_em_collect, batch, 1, 1, 0, st, dit, dstat);
+  return DFM_OK;
+}
+
 template <int RT>
 static int launch_fused2(dfm_handle* h, const FusedArgs& fa, int B, int T, int N, Arena* arena, bool dry) {
   size_t smem = fused2_smem_doubles<RT>(T, N) * 8;
@@ -235,6 +263,28 @@ static bool als_fused2_shape_ok(int T, int N, int r) {
           2 * F2_NCW * 72 + (size_t)F2_S * 8 * F2_TS + 32) * 8 <= 113 * 1024;
 }
 
+// resident CTAs (= panels processed concurrently) of the TMA fused EM kernel
+template <int RT> static int fused2_capacity_t(int T, int N) {
+#ifdef DFM_EMU
+  (void)T; (void)N; return 4;
+#else
+  size_t smem = fused2_smem_doubles<RT>(T, N) * 8;
+  DFM_SET_SMEM(k_em_fused2<RT>, smem);
+  int dev = 0, nsm = 148, occ = 1;
+  cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_em_fused2<RT>, 256, smem);
+  return nsm * (occ < 1 ? 1 : occ);
+#endif
+}
+static int fused2_capacity(int r, int T, int N) {
+  switch (r) {
+#define DFM_CASEC(RT) case RT: return fused2_capacity_t<RT>(T, N);
+    DFM_CASEC(1) DFM_CASEC(2) DFM_CASEC(3) DFM_CASEC(4) DFM_CASEC(5) DFM_CASEC(6) DFM_CASEC(7) DFM_CASEC(8)
+#undef DFM_CASEC
+  }
+  return 1;
+}
+
 static bool fused2_shape_ok(int T, int N, int r, int p) {
   if (p != 1 || r < 1 || r > 8 || T < 4 || (T & 1)) return false;
   size_t need = ((size_t)FZ * pad4mod16(T) + (size_t)r * pad4mod16(N) + 3 * (size_t)N + 30 * (size_t)r * r + 2 * (size_t)r +
@@ -275,6 +325,10 @@ int dfm_create_on_stream(int device, void* cuda_stream, dfm_handle** out) {
   if (!h) return DFM_ERR_CUDA;
   h->device = device; h->ws = nullptr; h->ws_bytes = 0; h->launches = 0; h->err[0] = 0;
   h->profile = 0; h->prof = new std::vector<ProfRec>();
+  h->copy_stream = nullptr;
+#ifndef DFM_EMU
+  if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete h->prof; delete h; return DFM_ERR_CUDA; }
+#endif
   if (cuda_stream) { h->stream = (cudaStream_t)cuda_stream; h->own_stream = false; }
   else { if (cudaStreamCreate(&h->stream) != cudaSuccess) { delete h; return DFM_ERR_CUDA; } h->own_stream = true; }
   DFM_SET_SMEM(k_em_filter_smooth, kMaxSmem); DFM_SET_SMEM(k_als_factor, kMaxSmem); DFM_SET_SMEM(k_em_contract, kMaxSmem);
@@ -292,6 +346,9 @@ int dfm_destroy(dfm_handle* h) {
   cudaStreamSynchronize(h->stream);
   if (h->ws) cudaFree(h->ws);
   if (h->own_stream) cudaStreamDestroy(h->stream);
+#ifndef DFM_EMU
+  if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+#endif
   delete h->prof;
   delete h;
   return DFM_OK;
@@ -681,7 +738,88 @@ int dfm_em_kalman(dfm_handle* h, const double* X, const dfm_em_opts* o, const df
       dPp = a.get<double>(B * T * kk); dPf = a.get<double>(B * T * kk); dSff = a.get<double>(B * rr);
     }
     if (!pass) { int rc = ensure_ws(h, a.off); if (rc) return rc; continue; }
-    const double* x; int rc = stage_in(h, X, dXb, B * TN, mem, &x); if (rc) return rc;
+    int rc = DFM_OK;
+    bool computed = false;                // set when the pipelined branch already produced device results via the general path
+#ifndef DFM_EMU
+    // ---------------------------------------------------------------- pipelined host path
+    // Host buffers + TMA fused kernel + more panels than the kernel holds at once: chunk the batch at the
+    // kernel's capacity, enqueue ALL H2D copies on the copy stream up front, let chunk c's kernels wait on
+    // its copy event and start its D2H as soon as they finish -> copies hide behind the kernels.
+    if (mem == DFM_MEM_HOST && fused && use2 && !getenv("DFM_NO_PIPELINE")) {
+      const int cap = fused2_capacity(r, T, N);
+      if (batch > cap) {
+        const int nch = (batch + cap - 1) / cap;
+        std::vector<cudaEvent_t> ev_in(nch), ev_done(nch);
+        for (int c = 0; c < nch; ++c) { cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming); cudaEventCreateWithFlags(&ev_done[c], cudaEventDisableTiming); }
+        cudaStream_t cs = h->copy_stream;
+        for (int c = 0; c < nch; ++c) {
+          size_t b0 = (size_t)c * cap, bc = std::min<size_t>(cap, B - b0);
+          cudaMemcpyAsync(dXb + b0 * TN, X + b0 * TN, bc * TN * 8, cudaMemcpyHostToDevice, cs);
+          cudaMemcpyAsync(dL + b0 * N * r, init->Lam + b0 * N * r, bc * N * r * 8, cudaMemcpyHostToDevice, cs);
+          cudaMemcpyAsync(dR + b0 * N, init->R + b0 * N, bc * N * 8, cudaMemcpyHostToDevice, cs);
+          cudaMemcpyAsync(dA + b0 * rk, init->A + b0 * rk, bc * rk * 8, cudaMemcpyHostToDevice, cs);
+          cudaMemcpyAsync(dQ + b0 * rr, init->Q + b0 * rr, bc * rr * 8, cudaMemcpyHostToDevice, cs);
+          if (init->P0) cudaMemcpyAsync(dP0 + b0 * kk, init->P0 + b0 * kk, bc * kk * 8, cudaMemcpyHostToDevice, cs);
+          cudaEventRecord(ev_in[c], cs);
+        }
+        bool unbalanced = false;
+        for (int c = 0; c < nch && !unbalanced; ++c) {
+          size_t b0 = (size_t)c * cap, bc = std::min<size_t>(cap, B - b0);
+          int bci = (int)bc;
+          cudaStreamWaitEvent(h->stream, ev_in[c], 0);
+          if (!init->P0) L(k_lyapunov, bci, 1, 128, (size_t)(3 * kk + 8) * 8, dA + b0 * rk, dQ + b0 * rr, r, p, dP0 + b0 * kk, 12);
+          { long long n = (long long)bc * mi; L(k_fill, (int)std::min<long long>((n + 255) / 256, 1024), 1, 256, 0, dll + b0 * mi, n, DFM_NAN); }
+          CK(cudaMemsetAsync(dflag, 0, sizeof(int), h->stream));
+          L(k_em_scan_fused, N, bci, 64, 0, dXb + b0 * TN, dL + b0 * N * r, dR + b0 * N, T, N, r, dflag);
+          int hflag = 0;
+          CK(cudaMemcpyAsync(&hflag, dflag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+          CK(cudaStreamSynchronize(h->stream));
+          if (hflag) { unbalanced = true; break; }
+          FusedArgs fa{};
+          fa.X = dXb + b0 * TN; fa.Lam = dL + b0 * N * r; fa.R = dR + b0 * N; fa.A = dA + b0 * rk; fa.Q = dQ + b0 * rr; fa.P0 = dP0 + b0 * kk;
+          fa.Fs = dFs + b0 * T * r; fa.PsF = dPsF + b0 * T * np; fa.loglik = dll + b0 * mi; fa.iters = dit + b0; fa.status = dstat + b0;
+          fa.B = bci; fa.T = T; fa.N = N; fa.max_iter = mi; fa.tol = o->tol; fa.phase_cycles = nullptr;
+          Arena a2(h->ws); a2.off = fused_off;
+          switch (r) {
+#define DFM_CASEP(RT) case RT: rc = launch_fused2<RT>(h, fa, bci, T, N, &a2, false); break;
+            DFM_CASEP(1) DFM_CASEP(2) DFM_CASEP(3) DFM_CASEP(4) DFM_CASEP(5) DFM_CASEP(6) DFM_CASEP(7) DFM_CASEP(8)
+#undef DFM_CASEP
+          }
+          if (rc) break;
+          if (out->PF) { long long n = (long long)T * rr; L(k_unpack_psf, (int)std::min<long long>((n + 255) / 256, 1024), bci, 256, 0, dPsF + b0 * T * np, T, r, dPFfull + b0 * T * rr); }
+          cudaEventRecord(ev_done[c], h->stream);
+          cudaStreamWaitEvent(cs, ev_done[c], 0);
+#define DFM_OUTP(dst, src, per) if (dst) cudaMemcpyAsync((dst) + b0 * (per), (src) + b0 * (per), bc * (per) * sizeof(*(src)), cudaMemcpyDeviceToHost, cs)
+          DFM_OUTP(out->Lam, dL, (size_t)N * r); DFM_OUTP(out->R, dR, (size_t)N); DFM_OUTP(out->A, dA, (size_t)rk); DFM_OUTP(out->Q, dQ, (size_t)rr);
+          DFM_OUTP(out->P0, dP0, (size_t)kk); DFM_OUTP(out->F, dFs, (size_t)T * r); DFM_OUTP(out->PF, dPFfull, (size_t)T * rr);
+          DFM_OUTP(out->loglik, dll, (size_t)mi); DFM_OUTP(out->iters, dit, (size_t)1); DFM_OUTP(out->status, dstat, (size_t)1);
+#undef DFM_OUTP
+        }
+        cudaStreamSynchronize(cs); cudaStreamSynchronize(h->stream);
+        for (int c = 0; c < nch; ++c) { cudaEventDestroy(ev_in[c]); cudaEventDestroy(ev_done[c]); }
+        if (rc) return rc;
+        if (!unbalanced) { CK(cudaGetLastError()); return DFM_OK; }
+        // a chunk has missing data: everything is on the device already -> general path on the whole batch
+        if (o->path == 3) return fail(h, DFM_ERR_UNSUPPORTED, "dfm_em_kalman: fused path needs a balanced panel (no NaN)");
+        fused = false;
+        const double* xg = dXb;
+        // earlier chunks were already updated in place by the fused kernel: restore the initial parameters
+        CK(cudaMemcpyAsync(dL, init->Lam, B * N * r * 8, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(dR, init->R, B * N * 8, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(dA, init->A, B * rk * 8, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(dQ, init->Q, B * rr * 8, cudaMemcpyHostToDevice, h->stream));
+        if (init->P0) CK(cudaMemcpyAsync(dP0, init->P0, B * kk * 8, cudaMemcpyHostToDevice, h->stream));
+        if (!init->P0) L(k_lyapunov, batch, 1, 128, (size_t)(3 * kk + 8) * 8, dA, dQ, r, p, dP0, 12);
+        { long long n = (long long)B * mi; L(k_fill, (int)std::min<long long>((n + 255) / 256, 1024), 1, 256, 0, dll, n, DFM_NAN); }
+        rc = run_em_general(h, xg, o, dL, dR, dA, dQ, dP0, dAn, dQn, dW, dlogR, dC, dBt, dqt, dslr, dnt, dCt, dzp, dzf, dPp, dPf, dFs, dPsF, dSff, dll, st, dit,
+                            dstat, active, ntC, nblkC, smFS);
+        if (rc) return rc;
+        computed = true;
+      }
+    }
+#endif
+    if (!computed) {
+    const double* x; rc = stage_in(h, X, dXb, B * TN, mem, &x); if (rc) return rc;
     cudaMemcpyKind kin = mem == DFM_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     CK(cudaMemcpyAsync(dL, init->Lam, B * N * r * 8, kin, h->stream));
     CK(cudaMemcpyAsync(dR, init->R, B * N * 8, kin, h->stream));
@@ -748,24 +886,11 @@ int dfm_em_kalman(dfm_handle* h, const double* X, const dfm_em_opts* o, const df
       }
 #endif
     } else {
-      L(k_em_state_init, batch, 1, 1, 0, st);
-      L(k_em_scan, N, batch, 64, 0, x, dL, T, N, r, st);
-      L(k_em_prep, batch, 1, 128, 0, dL, dR, N, r, p, dW, dlogR, dC, dA, dAn, dQ, dQn, st, mi, 0);
-      int h_active = batch;
-      for (int it = 0; it < mi && h_active > 0; ++it) {
-        L(k_em_contract, nblkC, batch, ntC, ((size_t)(np + r) * ntC + 8) * 8, x, dL, dW, dR, dlogR, dC, T, N, r, dBt, dqt, dslr, dnt, dCt, st);
-        L(k_em_filter_smooth, batch, 1, 128, smFS, dA, dQ, dP0, dC, dBt, dqt, dslr, dnt, dCt, T, r, p, dzp, dzf, dPp, dPf,
-          dFs, dPsF, dSff, dAn, dQn, dll, mi, o->tol, st);
-        L(k_em_mstep_series, N, batch, 64, (size_t)(2 * np + r + 8) * 8, x, dFs, dPsF, dSff, T, N, r, dL, dR, st);
-        L(k_em_prep, batch, 1, 128, 0, dL, dR, N, r, p, dW, dlogR, dC, dA, dAn, dQ, dQn, st, mi, 1);
-        if (o->tol > 0 && ((it & 3) == 3)) {
-          L(k_em_count_active, 1, 1, 128, 48 * 8, st, batch, active);
-          CK(cudaMemcpyAsync(&h_active, active, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-          CK(cudaStreamSynchronize(h->stream));
-        }
-      }
-      L(k_em_collect, batch, 1, 1, 0, st, dit, dstat);
+      rc = run_em_general(h, x, o, dL, dR, dA, dQ, dP0, dAn, dQn, dW, dlogR, dC, dBt, dqt, dslr, dnt, dCt, dzp, dzf, dPp, dPf, dFs, dPsF, dSff, dll, st, dit,
+                          dstat, active, ntC, nblkC, smFS);
+      if (rc) return rc;
     }
+    }   // !computed
     rc = copy_out(h, out->Lam, dL, B * N * r, mem); if (rc) return rc;
     rc = copy_out(h, out->R, dR, B * N, mem); if (rc) return rc;
     rc = copy_out(h, out->A, dA, B * rk, mem); if (rc) return rc;
