@@ -719,19 +719,16 @@ int dfm_em_kalman(dfm_handle* h, const double* X, const dfm_em_opts* o, const df
            *dslr = nullptr, *dCt = nullptr, *dzp = nullptr, *dzf = nullptr, *dPp = nullptr, *dPf = nullptr, *dSff = nullptr;
     int* dnt = nullptr;
     int* dflag = a.get<int>(4);
-    Arena fa_arena(nullptr);
-    size_t fused_off = a.off;
-    if (fused && !(fused_ok || fused2_ok)) fused = false;
-    if ((fused_ok || fused2_ok) && o->path != 1) {      // scratch of the fused kernel (superset allocation: the path is chosen after the scan)
-      FusedArgs dummy{}; Arena tmpa(nullptr);
+    const size_t fused_off = a.off;                     // the fused kernels' scratch starts here (re-derived at launch time)
+    if ((fused_ok || fused2_ok) && o->path != 1) {      // superset allocation: the path is only chosen after the NaN scan
+      FusedArgs dummy{};
       switch (r) {
 #define DFM_CASE(RT) case RT: launch_fused<RT>(h, dummy, batch, T, N, nullptr, &a, true); break;
         DFM_CASE(1) DFM_CASE(2) DFM_CASE(3) DFM_CASE(4) DFM_CASE(5) DFM_CASE(6) DFM_CASE(7) DFM_CASE(8)
 #undef DFM_CASE
       }
     }
-    (void)fa_arena; (void)fused_off;
-    {
+    {   // general-path buffers (also the fallback when the scan finds missing data)
       dAn = a.get<double>(B * rk); dQn = a.get<double>(B * rr); dW = a.get<double>(B * N * r); dlogR = a.get<double>(B * N);
       dC = a.get<double>(B * rr); dBt = a.get<double>(B * T * r); dqt = a.get<double>(B * T); dslr = a.get<double>(B * T);
       dnt = a.get<int>(B * T); dCt = a.get<double>(B * T * np); dzp = a.get<double>(B * T * k); dzf = a.get<double>(B * T * k);
@@ -855,8 +852,7 @@ int dfm_em_kalman(dfm_handle* h, const double* X, const dfm_em_opts* o, const df
         fa.phase_cycles = dph;
       }
 #endif
-      // re-derive the scratch pointer: it was the first allocation after dflag in this pass
-      Arena a2(h->ws); a2.off = fused_off;
+      Arena a2(h->ws); a2.off = fused_off;             // scratch pointer (first allocation after dflag in this pass)
       if (use2) {
         switch (r) {
 #define DFM_CASE2(RT) case RT: rc = launch_fused2<RT>(h, fa, batch, T, N, &a2, false); break;
