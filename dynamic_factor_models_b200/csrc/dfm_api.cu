@@ -845,10 +845,11 @@ int dfm_em_kalman(dfm_handle* h, const double* X, const dfm_em_opts* o, const df
       fa.iters = dit; fa.status = dstat; fa.B = batch; fa.T = T; fa.N = N; fa.max_iter = mi; fa.tol = o->tol;
       fa.phase_cycles = nullptr;
 #ifndef DFM_EMU
+      if (const char* sg = getenv("DFM_FUSED_STAGGER")) fa.stagger = atoi(sg);
       if (getenv("DFM_FUSED_PHASES")) {            // diagnostics: per-phase clock64 totals printed to stderr
         static long long* dph = nullptr;
-        if (!dph) cudaMalloc((void**)&dph, 148 * 8 * 16 * sizeof(long long));
-        cudaMemsetAsync(dph, 0, 148 * 8 * 16 * sizeof(long long), h->stream);
+        if (!dph) cudaMalloc((void**)&dph, 148 * 8 * DFM_PH * sizeof(long long));
+        cudaMemsetAsync(dph, 0, 148 * 8 * DFM_PH * sizeof(long long), h->stream);
         fa.phase_cycles = dph;
       }
 #endif
@@ -868,15 +869,17 @@ int dfm_em_kalman(dfm_handle* h, const double* X, const dfm_em_opts* o, const df
       if (rc) return rc;
 #ifndef DFM_EMU
       if (fa.phase_cycles) {
-        std::vector<long long> hp(148 * 8 * 16);
+        std::vector<long long> hp(148 * 8 * DFM_PH);
         cudaStreamSynchronize(h->stream);
         cudaMemcpy(hp.data(), fa.phase_cycles, hp.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-        double tot[16] = {0}; int nb = 0;
-        for (int g = 0; g < 148 * 8; ++g) { double s_ = 0; for (int k_ = 0; k_ < 12; ++k_) s_ += hp[(size_t)g * 16 + k_]; if (s_ > 0) { ++nb; for (int k_ = 0; k_ < 16; ++k_) tot[k_] += hp[(size_t)g * 16 + k_]; } }
+        double tot[DFM_PH] = {0}; int nb = 0;
+        for (int g = 0; g < 148 * 8; ++g) { double s_ = 0; for (int k_ = 0; k_ < 12; ++k_) s_ += hp[(size_t)g * DFM_PH + k_]; if (s_ > 0) { ++nb; for (int k_ = 0; k_ < DFM_PH; ++k_) tot[k_] += hp[(size_t)g * DFM_PH + k_]; } }
         const char* nm[12] = {"loop/params", "P0 prep", "P1 E-contract", "P2 cov chain", "P3 fwd means", "P4 loglik", "P5 bwd means", "P7 sums", "P8 M-contract", "P9 solves", "iter close", "outputs"};
         // tick k measures the phase that ENDS at tick k: tick0 ends loop/param load, tick1 ends P0, ...
         double all = 0; for (int k_ = 0; k_ < 12; ++k_) all += tot[k_];
         fprintf(stderr, "[dfm fused chain] forward loop %.0f cyc/CTA, backward loop %.0f cyc/CTA\n", tot[12] / (nb ? nb : 1), tot[13] / (nb ? nb : 1));
+        fprintf(stderr, "[dfm fused roles] E pass: producer %.0f, consumer w1 %.0f, chain warp (in slots 12+13) | M pass: producer %.0f, consumer w1 %.0f, sums+solves warp %.0f cyc/CTA\n",
+                tot[14] / (nb ? nb : 1), tot[15] / (nb ? nb : 1), tot[17] / (nb ? nb : 1), tot[18] / (nb ? nb : 1), tot[19] / (nb ? nb : 1));
         fprintf(stderr, "[dfm fused phases] %d CTAs, mean cycles per CTA: %.0f\n", nb, all / (nb ? nb : 1));
         for (int k_ = 0; k_ < 12; ++k_) fprintf(stderr, "  %-14s %6.2f%%  %12.0f cyc/CTA\n", nm[k_], 100.0 * tot[k_] / all, tot[k_] / (nb ? nb : 1));
       }

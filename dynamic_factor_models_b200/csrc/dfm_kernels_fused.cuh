@@ -42,6 +42,7 @@ namespace dfm {
 #define LI(n_, c_) ((c_) * Np + (n_))
 __host__ __device__ inline int pad4mod16(int x) { return x + ((4 - x % 16) + 16) % 16; }
 
+#define DFM_PH 24   // diagnostic slots per CTA
 struct FusedArgs {
   const double* X;      // [B][N][T] column-major panels
   double* Lam;          // [B][N*r] column-major (in: init, out: final)
@@ -56,12 +57,13 @@ struct FusedArgs {
   double* scratch;      // [gridDim.x][T * FUSED_SCR]
   int B, T, N, max_iter;
   double tol;
-  long long* phase_cycles;   // optional [gridDim.x][16] per-phase clock64() totals (diagnostics; NULL = off)
+  int stagger;               // diagnostics: start delay (cycles) of the second co-resident CTA wave (0 = off)
+  long long* phase_cycles;   // optional [gridDim.x][DFM_PH] per-phase clock64() totals (diagnostics; NULL = off)
 };
 #ifdef DFM_EMU
 #define DFM_TICK(k_) ((void)0)
 #else
-#define DFM_TICK(k_) do { if (a.phase_cycles && threadIdx.x == 0) { long long now_ = clock64(); a.phase_cycles[(size_t)blockIdx.x * 16 + (k_)] += now_ - tick_; tick_ = now_; } } while (0)
+#define DFM_TICK(k_) do { if (a.phase_cycles && threadIdx.x == 0) { long long now_ = clock64(); a.phase_cycles[(size_t)blockIdx.x * DFM_PH + (k_)] += now_ - tick_; tick_ = now_; } } while (0)
 #endif
 #define FUSED_SCR(R_) (5 * (R_) * (R_) + 1)
 
@@ -524,8 +526,8 @@ __global__ void DFM_FUSED_BOUNDS k_em_fused(FusedArgs a) {
       const int nE = ctl[0], frozen = ctl[3];
 #ifndef DFM_EMU
       if (a.phase_cycles && threadIdx.x == 0) {      // diagnostics: chain lengths
-        a.phase_cycles[(size_t)blockIdx.x * 16 + 12] += nE; a.phase_cycles[(size_t)blockIdx.x * 16 + 13] += (ctl[1] < 0 ? T - 1 : T - 1 - ctl[1]);
-        a.phase_cycles[(size_t)blockIdx.x * 16 + 14] += 1; a.phase_cycles[(size_t)blockIdx.x * 16 + 15] += frozen;
+        a.phase_cycles[(size_t)blockIdx.x * DFM_PH + 12] += nE; a.phase_cycles[(size_t)blockIdx.x * DFM_PH + 13] += (ctl[1] < 0 ? T - 1 : T - 1 - ctl[1]);
+        a.phase_cycles[(size_t)blockIdx.x * DFM_PH + 14] += 1; a.phase_cycles[(size_t)blockIdx.x * DFM_PH + 15] += frozen;
       }
 #endif
       DFM_TICK(3);

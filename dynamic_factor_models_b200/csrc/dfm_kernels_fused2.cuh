@@ -187,6 +187,14 @@ __device__ __forceinline__ void f2_consume_M(F2Ring& rg, int cw, int T, int N, i
 #endif  // !DFM_EMU
 
 #ifdef DFM_EMU
+#define F2_ROLE_T0() ((void)0)
+#define F2_ROLE_T1(k_) ((void)0)
+#else
+// diagnostics: time from the start of a pass until this warp role is done (lane 0 of the warp)
+#define F2_ROLE_T0() long long role_t0_ = a.phase_cycles ? clock64() : 0
+#define F2_ROLE_T1(k_) do { if (a.phase_cycles && DFM_LANE == 0) a.phase_cycles[(size_t)blockIdx.x * DFM_PH + (k_)] += clock64() - role_t0_; } while (0)
+#endif
+#ifdef DFM_EMU
 #define DFM_FUSED2_BOUNDS
 #else
 #define DFM_FUSED2_BOUNDS __launch_bounds__(256, 2)
@@ -240,6 +248,9 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
   long long tick_ = clock64();
 #endif
 
+#ifndef DFM_EMU
+  if (a.stagger > 0 && blockIdx.x >= gridDim.x / 2) { long long t0_ = clock64(); while (clock64() - t0_ < a.stagger) __nanosleep(500); }
+#endif
   for (int b = DFM_BX; b < a.B; b += DFM_GX) {
     const double* X = a.X + (size_t)b * T * N;
     // ---- load parameters (global column-major -> shared row-major)
@@ -291,8 +302,9 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
         // TMA pass (see f2_produce / f2_consume_E): warp 0 produces, warps 1..6 consume, warp 7 runs the
         // data-independent covariance chain concurrently
         const long long nitems = (long long)((N + 7) / 8) * ((T + F2_TC - 1) / F2_TC);
-        if (DFM_WARP == 0) f2_produce(rg, &tmap, b * N, T, N, /*c_outer=*/true);
-        else if (DFM_WARP <= F2_NCW) qacc += f2_consume_E<R>(rg, DFM_WARP - 1, T, N, Tp, Np, Z, Lam, rinv);
+        F2_ROLE_T0();
+        if (DFM_WARP == 0) { f2_produce(rg, &tmap, b * N, T, N, /*c_outer=*/true); F2_ROLE_T1(14); }
+        else if (DFM_WARP <= F2_NCW) { qacc += f2_consume_E<R>(rg, DFM_WARP - 1, T, N, Tp, Np, Z, Lam, rinv); if (DFM_WARP == 1) F2_ROLE_T1(15); }
         else {
           rg.skip(nitems);                                                   // keep the ring position in step
         {   // ---- covariance chain (data independent), on the chain warp, concurrently with the E pass
@@ -399,7 +411,7 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
         }
         if (DFM_LANE == 0) { ctl[0] = nE; ctl[1] = tb; ctl[3] = frozen; }
 #ifndef DFM_EMU
-        if (a.phase_cycles && threadIdx.x == 0) { long long c2_ = clock64(); a.phase_cycles[(size_t)blockIdx.x * 16 + 12] += c1_ - c0_; a.phase_cycles[(size_t)blockIdx.x * 16 + 13] += c2_ - c1_; }
+        if (a.phase_cycles && DFM_LANE == 0) { long long c2_ = clock64(); a.phase_cycles[(size_t)blockIdx.x * DFM_PH + 12] += c1_ - c0_; a.phase_cycles[(size_t)blockIdx.x * DFM_PH + 13] += c2_ - c1_; }
 #endif
 #ifdef DFM_EMU
         if (getenv("DFM_DEBUG_CHAIN")) printf("[chain] b=%d it=%d nE=%d frozen=%d tb=%d (T=%d)\n", b, it, nE, frozen, tb, T);
@@ -519,7 +531,7 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
         }
         if (DFM_LANE == 0) { ctl[0] = nE; ctl[1] = tb; ctl[3] = frozen; }
 #ifndef DFM_EMU
-        if (a.phase_cycles && threadIdx.x == 0) { long long c2_ = clock64(); a.phase_cycles[(size_t)blockIdx.x * 16 + 12] += c1_ - c0_; a.phase_cycles[(size_t)blockIdx.x * 16 + 13] += c2_ - c1_; }
+        if (a.phase_cycles && DFM_LANE == 0) { long long c2_ = clock64(); a.phase_cycles[(size_t)blockIdx.x * DFM_PH + 12] += c1_ - c0_; a.phase_cycles[(size_t)blockIdx.x * DFM_PH + 13] += c2_ - c1_; }
 #endif
 #ifdef DFM_EMU
         if (getenv("DFM_DEBUG_CHAIN")) printf("[chain] b=%d it=%d nE=%d frozen=%d tb=%d (T=%d)\n", b, it, nE, frozen, tb, T);
@@ -651,8 +663,9 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
         const long long nitems = (long long)((N + 7) / 8) * ((T + F2_TC - 1) / F2_TC);
-        if (DFM_WARP == 0) f2_produce(rg, &tmap, b * N, T, N, /*c_outer=*/false);
-        else if (DFM_WARP <= F2_NCW) f2_consume_M<R>(rg, DFM_WARP - 1, T, N, Tp, Np, Z, Lam, sxx, part);
+        F2_ROLE_T0();
+        if (DFM_WARP == 0) { f2_produce(rg, &tmap, b * N, T, N, /*c_outer=*/false); F2_ROLE_T1(17); }
+        else if (DFM_WARP <= F2_NCW) { f2_consume_M<R>(rg, DFM_WARP - 1, T, N, Tp, Np, Z, Lam, sxx, part); if (DFM_WARP == 1) F2_ROLE_T1(18); }
         else {
           rg.skip(nitems);
         {   // ---- moment sums + M-step r x r solves (all inputs are ready before the M pass): on the idle
@@ -689,6 +702,7 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
         for (int e = DFM_LANE; e < RR; e += DFM_WSZ) Pn[e] = (Pi[e] - Pn[e]) / (double)(T - 1);
         DFM_WSYNC();
         w_sym<R>(Pn);                                              // Q_new
+        F2_ROLE_T1(19);
       }
         }
       }
