@@ -880,6 +880,9 @@ int dfm_em_kalman(dfm_handle* h, const double* X, const dfm_em_opts* o, const df
         fprintf(stderr, "[dfm fused chain] forward loop %.0f cyc/CTA, backward loop %.0f cyc/CTA\n", tot[12] / (nb ? nb : 1), tot[13] / (nb ? nb : 1));
         fprintf(stderr, "[dfm fused roles] E pass: producer %.0f, consumer w1 %.0f, chain warp (in slots 12+13) | M pass: producer %.0f, consumer w1 %.0f, sums+solves warp %.0f cyc/CTA\n",
                 tot[14] / (nb ? nb : 1), tot[15] / (nb ? nb : 1), tot[17] / (nb ? nb : 1), tot[18] / (nb ? nb : 1), tot[19] / (nb ? nb : 1));
+        fprintf(stderr, "[dfm fused P3/P5 split] P3 prepass %.0f, explicit %.0f, scan fwd: pw+pass1 %.0f, boundary %.0f, pass2 %.0f | scan bwd: %.0f, %.0f, %.0f cyc/CTA\n",
+                tot[20] / (nb ? nb : 1), tot[21] / (nb ? nb : 1), tot[22] / (nb ? nb : 1), tot[23] / (nb ? nb : 1), tot[24] / (nb ? nb : 1), tot[25] / (nb ? nb : 1),
+                tot[26] / (nb ? nb : 1), tot[27] / (nb ? nb : 1));
         fprintf(stderr, "[dfm fused phases] %d CTAs, mean cycles per CTA: %.0f\n", nb, all / (nb ? nb : 1));
         for (int k_ = 0; k_ < 12; ++k_) fprintf(stderr, "  %-14s %6.2f%%  %12.0f cyc/CTA\n", nm[k_], 100.0 * tot[k_] / all, tot[k_] / (nb ? nb : 1));
       }

@@ -42,7 +42,7 @@ namespace dfm {
 #define LI(n_, c_) ((c_) * Np + (n_))
 __host__ __device__ inline int pad4mod16(int x) { return x + ((4 - x % 16) + 16) % 16; }
 
-#define DFM_PH 24   // diagnostic slots per CTA
+#define DFM_PH 32   // diagnostic slots per CTA
 struct FusedArgs {
   const double* X;      // [B][N][T] column-major panels
   double* Lam;          // [B][N*r] column-major (in: init, out: final)
@@ -194,13 +194,27 @@ DFM_HELPER double w_inv(double* Ai, const double* A, double* tmp, int* bad) {
 // Exact up to rounding (linear recurrence).  Called by ALL threads; ends with a block barrier.
 // smem: pw, pw2 [R*R], bnd [(chunks+1) * R].  Requires blockDim = 128 (16 groups) on the GPU.
 template <int R>
-__device__ __forceinline__ void blk_recur(double* Z, int Tp, const double* Cf, double* pw, double* pw2, double* bnd, int t0, int n, int dir, int ng) {
+__device__ __forceinline__ void blk_recur(double* Z, int Tp, const double* Cf, double* pw, double* pw2, double* bnd, int t0, int n, int dir, int nthr,
+                                          long long* prof = nullptr) {
   if (n <= 0) return;
+  // nthr = number of threads taking part (threads 0 .. nthr-1 of the CTA, a multiple of 32); they synchronise
+  // on named barrier 2, so the remaining warps of the CTA may do something else meanwhile
+  const int ng = nthr / 8;
+#ifndef DFM_EMU
+#define BLK_SYNC() asm volatile("bar.sync 2, %0;" ::"r"(nthr) : "memory")
+#else
+#define BLK_SYNC() ((void)0)
+#endif
+#ifndef DFM_EMU
+  long long pt_ = prof ? clock64() : 0;
+#define BLK_PROF(k_) do { if (prof && threadIdx.x == 0) { long long now_ = clock64(); prof[k_] += now_ - pt_; pt_ = now_; } } while (0)
+#else
+#define BLK_PROF(k_) ((void)0)
+#endif
   // ng = number of 8-lane groups of the CTA (blockDim / 8).  chunk length: odd (=> the 4 groups of a
   // warp hit different banks) and at most ng chunks.  bnd: [(3 ng + 1) R + R R] doubles.
-  int Lc = 1;
-  while (Lc * ng < n) Lc <<= 1;
-  if (Lc > 1) Lc += 1;
+  int Lc = (n + ng - 1) / ng;
+  if (Lc > 1 && !(Lc & 1)) Lc += 1;
   const int nch = (n + Lc - 1) / Lc;
   // pw = Cf^Lc by binary exponentiation (warp 0; a handful of r x r products); bnd[0..R*R) is scratch
   if (DFM_WARP == 0 && nch > 1) {
@@ -225,28 +239,38 @@ __device__ __forceinline__ void blk_recur(double* Z, int Tp, const double* Cf, d
     }
   }
 #else
+  // state of the group's chunk lives in registers (lane gl = component gl); the matrix-vector product
+  // gathers the 8 components with width-8 shuffles: no shared-memory round trip on the serial chain
   const int g = threadIdx.x >> 3, gl = threadIdx.x & 7;           // ng groups >= nch
   const int s0 = g * Lc;
   const int len = (g < nch) ? ((n - s0 < Lc) ? n - s0 : Lc) : 0;
-  const bool act = gl < R && len > 0;
+  const bool lane_on = gl < R;
   double cf[R];
 #pragma unroll
-  for (int j = 0; j < R; ++j) cf[j] = (gl < R) ? Cf[gl * R + j] : 0.0;
-  for (int s = 0; s < Lc; ++s) {
-    if (act && s < len && !(g > 0 && s == 0)) {
-      const int t = t0 + dir * (s0 + s);
-      const double* zp = Z + (t - dir);
-      double a0 = Z[ZI(t, gl)], a1 = 0.0;
+  for (int j = 0; j < R; ++j) cf[j] = lane_on ? Cf[gl * R + j] : 0.0;
+  {
+    double cur = (g == 0 && lane_on) ? Z[ZI(t0 - dir, gl)] : 0.0;      // chunk 0 continues the true state, the others start from 0
+    double u = (lane_on && len > 0) ? Z[ZI(t0 + dir * s0, gl)] : 0.0;
+    for (int s = 0; s < Lc; ++s) {                                     // uniform trip count: every lane takes part in the shuffles
+      const bool on = lane_on && s < len;
+      const double un = (lane_on && s + 1 < len) ? Z[ZI(t0 + dir * (s0 + s + 1), gl)] : 0.0;   // next input, off the chain
+      double a0 = u, a1 = 0.0;
 #pragma unroll
-      for (int j = 0; j < R; j += 2) { a0 += cf[j] * zp[j * Tp]; if (j + 1 < R) a1 += cf[j + 1] * zp[(j + 1) * Tp]; }
-      Z[ZI(t, gl)] = a0 + a1;
+      for (int j = 0; j < R; ++j) {
+        const double v = __shfl_sync(0xffffffffu, cur, j, 8);
+        if (j & 1) a1 += cf[j] * v; else a0 += cf[j] * v;
+      }
+      const double nx = a0 + a1;
+      if (on) { Z[ZI(t0 + dir * (s0 + s), gl)] = nx; cur = nx; }
+      u = un;
     }
-    __syncwarp();
   }
 #endif
-  DFM_SYNC();
+  BLK_SYNC();
+  BLK_PROF(0);
   if (nch > 1) {
     // ---- boundary propagation: bnd[g] = true state entering chunk g (g >= 1)
+#ifdef DFM_EMU
     if (DFM_WARP == 0) {
       for (int gg = 1; gg < nch; ++gg) {
         const int tend = t0 + dir * (gg * Lc - 1);            // last step of chunk gg-1
@@ -258,7 +282,31 @@ __device__ __forceinline__ void blk_recur(double* Z, int Tp, const double* Cf, d
         DFM_WSYNC();
       }
     }
-    DFM_SYNC();
+#else
+    if (DFM_WARP == 0) {
+      const int gl = threadIdx.x & 7;
+      const bool lane_on = gl < R;
+      double pr[R];
+#pragma unroll
+      for (int j = 0; j < R; ++j) pr[j] = lane_on ? pw[gl * R + j] : 0.0;
+      double b = lane_on ? Z[ZI(t0 + dir * (Lc - 1), gl)] : 0.0;          // end of chunk 0 = true state entering chunk 1
+      double loc = (lane_on && nch > 2) ? Z[ZI(t0 + dir * (2 * Lc - 1), gl)] : 0.0;
+      for (int gg = 1; gg < nch; ++gg) {
+        if (lane_on && threadIdx.x < 8) bnd[gg * R + gl] = b;
+        const double locn = (lane_on && gg + 2 < nch) ? Z[ZI(t0 + dir * ((gg + 2) * Lc - 1), gl)] : 0.0;
+        double a0 = loc, a1 = 0.0;
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          const double v = __shfl_sync(0xffffffffu, b, j, 8);
+          if (j & 1) a1 += pr[j] * v; else a0 += pr[j] * v;
+        }
+        b = a0 + a1;                                                        // true end state of chunk gg = entering state of chunk gg+1
+        loc = locn;
+      }
+    }
+#endif
+    BLK_SYNC();
+    BLK_PROF(1);
     // ---- pass 2: add Cf^(s+1) bnd[g]
 #ifdef DFM_EMU
     for (int g = 1; g < nch; ++g) {
@@ -273,26 +321,25 @@ __device__ __forceinline__ void blk_recur(double* Z, int Tp, const double* Cf, d
     }
 #else
     {
-      const bool act2 = act && g > 0;
-      double* cb = bnd + (size_t)(ng + 1 + 2 * g) * R;           // per-group ping-pong vector [2][R]
-      if (act2) cb[gl] = bnd[g * R + gl];
-      __syncwarp();
+      const bool act2 = lane_on && g > 0 && len > 0;
+      double c = act2 ? bnd[g * R + gl] : 0.0;
       for (int s = 0; s < Lc; ++s) {
-        if (act2) {
-          const double* cp = cb + (s & 1) * R;
-          double a0 = 0.0, a1 = 0.0;
+        double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-          for (int j = 0; j < R; j += 2) { a0 += cf[j] * cp[j]; if (j + 1 < R) a1 += cf[j + 1] * cp[j + 1]; }
-          a0 += a1;
-          cb[((s + 1) & 1) * R + gl] = a0;
-          if (s < len) Z[ZI(t0 + dir * (s0 + s), gl)] += a0;
+        for (int j = 0; j < R; ++j) {
+          const double v = __shfl_sync(0xffffffffu, c, j, 8);
+          if (j & 1) a1 += cf[j] * v; else a0 += cf[j] * v;
         }
-        __syncwarp();
+        c = a0 + a1;
+        if (act2 && s < len) Z[ZI(t0 + dir * (s0 + s), gl)] += c;
       }
     }
 #endif
-    DFM_SYNC();
+    BLK_SYNC();
+    BLK_PROF(2);
   }
+#undef BLK_PROF
+#undef BLK_SYNC
 }
 
 // ================================================================================================
@@ -562,7 +609,7 @@ __global__ void DFM_FUSED_BOUNDS k_em_fused(FusedArgs a) {
       }
       DFM_SYNC();
       // frozen steps: z_t = Phi_inf z_{t-1} + u_t, parallel in time over the CTA
-      if (frozen) blk_recur<R>(Z, Tp, Phinf, T1, T2, bnd, (nE > 0 ? nE : 1), T - (nE > 0 ? nE : 1), +1, 16);
+      if (frozen) blk_recur<R>(Z, Tp, Phinf, T1, T2, bnd, (nE > 0 ? nE : 1), T - (nE > 0 ? nE : 1), +1, 128);
       DFM_TICK(4);
       // ---------------------------------------------------------------- P4: log-likelihood (parallel over t)
       double llp = 0.0;
@@ -605,7 +652,7 @@ __global__ void DFM_FUSED_BOUNDS k_em_fused(FusedArgs a) {
       }
       DFM_SYNC();
       // frozen range: z_t = J_inf z_{t+1} + v_t, parallel in time over the CTA
-      if (frozen) blk_recur<R>(Z, Tp, Jinf, T1, T2, bnd, T - 2, (T - 2) - (nE - 1) + 1, -1, 16);
+      if (frozen) blk_recur<R>(Z, Tp, Jinf, T1, T2, bnd, T - 2, (T - 2) - (nE - 1) + 1, -1, 128);
       if (DFM_WARP == 0) {
         const int lo = frozen ? nE - 1 : T;
         // explicit range: zs_t = zf_t + J_t (zs_{t+1} - M zf_t)

@@ -24,15 +24,23 @@ struct CUtensorMap { char opaque[128]; };
 namespace dfm {
 
 #ifndef F2_S
-#define F2_S 6          // ring stages
+#define F2_S 4          // ring stages
 #endif
-#define F2_TC 96        // periods per stage (12 DMMA row blocks / 24 k-chunks per stage)
-#define F2_TS 100       // row stride in the ring (== 4 mod 16: conflict-free fragments)
+#ifndef F2_TC
+#define F2_TC 132       // periods per stage == row pitch in the ring; must be == 4 or 12 (mod 16) so that the
+#endif                  // DMMA fragment loads are bank-conflict free, and <= 256 (TMA box limit)
+#define F2_TS F2_TC     // (box width == chunk stride: no re-read of periods; T = 500 -> 4 chunks)
 #ifndef F2_PF
 #define F2_PF 0
 #endif
-// F2_PF: L2 prefetch distance (stages), 0 = off:        // L2 prefetch distance (stages)
-#define F2_NCW 6        // consumer warps (warps 1..6; warp 0 = producer, warp 7 idles during the passes)
+// F2_PF: L2 prefetch distance (stages), 0 = off (measured slower: profiles/README.md)
+#define F2_NCW 6        // consumer warps (warps 1..6; warp 0 = producer, warp 7 = chain / solves)
+#define F2_GPARTS_S 4                                    // scalar Gram path: time slices per matrix entry
+#define F2_GPARTS ((R == 8) ? (F2_NCW + 1) : F2_GPARTS_S)   // partial Gram matrices (tensor path: one per warp of P3-P5)
+#define F2_NRB (((F2_TC + 7) / 8 + F2_NCW - 1) / F2_NCW)   // 8-period DMMA row blocks per consumer warp and stage (E pass)
+#define F2_NKC (((F2_TC + 3) / 4 + F2_NCW - 1) / F2_NCW)   // 4-period DMMA k-chunks per consumer warp and stage (M pass)
+static_assert(F2_TC % 16 == 4 || F2_TC % 16 == 12, "ring pitch must be 4 or 12 mod 16");
+static_assert(F2_TC <= 256 && (F2_TC * 64) % 128 == 0, "TMA box / stage alignment");
 #define F2_NEXS(R_) ((F2_S * 8 * F2_TS) / FUSED_SCR(R_))
 
 #ifndef DFM_EMU
@@ -100,33 +108,48 @@ __device__ __forceinline__ double f2_consume_E(F2Ring& rg, int cw, int T, int N,
   double qacc = 0.0;
   for (int c = 0; c < nck; ++c) {
     const int len = (T - c * F2_TC < F2_TC) ? T - c * F2_TC : F2_TC;
-    const int tl0 = cw * 8 + lr, tl1 = (cw + F2_NCW) * 8 + lr;       // F2_TC / 8 = 2 * F2_NCW row blocks
-    const bool v0 = tl0 < len, v1 = tl1 < len;
-    double d00 = 0.0, d01 = 0.0, d10 = 0.0, d11 = 0.0;
+    // row blocks cw, cw + NCW, ...: one independent accumulator pair per (row block, k half) so that no
+    // two DMMAs of a stage depend on each other (the chains only link consecutive stages)
+    double d[F2_NRB][2][2];
+#pragma unroll
+    for (int j = 0; j < F2_NRB; ++j) { d[j][0][0] = 0.0; d[j][0][1] = 0.0; d[j][1][0] = 0.0; d[j][1][1] = 0.0; }
     for (int sb = 0; sb < nsb; ++sb) {
       f2_mbar_wait(&rg.full[rg.rs], rg.rph);
       const double* tile = rg.ring + (size_t)rg.rs * 8 * F2_TS;
+      // all fragment loads of the stage first (no branches in between: the warp issues in order, so a
+      // load placed after a DMMA would only start once that DMMA's operands had arrived), then the math
+      double rn[2], lm[2], av[2][F2_NRB];
 #pragma unroll
       for (int kc = 0; kc < 2; ++kc) {
         const int n = sb * 8 + kc * 4 + lc;
         const bool nok = n < N;
-        const double rn = nok ? (rinv ? rinv[n] : 1.0) : 0.0;
-        const double lam = (nok && lr < R) ? Lam[LI(n, lr)] : 0.0;
-        const double a0 = (nok && v0) ? tile[(kc * 4 + lc) * F2_TS + tl0] : 0.0;
-        const double a1 = (nok && v1) ? tile[(kc * 4 + lc) * F2_TS + tl1] : 0.0;
-        const double ar0 = a0 * rn, ar1 = a1 * rn;
-        qacc += a0 * ar0 + a1 * ar1;
-        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                     : "+d"(d00), "+d"(d01) : "d"(ar0), "d"(lam));
-        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                     : "+d"(d10), "+d"(d11) : "d"(ar1), "d"(lam));
+        rn[kc] = nok ? (rinv ? rinv[n] : 1.0) : 0.0;
+        lm[kc] = (nok && lr < R) ? Lam[LI(n, lr)] : 0.0;
+        const double* trow = tile + (kc * 4 + lc) * F2_TS + lr;
+#pragma unroll
+        for (int j = 0; j < F2_NRB; ++j) {
+          const int t0 = (cw + j * F2_NCW) * 8;
+          av[kc][j] = (nok && t0 + lr < len) ? trow[t0] : 0.0;
+        }
       }
+#pragma unroll
+      for (int kc = 0; kc < 2; ++kc)
+#pragma unroll
+        for (int j = 0; j < F2_NRB; ++j) {
+          const double ar = av[kc][j] * rn[kc];
+          qacc += av[kc][j] * ar;
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                       : "+d"(d[j][kc][0]), "+d"(d[j][kc][1]) : "d"(ar), "d"(lm[kc]));
+        }
       __syncwarp();
       if (lane == 0) f2_mbar_arrive(&rg.empty[rg.rs]);
       rg.advance();
     }
-    if (v0) { const int t = c * F2_TC + tl0; Z[ZI(t, 2 * lc)] = d00; Z[ZI(t, 2 * lc + 1)] = d01; }
-    if (v1) { const int t = c * F2_TC + tl1; Z[ZI(t, 2 * lc)] = d10; Z[ZI(t, 2 * lc + 1)] = d11; }
+#pragma unroll
+    for (int j = 0; j < F2_NRB; ++j) {
+      const int tl = (cw + j * F2_NCW) * 8 + lr;
+      if (tl < len) { const int t = c * F2_TC + tl; Z[ZI(t, 2 * lc)] = d[j][0][0] + d[j][1][0]; Z[ZI(t, 2 * lc + 1)] = d[j][0][1] + d[j][1][1]; }
+    }
   }
   return qacc;
 }
@@ -139,26 +162,30 @@ __device__ __forceinline__ void f2_consume_M(F2Ring& rg, int cw, int T, int N, i
                                              double* sxx, double* part) {
   const int lane = threadIdx.x & 31, lr = lane >> 2, lc = lane & 3;
   const int nsb = (N + 7) / 8, nck = (T + F2_TC - 1) / F2_TC;
-  double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0, s2 = 0.0;
+  double d[F2_NKC][2], s2 = 0.0;                                  // one accumulator pair per k-chunk slot: independent DMMAs
+#pragma unroll
+  for (int j = 0; j < F2_NKC; ++j) { d[j][0] = 0.0; d[j][1] = 0.0; }
   for (int sb = 0; sb < nsb; ++sb)
     for (int c = 0; c < nck; ++c) {
       f2_mbar_wait(&rg.full[rg.rs], rg.rph);
       const double* tile = rg.ring + (size_t)rg.rs * 8 * F2_TS;
       const int len = (T - c * F2_TC < F2_TC) ? T - c * F2_TC : F2_TC;
       const bool nok = sb * 8 + lr < N;
-      const double* zc = Z + (size_t)lr * Tp + c * F2_TC;
+      const double* zc = Z + (size_t)lr * Tp + c * F2_TC + lc;
+      const double* trow = tile + lr * F2_TS + lc;
+      double av[F2_NKC], bv[F2_NKC];                            // k-chunks cw, cw + NCW, ...: loads first, then the math
 #pragma unroll
-      for (int j = 0; j < 4; j += 2) {                           // k-chunks cw, cw+6, cw+12, cw+18 (F2_TC/4 = 4 * F2_NCW)
-        const int tla = (cw + j * F2_NCW) * 4 + lc, tlb = (cw + (j + 1) * F2_NCW) * 4 + lc;
-        const double ava = (nok && tla < len) ? tile[lr * F2_TS + tla] : 0.0;
-        const double avb = (nok && tlb < len) ? tile[lr * F2_TS + tlb] : 0.0;
-        const double bva = (tla < len) ? zc[tla] : 0.0;
-        const double bvb = (tlb < len) ? zc[tlb] : 0.0;
-        s2 += ava * ava + avb * avb;
+      for (int j = 0; j < F2_NKC; ++j) {
+        const int t0 = (cw + j * F2_NCW) * 4;
+        const bool tok = t0 + lc < len;
+        av[j] = (nok && tok) ? trow[t0] : 0.0;
+        bv[j] = tok ? zc[t0] : 0.0;
+      }
+#pragma unroll
+      for (int j = 0; j < F2_NKC; ++j) {
+        s2 += av[j] * av[j];
         asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                     : "+d"(d0), "+d"(d1) : "d"(ava), "d"(bva));
-        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                     : "+d"(e0), "+d"(e1) : "d"(avb), "d"(bvb));
+                     : "+d"(d[j][0]), "+d"(d[j][1]) : "d"(av[j]), "d"(bv[j]));
       }
       __syncwarp();
       if (lane == 0) f2_mbar_arrive(&rg.empty[rg.rs]);
@@ -166,7 +193,10 @@ __device__ __forceinline__ void f2_consume_M(F2Ring& rg, int cw, int T, int N, i
       if (c == nck - 1) {
         s2 += __shfl_xor_sync(0xffffffffu, s2, 1); s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
         double* pb = part + (size_t)(sb & 1) * F2_NCW * 72 + cw * 72;
-        pb[2 * lane] = d0 + e0; pb[2 * lane + 1] = d1 + e1;
+        double t0_ = 0.0, t1_ = 0.0;
+#pragma unroll
+        for (int j = 0; j < F2_NKC; ++j) { t0_ += d[j][0]; t1_ += d[j][1]; d[j][0] = 0.0; d[j][1] = 0.0; }
+        pb[2 * lane] = t0_; pb[2 * lane + 1] = t1_;
         if (lc == 0) pb[64 + lr] = s2;
         asm volatile("bar.sync 1, %0;" ::"n"(F2_NCW * 32) : "memory");
         const int ct = cw * 32 + lane;                          // 0 .. F2_NCW*32-1
@@ -180,7 +210,7 @@ __device__ __forceinline__ void f2_consume_M(F2Ring& rg, int cw, int T, int N, i
             if (n < N && col < R) Lam[LI(n, col)] = tot_;
           } else { const int n = sb * 8 + (ct - 64); if (n < N) sxx[n] = tot_; }
         }
-        d0 = 0.0; d1 = 0.0; e0 = 0.0; e1 = 0.0; s2 = 0.0;
+        s2 = 0.0;
       }
     }
 }
@@ -189,10 +219,24 @@ __device__ __forceinline__ void f2_consume_M(F2Ring& rg, int cw, int T, int N, i
 #ifdef DFM_EMU
 #define F2_ROLE_T0() ((void)0)
 #define F2_ROLE_T1(k_) ((void)0)
+#define F2_SUB(k_) ((void)0)
+#define F2_SUBP(k_) nullptr
+#define F2_PSYNC() ((void)0)
+#define F2_PTID 0
+#define F2_PNT 1
+#define F2_PNT_GPU ((F2_NCW + 1) * 32)
 #else
 // diagnostics: time from the start of a pass until this warp role is done (lane 0 of the warp)
 #define F2_ROLE_T0() long long role_t0_ = a.phase_cycles ? clock64() : 0
 #define F2_ROLE_T1(k_) do { if (a.phase_cycles && DFM_LANE == 0) a.phase_cycles[(size_t)blockIdx.x * DFM_PH + (k_)] += clock64() - role_t0_; } while (0)
+// sub-phase split of the tick interval in progress (thread 0): cycles since the last DFM_TICK / F2_SUB
+#define F2_SUB(k_) do { if (a.phase_cycles && threadIdx.x == 0) { long long now_ = clock64(); a.phase_cycles[(size_t)blockIdx.x * DFM_PH + (k_)] += now_ - sub_; sub_ = now_; } } while (0)
+#define F2_SUBP(k_) (a.phase_cycles ? a.phase_cycles + (size_t)blockIdx.x * DFM_PH + (k_) : nullptr)
+// the mean recursions P3-P5 run on warps 0..F2_NCW (named barrier 2) while the chain warp does the backward covariances
+#define F2_PNT_GPU ((F2_NCW + 1) * 32)
+#define F2_PSYNC() asm volatile("bar.sync 2, %0;" ::"n"(F2_PNT_GPU) : "memory")
+#define F2_PTID ((int)threadIdx.x)
+#define F2_PNT F2_PNT_GPU
 #endif
 #ifdef DFM_EMU
 #define DFM_FUSED2_BOUNDS
@@ -286,6 +330,134 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
       }
       DFM_SYNC();
       DFM_TICK(1);
+      // ---- covariance chain (data independent).  Forward part: on the chain warp concurrently with the E pass;
+      //      backward part (smoothed covariances + covariance parts of the moment sums): on the chain warp
+      //      concurrently with the mean recursions P3-P5, which only need the forward quantities (Pf, Phi, J).
+      auto chain_fwd = [&]() {
+        int* bad = &ctl[2];
+        // forward
+        for (int e = DFM_LANE; e < RR; e += DFM_WSZ) { int i = e / R, j = e % R; Pp[e] = a.P0[(size_t)b * RR + i + R * j]; }
+        DFM_WSYNC();
+        int nE = T, frozen_at = -1, t = 0;
+#ifndef DFM_EMU
+        long long c0_ = clock64();
+#endif
+        while (t < T) {
+          double ldp = w_inv<R>(Pi, Pp, tmp, bad);
+          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) Wm[e] = Pi[e] + C[e];
+          DFM_WSYNC();
+          double ldw = w_inv<R>(Pf, Wm, tmp, bad);
+          w_gemm<R>(G, Pf, false, Pi, false);
+          w_gemm<R>(Phi, G, false, M, false);
+          if (t >= 1) { w_gemm<R>(T1, Pfprev, false, M, true); w_gemm<R>(Jm, T1, false, Pi, false); }   // J_{t-1}
+          w_gemm<R>(T1, M, false, Pf, false);
+          w_gemm<R>(Pn, T1, false, M, true);
+          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) Pn[e] += Q[e];
+          DFM_WSYNC();
+          w_sym<R>(Pn);
+          double* s_ = GSC(t);
+          double dmax = 0.0, pmax = 0.0;
+          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) {
+            s_[e] = Pf[e]; s_[RR + e] = Phi[e]; s_[3 * RR + e] = Wm[e];
+            if (t >= 1) GSC(t - 1)[2 * RR + e] = Jm[e];
+            dmax = fmax(dmax, fabs(Pn[e] - Pp[e])); pmax = fmax(pmax, fabs(Pp[e]));
+            Pfprev[e] = Pf[e];
+          }
+          if (DFM_LANE == 0) s_[5 * RR] = ldp + ldw;
+          dmax = w_max(dmax); pmax = w_max(pmax);
+          DFM_WSYNC();
+          if (frozen_at >= 0 && t == frozen_at + 1) {
+            nE = t + 1;
+            for (int e = DFM_LANE; e < RR; e += DFM_WSZ) { Pfinf[e] = Pf[e]; Phinf[e] = Phi[e]; Winf[e] = Wm[e]; }
+            if (DFM_LANE == 0) scal[1] = ldp + ldw;
+            DFM_WSYNC();
+            w_gemm<R>(T1, Pf, false, M, true);
+            w_gemm<R>(Jinf, T1, false, Pi, false);                 // J_inf = Pf_inf M' Pi_inf
+            break;
+          }
+          if (frozen_at < 0 && dmax <= eps * pmax) frozen_at = t;
+          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) Pp[e] = Pn[e];
+          DFM_WSYNC();
+          ++t;
+        }
+        const int frozen = nE < T;
+        if (DFM_LANE == 0) { ctl[0] = nE; ctl[3] = frozen; }
+#ifndef DFM_EMU
+        if (a.phase_cycles && DFM_LANE == 0) a.phase_cycles[(size_t)blockIdx.x * DFM_PH + 12] += clock64() - c0_;
+#endif
+        // I - J_inf M  (for the parallel pre-pass of the backward mean recursion)
+        if (frozen) {
+          w_gemm<R>(IJM, Jinf, false, M, false);
+          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) { int i = e / R, j = e % R; IJM[e] = ((i == j) ? 1.0 : 0.0) - IJM[e]; }
+        }
+        DFM_WSYNC();
+      };
+      auto chain_bwd = [&]() {
+        const int nE = ctl[0], frozen = ctl[3];
+        int t;
+#ifndef DFM_EMU
+        long long c1_ = a.phase_cycles ? clock64() : 0;
+#endif
+        // backward covariance chain + covariance parts of the moment sums
+        for (int e = DFM_LANE; e < RR; e += DFM_WSZ) {
+          double v = frozen ? Pfinf[e] : (GSC(T - 1))[e];
+          Psn[e] = v; SPall[e] = v; SPff2[e] = v; SP00[e] = 0.0; SP11[e] = 0.0;
+          GPS(T - 1)[e] = v;
+        }
+        DFM_WSYNC();
+        const int lo = frozen ? nE - 1 : T;
+        int tb = -1;                        // frozen smoothed range is [lo, tb)
+        t = T - 2;
+        while (t >= 0) {
+          const double* pf_t = (t < nE) ? GSC(t) : Pfinf;
+          const double* j_t = (t < nE - 1) ? GSC(t) + 2 * RR : Jinf;
+          // Pp_{t+1} = M Pf_t M' + Q (recomputed: cheaper than storing)
+          w_gemm<R>(T1, M, false, pf_t, false);
+          w_gemm<R>(T2, T1, false, M, true);
+          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) T2[e] = Psn[e] - (T2[e] + Q[e]);
+          DFM_WSYNC();
+          w_sym<R>(T2);                                           // D = Ps_{t+1} - Pp_{t+1}
+          w_gemm<R>(T1, j_t, false, T2, false);
+          w_gemm<R>(Ps, T1, false, j_t, true);
+          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) Ps[e] += pf_t[e];
+          DFM_WSYNC();
+          w_sym<R>(Ps);
+          w_gemm<R>(T1, Psn, false, j_t, true);                    // Ps_{t+1} J_t'
+          double dmax = 0.0, pmax = 0.0;
+          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) {
+            SP11[e] += T1[e]; SPall[e] += Ps[e]; SP00[e] += Ps[e];
+            if (t >= 1) SPff2[e] += Ps[e];
+            GPS(t)[e] = Ps[e];
+            dmax = fmax(dmax, fabs(Ps[e] - Psn[e])); pmax = fmax(pmax, fabs(Ps[e]));
+          }
+          dmax = w_max(dmax); pmax = w_max(pmax);
+          DFM_WSYNC();
+          bool conv = frozen && t > lo && dmax <= eps * pmax;
+          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) Psn[e] = Ps[e];
+          DFM_WSYNC();
+          if (conv) {
+            tb = t;
+            double cnt = (double)(t - lo);
+            w_gemm<R>(T1, Ps, false, Jinf, true);
+            for (int e = DFM_LANE; e < RR; e += DFM_WSZ) {
+              SPall[e] += cnt * Ps[e]; SP00[e] += cnt * Ps[e];
+              SPff2[e] += ((lo >= 1) ? cnt : cnt - 1.0) * Ps[e];
+              SP11[e] += cnt * T1[e];
+              Ppinf[e] = Ps[e];                                  // Ps_inf (smoothed covariance of the frozen range)
+            }
+            DFM_WSYNC();
+            t = lo - 1;
+          } else --t;
+        }
+        if (DFM_LANE == 0) ctl[1] = tb;
+#ifndef DFM_EMU
+        if (a.phase_cycles && DFM_LANE == 0) a.phase_cycles[(size_t)blockIdx.x * DFM_PH + 13] += clock64() - c1_;
+#endif
+#ifdef DFM_EMU
+        if (getenv("DFM_DEBUG_CHAIN")) printf("[chain] b=%d it=%d nE=%d frozen=%d tb=%d (T=%d)\n", b, it, nE, frozen, tb, T);
+#endif
+        DFM_WSYNC();
+      };
       // ---------------------------------------------------------------- P1: E-step contraction (panel pass 1)
       double qacc = 0.0;
 #ifdef DFM_EMU
@@ -307,242 +479,13 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
         else if (DFM_WARP <= F2_NCW) { qacc += f2_consume_E<R>(rg, DFM_WARP - 1, T, N, Tp, Np, Z, Lam, rinv); if (DFM_WARP == 1) F2_ROLE_T1(15); }
         else {
           rg.skip(nitems);                                                   // keep the ring position in step
-        {   // ---- covariance chain (data independent), on the chain warp, concurrently with the E pass
-        int* bad = &ctl[2];
-        // forward
-        for (int e = DFM_LANE; e < RR; e += DFM_WSZ) { int i = e / R, j = e % R; Pp[e] = a.P0[(size_t)b * RR + i + R * j]; }
-        DFM_WSYNC();
-        int nE = T, frozen_at = -1, t = 0;
-#ifndef DFM_EMU
-        long long c0_ = clock64();
-#endif
-        while (t < T) {
-          double ldp = w_inv<R>(Pi, Pp, tmp, bad);
-          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) Wm[e] = Pi[e] + C[e];
-          DFM_WSYNC();
-          double ldw = w_inv<R>(Pf, Wm, tmp, bad);
-          w_gemm<R>(G, Pf, false, Pi, false);
-          w_gemm<R>(Phi, G, false, M, false);
-          if (t >= 1) { w_gemm<R>(T1, Pfprev, false, M, true); w_gemm<R>(Jm, T1, false, Pi, false); }   // J_{t-1}
-          w_gemm<R>(T1, M, false, Pf, false);
-          w_gemm<R>(Pn, T1, false, M, true);
-          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) Pn[e] += Q[e];
-          DFM_WSYNC();
-          w_sym<R>(Pn);
-          double* s_ = GSC(t);
-          double dmax = 0.0, pmax = 0.0;
-          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) {
-            s_[e] = Pf[e]; s_[RR + e] = Phi[e]; s_[3 * RR + e] = Wm[e];
-            if (t >= 1) GSC(t - 1)[2 * RR + e] = Jm[e];
-            dmax = fmax(dmax, fabs(Pn[e] - Pp[e])); pmax = fmax(pmax, fabs(Pp[e]));
-            Pfprev[e] = Pf[e];
-          }
-          if (DFM_LANE == 0) s_[5 * RR] = ldp + ldw;
-          dmax = w_max(dmax); pmax = w_max(pmax);
-          DFM_WSYNC();
-          if (frozen_at >= 0 && t == frozen_at + 1) {
-            nE = t + 1;
-            for (int e = DFM_LANE; e < RR; e += DFM_WSZ) { Pfinf[e] = Pf[e]; Phinf[e] = Phi[e]; Winf[e] = Wm[e]; }
-            if (DFM_LANE == 0) scal[1] = ldp + ldw;
-            DFM_WSYNC();
-            w_gemm<R>(T1, Pf, false, M, true);
-            w_gemm<R>(Jinf, T1, false, Pi, false);                 // J_inf = Pf_inf M' Pi_inf
-            break;
-          }
-          if (frozen_at < 0 && dmax <= eps * pmax) frozen_at = t;
-          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) Pp[e] = Pn[e];
-          DFM_WSYNC();
-          ++t;
-        }
-        const int frozen = nE < T;
-#ifndef DFM_EMU
-        long long c1_ = clock64();
-#endif
-        // backward covariance chain + covariance parts of the moment sums
-        for (int e = DFM_LANE; e < RR; e += DFM_WSZ) {
-          double v = frozen ? Pfinf[e] : (GSC(T - 1))[e];
-          Psn[e] = v; SPall[e] = v; SPff2[e] = v; SP00[e] = 0.0; SP11[e] = 0.0;
-          GPS(T - 1)[e] = v;
-        }
-        DFM_WSYNC();
-        const int lo = frozen ? nE - 1 : T;
-        int tb = -1;                        // frozen smoothed range is [lo, tb)
-        t = T - 2;
-        while (t >= 0) {
-          const double* pf_t = (t < nE) ? GSC(t) : Pfinf;
-          const double* j_t = (t < nE - 1) ? GSC(t) + 2 * RR : Jinf;
-          // Pp_{t+1} = M Pf_t M' + Q (recomputed: cheaper than storing)
-          w_gemm<R>(T1, M, false, pf_t, false);
-          w_gemm<R>(T2, T1, false, M, true);
-          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) T2[e] = Psn[e] - (T2[e] + Q[e]);
-          DFM_WSYNC();
-          w_sym<R>(T2);                                           // D = Ps_{t+1} - Pp_{t+1}
-          w_gemm<R>(T1, j_t, false, T2, false);
-          w_gemm<R>(Ps, T1, false, j_t, true);
-          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) Ps[e] += pf_t[e];
-          DFM_WSYNC();
-          w_sym<R>(Ps);
-          w_gemm<R>(T1, Psn, false, j_t, true);                    // Ps_{t+1} J_t'
-          double dmax = 0.0, pmax = 0.0;
-          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) {
-            SP11[e] += T1[e]; SPall[e] += Ps[e]; SP00[e] += Ps[e];
-            if (t >= 1) SPff2[e] += Ps[e];
-            GPS(t)[e] = Ps[e];
-            dmax = fmax(dmax, fabs(Ps[e] - Psn[e])); pmax = fmax(pmax, fabs(Ps[e]));
-          }
-          dmax = w_max(dmax); pmax = w_max(pmax);
-          DFM_WSYNC();
-          bool conv = frozen && t > lo && dmax <= eps * pmax;
-          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) Psn[e] = Ps[e];
-          DFM_WSYNC();
-          if (conv) {
-            tb = t;
-            double cnt = (double)(t - lo);
-            w_gemm<R>(T1, Ps, false, Jinf, true);
-            for (int e = DFM_LANE; e < RR; e += DFM_WSZ) {
-              SPall[e] += cnt * Ps[e]; SP00[e] += cnt * Ps[e];
-              SPff2[e] += ((lo >= 1) ? cnt : cnt - 1.0) * Ps[e];
-              SP11[e] += cnt * T1[e];
-              Ppinf[e] = Ps[e];                                  // Ps_inf (smoothed covariance of the frozen range)
-            }
-            DFM_WSYNC();
-            t = lo - 1;
-          } else --t;
-        }
-        if (DFM_LANE == 0) { ctl[0] = nE; ctl[1] = tb; ctl[3] = frozen; }
-#ifndef DFM_EMU
-        if (a.phase_cycles && DFM_LANE == 0) { long long c2_ = clock64(); a.phase_cycles[(size_t)blockIdx.x * DFM_PH + 12] += c1_ - c0_; a.phase_cycles[(size_t)blockIdx.x * DFM_PH + 13] += c2_ - c1_; }
-#endif
-#ifdef DFM_EMU
-        if (getenv("DFM_DEBUG_CHAIN")) printf("[chain] b=%d it=%d nE=%d frozen=%d tb=%d (T=%d)\n", b, it, nE, frozen, tb, T);
-#endif
-        // I - J_inf M  (for the parallel pre-pass of the backward mean recursion)
-        if (frozen) {
-          w_gemm<R>(IJM, Jinf, false, M, false);
-          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) { int i = e / R, j = e % R; IJM[e] = ((i == j) ? 1.0 : 0.0) - IJM[e]; }
-        }
-        DFM_WSYNC();
-      }
+          chain_fwd();
         }
       }
 #endif
 #ifdef DFM_EMU
-        {   // ---- covariance chain (data independent), on the chain warp, concurrently with the E pass
-        int* bad = &ctl[2];
-        // forward
-        for (int e = DFM_LANE; e < RR; e += DFM_WSZ) { int i = e / R, j = e % R; Pp[e] = a.P0[(size_t)b * RR + i + R * j]; }
-        DFM_WSYNC();
-        int nE = T, frozen_at = -1, t = 0;
-#ifndef DFM_EMU
-        long long c0_ = clock64();
-#endif
-        while (t < T) {
-          double ldp = w_inv<R>(Pi, Pp, tmp, bad);
-          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) Wm[e] = Pi[e] + C[e];
-          DFM_WSYNC();
-          double ldw = w_inv<R>(Pf, Wm, tmp, bad);
-          w_gemm<R>(G, Pf, false, Pi, false);
-          w_gemm<R>(Phi, G, false, M, false);
-          if (t >= 1) { w_gemm<R>(T1, Pfprev, false, M, true); w_gemm<R>(Jm, T1, false, Pi, false); }   // J_{t-1}
-          w_gemm<R>(T1, M, false, Pf, false);
-          w_gemm<R>(Pn, T1, false, M, true);
-          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) Pn[e] += Q[e];
-          DFM_WSYNC();
-          w_sym<R>(Pn);
-          double* s_ = GSC(t);
-          double dmax = 0.0, pmax = 0.0;
-          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) {
-            s_[e] = Pf[e]; s_[RR + e] = Phi[e]; s_[3 * RR + e] = Wm[e];
-            if (t >= 1) GSC(t - 1)[2 * RR + e] = Jm[e];
-            dmax = fmax(dmax, fabs(Pn[e] - Pp[e])); pmax = fmax(pmax, fabs(Pp[e]));
-            Pfprev[e] = Pf[e];
-          }
-          if (DFM_LANE == 0) s_[5 * RR] = ldp + ldw;
-          dmax = w_max(dmax); pmax = w_max(pmax);
-          DFM_WSYNC();
-          if (frozen_at >= 0 && t == frozen_at + 1) {
-            nE = t + 1;
-            for (int e = DFM_LANE; e < RR; e += DFM_WSZ) { Pfinf[e] = Pf[e]; Phinf[e] = Phi[e]; Winf[e] = Wm[e]; }
-            if (DFM_LANE == 0) scal[1] = ldp + ldw;
-            DFM_WSYNC();
-            w_gemm<R>(T1, Pf, false, M, true);
-            w_gemm<R>(Jinf, T1, false, Pi, false);                 // J_inf = Pf_inf M' Pi_inf
-            break;
-          }
-          if (frozen_at < 0 && dmax <= eps * pmax) frozen_at = t;
-          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) Pp[e] = Pn[e];
-          DFM_WSYNC();
-          ++t;
-        }
-        const int frozen = nE < T;
-#ifndef DFM_EMU
-        long long c1_ = clock64();
-#endif
-        // backward covariance chain + covariance parts of the moment sums
-        for (int e = DFM_LANE; e < RR; e += DFM_WSZ) {
-          double v = frozen ? Pfinf[e] : (GSC(T - 1))[e];
-          Psn[e] = v; SPall[e] = v; SPff2[e] = v; SP00[e] = 0.0; SP11[e] = 0.0;
-          GPS(T - 1)[e] = v;
-        }
-        DFM_WSYNC();
-        const int lo = frozen ? nE - 1 : T;
-        int tb = -1;                        // frozen smoothed range is [lo, tb)
-        t = T - 2;
-        while (t >= 0) {
-          const double* pf_t = (t < nE) ? GSC(t) : Pfinf;
-          const double* j_t = (t < nE - 1) ? GSC(t) + 2 * RR : Jinf;
-          // Pp_{t+1} = M Pf_t M' + Q (recomputed: cheaper than storing)
-          w_gemm<R>(T1, M, false, pf_t, false);
-          w_gemm<R>(T2, T1, false, M, true);
-          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) T2[e] = Psn[e] - (T2[e] + Q[e]);
-          DFM_WSYNC();
-          w_sym<R>(T2);                                           // D = Ps_{t+1} - Pp_{t+1}
-          w_gemm<R>(T1, j_t, false, T2, false);
-          w_gemm<R>(Ps, T1, false, j_t, true);
-          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) Ps[e] += pf_t[e];
-          DFM_WSYNC();
-          w_sym<R>(Ps);
-          w_gemm<R>(T1, Psn, false, j_t, true);                    // Ps_{t+1} J_t'
-          double dmax = 0.0, pmax = 0.0;
-          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) {
-            SP11[e] += T1[e]; SPall[e] += Ps[e]; SP00[e] += Ps[e];
-            if (t >= 1) SPff2[e] += Ps[e];
-            GPS(t)[e] = Ps[e];
-            dmax = fmax(dmax, fabs(Ps[e] - Psn[e])); pmax = fmax(pmax, fabs(Ps[e]));
-          }
-          dmax = w_max(dmax); pmax = w_max(pmax);
-          DFM_WSYNC();
-          bool conv = frozen && t > lo && dmax <= eps * pmax;
-          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) Psn[e] = Ps[e];
-          DFM_WSYNC();
-          if (conv) {
-            tb = t;
-            double cnt = (double)(t - lo);
-            w_gemm<R>(T1, Ps, false, Jinf, true);
-            for (int e = DFM_LANE; e < RR; e += DFM_WSZ) {
-              SPall[e] += cnt * Ps[e]; SP00[e] += cnt * Ps[e];
-              SPff2[e] += ((lo >= 1) ? cnt : cnt - 1.0) * Ps[e];
-              SP11[e] += cnt * T1[e];
-              Ppinf[e] = Ps[e];                                  // Ps_inf (smoothed covariance of the frozen range)
-            }
-            DFM_WSYNC();
-            t = lo - 1;
-          } else --t;
-        }
-        if (DFM_LANE == 0) { ctl[0] = nE; ctl[1] = tb; ctl[3] = frozen; }
-#ifndef DFM_EMU
-        if (a.phase_cycles && DFM_LANE == 0) { long long c2_ = clock64(); a.phase_cycles[(size_t)blockIdx.x * DFM_PH + 12] += c1_ - c0_; a.phase_cycles[(size_t)blockIdx.x * DFM_PH + 13] += c2_ - c1_; }
-#endif
-#ifdef DFM_EMU
-        if (getenv("DFM_DEBUG_CHAIN")) printf("[chain] b=%d it=%d nE=%d frozen=%d tb=%d (T=%d)\n", b, it, nE, frozen, tb, T);
-#endif
-        // I - J_inf M  (for the parallel pre-pass of the backward mean recursion)
-        if (frozen) {
-          w_gemm<R>(IJM, Jinf, false, M, false);
-          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) { int i = e / R, j = e % R; IJM[e] = ((i == j) ? 1.0 : 0.0) - IJM[e]; }
-        }
-        DFM_WSYNC();
-      }
+      chain_fwd();
+      chain_bwd();
 #endif
       DFM_SYNC();
       {   // explicit covariance steps: global scratch -> (now idle) ring, one cooperative copy
@@ -556,9 +499,17 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
       DFM_SYNC();
       const int nE = ctl[0], frozen = ctl[3];
       DFM_TICK(3);
+#ifndef DFM_EMU
+      long long sub_ = a.phase_cycles ? clock64() : 0;
+#endif
+#ifndef DFM_EMU
+      if (DFM_WARP == F2_NCW + 1) chain_bwd();                 // warp 7: backward covariance chain, concurrently with P3-P5 on warps 0..6
+      else
+#endif
+      {
       // ---------------------------------------------------------------- P3: forward means
       // parallel pre-pass over the frozen range: Z[t] <- Pf_inf b_t
-      for (int t = nE + DFM_TID; t < T; t += DFM_NT) {
+      for (int t = nE + F2_PTID; t < T; t += F2_PNT) {
         double bb[R], u[R];
 #pragma unroll
         for (int j = 0; j < R; ++j) bb[j] = Z[ZI(t, j)];
@@ -569,7 +520,8 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
 #pragma unroll
         for (int i = 0; i < R; ++i) Z[ZI(t, i)] = u[i];
       }
-      DFM_SYNC();
+      F2_PSYNC();
+      F2_SUB(20);
       if (DFM_WARP == 0) {
         // explicit steps
         for (int t = 0; t < nE; ++t) {
@@ -585,13 +537,70 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
           DFM_WSYNC();
         }
       }
-      DFM_SYNC();
+      F2_PSYNC();
+      F2_SUB(21);
       // frozen steps: z_t = Phi_inf z_{t-1} + u_t, parallel in time over the CTA
-      if (frozen) blk_recur<R>(Z, Tp, Phinf, T1, T2, bnd, (nE > 0 ? nE : 1), T - (nE > 0 ? nE : 1), +1, 32);
+      if (frozen) blk_recur<R>(Z, Tp, Phinf, Pp, Pi, bnd, (nE > 0 ? nE : 1), T - (nE > 0 ? nE : 1), +1, F2_PNT_GPU, F2_SUBP(22));
       DFM_TICK(4);
-      // ---------------------------------------------------------------- P4: log-likelihood (parallel over t)
+      // ---------------------------------------------------------------- P4: log-likelihood
+      // innovation form: ll_t = -1/2 (N log 2pi + sum log R + ld_t + quad_t),
+      //   quad_t = -(zp'C zp + 2 zp'W d + d'W d),  zp = M zf_{t-1}, d = zf_t - zp,  W = Pi + C
+      // which collapses to  quad_t = zf_{t-1}' K zf_{t-1} - zf_t' W zf_t  with K = M'(W - C) M.  Over the frozen
+      // range (W, K constant) the sum only needs the second-moment matrix of the filtered means:
+      //   sum_t quad_t = tr(K (Gf + z_{nE-1} z_{nE-1}' - z_{T-1} z_{T-1}')) - tr(W Gf),   Gf = sum_{t>=nE} zf_t zf_t'.
       double llp = 0.0;
-      for (int t = DFM_TID; t < T; t += DFM_NT) {
+      const bool gram = frozen && nE >= 1 && nE < T;
+      const int tex = gram ? nE : T;                         // periods handled one by one
+      if (gram) {
+        double* gp = bnd;                                    // [F2_GPARTS][RR] partial Gram sums, then K (scan workspace is idle)
+#ifndef DFM_EMU
+        if (R == 8) {
+          // Gram matrix on the FP64 tensor path: D[8x8] += Zc Zc' for 4-period chunks; the A and the B fragment of
+          // DMMA.8x8x4 are the same register (A[i][k] = B[k][i] = z_i(t0 + k)); warp w takes chunks w, w+7, ...
+          const int lr = DFM_LANE >> 2, lc = DFM_LANE & 3;
+          const double* zr = Z + (size_t)lr * Tp;
+          double g0 = 0.0, g1 = 0.0, h0 = 0.0, h1 = 0.0;
+          for (int t0 = nE + 4 * DFM_WARP; t0 < T; t0 += 8 * (F2_NCW + 1)) {
+            const int ta = t0 + lc, tb_ = t0 + 4 * (F2_NCW + 1) + lc;
+            const double va = (ta < T) ? zr[ta] : 0.0, vb = (tb_ < T) ? zr[tb_] : 0.0;
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(g0), "+d"(g1) : "d"(va), "d"(va));
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(h0), "+d"(h1) : "d"(vb), "d"(vb));
+          }
+          gp[DFM_WARP * 64 + 2 * DFM_LANE] = g0 + h0; gp[DFM_WARP * 64 + 2 * DFM_LANE + 1] = g1 + h1;     // element (lr, 2 lc), (lr, 2 lc + 1)
+        } else
+#endif
+        {
+          const int nfz = T - nE, q4 = (nfz + F2_GPARTS_S - 1) / F2_GPARTS_S;
+          for (int e = F2_PTID; e < F2_GPARTS * RR; e += F2_PNT) {
+            const int q = e / RR, ee = e % RR, i = ee / R, jj = ee % R;
+            double s0_ = 0.0, s1_ = 0.0;
+            if (q < F2_GPARTS_S) {
+              const int lo = nE + q * q4, hi = (lo + q4 < T) ? lo + q4 : T;
+              int t = lo;
+              for (; t + 1 < hi; t += 2) { s0_ += Z[ZI(t, i)] * Z[ZI(t, jj)]; s1_ += Z[ZI(t + 1, i)] * Z[ZI(t + 1, jj)]; }
+              if (t < hi) s0_ += Z[ZI(t, i)] * Z[ZI(t, jj)];
+            }
+            gp[e] = s0_ + s1_;
+          }
+        }
+        if (DFM_WARP == 0) {                                 // K = M'(W_inf - C) M on warp 0 meanwhile (T2 = W - C, T1 = T2 M)
+          for (int e = DFM_LANE; e < RR; e += DFM_WSZ) Wm[e] = Winf[e] - C[e];     // (Wm, G: forward-chain temporaries, idle now;
+          DFM_WSYNC();                                                             //  T1/T2 belong to the backward chain on warp 7)
+          w_gemm<R>(G, Wm, false, M, false);
+          w_gemm<R>(gp + F2_GPARTS * RR, M, true, G, false);
+        }
+        F2_PSYNC();
+        for (int e = F2_PTID; e < RR; e += F2_PNT) {
+          const int i = e / R, jj = e % R;
+          double gf = 0.0;
+#pragma unroll
+          for (int q = 0; q < F2_GPARTS; ++q) gf += gp[q * RR + e];
+          const double gs = gf + Z[ZI(nE - 1, i)] * Z[ZI(nE - 1, jj)] - Z[ZI(T - 1, i)] * Z[ZI(T - 1, jj)];
+          llp += -0.5 * (gp[F2_GPARTS * RR + e] * gs - Winf[e] * gf);
+        }
+        if (F2_PTID == 0) llp += -0.5 * (double)(T - nE) * ((double)N * 1.8378770664093454835606594728112 + scal[0] + scal[1]);
+      }
+      for (int t = F2_PTID; t < tex; t += F2_PNT) {
         const double* Wt = (t < nE) ? SCRP(t) + 3 * RR : Winf;
         double ldt = (t < nE) ? (SCRP(t))[5 * RR] : scal[1];
         double zp[R], d[R];
@@ -610,13 +619,21 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
         }
         llp += -0.5 * ((double)N * 1.8378770664093454835606594728112 + scal[0] + ldt + quad);
       }
-      llp = block_sum(llp, red);
-      const double ll = llp - 0.5 * scal[2];
+      {   // sum over the F2_PNT threads of this section (fixed order), result in scal[3]
+#ifndef DFM_EMU
+        for (int o = 16; o > 0; o >>= 1) llp += __shfl_down_sync(0xffffffffu, llp, o);
+        if (DFM_LANE == 0) red[DFM_WARP] = llp;
+        F2_PSYNC();
+        if (threadIdx.x == 0) { double s_ = 0.0; for (int w_ = 0; w_ <= F2_NCW; ++w_) s_ += red[w_]; scal[3] = s_ - 0.5 * scal[2]; }
+#else
+        scal[3] = llp - 0.5 * scal[2];
+#endif
+      }
       DFM_TICK(5);
       // ---------------------------------------------------------------- P5: backward means
       if (frozen) {
         int lo = nE - 1;
-        for (int t = lo + DFM_TID; t < T - 1; t += DFM_NT) {       // Z[t] <- (I - J_inf M) zf_t
+        for (int t = lo + F2_PTID; t < T - 1; t += F2_PNT) {       // Z[t] <- (I - J_inf M) zf_t
           double zz[R], v[R];
 #pragma unroll
           for (int j = 0; j < R; ++j) zz[j] = Z[ZI(t, j)];
@@ -628,9 +645,9 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
           for (int i = 0; i < R; ++i) Z[ZI(t, i)] = v[i];
         }
       }
-      DFM_SYNC();
+      F2_PSYNC();
       // frozen range: z_t = J_inf z_{t+1} + v_t, parallel in time over the CTA
-      if (frozen) blk_recur<R>(Z, Tp, Jinf, T1, T2, bnd, T - 2, (T - 2) - (nE - 1) + 1, -1, 32);
+      if (frozen) blk_recur<R>(Z, Tp, Jinf, Pp, Pi, bnd, T - 2, (T - 2) - (nE - 1) + 1, -1, F2_PNT_GPU, F2_SUBP(25));
       if (DFM_WARP == 0) {
         const int lo = frozen ? nE - 1 : T;
         // explicit range: zs_t = zf_t + J_t (zs_{t+1} - M zf_t)
@@ -644,7 +661,9 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
           DFM_WSYNC();
         }
       }
+      }
       DFM_SYNC();
+      const double ll = scal[3];
       DFM_TICK(6);
       DFM_TICK(7);
       // ---------------------------------------------------------------- P8: M-step contraction (panel pass 2)

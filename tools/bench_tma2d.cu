@@ -49,22 +49,26 @@ __global__ void __launch_bounds__(256) k_ring(const __grid_constant__ CUtensorMa
   for (int b = blockIdx.x; b < p.B; b += gridDim.x) ++npan;
   const long long total = (long long)npan * per_panel;
   double acc0 = 0.0, acc1 = 0.0;
+  // ring position tracked incrementally (no integer divisions on the critical path)
   if (warp < p.nprod) {
+    int slot = warp % p.S, turn = warp / p.S;
+    int pi = 0, r = warp;                       // panel index of this CTA, item within the panel
+    while (r >= per_panel) { r -= per_panel; ++pi; }
     for (long long it = warp; it < total; it += p.nprod) {
-      const int slot = (int)(it % p.S); const long long turn = it / p.S;
       if (turn > 0) mb_wait(&empty[slot], (uint32_t)((turn - 1) & 1));
       if (lane == 0) {
-        const int pi = (int)(it / per_panel), r = (int)(it % per_panel);
-        const int b = blockIdx.x + pi * gridDim.x, c = r / nsb, sb = r % nsb;
+        const int b = blockIdx.x + pi * gridDim.x, c = r / nsb, sb = r - c * nsb;
         mb_expect(&full[slot], (uint32_t)(stage * 8));
         tma2d(ring + (size_t)slot * stage, &tm, c * p.bc, b * p.N + sb * p.br, &full[slot]);
       }
       __syncwarp();
+      slot += p.nprod; while (slot >= p.S) { slot -= p.S; ++turn; }
+      r += p.nprod; while (r >= per_panel) { r -= per_panel; ++pi; }
     }
   } else if (warp < p.nprod + p.ncons) {
+    int slot = 0; uint32_t ph = 0;
     for (long long it = 0; it < total; ++it) {
-      const int slot = (int)(it % p.S); const long long turn = it / p.S;
-      mb_wait(&full[slot], (uint32_t)(turn & 1));
+      mb_wait(&full[slot], ph);
       const double* tile = ring + (size_t)slot * stage;
       for (int k = 0; k < p.work; k += 2) {
         double a0 = tile[((lane & 3) + (k & 4)) * p.bc + (lane >> 2) + 8 * (warp - p.nprod)];
@@ -77,6 +81,7 @@ __global__ void __launch_bounds__(256) k_ring(const __grid_constant__ CUtensorMa
       if (p.work == 0) acc0 += tile[lane];
       __syncwarp();
       if (lane == 0) mb_arrive(&empty[slot]);
+      if (++slot == p.S) { slot = 0; ph ^= 1; }
     }
   }
   if (acc0 + acc1 == 123.456) out[blockIdx.x] = acc0;

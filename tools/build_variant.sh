@@ -1,0 +1,6 @@
+#!/bin/bash
+# build a tuning variant of the library: tools/build_variant.sh NAME -DF2_TC=.. -DF2_S=..   -> tools/variants/libdfm_NAME.so
+cd /root/repo
+name=$1; shift
+nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr "$@" \
+  -shared dynamic_factor_models_b200/csrc/dfm_api.cu -o tools/variants/libdfm_$name.so -lcudart -ldl
