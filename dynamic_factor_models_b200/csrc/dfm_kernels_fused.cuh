@@ -185,17 +185,37 @@ DFM_HELPER double w_inv(double* Ai, const double* A, double* tmp, int* bad) {
   return log(pp);
 }
 
+// chunk length of the parallel-in-time scan for n steps on ng 8-lane groups: odd (the 4 groups of a warp then hit
+// different banks) and at most ng chunks
+__device__ __forceinline__ int blk_chunk_len(int n, int ng) {
+  int Lc = (n + ng - 1) / ng;
+  if (Lc > 1 && !(Lc & 1)) Lc += 1;
+  return Lc;
+}
+
+// pw <- Cf^ex by binary exponentiation (one warp; base, pw2: R*R scratch each)
+template <int R>
+__device__ __forceinline__ void w_matpow(double* pw, const double* Cf, int ex0, double* base, double* pw2) {
+  for (int e = DFM_LANE; e < R * R; e += DFM_WSZ) { int i = e / R, j = e % R; pw[e] = (i == j) ? 1.0 : 0.0; base[e] = Cf[e]; }
+  DFM_WSYNC();
+  for (int ex = ex0; ex > 0; ex >>= 1) {
+    if (ex & 1) { w_gemm<R>(pw2, pw, false, base, false); for (int e = DFM_LANE; e < R * R; e += DFM_WSZ) pw[e] = pw2[e]; DFM_WSYNC(); }
+    if (ex > 1) { w_gemm<R>(pw2, base, false, base, false); for (int e = DFM_LANE; e < R * R; e += DFM_WSZ) base[e] = pw2[e]; DFM_WSYNC(); }
+  }
+}
+
 // Constant-coefficient linear recursion  Z[t] <- Cf Z[t - dir] + Z[t],  t = t0, t0+dir, ... (n steps),
-// parallel in time over the whole CTA: the n steps are cut into chunks of Lc (a power of two)
+// parallel in time over nthr threads of the CTA: the n steps are cut into chunks of Lc = blk_chunk_len(n, nthr/8)
 // owned by 8-lane groups (lane = state component, coefficient row in registers);
 //   pass 1  every chunk runs the recursion from a zero state (chunk 0 from the true state),
 //   bound   one group propagates the true chunk-end states with Cf^Lc (pw, by repeated squaring),
 //   pass 2  every chunk adds Cf^(s+1) * (true state entering the chunk).
 // Exact up to rounding (linear recurrence).  Called by ALL threads; ends with a block barrier.
-// smem: pw, pw2 [R*R], bnd [(chunks+1) * R].  Requires blockDim = 128 (16 groups) on the GPU.
+// smem: pw, pw2 [R*R], bnd [(3 ng + 1) R + R R].  pw_ready: pw already holds Cf^Lc (computed elsewhere, e.g. by the
+// chain warp of k_em_fused2 while the panel streams); otherwise warp 0 computes it here.
 template <int R>
 __device__ __forceinline__ void blk_recur(double* Z, int Tp, const double* Cf, double* pw, double* pw2, double* bnd, int t0, int n, int dir, int nthr,
-                                          long long* prof = nullptr) {
+                                          long long* prof = nullptr, bool pw_ready = false) {
   if (n <= 0) return;
   // nthr = number of threads taking part (threads 0 .. nthr-1 of the CTA, a multiple of 32); they synchronise
   // on named barrier 2, so the remaining warps of the CTA may do something else meanwhile
@@ -213,19 +233,9 @@ __device__ __forceinline__ void blk_recur(double* Z, int Tp, const double* Cf, d
 #endif
   // ng = number of 8-lane groups of the CTA (blockDim / 8).  chunk length: odd (=> the 4 groups of a
   // warp hit different banks) and at most ng chunks.  bnd: [(3 ng + 1) R + R R] doubles.
-  int Lc = (n + ng - 1) / ng;
-  if (Lc > 1 && !(Lc & 1)) Lc += 1;
+  const int Lc = blk_chunk_len(n, ng);
   const int nch = (n + Lc - 1) / Lc;
-  // pw = Cf^Lc by binary exponentiation (warp 0; a handful of r x r products); bnd[0..R*R) is scratch
-  if (DFM_WARP == 0 && nch > 1) {
-    double* base = bnd + (size_t)(3 * ng + 1) * R;                // R*R scratch beyond the boundary + ping-pong vectors
-    for (int e = DFM_LANE; e < R * R; e += DFM_WSZ) { int i = e / R, j = e % R; pw[e] = (i == j) ? 1.0 : 0.0; base[e] = Cf[e]; }
-    DFM_WSYNC();
-    for (int ex = Lc; ex > 0; ex >>= 1) {
-      if (ex & 1) { w_gemm<R>(pw2, pw, false, base, false); for (int e = DFM_LANE; e < R * R; e += DFM_WSZ) pw[e] = pw2[e]; DFM_WSYNC(); }
-      if (ex > 1) { w_gemm<R>(pw2, base, false, base, false); for (int e = DFM_LANE; e < R * R; e += DFM_WSZ) base[e] = pw2[e]; DFM_WSYNC(); }
-    }
-  }
+  if (DFM_WARP == 0 && nch > 1 && !pw_ready) w_matpow<R>(pw, Cf, Lc, bnd + (size_t)(3 * ng + 1) * R, pw2);   // scratch beyond the boundary vectors
   // ---- pass 1
 #ifdef DFM_EMU
   for (int g = 0; g < nch; ++g) {

@@ -389,6 +389,12 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
         if (frozen) {
           w_gemm<R>(IJM, Jinf, false, M, false);
           for (int e = DFM_LANE; e < RR; e += DFM_WSZ) { int i = e / R, j = e % R; IJM[e] = ((i == j) ? 1.0 : 0.0) - IJM[e]; }
+          DFM_WSYNC();
+          // chunk-length powers of the two scan matrices (P3: Phi_inf, P5: J_inf), off the critical path of P3/P5.
+          // Phi and Pn are free from here until the M-step solves; T1/T2 serve as scratch.
+          const int n3 = T - (nE > 0 ? nE : 1), n5 = (T - 2) - (nE - 1) + 1;
+          if (n3 > 0) w_matpow<R>(Phi, Phinf, blk_chunk_len(n3, F2_PNT_GPU / 8), T1, T2);
+          if (n5 > 0) w_matpow<R>(Pn, Jinf, blk_chunk_len(n5, F2_PNT_GPU / 8), T1, T2);
         }
         DFM_WSYNC();
       };
@@ -540,7 +546,7 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
       F2_PSYNC();
       F2_SUB(21);
       // frozen steps: z_t = Phi_inf z_{t-1} + u_t, parallel in time over the CTA
-      if (frozen) blk_recur<R>(Z, Tp, Phinf, Pp, Pi, bnd, (nE > 0 ? nE : 1), T - (nE > 0 ? nE : 1), +1, F2_PNT_GPU, F2_SUBP(22));
+      if (frozen) blk_recur<R>(Z, Tp, Phinf, Phi, Pi, bnd, (nE > 0 ? nE : 1), T - (nE > 0 ? nE : 1), +1, F2_PNT_GPU, F2_SUBP(22), true);
       DFM_TICK(4);
       // ---------------------------------------------------------------- P4: log-likelihood
       // innovation form: ll_t = -1/2 (N log 2pi + sum log R + ld_t + quad_t),
@@ -550,7 +556,10 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
       //   sum_t quad_t = tr(K (Gf + z_{nE-1} z_{nE-1}' - z_{T-1} z_{T-1}')) - tr(W Gf),   Gf = sum_{t>=nE} zf_t zf_t'.
       double llp = 0.0;
       const bool gram = frozen && nE >= 1 && nE < T;
-      const int tex = gram ? nE : T;                         // periods handled one by one
+      // explicit periods t < nE: one thread per (t, component) in two stages when their (zp, d) vectors fit
+      // in the idle scan workspace; otherwise (and for a chain that never froze) one thread per period
+      const bool split = gram && 2 * nE * R <= (97 * R + RR) - (F2_GPARTS + 1) * RR;
+      const int tex = gram ? (split ? 0 : nE) : T;           // periods handled one thread each
       if (gram) {
         double* gp = bnd;                                    // [F2_GPARTS][RR] partial Gram sums, then K (scan workspace is idle)
 #ifndef DFM_EMU
@@ -583,6 +592,18 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
             gp[e] = s0_ + s1_;
           }
         }
+        if (split) {                                         // stage A: zp = M zf_{t-1}, d = zf_t - zp
+          double* zd = gp + (F2_GPARTS + 1) * RR;
+          for (int e = F2_PTID; e < nE * R; e += F2_PNT) {
+            const int t = e / R, i = e % R;
+            double s_ = 0.0;
+            if (t >= 1) {
+#pragma unroll
+              for (int j = 0; j < R; ++j) s_ += M[i * R + j] * Z[ZI(t - 1, j)];
+            }
+            zd[2 * e] = s_; zd[2 * e + 1] = Z[ZI(t, i)] - s_;
+          }
+        }
         if (DFM_WARP == 0) {                                 // K = M'(W_inf - C) M on warp 0 meanwhile (T2 = W - C, T1 = T2 M)
           for (int e = DFM_LANE; e < RR; e += DFM_WSZ) Wm[e] = Winf[e] - C[e];     // (Wm, G: forward-chain temporaries, idle now;
           DFM_WSYNC();                                                             //  T1/T2 belong to the backward chain on warp 7)
@@ -599,6 +620,20 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
           llp += -0.5 * (gp[F2_GPARTS * RR + e] * gs - Winf[e] * gf);
         }
         if (F2_PTID == 0) llp += -0.5 * (double)(T - nE) * ((double)N * 1.8378770664093454835606594728112 + scal[0] + scal[1]);
+        if (split) {                                         // stage B: row i of  zp'C zp + 2 zp'W_t d + d'W_t d
+          const double* zd = gp + (F2_GPARTS + 1) * RR;
+          for (int e = F2_PTID; e < nE * R; e += F2_PNT) {
+            const int t = e / R, i = e % R;
+            const double* Wt = SCRP(t) + 3 * RR;
+            const double* zt = zd + 2 * (size_t)t * R;
+            double cz = 0.0, g = 0.0;
+#pragma unroll
+            for (int j = 0; j < R; ++j) { cz += C[i * R + j] * zt[2 * j]; g += Wt[i * R + j] * zt[2 * j + 1]; }
+            const double zpi = zt[2 * i], di = zt[2 * i + 1];
+            llp += 0.5 * (zpi * cz + 2.0 * zpi * g + g * di);
+            if (i == 0) llp += -0.5 * ((double)N * 1.8378770664093454835606594728112 + scal[0] + (SCRP(t))[5 * RR]);
+          }
+        }
       }
       for (int t = F2_PTID; t < tex; t += F2_PNT) {
         const double* Wt = (t < nE) ? SCRP(t) + 3 * RR : Winf;
@@ -647,7 +682,7 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
       }
       F2_PSYNC();
       // frozen range: z_t = J_inf z_{t+1} + v_t, parallel in time over the CTA
-      if (frozen) blk_recur<R>(Z, Tp, Jinf, Pp, Pi, bnd, T - 2, (T - 2) - (nE - 1) + 1, -1, F2_PNT_GPU, F2_SUBP(25));
+      if (frozen) blk_recur<R>(Z, Tp, Jinf, Pn, Pi, bnd, T - 2, (T - 2) - (nE - 1) + 1, -1, F2_PNT_GPU, F2_SUBP(25), true);
       if (DFM_WARP == 0) {
         const int lo = frozen ? nE - 1 : T;
         // explicit range: zs_t = zf_t + J_t (zs_{t+1} - M zf_t)

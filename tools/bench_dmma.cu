@@ -30,7 +30,11 @@ __global__ void k(int iters, double* out, long long* cyc) {
         asm volatile("mma.sync.aligned.m16n8k16.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7,%8,%9,%10,%11}, {%12,%13,%14,%15}, {%0,%1,%2,%3};"
                      : "+d"(d[j][0]), "+d"(d[j][1]), "+d"(d[j][2]), "+d"(d[j][3])
                      : "d"(a0), "d"(a1), "d"(a2), "d"(a3), "d"(a4), "d"(a5), "d"(a6), "d"(a7), "d"(b0), "d"(b1), "d"(b2), "d"(b3));
-      else { d[j][0] = fma(a0, b0, d[j][0]); d[j][1] = fma(a1, b1, d[j][1]); d[j][2] = fma(a2, b2, d[j][2]); d[j][3] = fma(a3, b3, d[j][3]); }
+      else if (SHAPE == 4) { d[j][0] = fma(a0, b0, d[j][0]); d[j][1] = fma(a1, b1, d[j][1]); d[j][2] = fma(a2, b2, d[j][2]); d[j][3] = fma(a3, b3, d[j][3]); }
+      else if (SHAPE == 5) { d[j][0] = fma(a0, b0, d[j][0]); }                       // one dependent DFMA chain
+      else if (SHAPE == 6) { d[j][0] = d[j][0] + a0; }                               // one dependent DADD chain
+      else if (SHAPE == 7) { d[j][0] = __shfl_sync(0xffffffffu, d[j][0], (threadIdx.x + 1) & 7, 8); }   // 64-bit shuffle chain
+      else if (SHAPE == 8) { d[j][0] = d[j][0] * b0; }                               // DMUL chain
     }
   }
   long long t1 = clock64();
@@ -58,6 +62,8 @@ void run(const char* name, double fma_per_op, int warps) {
 }
 
 int main() {
+  run<5, 1>("DFMA dependent chain", 32, 4); run<6, 1>("DADD dependent chain", 32, 4); run<8, 1>("DMUL dependent chain", 32, 4);
+  run<7, 1>("SHFL.64 dependent chain", 32, 4); run<5, 1>("DFMA dep chain, 16 warps", 32, 16);
   for (int w : {4, 8, 16}) {
     if (w == 4) { run<0, 1>("DMMA m8n8k4 (dep chain)", 256, 4); run<3, 1>("DMMA m16n8k16 (dep chain)", 2048, 4); }
     if (w == 4) { run<0, 8>("DMMA m8n8k4", 256, 4); run<1, 8>("DMMA m16n8k4", 512, 4); run<2, 8>("DMMA m16n8k8", 1024, 4); run<3, 8>("DMMA m16n8k16", 2048, 4); run<4, 8>("DFMA x4 per lane", 128, 4); }
