@@ -299,7 +299,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu:
         from oracle.c import kem
         cores = os.cpu_count() or kem.max_threads()
-        Bs = min(B, 4 * cores)
+        Bs = min(B, 8 * cores)                       # ~10 s of CPU work on the 128-thread box
         Lh = lambda t, rows, cols: np.ascontiguousarray(t[:Bs * rows * cols].cpu().numpy().reshape(Bs, cols, rows).transpose(0, 2, 1))
         init = (Lh(dLam0, NS, R_), dR0[:Bs * NS].cpu().numpy().reshape(Bs, NS), Lh(dA0, R_, k), Lh(dQ0, R_, R_))
         cpu_em(Xh[:2], tuple(a[:2] for a in init), 2, nthreads=cores)

@@ -318,6 +318,26 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
       DFM_SYNC();
       {   // C = Lam' R^-1 Lam: RR outputs x (NT / RR) slices of the series range, combined in fixed order
         const int nsl = (DFM_NT >= 4 * RR) ? 4 : 1;
+#ifndef DFM_EMU
+        if (R == 8) {
+          // tensor path: C = (Lam .* rinv)' Lam as DMMA.8x8x4 over 4-series chunks; the B fragment is the Lam value the
+          // A fragment is built from.  Warps 0..3 produce the nsl = 4 partial tiles (chunks w, w+4, w+8, ...).
+          if (DFM_WARP < 4) {
+            const int lr = DFM_LANE >> 2, lc = DFM_LANE & 3;
+            const double* lrow = Lam + (size_t)lr * Np;
+            double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+            for (int ch = DFM_WARP; 4 * ch < N; ch += 8) {
+              const int na = 4 * ch + lc, nb = 4 * (ch + 4) + lc;
+              const double la = (na < N) ? lrow[na] : 0.0, ra = (na < N) ? rinv[na] : 0.0;
+              const double lb = (nb < N) ? lrow[nb] : 0.0, rb = (nb < N) ? rinv[nb] : 0.0;
+              const double aa = la * ra, ab = lb * rb;
+              asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(aa), "d"(la));
+              asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(e0), "+d"(e1) : "d"(ab), "d"(lb));
+            }
+            T1[DFM_WARP * RR + 2 * DFM_LANE] = c0 + e0; T1[DFM_WARP * RR + 2 * DFM_LANE + 1] = c1 + e1;
+          }
+        } else
+#endif
         for (int e = DFM_TID; e < nsl * RR; e += DFM_NT) {
           int sl = e / RR, ee = e % RR, i = ee / R, j = ee % R;
           int n0 = (int)((long long)N * sl / nsl), n1 = (int)((long long)N * (sl + 1) / nsl);
@@ -493,16 +513,8 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
       chain_fwd();
       chain_bwd();
 #endif
-      DFM_SYNC();
-      {   // explicit covariance steps: global scratch -> (now idle) ring, one cooperative copy
-        const int ncp = (ctl[0] < F2_NEXS(R)) ? ctl[0] : F2_NEXS(R);
-        for (int e = DFM_TID; e < ncp * FUSED_SCR(R); e += DFM_NT) ring[e] = gscr[e];
-      }
-      qacc = block_sum(qacc, red);
-      if (DFM_TID == 0) scal[2] = qacc;
-      DFM_SYNC();
+      DFM_SYNC();                                            // E pass and forward chain complete
       DFM_TICK(2);
-      DFM_SYNC();
       const int nE = ctl[0], frozen = ctl[3];
       DFM_TICK(3);
 #ifndef DFM_EMU
@@ -513,6 +525,11 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
       else
 #endif
       {
+      {   // explicit covariance steps: global scratch -> (now idle) ring, one cooperative copy; first read after
+          // the barrier that follows the pre-pass below
+        const int ncp = (nE < F2_NEXS(R)) ? nE : F2_NEXS(R);
+        for (int e = F2_PTID; e < ncp * FUSED_SCR(R); e += F2_PNT) ring[e] = gscr[e];
+      }
       // ---------------------------------------------------------------- P3: forward means
       // parallel pre-pass over the frozen range: Z[t] <- Pf_inf b_t
       for (int t = nE + F2_PTID; t < T; t += F2_PNT) {
@@ -554,7 +571,7 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
       // which collapses to  quad_t = zf_{t-1}' K zf_{t-1} - zf_t' W zf_t  with K = M'(W - C) M.  Over the frozen
       // range (W, K constant) the sum only needs the second-moment matrix of the filtered means:
       //   sum_t quad_t = tr(K (Gf + z_{nE-1} z_{nE-1}' - z_{T-1} z_{T-1}')) - tr(W Gf),   Gf = sum_{t>=nE} zf_t zf_t'.
-      double llp = 0.0;
+      double llp = -0.5 * qacc;                              // this thread's share of -1/2 sum x' R^-1 x (E pass)
       const bool gram = frozen && nE >= 1 && nE < T;
       // explicit periods t < nE: one thread per (t, component) in two stages when their (zp, d) vectors fit
       // in the idle scan workspace; otherwise (and for a chain that never froze) one thread per period
@@ -659,9 +676,9 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
         for (int o = 16; o > 0; o >>= 1) llp += __shfl_down_sync(0xffffffffu, llp, o);
         if (DFM_LANE == 0) red[DFM_WARP] = llp;
         F2_PSYNC();
-        if (threadIdx.x == 0) { double s_ = 0.0; for (int w_ = 0; w_ <= F2_NCW; ++w_) s_ += red[w_]; scal[3] = s_ - 0.5 * scal[2]; }
+        if (threadIdx.x == 0) { double s_ = 0.0; for (int w_ = 0; w_ <= F2_NCW; ++w_) s_ += red[w_]; scal[3] = s_; }
 #else
-        scal[3] = llp - 0.5 * scal[2];
+        scal[3] = llp;
 #endif
       }
       DFM_TICK(5);
