@@ -46,7 +46,8 @@ struct ProfRec { const char* name;
 struct dfm_handle {
   int device;
   cudaStream_t stream;
-  cudaStream_t copy_stream;    // second stream: H2D/D2H of chunk k+1 / k-1 overlap the kernels of chunk k
+  cudaStream_t copy_stream;    // second stream: the H2D copies of the streaming host path run here, under the EM kernel
+  int* pinned_one;             // pinned host int == 1: source of the stream-ordered "chunk has landed" flag copies
   bool own_stream;
   char* ws;
   size_t ws_bytes;
@@ -59,6 +60,7 @@ struct dfm_handle {
 namespace {
 
 const size_t kMaxSmem = 220 * 1024;
+const int kMaxReadyChunks = 4096;
 
 struct Arena {
   char* base; size_t off;
@@ -325,9 +327,11 @@ int dfm_create_on_stream(int device, void* cuda_stream, dfm_handle** out) {
   if (!h) return DFM_ERR_CUDA;
   h->device = device; h->ws = nullptr; h->ws_bytes = 0; h->launches = 0; h->err[0] = 0;
   h->profile = 0; h->prof = new std::vector<ProfRec>();
-  h->copy_stream = nullptr;
+  h->copy_stream = nullptr; h->pinned_one = nullptr;
 #ifndef DFM_EMU
   if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete h->prof; delete h; return DFM_ERR_CUDA; }
+  if (cudaHostAlloc((void**)&h->pinned_one, sizeof(int), cudaHostAllocDefault) != cudaSuccess) { delete h->prof; delete h; return DFM_ERR_CUDA; }
+  *h->pinned_one = 1;
 #endif
   if (cuda_stream) { h->stream = (cudaStream_t)cuda_stream; h->own_stream = false; }
   else { if (cudaStreamCreate(&h->stream) != cudaSuccess) { delete h; return DFM_ERR_CUDA; } h->own_stream = true; }
@@ -348,6 +352,7 @@ int dfm_destroy(dfm_handle* h) {
   if (h->own_stream) cudaStreamDestroy(h->stream);
 #ifndef DFM_EMU
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+  if (h->pinned_one) cudaFreeHost(h->pinned_one);
 #endif
   delete h->prof;
   delete h;
@@ -719,6 +724,7 @@ int dfm_em_kalman(dfm_handle* h, const double* X, const dfm_em_opts* o, const df
            *dslr = nullptr, *dCt = nullptr, *dzp = nullptr, *dzf = nullptr, *dPp = nullptr, *dPf = nullptr, *dSff = nullptr;
     int* dnt = nullptr;
     int* dflag = a.get<int>(4);
+    int* dready = a.get<int>(kMaxReadyChunks);          // streaming host path: one "landed" flag per chunk of panels
     const size_t fused_off = a.off;                     // the fused kernels' scratch starts here (re-derived at launch time)
     if ((fused_ok || fused2_ok) && o->path != 1) {      // superset allocation: the path is only chosen after the NaN scan
       FusedArgs dummy{};
@@ -738,63 +744,75 @@ int dfm_em_kalman(dfm_handle* h, const double* X, const dfm_em_opts* o, const df
     int rc = DFM_OK;
     bool computed = false;                // set when the pipelined branch already produced device results via the general path
 #ifndef DFM_EMU
-    // ---------------------------------------------------------------- pipelined host path
-    // Host buffers + TMA fused kernel + more panels than the kernel holds at once: chunk the batch at the
-    // kernel's capacity, enqueue ALL H2D copies on the copy stream up front, let chunk c's kernels wait on
-    // its copy event and start its D2H as soon as they finish -> copies hide behind the kernels.
+    // ---------------------------------------------------------------- streaming host path
+    // Host buffers + TMA fused kernel + more panels than are resident at once: ONE launch of the EM kernel, started
+    // before the data is on the device.  The copy stream uploads the batch in chunks of panels (X and the initial
+    // parameters), each chunk followed by a 4-byte copy that sets its "landed" flag; a CTA spins on the flag of the
+    // panel it is about to start (ld.acquire.sys) -- the copy engine is in order, so the flag implies the data.  The
+    // upload (PCIe, ~55 GB/s) runs under the kernel (HBM-bound, slower than the link), P0 and the log-likelihood
+    // pre-fill are done inside the kernel (no other kernel can become resident next to it), and the balance check
+    // is deferred: a panel with NaNs ends with status 3, which triggers the scan + general-path fallback below.
     if (mem == DFM_MEM_HOST && fused && use2 && !getenv("DFM_NO_PIPELINE")) {
       const int cap = fused2_capacity(r, T, N);
       if (batch > cap) {
-        const int nch = (batch + cap - 1) / cap;
-        std::vector<cudaEvent_t> ev_in(nch), ev_done(nch);
-        for (int c = 0; c < nch; ++c) { cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming); cudaEventCreateWithFlags(&ev_done[c], cudaEventDisableTiming); }
+        int chunk = 32;                                              // ~25 MB of C2-shaped panels: the first CTAs start after ~0.5 ms
+        while ((batch + chunk - 1) / chunk > kMaxReadyChunks) chunk *= 2;
+        const int nch = (batch + chunk - 1) / chunk;
         cudaStream_t cs = h->copy_stream;
+        cudaEvent_t ev0, ev_k;
+        cudaEventCreateWithFlags(&ev0, cudaEventDisableTiming); cudaEventCreateWithFlags(&ev_k, cudaEventDisableTiming);
+        CK(cudaMemsetAsync(dready, 0, (size_t)nch * sizeof(int), cs));
+        cudaEventRecord(ev0, cs);
+        cudaStreamWaitEvent(h->stream, ev0, 0);                        // flags are zero before the kernel can read them
+        FusedArgs fa{};
+        fa.X = dXb; fa.Lam = dL; fa.R = dR; fa.A = dA; fa.Q = dQ; fa.P0 = dP0; fa.Fs = dFs; fa.PsF = dPsF; fa.loglik = dll;
+        fa.iters = dit; fa.status = dstat; fa.B = batch; fa.T = T; fa.N = N; fa.max_iter = mi; fa.tol = o->tol; fa.phase_cycles = nullptr;
+        fa.ready = dready; fa.ready_chunk = chunk;
+        fa.P0out = init->P0 ? nullptr : dP0; fa.p0_steps = 12;        // P0 in the kernel unless the caller gave one (the loglik rows are pre-filled there too)
+        {
+          Arena a2(h->ws); a2.off = fused_off;
+          switch (r) {
+#define DFM_CASEP(RT) case RT: rc = launch_fused2<RT>(h, fa, batch, T, N, &a2, false); break;
+            DFM_CASEP(1) DFM_CASEP(2) DFM_CASEP(3) DFM_CASEP(4) DFM_CASEP(5) DFM_CASEP(6) DFM_CASEP(7) DFM_CASEP(8)
+#undef DFM_CASEP
+          }
+        }
+        if (rc) { cudaEventDestroy(ev0); cudaEventDestroy(ev_k); return rc; }
         for (int c = 0; c < nch; ++c) {
-          size_t b0 = (size_t)c * cap, bc = std::min<size_t>(cap, B - b0);
+          size_t b0 = (size_t)c * chunk, bc = std::min<size_t>(chunk, B - b0);
           cudaMemcpyAsync(dXb + b0 * TN, X + b0 * TN, bc * TN * 8, cudaMemcpyHostToDevice, cs);
           cudaMemcpyAsync(dL + b0 * N * r, init->Lam + b0 * N * r, bc * N * r * 8, cudaMemcpyHostToDevice, cs);
           cudaMemcpyAsync(dR + b0 * N, init->R + b0 * N, bc * N * 8, cudaMemcpyHostToDevice, cs);
           cudaMemcpyAsync(dA + b0 * rk, init->A + b0 * rk, bc * rk * 8, cudaMemcpyHostToDevice, cs);
           cudaMemcpyAsync(dQ + b0 * rr, init->Q + b0 * rr, bc * rr * 8, cudaMemcpyHostToDevice, cs);
           if (init->P0) cudaMemcpyAsync(dP0 + b0 * kk, init->P0 + b0 * kk, bc * kk * 8, cudaMemcpyHostToDevice, cs);
-          cudaEventRecord(ev_in[c], cs);
+          cudaMemcpyAsync(dready + c, h->pinned_one, sizeof(int), cudaMemcpyHostToDevice, cs);
         }
-        bool unbalanced = false;
-        for (int c = 0; c < nch && !unbalanced; ++c) {
-          size_t b0 = (size_t)c * cap, bc = std::min<size_t>(cap, B - b0);
-          int bci = (int)bc;
-          cudaStreamWaitEvent(h->stream, ev_in[c], 0);
-          if (!init->P0) L(k_lyapunov, bci, 1, 128, (size_t)(3 * kk + 8) * 8, dA + b0 * rk, dQ + b0 * rr, r, p, dP0 + b0 * kk, 12);
-          { long long n = (long long)bc * mi; L(k_fill, (int)std::min<long long>((n + 255) / 256, 1024), 1, 256, 0, dll + b0 * mi, n, DFM_NAN); }
+        if (out->PF) { long long n = (long long)T * rr; L(k_unpack_psf, (int)std::min<long long>((n + 255) / 256, 1024), batch, 256, 0, dPsF, T, r, dPFfull); }
+        std::vector<int> hstat(B);
+        CK(cudaMemcpyAsync(hstat.data(), dstat, B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        cudaEventRecord(ev_k, h->stream);
+        // results: split over both streams (two copy engines) once the kernel is done
+        cudaStreamWaitEvent(cs, ev_k, 0);
+#define DFM_OUTS(st_, dst, src, n_) if (dst) cudaMemcpyAsync((dst), (src), (size_t)(n_) * sizeof(*(src)), cudaMemcpyDeviceToHost, st_)
+        DFM_OUTS(cs, out->F, dFs, B * T * r);
+        DFM_OUTS(h->stream, out->Lam, dL, B * N * r); DFM_OUTS(h->stream, out->R, dR, B * N); DFM_OUTS(h->stream, out->A, dA, B * rk);
+        DFM_OUTS(h->stream, out->Q, dQ, B * rr); DFM_OUTS(h->stream, out->P0, dP0, B * kk); DFM_OUTS(h->stream, out->PF, dPFfull, B * T * rr);
+        DFM_OUTS(h->stream, out->loglik, dll, B * mi); DFM_OUTS(h->stream, out->iters, dit, B); DFM_OUTS(h->stream, out->status, dstat, B);
+#undef DFM_OUTS
+        cudaError_t e1 = cudaStreamSynchronize(cs), e2 = cudaStreamSynchronize(h->stream);
+        cudaEventDestroy(ev0); cudaEventDestroy(ev_k);
+        if (e1 != cudaSuccess || e2 != cudaSuccess) CK(e1 != cudaSuccess ? e1 : e2);
+        bool unbalanced = false, failed = false;
+        for (size_t bb = 0; bb < B; ++bb) failed = failed || hstat[bb] == 3;
+        if (failed) {                                                // NaN log-likelihood somewhere: missing data or a numerical failure?
           CK(cudaMemsetAsync(dflag, 0, sizeof(int), h->stream));
-          L(k_em_scan_fused, N, bci, 64, 0, dXb + b0 * TN, dL + b0 * N * r, dR + b0 * N, T, N, r, dflag);
+          L(k_em_scan_fused, N, batch, 64, 0, dXb, dL, dR, T, N, r, dflag);      // (X only matters: Lam/R of failed panels are NaN anyway)
           int hflag = 0;
           CK(cudaMemcpyAsync(&hflag, dflag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
           CK(cudaStreamSynchronize(h->stream));
-          if (hflag) { unbalanced = true; break; }
-          FusedArgs fa{};
-          fa.X = dXb + b0 * TN; fa.Lam = dL + b0 * N * r; fa.R = dR + b0 * N; fa.A = dA + b0 * rk; fa.Q = dQ + b0 * rr; fa.P0 = dP0 + b0 * kk;
-          fa.Fs = dFs + b0 * T * r; fa.PsF = dPsF + b0 * T * np; fa.loglik = dll + b0 * mi; fa.iters = dit + b0; fa.status = dstat + b0;
-          fa.B = bci; fa.T = T; fa.N = N; fa.max_iter = mi; fa.tol = o->tol; fa.phase_cycles = nullptr;
-          Arena a2(h->ws); a2.off = fused_off;
-          switch (r) {
-#define DFM_CASEP(RT) case RT: rc = launch_fused2<RT>(h, fa, bci, T, N, &a2, false); break;
-            DFM_CASEP(1) DFM_CASEP(2) DFM_CASEP(3) DFM_CASEP(4) DFM_CASEP(5) DFM_CASEP(6) DFM_CASEP(7) DFM_CASEP(8)
-#undef DFM_CASEP
-          }
-          if (rc) break;
-          if (out->PF) { long long n = (long long)T * rr; L(k_unpack_psf, (int)std::min<long long>((n + 255) / 256, 1024), bci, 256, 0, dPsF + b0 * T * np, T, r, dPFfull + b0 * T * rr); }
-          cudaEventRecord(ev_done[c], h->stream);
-          cudaStreamWaitEvent(cs, ev_done[c], 0);
-#define DFM_OUTP(dst, src, per) if (dst) cudaMemcpyAsync((dst) + b0 * (per), (src) + b0 * (per), bc * (per) * sizeof(*(src)), cudaMemcpyDeviceToHost, cs)
-          DFM_OUTP(out->Lam, dL, (size_t)N * r); DFM_OUTP(out->R, dR, (size_t)N); DFM_OUTP(out->A, dA, (size_t)rk); DFM_OUTP(out->Q, dQ, (size_t)rr);
-          DFM_OUTP(out->P0, dP0, (size_t)kk); DFM_OUTP(out->F, dFs, (size_t)T * r); DFM_OUTP(out->PF, dPFfull, (size_t)T * rr);
-          DFM_OUTP(out->loglik, dll, (size_t)mi); DFM_OUTP(out->iters, dit, (size_t)1); DFM_OUTP(out->status, dstat, (size_t)1);
-#undef DFM_OUTP
+          unbalanced = hflag != 0;
         }
-        cudaStreamSynchronize(cs); cudaStreamSynchronize(h->stream);
-        for (int c = 0; c < nch; ++c) { cudaEventDestroy(ev_in[c]); cudaEventDestroy(ev_done[c]); }
-        if (rc) return rc;
         if (!unbalanced) { CK(cudaGetLastError()); return DFM_OK; }
         // a chunk has missing data: everything is on the device already -> general path on the whole batch
         if (o->path == 3) return fail(h, DFM_ERR_UNSUPPORTED, "dfm_em_kalman: fused path needs a balanced panel (no NaN)");

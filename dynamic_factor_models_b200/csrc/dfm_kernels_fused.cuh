@@ -57,6 +57,12 @@ struct FusedArgs {
   double* scratch;      // [gridDim.x][T * FUSED_SCR]
   int B, T, N, max_iter;
   double tol;
+  // streaming host path (k_em_fused2 only): the kernel is launched BEFORE the panels are on the device; ready[c] is
+  // set (by a stream-ordered 4-byte H2D copy that follows chunk c's data on the copy stream) once panels
+  // [c * ready_chunk, (c+1) * ready_chunk) and their initial parameters have arrived.  NULL = everything resident.
+  const int* ready; int ready_chunk;
+  double* P0out;             // non-NULL: compute P0 in the kernel (Lyapunov doubling of (A, Q), p0_steps steps, as k_lyapunov)
+  int p0_steps;              //           and store it here ([B][r*r]).  With ready or P0out set the kernel also pre-fills its loglik rows.
   int stagger;               // diagnostics: start delay (cycles) of the second co-resident CTA wave (0 = off)
   long long* phase_cycles;   // optional [gridDim.x][DFM_PH] per-phase clock64() totals (diagnostics; NULL = off)
 };

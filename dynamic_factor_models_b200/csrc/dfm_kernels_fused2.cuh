@@ -297,6 +297,15 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
 #endif
   for (int b = DFM_BX; b < a.B; b += DFM_GX) {
     const double* X = a.X + (size_t)b * T * N;
+#ifndef DFM_EMU
+    if (a.ready) {                             // streaming host path: wait until this panel's chunk has landed
+      if (threadIdx.x == 0) {
+        const int* f_ = a.ready + b / a.ready_chunk; int v_ = 0;
+        for (;;) { asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v_) : "l"(f_) : "memory"); if (v_) break; __nanosleep(256); }
+      }
+      __syncthreads();
+    }
+#endif
     // ---- load parameters (global column-major -> shared row-major)
     for (int e = DFM_TID; e < N * R; e += DFM_NT) { int i = e % N, c = e / N; Lam[LI(i, c)] = a.Lam[(size_t)b * N * R + e]; }
     for (int e = DFM_TID; e < N; e += DFM_NT) Rv[e] = a.R[(size_t)b * N + e];
@@ -306,6 +315,33 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
     }
     if (DFM_TID == 0) ctl[2] = 0;
     DFM_SYNC();
+    if (a.P0out || a.ready) {
+      // initial state covariance in the kernel: P0 = sum_i A^i Q A'^i by doubling (same recursion as k_lyapunov), on
+      // the first RR threads; Pp = P, Pi = A^(2^s).  This panel's log-likelihood row is pre-filled here as well.
+      for (int e = DFM_TID; e < a.max_iter; e += DFM_NT) a.loglik[(size_t)b * a.max_iter + e] = DFM_NAN;
+      if (a.P0out) {
+        // plain sequential dot products in the order of k_lyapunov / bm_gemm: bit-identical P0 on both host paths
+        for (int e = DFM_TID; e < RR; e += DFM_NT) { Pp[e] = Q[e]; Pi[e] = M[e]; }
+        DFM_SYNC();
+        for (int s_ = 0; s_ < a.p0_steps; ++s_) {
+          for (int e = DFM_TID; e < RR; e += DFM_NT) { const int i = e / R, j = e % R; double v = 0.0; for (int l = 0; l < R; ++l) v += Pi[i * R + l] * Pp[l * R + j]; Wm[e] = v; }
+          DFM_SYNC();
+          for (int e = DFM_TID; e < RR; e += DFM_NT) { const int i = e / R, j = e % R; double v = 0.0; for (int l = 0; l < R; ++l) v += Wm[i * R + l] * Pi[j * R + l]; G[e] = v; }
+          DFM_SYNC();
+          for (int e = DFM_TID; e < RR; e += DFM_NT) {
+            const int i = e / R, j = e % R; double v = 0.0; for (int l = 0; l < R; ++l) v += Pi[i * R + l] * Pi[l * R + j];
+            Wm[e] = v; Pp[e] = Pp[e] + 1.0 * G[e];
+          }
+          DFM_SYNC();
+          for (int e = DFM_TID; e < RR; e += DFM_NT) Pi[e] = Wm[e];
+          DFM_SYNC();
+        }
+        for (int e = DFM_TID; e < RR; e += DFM_NT) { const int i = e / R, j = e % R; if (i > j) { const double v = 0.5 * (Pp[i * R + j] + Pp[j * R + i]); Pp[i * R + j] = v; Pp[j * R + i] = v; } }
+        DFM_SYNC();
+        for (int e = DFM_TID; e < RR; e += DFM_NT) { const int i = e / R, j = e % R; a.P0out[(size_t)b * RR + i + R * j] = Pp[e]; }
+      }
+      DFM_SYNC();                                  // (the chain warp reads a.P0 == a.P0out of this panel from global)
+    }
     int it = 0, status = 0;
     double ll_prev = 0.0;
     for (; it < a.max_iter; ++it) {
