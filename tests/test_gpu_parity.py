@@ -169,8 +169,9 @@ def _many_small_panels(B, N=16, r=2, T=40):
 
 
 def test_pipelined_host_path_matches_monolithic(lib):
-    """Host buffers + batch larger than the fused kernel's capacity -> chunked H2D/compute/D2H pipeline;
-    must equal the single-shot path bit for bit, and a few panels are checked against the oracle."""
+    """Host buffers + batch larger than the fused kernel's capacity -> streaming path (one launch that starts
+    before the upload, chunks signalled by stream-ordered flag copies, P0 computed in the kernel); must equal
+    the upload-then-compute path bit for bit, and a few panels are checked against the oracle."""
     import os
     from oracle import kalman_em as K
     Xb, Lam, Rv, A, Q = _many_small_panels(1500)
