@@ -754,6 +754,42 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
       const double ll = scal[3];
       DFM_TICK(6);
       DFM_TICK(7);
+      // ---- moment sums + M-step r x r solves (all inputs are ready before the M pass): on the chain warp,
+      //      concurrently with the pass
+      auto mstep_small = [&]() {
+        int* bad = &ctl[2];
+        // mean parts of the moment sums (needs only the smoothed means in Z)
+        for (int e = DFM_LANE; e < 2 * RR; e += DFM_WSZ) {
+          int which = e / RR, ee = e % RR, i = ee / R, j = ee % R;
+          double s0 = 0.0, s1 = 0.0;
+          if (which == 0) { for (int t = 0; t + 1 < T; t += 2) { s0 += Z[ZI(t, i)] * Z[ZI(t, j)]; s1 += Z[ZI(t + 1, i)] * Z[ZI(t + 1, j)]; }
+                            if (T & 1) s0 += Z[ZI(T - 1, i)] * Z[ZI(T - 1, j)]; Sm[ee] = s0 + s1; }
+          else { for (int t = 1; t + 1 < T; t += 2) { s0 += Z[ZI(t, i)] * Z[ZI(t - 1, j)]; s1 += Z[ZI(t + 1, i)] * Z[ZI(t, j)]; }
+                 if (!(T & 1)) s0 += Z[ZI(T - 1, i)] * Z[ZI(T - 2, j)]; S11m[ee] = s0 + s1; }
+        }
+        DFM_WSYNC();
+
+        // measurement: S = SffAll;  Lam_i = S^-1 Sxf_i
+        for (int e = DFM_LANE; e < RR; e += DFM_WSZ) T1[e] = Sm[e] + SPall[e];
+        DFM_WSYNC();
+        w_sym<R>(T1);
+        w_inv<R>(G, T1, tmp, bad);                                 // G = S^-1, T1 = S
+        // transition: A = S11 S00^-1 ; Q = (Sff2 - A S11') / (T-1)
+        for (int e = DFM_LANE; e < RR; e += DFM_WSZ) {
+          int i = e / R, j = e % R;
+          Pp[e] = Sm[e] - Z[ZI(T - 1, i)] * Z[ZI(T - 1, j)] + SP00[e];        // S00
+          Pi[e] = Sm[e] - Z[ZI(0, i)] * Z[ZI(0, j)] + SPff2[e];                    // Sff2
+          Pf[e] = S11m[e] + SP11[e];                                                    // S11
+        }
+        DFM_WSYNC();
+        w_sym<R>(Pp);
+        w_inv<R>(Wm, Pp, tmp, bad);
+        w_gemm<R>(Phi, Pf, false, Wm, false);                      // A_new
+        w_gemm<R>(Pn, Phi, false, Pf, true);                       // A S11'
+        for (int e = DFM_LANE; e < RR; e += DFM_WSZ) Pn[e] = (Pi[e] - Pn[e]) / (double)(T - 1);
+        DFM_WSYNC();
+        w_sym<R>(Pn);                                              // Q_new
+      };
       // ---------------------------------------------------------------- P8: M-step contraction (panel pass 2)
 #ifdef DFM_EMU
       for (int n = 0; n < N; ++n) {
@@ -775,81 +811,13 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
         else if (DFM_WARP <= F2_NCW) { f2_consume_M<R>(rg, DFM_WARP - 1, T, N, Tp, Np, Z, Lam, sxx, part); if (DFM_WARP == 1) F2_ROLE_T1(18); }
         else {
           rg.skip(nitems);
-        {   // ---- moment sums + M-step r x r solves (all inputs are ready before the M pass): on the idle
-            // warp, concurrently with the pass
-        int* bad = &ctl[2];
-        // mean parts of the moment sums (needs only the smoothed means in Z)
-        for (int e = DFM_LANE; e < 2 * RR; e += DFM_WSZ) {
-          int which = e / RR, ee = e % RR, i = ee / R, j = ee % R;
-          double s0 = 0.0, s1 = 0.0;
-          if (which == 0) { for (int t = 0; t + 1 < T; t += 2) { s0 += Z[ZI(t, i)] * Z[ZI(t, j)]; s1 += Z[ZI(t + 1, i)] * Z[ZI(t + 1, j)]; }
-                            if (T & 1) s0 += Z[ZI(T - 1, i)] * Z[ZI(T - 1, j)]; Sm[ee] = s0 + s1; }
-          else { for (int t = 1; t + 1 < T; t += 2) { s0 += Z[ZI(t, i)] * Z[ZI(t - 1, j)]; s1 += Z[ZI(t + 1, i)] * Z[ZI(t, j)]; }
-                 if (!(T & 1)) s0 += Z[ZI(T - 1, i)] * Z[ZI(T - 2, j)]; S11m[ee] = s0 + s1; }
-        }
-        DFM_WSYNC();
-
-        // measurement: S = SffAll;  Lam_i = S^-1 Sxf_i
-        for (int e = DFM_LANE; e < RR; e += DFM_WSZ) T1[e] = Sm[e] + SPall[e];
-        DFM_WSYNC();
-        w_sym<R>(T1);
-        w_inv<R>(G, T1, tmp, bad);                                 // G = S^-1, T1 = S
-        // transition: A = S11 S00^-1 ; Q = (Sff2 - A S11') / (T-1)
-        for (int e = DFM_LANE; e < RR; e += DFM_WSZ) {
-          int i = e / R, j = e % R;
-          Pp[e] = Sm[e] - Z[ZI(T - 1, i)] * Z[ZI(T - 1, j)] + SP00[e];        // S00
-          Pi[e] = Sm[e] - Z[ZI(0, i)] * Z[ZI(0, j)] + SPff2[e];                    // Sff2
-          Pf[e] = S11m[e] + SP11[e];                                                    // S11
-        }
-        DFM_WSYNC();
-        w_sym<R>(Pp);
-        w_inv<R>(Wm, Pp, tmp, bad);
-        w_gemm<R>(Phi, Pf, false, Wm, false);                      // A_new
-        w_gemm<R>(Pn, Phi, false, Pf, true);                       // A S11'
-        for (int e = DFM_LANE; e < RR; e += DFM_WSZ) Pn[e] = (Pi[e] - Pn[e]) / (double)(T - 1);
-        DFM_WSYNC();
-        w_sym<R>(Pn);                                              // Q_new
-        F2_ROLE_T1(19);
-      }
+          mstep_small();
+          F2_ROLE_T1(19);
         }
       }
 #endif
 #ifdef DFM_EMU
-        {   // ---- moment sums + M-step r x r solves (all inputs are ready before the M pass): on the idle
-            // warp, concurrently with the pass
-        int* bad = &ctl[2];
-        // mean parts of the moment sums (needs only the smoothed means in Z)
-        for (int e = DFM_LANE; e < 2 * RR; e += DFM_WSZ) {
-          int which = e / RR, ee = e % RR, i = ee / R, j = ee % R;
-          double s0 = 0.0, s1 = 0.0;
-          if (which == 0) { for (int t = 0; t + 1 < T; t += 2) { s0 += Z[ZI(t, i)] * Z[ZI(t, j)]; s1 += Z[ZI(t + 1, i)] * Z[ZI(t + 1, j)]; }
-                            if (T & 1) s0 += Z[ZI(T - 1, i)] * Z[ZI(T - 1, j)]; Sm[ee] = s0 + s1; }
-          else { for (int t = 1; t + 1 < T; t += 2) { s0 += Z[ZI(t, i)] * Z[ZI(t - 1, j)]; s1 += Z[ZI(t + 1, i)] * Z[ZI(t, j)]; }
-                 if (!(T & 1)) s0 += Z[ZI(T - 1, i)] * Z[ZI(T - 2, j)]; S11m[ee] = s0 + s1; }
-        }
-        DFM_WSYNC();
-
-        // measurement: S = SffAll;  Lam_i = S^-1 Sxf_i
-        for (int e = DFM_LANE; e < RR; e += DFM_WSZ) T1[e] = Sm[e] + SPall[e];
-        DFM_WSYNC();
-        w_sym<R>(T1);
-        w_inv<R>(G, T1, tmp, bad);                                 // G = S^-1, T1 = S
-        // transition: A = S11 S00^-1 ; Q = (Sff2 - A S11') / (T-1)
-        for (int e = DFM_LANE; e < RR; e += DFM_WSZ) {
-          int i = e / R, j = e % R;
-          Pp[e] = Sm[e] - Z[ZI(T - 1, i)] * Z[ZI(T - 1, j)] + SP00[e];        // S00
-          Pi[e] = Sm[e] - Z[ZI(0, i)] * Z[ZI(0, j)] + SPff2[e];                    // Sff2
-          Pf[e] = S11m[e] + SP11[e];                                                    // S11
-        }
-        DFM_WSYNC();
-        w_sym<R>(Pp);
-        w_inv<R>(Wm, Pp, tmp, bad);
-        w_gemm<R>(Phi, Pf, false, Wm, false);                      // A_new
-        w_gemm<R>(Pn, Phi, false, Pf, true);                       // A S11'
-        for (int e = DFM_LANE; e < RR; e += DFM_WSZ) Pn[e] = (Pi[e] - Pn[e]) / (double)(T - 1);
-        DFM_WSYNC();
-        w_sym<R>(Pn);                                              // Q_new
-      }
+      mstep_small();
 #endif
       DFM_SYNC();
       DFM_TICK(8);
