@@ -9,6 +9,7 @@
 #include "dfm_kernels_fused2.cuh"
 #include <algorithm>
 #include <new>
+#include <thread>
 #include <vector>
 #ifndef DFM_EMU
 #include <dlfcn.h>
@@ -47,6 +48,8 @@ struct dfm_handle {
   int device;
   cudaStream_t stream;
   cudaStream_t copy_stream;    // second stream: the H2D copies of the streaming host path run here, under the EM kernel
+  cudaStream_t d2h_stream;     // third stream: results of finished panels go back while the kernel is still running
+  int* done_host; int* done_dev; size_t done_cap;   // per-panel completion flags (mapped pinned memory, written by the kernel)
   int* pinned_one;             // pinned host int == 1: source of the stream-ordered "chunk has landed" flag copies
   bool own_stream;
   char* ws;
@@ -327,9 +330,10 @@ int dfm_create_on_stream(int device, void* cuda_stream, dfm_handle** out) {
   if (!h) return DFM_ERR_CUDA;
   h->device = device; h->ws = nullptr; h->ws_bytes = 0; h->launches = 0; h->err[0] = 0;
   h->profile = 0; h->prof = new std::vector<ProfRec>();
-  h->copy_stream = nullptr; h->pinned_one = nullptr;
+  h->copy_stream = nullptr; h->pinned_one = nullptr; h->d2h_stream = nullptr; h->done_host = nullptr; h->done_dev = nullptr; h->done_cap = 0;
 #ifndef DFM_EMU
   if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete h->prof; delete h; return DFM_ERR_CUDA; }
+  if (cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking) != cudaSuccess) { delete h->prof; delete h; return DFM_ERR_CUDA; }
   if (cudaHostAlloc((void**)&h->pinned_one, sizeof(int), cudaHostAllocDefault) != cudaSuccess) { delete h->prof; delete h; return DFM_ERR_CUDA; }
   *h->pinned_one = 1;
 #endif
@@ -353,6 +357,8 @@ int dfm_destroy(dfm_handle* h) {
 #ifndef DFM_EMU
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
   if (h->pinned_one) cudaFreeHost(h->pinned_one);
+  if (h->d2h_stream) { cudaStreamSynchronize(h->d2h_stream); cudaStreamDestroy(h->d2h_stream); }
+  if (h->done_host) cudaFreeHost(h->done_host);
 #endif
   delete h->prof;
   delete h;
@@ -768,6 +774,15 @@ int dfm_em_kalman(dfm_handle* h, const double* X, const dfm_em_opts* o, const df
         fa.X = dXb; fa.Lam = dL; fa.R = dR; fa.A = dA; fa.Q = dQ; fa.P0 = dP0; fa.Fs = dFs; fa.PsF = dPsF; fa.loglik = dll;
         fa.iters = dit; fa.status = dstat; fa.B = batch; fa.T = T; fa.N = N; fa.max_iter = mi; fa.tol = o->tol; fa.phase_cycles = nullptr;
         fa.ready = dready; fa.ready_chunk = chunk;
+        if (h->done_cap < B) {                                        // completion flags the kernel writes straight into host memory
+          if (h->done_host) cudaFreeHost(h->done_host);
+          h->done_host = nullptr; h->done_cap = 0;
+          CK(cudaHostAlloc((void**)&h->done_host, B * sizeof(int), cudaHostAllocMapped));
+          CK(cudaHostGetDevicePointer((void**)&h->done_dev, h->done_host, 0));
+          h->done_cap = B;
+        }
+        memset(h->done_host, 0, B * sizeof(int));
+        fa.done = h->done_dev;
         fa.P0out = init->P0 ? nullptr : dP0; fa.p0_steps = 12;        // P0 in the kernel unless the caller gave one (the loglik rows are pre-filled there too)
         {
           Arena a2(h->ws); a2.off = fused_off;
@@ -788,18 +803,40 @@ int dfm_em_kalman(dfm_handle* h, const double* X, const dfm_em_opts* o, const df
           if (init->P0) cudaMemcpyAsync(dP0 + b0 * kk, init->P0 + b0 * kk, bc * kk * 8, cudaMemcpyHostToDevice, cs);
           cudaMemcpyAsync(dready + c, h->pinned_one, sizeof(int), cudaMemcpyHostToDevice, cs);
         }
-        if (out->PF) { long long n = (long long)T * rr; L(k_unpack_psf, (int)std::min<long long>((n + 255) / 256, 1024), batch, 256, 0, dPsF, T, r, dPFfull); }
+        // results of finished panels go back on a third stream while the kernel is still running: the host polls the
+        // completion flags and ships whole chunks of 128 panels in order (everything except the unpacked PF, which
+        // needs a kernel of its own after the EM kernel)
+        {
+          const size_t dch = 128;
+          volatile const int* dn = h->done_host;
+          size_t next = 0; bool kernel_done = false;
+          auto ship = [&](size_t b0, size_t b1) {
+            const size_t nb = b1 - b0;
+#define DFM_OUTS(dst, src, per) if (dst) cudaMemcpyAsync((dst) + b0 * (per), (src) + b0 * (per), nb * (per) * sizeof(*(src)), cudaMemcpyDeviceToHost, h->d2h_stream)
+            DFM_OUTS(out->F, dFs, (size_t)T * r); DFM_OUTS(out->Lam, dL, (size_t)N * r); DFM_OUTS(out->R, dR, (size_t)N); DFM_OUTS(out->A, dA, (size_t)rk);
+            DFM_OUTS(out->Q, dQ, (size_t)rr); DFM_OUTS(out->P0, dP0, (size_t)kk); DFM_OUTS(out->loglik, dll, (size_t)mi);
+            DFM_OUTS(out->iters, dit, (size_t)1); DFM_OUTS(out->status, dstat, (size_t)1);
+#undef DFM_OUTS
+          };
+          while (next < B) {
+            size_t b1 = std::min<size_t>(B, next + dch);
+            bool all = true;
+            if (!kernel_done) for (size_t bb = next; bb < b1; ++bb) if (!dn[bb]) { all = false; break; }
+            if (all) { ship(next, b1); next = b1; continue; }
+            cudaError_t q = cudaStreamQuery(h->stream);
+            if (q != cudaErrorNotReady) kernel_done = true;            // finished (or failed: reported by the synchronize below)
+            else std::this_thread::yield();
+          }
+        }
+        if (out->PF) {
+          long long n = (long long)T * rr;
+          L(k_unpack_psf, (int)std::min<long long>((n + 255) / 256, 1024), batch, 256, 0, dPsF, T, r, dPFfull);
+          cudaMemcpyAsync(out->PF, dPFfull, B * T * rr * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+        }
         std::vector<int> hstat(B);
         CK(cudaMemcpyAsync(hstat.data(), dstat, B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         cudaEventRecord(ev_k, h->stream);
-        // results: split over both streams (two copy engines) once the kernel is done
-        cudaStreamWaitEvent(cs, ev_k, 0);
-#define DFM_OUTS(st_, dst, src, n_) if (dst) cudaMemcpyAsync((dst), (src), (size_t)(n_) * sizeof(*(src)), cudaMemcpyDeviceToHost, st_)
-        DFM_OUTS(cs, out->F, dFs, B * T * r);
-        DFM_OUTS(h->stream, out->Lam, dL, B * N * r); DFM_OUTS(h->stream, out->R, dR, B * N); DFM_OUTS(h->stream, out->A, dA, B * rk);
-        DFM_OUTS(h->stream, out->Q, dQ, B * rr); DFM_OUTS(h->stream, out->P0, dP0, B * kk); DFM_OUTS(h->stream, out->PF, dPFfull, B * T * rr);
-        DFM_OUTS(h->stream, out->loglik, dll, B * mi); DFM_OUTS(h->stream, out->iters, dit, B); DFM_OUTS(h->stream, out->status, dstat, B);
-#undef DFM_OUTS
+        cudaStreamSynchronize(h->d2h_stream);
         cudaError_t e1 = cudaStreamSynchronize(cs), e2 = cudaStreamSynchronize(h->stream);
         cudaEventDestroy(ev0); cudaEventDestroy(ev_k);
         if (e1 != cudaSuccess || e2 != cudaSuccess) CK(e1 != cudaSuccess ? e1 : e2);

@@ -61,6 +61,7 @@ struct FusedArgs {
   // set (by a stream-ordered 4-byte H2D copy that follows chunk c's data on the copy stream) once panels
   // [c * ready_chunk, (c+1) * ready_chunk) and their initial parameters have arrived.  NULL = everything resident.
   const int* ready; int ready_chunk;
+  int* done;                 // streaming host path: done[b] = 1 (mapped pinned host memory) once panel b's results are in device memory
   double* P0out;             // non-NULL: compute P0 in the kernel (Lyapunov doubling of (A, Q), p0_steps steps, as k_lyapunov)
   int p0_steps;              //           and store it here ([B][r*r]).  With ready or P0out set the kernel also pre-fills its loglik rows.
   int stagger;               // diagnostics: start delay (cycles) of the second co-resident CTA wave (0 = off)
@@ -218,10 +219,13 @@ __device__ __forceinline__ void w_matpow(double* pw, const double* Cf, int ex0, 
 //   pass 2  every chunk adds Cf^(s+1) * (true state entering the chunk).
 // Exact up to rounding (linear recurrence).  Called by ALL threads; ends with a block barrier.
 // smem: pw, pw2 [R*R], bnd [(3 ng + 1) R + R R].  pw_ready: pw already holds Cf^Lc (computed elsewhere, e.g. by the
-// chain warp of k_em_fused2 while the panel streams); otherwise warp 0 computes it here.
+// chain warp of k_em_fused2 while the panel streams); otherwise warp 0 computes it here.  pl1..pl4 (optional, GPU):
+// pw^2, pw^4, pw^8, pw^16 -- the boundary propagation is then a Kogge-Stone scan over the chunks (5 levels, all groups
+// in parallel) instead of nch - 1 serial matrix-vector steps.
 template <int R>
 __device__ __forceinline__ void blk_recur(double* Z, int Tp, const double* Cf, double* pw, double* pw2, double* bnd, int t0, int n, int dir, int nthr,
-                                          long long* prof = nullptr, bool pw_ready = false) {
+                                          long long* prof = nullptr, bool pw_ready = false, const double* pl1 = nullptr, const double* pl2 = nullptr,
+                                          const double* pl3 = nullptr, const double* pl4 = nullptr) {
   if (n <= 0) return;
   // nthr = number of threads taking part (threads 0 .. nthr-1 of the CTA, a multiple of 32); they synchronise
   // on named barrier 2, so the remaining warps of the CTA may do something else meanwhile
@@ -264,8 +268,8 @@ __device__ __forceinline__ void blk_recur(double* Z, int Tp, const double* Cf, d
   double cf[R];
 #pragma unroll
   for (int j = 0; j < R; ++j) cf[j] = lane_on ? Cf[gl * R + j] : 0.0;
+  double cur = (g == 0 && lane_on) ? Z[ZI(t0 - dir, gl)] : 0.0;        // chunk 0 continues the true state, the others start from 0
   {
-    double cur = (g == 0 && lane_on) ? Z[ZI(t0 - dir, gl)] : 0.0;      // chunk 0 continues the true state, the others start from 0
     double u = (lane_on && len > 0) ? Z[ZI(t0 + dir * s0, gl)] : 0.0;
     for (int s = 0; s < Lc; ++s) {                                     // uniform trip count: every lane takes part in the shuffles
       const bool on = lane_on && s < len;
@@ -299,7 +303,34 @@ __device__ __forceinline__ void blk_recur(double* Z, int Tp, const double* Cf, d
       }
     }
 #else
-    if (DFM_WARP == 0) {
+    if (pl1 && nch <= 32) {
+      // Kogge-Stone over the chunk-end states: after level l, x_g = sum_{j < 2^(l+1)} pw^j e_{g-j}; the level
+      // matrix pw^(2^l) is read row-wise from shared memory, x_{g-2^l} through a double-buffered exchange array
+      double x = cur;                                                    // e_g: local end state of my chunk (true for chunk 0)
+      double* xb = bnd + (size_t)(ng + 1) * R;                           // [2][ng][R]
+      const double* lv[5] = {pw, pl1, pl2, pl3, pl4};
+#pragma unroll
+      for (int lvl = 0; lvl < 5; ++lvl) {
+        const int off = 1 << lvl;
+        if (off < nch) {                                                 // uniform
+          double* xw = xb + (size_t)(lvl & 1) * ng * R;
+          if (lane_on && g < nch) xw[g * R + gl] = x;
+          BLK_SYNC();
+          const bool use = lane_on && g >= off && g < nch;
+          const double yv = use ? xw[(g - off) * R + gl] : 0.0;
+          const double* prow = lv[lvl] + gl * R;
+          double a0 = x, a1 = 0.0;
+#pragma unroll
+          for (int j = 0; j < R; ++j) {
+            const double v = __shfl_sync(0xffffffffu, yv, j, 8);
+            const double pj = lane_on ? prow[j] : 0.0;
+            if (j & 1) a1 += pj * v; else a0 += pj * v;
+          }
+          x = a0 + a1;
+        }
+      }
+      if (lane_on && g + 1 < nch) bnd[(g + 1) * R + gl] = x;             // true end state of chunk g = state entering chunk g+1
+    } else if (DFM_WARP == 0) {
       const int gl = threadIdx.x & 7;
       const bool lane_on = gl < R;
       double pr[R];

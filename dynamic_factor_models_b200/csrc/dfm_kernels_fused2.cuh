@@ -41,7 +41,8 @@ namespace dfm {
 #define F2_NKC (((F2_TC + 3) / 4 + F2_NCW - 1) / F2_NCW)   // 4-period DMMA k-chunks per consumer warp and stage (M pass)
 static_assert(F2_TC % 16 == 4 || F2_TC % 16 == 12, "ring pitch must be 4 or 12 mod 16");
 static_assert(F2_TC <= 256 && (F2_TC * 64) % 128 == 0, "TMA box / stage alignment");
-#define F2_NEXS(R_) ((F2_S * 8 * F2_TS) / FUSED_SCR(R_))
+#define F2_NEXS(R_) ((F2_S * 8 * F2_TS - 4 * (R_) * (R_)) / FUSED_SCR(R_))   // the last 4 R^2 doubles of the idle ring hold scan matrices
+#define F2_RTAIL(R_) (F2_S * 8 * F2_TS - 4 * (R_) * (R_))
 
 #ifndef DFM_EMU
 __device__ __forceinline__ uint32_t f2_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -449,8 +450,27 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
           // chunk-length powers of the two scan matrices (P3: Phi_inf, P5: J_inf), off the critical path of P3/P5.
           // Phi and Pn are free from here until the M-step solves; T1/T2 serve as scratch.
           const int n3 = T - (nE > 0 ? nE : 1), n5 = (T - 2) - (nE - 1) + 1;
-          if (n3 > 0) w_matpow<R>(Phi, Phinf, blk_chunk_len(n3, F2_PNT_GPU / 8), T1, T2);
-          if (n5 > 0) w_matpow<R>(Pn, Jinf, blk_chunk_len(n5, F2_PNT_GPU / 8), T1, T2);
+          if (n3 > 0) {
+            w_matpow<R>(Phi, Phinf, blk_chunk_len(n3, F2_PNT_GPU / 8), T1, T2);
+            // Kogge-Stone levels of the forward scan: (Phi^Lc)^2, ^4, ^8, ^16 in forward-chain temporaries that are idle now
+            w_gemm<R>(Pp, Phi, false, Phi, false); w_gemm<R>(Pi, Pp, false, Pp, false);
+            w_gemm<R>(Pf, Pi, false, Pi, false);   w_gemm<R>(Jm, Pf, false, Pf, false);
+          }
+          if (n5 > 0) {
+            w_matpow<R>(Pn, Jinf, blk_chunk_len(n5, F2_PNT_GPU / 8), T1, T2);
+            // ... of the backward scan: parked in the unused slots of the last scratch entry (the ring is busy with
+            // the E pass), copied into the ring tail together with the explicit steps
+            double* gl_ = GSC(T - 1);
+            w_gemm<R>(T1, Pn, false, Pn, false);
+            for (int e = DFM_LANE; e < RR; e += DFM_WSZ) gl_[e] = T1[e];
+            w_gemm<R>(T2, T1, false, T1, false);
+            for (int e = DFM_LANE; e < RR; e += DFM_WSZ) gl_[RR + e] = T2[e];
+            w_gemm<R>(T1, T2, false, T2, false);
+            for (int e = DFM_LANE; e < RR; e += DFM_WSZ) gl_[2 * RR + e] = T1[e];
+            w_gemm<R>(T2, T1, false, T1, false);
+            for (int e = DFM_LANE; e < RR; e += DFM_WSZ) gl_[3 * RR + e] = T2[e];
+            DFM_WSYNC();
+          }
         }
         DFM_WSYNC();
       };
@@ -565,6 +585,7 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
           // the barrier that follows the pre-pass below
         const int ncp = (nE < F2_NEXS(R)) ? nE : F2_NEXS(R);
         for (int e = F2_PTID; e < ncp * FUSED_SCR(R); e += F2_PNT) ring[e] = gscr[e];
+        if (frozen) for (int e = F2_PTID; e < 4 * RR; e += F2_PNT) ring[F2_RTAIL(R) + e] = GSC(T - 1)[e];   // backward-scan level matrices
       }
       // ---------------------------------------------------------------- P3: forward means
       // parallel pre-pass over the frozen range: Z[t] <- Pf_inf b_t
@@ -599,7 +620,7 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
       F2_PSYNC();
       F2_SUB(21);
       // frozen steps: z_t = Phi_inf z_{t-1} + u_t, parallel in time over the CTA
-      if (frozen) blk_recur<R>(Z, Tp, Phinf, Phi, Pi, bnd, (nE > 0 ? nE : 1), T - (nE > 0 ? nE : 1), +1, F2_PNT_GPU, F2_SUBP(22), true);
+      if (frozen) blk_recur<R>(Z, Tp, Phinf, Phi, Pi, bnd, (nE > 0 ? nE : 1), T - (nE > 0 ? nE : 1), +1, F2_PNT_GPU, F2_SUBP(22), true, Pp, Pi, Pf, Jm);
       DFM_TICK(4);
       // ---------------------------------------------------------------- P4: log-likelihood
       // innovation form: ll_t = -1/2 (N log 2pi + sum log R + ld_t + quad_t),
@@ -735,7 +756,7 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
       }
       F2_PSYNC();
       // frozen range: z_t = J_inf z_{t+1} + v_t, parallel in time over the CTA
-      if (frozen) blk_recur<R>(Z, Tp, Jinf, Pn, Pi, bnd, T - 2, (T - 2) - (nE - 1) + 1, -1, F2_PNT_GPU, F2_SUBP(25), true);
+      if (frozen) blk_recur<R>(Z, Tp, Jinf, Pn, Pi, bnd, T - 2, (T - 2) - (nE - 1) + 1, -1, F2_PNT_GPU, F2_SUBP(25), true, ring + F2_RTAIL(R), ring + F2_RTAIL(R) + RR, ring + F2_RTAIL(R) + 2 * RR, ring + F2_RTAIL(R) + 3 * RR);
       if (DFM_WARP == 0) {
         const int lo = frozen ? nE - 1 : T;
         // explicit range: zs_t = zf_t + J_t (zs_{t+1} - M zf_t)
@@ -872,7 +893,13 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
       }
     }
     if (DFM_TID == 0) { a.iters[b] = it > a.max_iter ? a.max_iter : it; a.status[b] = status; }
+#ifndef DFM_EMU
+    if (a.done) __threadfence_system();            // results visible to the copy engine before the host is told
+#endif
     DFM_SYNC();
+#ifndef DFM_EMU
+    if (a.done && threadIdx.x == 0) *(volatile int*)(a.done + b) = 1;
+#endif
     DFM_TICK(11);
   }
 }
