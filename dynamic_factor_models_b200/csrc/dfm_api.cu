@@ -793,15 +793,25 @@ int dfm_em_kalman(dfm_handle* h, const double* X, const dfm_em_opts* o, const df
           }
         }
         if (rc) { cudaEventDestroy(ev0); cudaEventDestroy(ev_k); return rc; }
-        for (int c = 0; c < nch; ++c) {
+        cudaError_t up = cudaSuccess;                                  // first failure while enqueueing the upload
+        for (int c = 0; c < nch && up == cudaSuccess; ++c) {
           size_t b0 = (size_t)c * chunk, bc = std::min<size_t>(chunk, B - b0);
-          cudaMemcpyAsync(dXb + b0 * TN, X + b0 * TN, bc * TN * 8, cudaMemcpyHostToDevice, cs);
-          cudaMemcpyAsync(dL + b0 * N * r, init->Lam + b0 * N * r, bc * N * r * 8, cudaMemcpyHostToDevice, cs);
-          cudaMemcpyAsync(dR + b0 * N, init->R + b0 * N, bc * N * 8, cudaMemcpyHostToDevice, cs);
-          cudaMemcpyAsync(dA + b0 * rk, init->A + b0 * rk, bc * rk * 8, cudaMemcpyHostToDevice, cs);
-          cudaMemcpyAsync(dQ + b0 * rr, init->Q + b0 * rr, bc * rr * 8, cudaMemcpyHostToDevice, cs);
-          if (init->P0) cudaMemcpyAsync(dP0 + b0 * kk, init->P0 + b0 * kk, bc * kk * 8, cudaMemcpyHostToDevice, cs);
-          cudaMemcpyAsync(dready + c, h->pinned_one, sizeof(int), cudaMemcpyHostToDevice, cs);
+#define DFM_UP(dst, src, n_) do { if (up == cudaSuccess) up = cudaMemcpyAsync((dst), (src), (size_t)(n_) * 8, cudaMemcpyHostToDevice, cs); } while (0)
+          DFM_UP(dXb + b0 * TN, X + b0 * TN, bc * TN); DFM_UP(dL + b0 * N * r, init->Lam + b0 * N * r, bc * N * r);
+          DFM_UP(dR + b0 * N, init->R + b0 * N, bc * N); DFM_UP(dA + b0 * rk, init->A + b0 * rk, bc * rk); DFM_UP(dQ + b0 * rr, init->Q + b0 * rr, bc * rr);
+          if (init->P0) DFM_UP(dP0 + b0 * kk, init->P0 + b0 * kk, bc * kk);
+#undef DFM_UP
+          if (up == cudaSuccess) up = cudaMemcpyAsync(dready + c, h->pinned_one, sizeof(int), cudaMemcpyHostToDevice, cs);
+        }
+        if (up != cudaSuccess) {
+          // an upload could not be enqueued: the kernel is already running and would wait for its flags for ever ->
+          // raise every flag (the CTAs then run on whatever is in the buffers), drain, report the error
+          cudaMemsetAsync(dready, 1, (size_t)nch * sizeof(int), cs);
+          cudaStreamSynchronize(cs); cudaStreamSynchronize(h->stream);
+          cudaEventDestroy(ev0); cudaEventDestroy(ev_k);
+          (void)cudaGetLastError();
+          snprintf(h->err, sizeof(h->err), "dfm_em_kalman: host-to-device upload failed (%s)", cudaGetErrorString(up));
+          return DFM_ERR_CUDA;
         }
         // results of finished panels go back on a third stream while the kernel is still running: the host polls the
         // completion flags and ships whole chunks of 128 panels in order (everything except the unpacked PF, which

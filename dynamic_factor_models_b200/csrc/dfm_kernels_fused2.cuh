@@ -1,14 +1,17 @@
-// dfm_kernels_fused2.cuh -- TMA-fed variant of the fused per-panel EM kernel (see dfm_kernels_fused.cuh
-// for the algorithm).  Differences:
-//  * 256 threads: warp 0 = TMA producer during the two panel passes, warps 1..7 = DMMA consumers;
-//  * both passes stream the column-major panel as CONTIGUOUS column runs with cp.async.bulk
-//    (SASS UBLKCP) into a 5-stage shared-memory ring guarded by mbarriers (full/empty).  Measured
-//    with tools/bench_stream.cu at this occupancy: LDG-to-fragment patterns 2.5-3.5 TB/s, bulk ring
-//    6.3-6.8 TB/s;
-//  * E pass = rank-8 updates Z[t-chunk] += X' (Lam/R) accumulated in shared memory, M pass = S_xf
-//    partial tiles per consumer warp + deterministic cross-warp reduction per series block;
-//  * the ring is idle between the passes and doubles as storage for the explicit covariance steps
-//    (no dependent global-memory round trips on the serial path).
+// dfm_kernels_fused2.cuh -- TMA-fed fused per-panel EM kernel k_em_fused2<R> (the default for balanced panels with
+// p = 1, r <= 8, even T) and the fused ALS sweep kernel k_als_fused2<R>.  See DESIGN.md section 4.1.
+//  * 256 threads in three roles: warp 0 = TMA producer during the two panel passes, warps 1..6 = DMMA consumers,
+//    warp 7 = "chain warp" (covariance recursions, moment sums, r x r M-step solves -- all data independent or
+//    r x r sized, overlapped with the passes and with the mean recursions);
+//  * both passes stream the column-major panel through ONE 2-D tensor-map copy per stage (cp.async.bulk.tensor.2d,
+//    SASS UTMALDG; box = F2_TC periods x 8 series) into an F2_S-stage shared-memory ring guarded by full/empty
+//    mbarriers.  Measured at this occupancy (tools/bench_stream.cu, tools/bench_tma2d.cu): LDG-to-fragment patterns
+//    2.5-3.5 TB/s, TMA ring 6.3-6.8 TB/s;
+//  * E pass: each consumer warp keeps the 8x8 accumulators of its row blocks in registers across all series blocks;
+//    M pass: S_xf partial tiles per consumer warp + deterministic cross-warp reduction per series block;
+//  * the ring is idle between the passes and doubles as storage for the explicit covariance steps and the level
+//    matrices of the backward scan (no dependent global-memory round trips on the serial path);
+//  * streaming host path: the kernel may be launched before its panels are on the device (FusedArgs::ready/done).
 // Requires T even (16-byte aligned column runs); otherwise dfm_em_kalman uses k_em_fused.
 #pragma once
 #include <algorithm>
@@ -30,10 +33,6 @@ namespace dfm {
 #define F2_TC 132       // periods per stage == row pitch in the ring; must be == 4 or 12 (mod 16) so that the
 #endif                  // DMMA fragment loads are bank-conflict free, and <= 256 (TMA box limit)
 #define F2_TS F2_TC     // (box width == chunk stride: no re-read of periods; T = 500 -> 4 chunks)
-#ifndef F2_PF
-#define F2_PF 0
-#endif
-// F2_PF: L2 prefetch distance (stages), 0 = off (measured slower: profiles/README.md)
 #define F2_NCW 6        // consumer warps (warps 1..6; warp 0 = producer, warp 7 = chain / solves)
 #define F2_GPARTS_S 4                                    // scalar Gram path: time slices per matrix entry
 #define F2_GPARTS ((R == 8) ? (F2_NCW + 1) : F2_GPARTS_S)   // partial Gram matrices (tensor path: one per warp of P3-P5)
@@ -52,16 +51,10 @@ __device__ __forceinline__ void f2_mbar_arrive(uint64_t* bar) { asm volatile("mb
 __device__ __forceinline__ void f2_mbar_wait(uint64_t* bar, uint32_t phase) {
   asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(f2_smem_u32(bar)), "r"(phase) : "memory");
 }
-__device__ __forceinline__ void f2_prefetch_l2(const void* src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-}
 // one 2-D tensor-map copy (SASS UTMALDG): box F2_TS periods x 8 series of the [T, B*N] view of the batch
 __device__ __forceinline__ void f2_tma_2d(void* dst, const CUtensorMap* tmap, int x, int y, uint64_t* bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                ::"r"(f2_smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(x), "r"(y), "r"(f2_smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void f2_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(f2_smem_u32(dst)), "l"(src), "r"(bytes), "r"(f2_smem_u32(bar)) : "memory");
 }
 #endif
 
