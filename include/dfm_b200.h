@@ -165,7 +165,11 @@ typedef struct {            /* outputs; any pointer may be NULL */
   int* status;              /* [batch] */
 } dfm_em_out;
 
-/* X: T x N STANDARDIZED panel (NaN = missing), e.g. dfm_standardize output. */
+/* X: T x N STANDARDIZED panel (NaN = missing), e.g. dfm_standardize output; batch panels back to back.
+ * Synchronous: results are in `out` on return.  With DFM_MEM_HOST and a batch larger than the number of panels the
+ * fused kernel keeps resident (296 on a B200 for C2-shaped panels) the upload, the EM iterations and the download
+ * overlap inside the call (one kernel launch that starts before the data has arrived) -- pinned
+ * host buffers make the copies truly asynchronous, pageable ones work but are staged by the CUDA runtime. */
 int dfm_em_kalman(dfm_handle* h, const double* X, const dfm_em_opts* opts, const dfm_em_init* init,
                   const dfm_em_out* out);
 
