@@ -5,6 +5,7 @@ the real CUDA parity tests are tests/test_gpu_parity.py (-m gpu)."""
 import os
 import sys
 
+import numpy as np
 import pytest
 
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), "emu"))
@@ -58,3 +59,26 @@ def test_fused2_em_r8(lib): P.check_em(lib, N=40, r=8, T=90, p=1, miss=0.0, path
 def test_fused2_em_r1(lib): P.check_em(lib, N=12, r=1, T=50, p=1, miss=0.0, path=3, iters=4)
 def test_fused2_em_convergence_rule(lib): P.check_em_convergence_rule(lib, path=3)
 def test_fused2_em_batch(lib): P.check_em_batch_balanced(lib, path=3)
+
+
+@pytest.mark.parametrize("vset", ["A", "B"])
+def test_table5_through_kernel_source(lib, panels, notebook_tables, vset):
+    """Golden Table 5 (Stock_Watson.ipynb:1250-1261) reproduced through the PRODUCT code path (kernel source under
+    host emulation): estimate!() on the C1 panel, a small VAR on observed series with leading missing values,
+    canonical correlations of levels and of VAR residuals.  Same check as tests/test_oracle_golden.py does for the
+    oracle."""
+    import dynamic_factor_models_b200 as D
+    from test_oracle_golden import TABLE5_VARS, _canonical_correlations
+    names = [str(n) for n in panels["all_names"]]
+    g = P.gpu_model(panels["all_bpdata"], panels["all_inclcode"], 8)
+    D.estimate(g, lib=lib)
+    cols = [names.index(v) for v in TABLE5_VARS[vset]]
+    X = panels["all_bpdata"][:, cols]
+    fv = g.factor_var_model
+    v = D.VARModel(X, fv.nlag, fv.withconst, fv.initperiod, fv.lastperiod)
+    D.estimate_var(v, lib=lib)
+    gold = notebook_tables["table5"][vset]
+    ok = ~np.isnan(np.column_stack([X, g.factor])).any(1)
+    np.testing.assert_allclose(_canonical_correlations(X[ok], g.factor[ok]), gold["level"], rtol=5e-5, atol=5e-7)
+    ok = ~np.isnan(np.column_stack([v.resid, fv.resid])).any(1)
+    np.testing.assert_allclose(_canonical_correlations(v.resid[ok], fv.resid[ok]), gold["resid"], rtol=5e-5, atol=5e-7)

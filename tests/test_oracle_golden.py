@@ -61,3 +61,39 @@ def test_table3_series_r2(panels, notebook_tables):
         R.estimate_factor(m, computeR2=False)
         R.estimate_factor_loading(m)
         np.testing.assert_allclose(m.r2[rows], gold[:, c], rtol=2e-5, atol=1e-7)
+
+
+def _canonical_correlations(X, Y):
+    """MultivariateStats.fit(CCA, X', Y'; method=:svd) with means removed: singular values of Qx'Qy."""
+    Xc, Yc = X - X.mean(0), Y - Y.mean(0)
+    qx, _ = np.linalg.qr(Xc); qy, _ = np.linalg.qr(Yc)
+    return np.linalg.svd(qx.T @ qy, compute_uv=False)
+
+
+TABLE5_VARS = {   # Stock_Watson.ipynb cell "Table 5" (variable sets A, B, O; C needs the stepwise selection, not restated)
+    "A": ["GDPC96", "PAYEMS", "PCECTPI", "FEDFUNDS"],
+    "B": ["GDPC96", "PAYEMS", "PCECTPI", "FEDFUNDS", "NAPMPRI", "WPU0561", "CP90_TBILL", "GS10_TB3M"],
+    "O": ["OILPROD_SA", "GLOBAL_ACT", "WPU0561", "GDPC96", "PAYEMS", "PCECTPI", "FEDFUNDS", "TWEXMMTH"],
+}
+
+
+@pytest.mark.parametrize("vset", ["A", "B", "O"])
+def test_table5_canonical_correlations(panels, notebook_tables, vset):
+    """Stock_Watson.ipynb:1250-1261: canonical correlations between a small VAR's variables (residuals) and
+    the 8 factors (factor-VAR residuals).  Pins estimate!() end to end including estimate_var! (:444-468) and
+    the residual placement `varm.resid` (:464) that the C4 bootstrap resamples.  6 significant digits."""
+    names = [str(n) for n in panels["all_names"]]
+    m = model(panels["all_bpdata"], panels["all_inclcode"], 8)
+    R.estimate(m)
+    cols = [names.index(v) for v in TABLE5_VARS[vset]]
+    X = panels["all_bpdata"][:, cols]
+    v = R.VARModel(X, m.factor_var_model.nlag, m.factor_var_model.withconst, m.factor_var_model.initperiod,
+                   m.factor_var_model.lastperiod)
+    R.estimate_var(v)
+    gold = notebook_tables["table5"][vset]
+    ok = ~np.isnan(np.column_stack([X, m.factor])).any(1)
+    lev = _canonical_correlations(X[ok], m.factor[ok])
+    np.testing.assert_allclose(lev, gold["level"], rtol=5e-5, atol=5e-7)
+    ok = ~np.isnan(np.column_stack([v.resid, m.factor_var_model.resid])).any(1)
+    res = _canonical_correlations(v.resid[ok], m.factor_var_model.resid[ok])
+    np.testing.assert_allclose(res, gold["resid"], rtol=5e-5, atol=5e-7)
