@@ -13,3 +13,4 @@ from .api import (  # noqa: F401
     impulse_response, bai_ng_criterion, amengual_watson_test, estimate_factor_numbers,
     standardize_data, pca_score, em_kalman, em_init_from_factors, set_default_library, get_library,
 )
+from . import ingest  # noqa: F401   (host-side panel ingestion: the step before the path)
