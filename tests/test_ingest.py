@@ -44,3 +44,23 @@ def test_transform_and_biweight_small():
     tr = ingest.biweight_trend(X, 4.0)
     assert np.isnan(tr[0, 1]) and np.allclose(tr[1:, 1], 1.0)              # local mean of a constant is the constant
     assert np.allclose(tr[4:6, 0], X[4:6, 0])                              # symmetric window around an interior point of a line
+
+
+@needs_workbook
+def test_workbook_to_table2B_through_product_code(notebook_tables):
+    """Workbook -> product ingestion -> estimate_factor! through the kernel source (host emulation build) ->
+    golden Table 2B row r = 8 (trace R2 0.501, BN-ICp2 -0.223; Stock_Watson.ipynb:619-628)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "emu"))
+    import build_emu
+    import dynamic_factor_models_b200 as D
+    lib = D.Library(build_emu.build())
+    try:
+        p = ingest.readin_data(XLSX, "All")
+        m = D.DFMModel(p.bpdata, p.inclcode, 20, 40, p.row(1959, 3), p.row(2014, 4), 0, 8, 1e-8, 4, 4)
+        D.estimate_factor(m, lib=lib)
+        gold = np.array(notebook_tables["table2B"])[7]                  # nfac, traceR2, margR2, BN-ICp2, AH-ER
+        assert abs((1 - m.fes.ssr / m.fes.tss) - gold[1]) < 6e-4
+        assert abs(D.bai_ng_criterion(m) - gold[3]) < 6e-4
+    finally:
+        lib.close()
