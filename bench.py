@@ -35,9 +35,10 @@ UNIT = "panel-EM-iterations/s"
 
 
 def make_panels(B, rep0):
-    """Frozen DGP of SURVEY.md 8d (oracle/dgp.py), vectorised AR recursion.  (B, T, N) float64."""
+    """Frozen DGP of SURVEY.md 8d (dynamic_factor_models_b200/replicate.py::simulate_panel; the same definition the
+    oracle freezes in oracle/dgp.py), vectorised AR recursion.  (B, T, N) float64."""
     from scipy.signal import lfilter
-    from oracle.dgp import SEED
+    from dynamic_factor_models_b200.replicate import SEED
     out = np.empty((B, T_, NS))
     for b in range(B):
         rng = np.random.Generator(np.random.Philox(key=[SEED, rep0 + b]))
