@@ -67,3 +67,17 @@ def test_shard_range(libpath):
     assert got[0][0] == 0 and got[-1][1] == 1000
     assert all(got[i][1] == got[i + 1][0] for i in range(7))
     assert lib.dfm_shard_range(10, 8, 8, None, None) == 1
+
+
+def test_header_is_plain_c99(tmp_path):
+    """The boundary is a C ABI: include/dfm_b200.h must compile as C (what Julia's ccall / cgo / JNI stubs bind)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "t.c"
+    src.write_text('#include "dfm_b200.h"\nint main(void) { dfm_em_opts o; dfm_factor_opts f; (void)o; (void)f; return DFM_OK; }\n')
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", inc, str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
