@@ -82,3 +82,10 @@ def test_table5_through_kernel_source(lib, panels, notebook_tables, vset):
     np.testing.assert_allclose(_canonical_correlations(X[ok], g.factor[ok]), gold["level"], rtol=5e-5, atol=5e-7)
     ok = ~np.isnan(np.column_stack([v.resid, fv.resid])).any(1)
     np.testing.assert_allclose(_canonical_correlations(v.resid[ok], fv.resid[ok]), gold["resid"], rtol=5e-5, atol=5e-7)
+
+
+@pytest.mark.parametrize("N,r,T", [(19, 5, 62), (33, 2, 44), (27, 7, 150), (50, 6, 36)])
+def test_fused2_em_ragged_shapes(lib, N, r, T):
+    """Shapes that are not multiples of the 8-series / 132-period stage geometry or of the scan chunking, and the
+    template instantiations the other tests do not touch (r = 2, 5, 6, 7)."""
+    P.check_em(lib, N=N, r=r, T=T, p=1, miss=0.0, path=3, iters=4)
