@@ -758,9 +758,10 @@ int dfm_em_kalman(dfm_handle* h, const double* X, const dfm_em_opts* o, const df
     // upload (PCIe, ~55 GB/s) runs under the kernel (HBM-bound, slower than the link), P0 and the log-likelihood
     // pre-fill are done inside the kernel (no other kernel can become resident next to it), and the balance check
     // is deferred: a panel with NaNs ends with status 3, which triggers the scan + general-path fallback below.
-    // (Not under a CUDA injection profiler: ncu makes every launch synchronous, so a kernel that waits for copies
+    // (Not under a CUDA injection profiler or CUDA_LAUNCH_BLOCKING=1: launches are synchronous there, so a kernel that waits for copies
     //  enqueued after its launch would never finish.  DFM_NO_PIPELINE=1 forces the upload-then-compute path too.)
-    const bool profiler = getenv("CUDA_INJECTION64_PATH") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR");
+    const char* clb = getenv("CUDA_LAUNCH_BLOCKING");
+    const bool profiler = getenv("CUDA_INJECTION64_PATH") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") || (clb && clb[0] == '1');
     if (mem == DFM_MEM_HOST && fused && use2 && !getenv("DFM_NO_PIPELINE") && !profiler) {
       const int cap = fused2_capacity(r, T, N);
       if (batch > cap) {
