@@ -81,8 +81,54 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def host_cores():
+    """Host CPU allowance of THIS process: logical CPUs, scheduler affinity, cgroup CPU quota, physical cores.
+    `threads` = what the CPU arm uses: one OpenMP thread per physical core inside the affinity mask, capped by the
+    cgroup quota (os.cpu_count() ignores both, which oversubscribed the 1-GPU lease in round 1)."""
+    info = {"logical": os.cpu_count()}
+    try:
+        aff = sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        aff = list(range(os.cpu_count() or 1))
+    info["affinity"] = len(aff)
+    quota = None
+    try:                                                   # cgroup v2
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            quota = float(q) / float(per)
+    except (OSError, ValueError):
+        try:                                               # cgroup v1
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read()); per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        except (OSError, ValueError):
+            pass
+    info["cgroup_quota"] = quota
+    phys = set()
+    for c in aff:
+        try:
+            base = f"/sys/devices/system/cpu/cpu{c}/topology/"
+            phys.add((open(base + "physical_package_id").read().strip(), open(base + "core_id").read().strip()))
+        except OSError:
+            phys.add(("?", str(c)))
+    info["physical"] = len(phys)
+    n = min(len(aff), len(phys))
+    if quota:
+        n = max(1, min(n, int(quota)))
+    info["threads"] = n
+    return info
+
+
+def _omp_env():
+    """Bind the OpenMP threads of the oracle C port (read by libgomp when the library is loaded)."""
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    os.environ.setdefault("OMP_PLACES", "cores")
+    os.environ.setdefault("OMP_WAIT_POLICY", "active")
+
+
 def cpu_em(Xs, init, iters, nthreads=0):
     """Oracle C port on host cores: (seconds, panel-iterations)."""
+    _omp_env()
     from oracle.c import kem
     t0 = time.perf_counter()
     out = kem.em_kalman_batch(Xs, init[0], init[1], init[2], init[3], p=P_, max_iter=iters, tol=0.0, nthreads=nthreads, want_F=True)
@@ -97,32 +143,46 @@ def host_init(Xs):
     return tuple(np.stack([i[j] for i in ini]) for j in range(4))
 
 
+CPU_SAMPLE_PANELS = 256          # the bounded CPU sample: the first 256 panels of the workload x em_iters iterations
+
+
+def cpu_sample(iters, steps=1, warmup=1, Xs=None, init=None):
+    """The CPU arm, used identically by `--impl reference` and by the product arm's `cpu_baseline`: the oracle's C port
+    (OpenMP over panels, threads bound one per physical core of this process's allowance) on the first
+    CPU_SAMPLE_PANELS panels of the C2-shaped workload, `iters` EM iterations per step.  Also times one thread."""
+    hc = host_cores()
+    n = hc["threads"]
+    if Xs is None:
+        Xs = make_panels(CPU_SAMPLE_PANELS, 0)
+        init = host_init(Xs)
+    for _ in range(warmup):
+        cpu_em(Xs[:2 * n], tuple(a[:2 * n] for a in init), 2, nthreads=n)
+    t = 0.0; units = 0; out = None
+    for _ in range(steps):
+        dt, u, out = cpu_em(Xs, init, iters, nthreads=n)
+        t += dt; units += u
+    dt1, u1, _ = cpu_em(Xs[:2], tuple(a[:2] for a in init), iters, nthreads=1)
+    return {"value": units / t, "unit": UNIT, "cores": n, "kind": "port", "host": hc,
+            "single_thread_value": u1 / dt1,
+            "sample": f"{Xs.shape[0]} panels x {iters} EM iterations per step, oracle C port (gcc -O3, OpenMP over panels, "
+                      f"{n} threads bound to physical cores), {t / steps:.1f} s/step"}, t, out
+
+
 def run_reference(args):
     """--impl reference: the CPU arm.  The reference is Julia (not installable here: no julia, no
-    network) and contains no Kalman/EM code, so the oracle's C port of the same EM is timed, with all
-    host threads, on a bounded sample of the same workload per step."""
+    network) and contains no Kalman/EM code, so the oracle's C port of the same EM is timed on the host cores this
+    process may use, on a bounded sample of the same workload per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle.c import kem
-    cores = os.cpu_count() or kem.max_threads()        # all host threads (torchrun pins OMP_NUM_THREADS=1: override)
-    Bs = 4 * cores
-    Xs = make_panels(Bs, 0)
-    init = host_init(Xs)
     iters = args.em_iters
-    for _ in range(args.warmup):
-        cpu_em(Xs, init, 2, nthreads=cores)
-    t = 0.0; n = 0
-    for _ in range(args.steps):
-        dt, units, _ = cpu_em(Xs, init, iters, nthreads=cores)
-        t += dt; n += units
-    v = n / t
-    sample = f"{Bs} panels x {iters} EM iterations per step (oracle C port, OpenMP over panels)"
+    cpu, t, _ = cpu_sample(iters, steps=args.steps, warmup=max(1, min(args.warmup, 2)))
+    v = cpu["value"]
     print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                       "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
                       "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                       "config": {"workload": f"C2-shaped panels N={NS} r={R_} T={T_}, Kalman-EM, bounded CPU sample", "em_iters": iters},
-                      "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                      "cpu_baseline": cpu,
                       "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
@@ -295,18 +355,14 @@ def main():
             als["cpu_restated_reference"] = {"value": 3 / dtc, "unit": "panel-ALS-sweeps/s", "cores": 1, "kind": "port",
                                              "sample": "1 panel x 3 sweeps, oracle/dfm_ref.py (numpy/scipy pivoted-QR loops mirroring the reference's control flow; includes one PCA/SVD)"}
 
-    # ---- CPU baseline (rank 0, N=1 only): oracle C port on a bounded sample of the same workload
+    # ---- CPU baseline (rank 0, N=1 only): the same bounded sample as `--impl reference`, started from the device-made
+    # initial parameters so that the factors can be compared
     cpu = None; rmse = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        from oracle.c import kem
-        cores = os.cpu_count() or kem.max_threads()
-        Bs = min(B, 8 * cores)                       # ~10 s of CPU work on the 128-thread box
+        Bs = min(B, CPU_SAMPLE_PANELS)
         Lh = lambda t, rows, cols: np.ascontiguousarray(t[:Bs * rows * cols].cpu().numpy().reshape(Bs, cols, rows).transpose(0, 2, 1))
         init = (Lh(dLam0, NS, R_), dR0[:Bs * NS].cpu().numpy().reshape(Bs, NS), Lh(dA0, R_, k), Lh(dQ0, R_, R_))
-        cpu_em(Xh[:2], tuple(a[:2] for a in init), 2, nthreads=cores)
-        dt, n, out = cpu_em(Xh[:Bs], init, iters, nthreads=cores)
-        cpu = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{Bs} of the same panels x {iters} EM iterations, oracle C port (gcc -O3, OpenMP over panels), {dt:.1f} s"}
+        cpu, _, out = cpu_sample(iters, steps=1, warmup=1, Xs=Xh[:Bs], init=init)
         Fg = dout["F"][:Bs * T_ * R_].cpu().numpy().reshape(Bs, R_, T_).transpose(0, 2, 1)
         rmse = float(np.sqrt(np.mean((Fg - out["F"]) ** 2)))
 

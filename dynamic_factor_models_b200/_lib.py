@@ -58,7 +58,7 @@ def default_library_path():
 EXPORTS = ["dfm_version", "dfm_status_string", "dfm_create", "dfm_create_on_stream", "dfm_destroy", "dfm_sync",
            "dfm_launch_count", "dfm_last_error", "dfm_profile_enable", "dfm_profile_query", "dfm_profile_reset",
            "dfm_profile_kernel_name", "dfm_standardize", "dfm_pca_score", "dfm_estimate_factor",
-           "dfm_estimate_loading", "dfm_estimate_var", "dfm_irf", "dfm_em_kalman", "dfm_em_init_from_factors",
+           "dfm_estimate_loading", "dfm_estimate_loading_ex", "dfm_estimate_var", "dfm_irf", "dfm_em_kalman", "dfm_em_init_from_factors",
            "dfm_allgather_results", "dfm_shard_range"]
 
 
@@ -120,6 +120,7 @@ class Library:
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(FactorStats)]
         L.dfm_estimate_loading.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(LoadingOpts), C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_void_p]
+        L.dfm_estimate_loading_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(LoadingOpts)] + [C.c_void_p] * 7
         L.dfm_estimate_var.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 6
         L.dfm_irf.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_ip,
                               C.c_int, C.c_int, C.c_void_p]
@@ -246,11 +247,13 @@ class Library:
             o.constr_r = rv.ctypes.data_as(c_dp)
         din, fin = to_cm(data), to_cm(F)
         lam = np.empty(B * ns * r); r2 = np.empty(B * ns); ac = np.empty(B * ns * n_uarlag); ser = np.empty(B * ns)
-        self.check(self.lib.dfm_estimate_loading(self.h, _ptr(din), _ptr(fin), C.byref(o), _ptr(lam), _ptr(r2), _ptr(ac), _ptr(ser)),
-                   "dfm_estimate_loading")
+        con = np.empty(B * ns); res = np.empty(B * ns * T); st = np.zeros(B, np.int32)
+        self.check(self.lib.dfm_estimate_loading_ex(self.h, _ptr(din), _ptr(fin), C.byref(o), _ptr(lam), _ptr(r2), _ptr(ac), _ptr(ser),
+                                                    _ptr(con), _ptr(res), _ptr(st)), "dfm_estimate_loading")
         del keep
         return dict(lam=from_cm(lam, ns, r, b), r2=r2.reshape(B, ns) if b else r2, uar_coef=from_cm(ac, ns, n_uarlag, b),
-                    uar_ser=ser.reshape(B, ns) if b else ser)
+                    uar_ser=ser.reshape(B, ns) if b else ser, constant=con.reshape(B, ns) if b else con,
+                    resid=from_cm(res, T, ns, b), status=st if b else int(st[0]))
 
     def estimate_var(self, F, p, withconst=True):
         F = np.asarray(F, float); b = F.shape[0] if F.ndim == 3 else None

@@ -234,16 +234,7 @@ def amengual_watson_test(m, nper=4, lib=None):
     yy = est[rows]; zz = xl[rows]
     K = zz.shape[1] + 1
     out = lib.estimate_loading(yy, zz, nt_min=m.nt_min_factor_estimation + K, n_uarlag=1)
-    lam = out["lam"]
-    fitted_ok = ~np.isnan(lam).any(axis=1)
-    # residuals: recompute on host from device coefficients is avoided -- use r2-free path: e = y - [z 1] b
-    # (b's constant is not returned; recover it from the series mean over used rows)
-    for s in np.flatnonzero(fitted_ok):
-        o = ~np.isnan(yy[:, s])
-        c0 = (yy[o, s] - zz[o] @ lam[s]).mean()
-        e = yy[o, s] - zz[o] @ lam[s] - c0
-        idx = np.flatnonzero(rows)[o]
-        res[idx, s] = e
+    res[rows] = out["resid"]                       # device residuals e = y - [z 1] b, NaN where missing / not fitted
     aw = np.empty(nstat); ssr = np.empty(nstat); r2 = np.full((ns, nstat), np.nan)
     for nfac in range(1, nstat + 1):
         d = DFMModel(res, np.ones(ns, int), m.nt_min_factor_estimation, m.nt_min_factorloading_estimation,

@@ -7,6 +7,7 @@
 #include "dfm_kernels_em.cuh"
 #include "dfm_kernels_fused.cuh"
 #include "dfm_kernels_fused2.cuh"
+#include "dfm_kernels_als_masked.cuh"
 #include <algorithm>
 #include <new>
 #include <thread>
@@ -261,6 +262,25 @@ static int launch_als_fused2(dfm_handle* h, const AlsFusedArgs& fa, int B, int T
   CUtensorMap tm; int rc_ = make_panel_tmap(h, fa.Xs, T, (long long)B * N, &tm); if (rc_) return rc_;
   L(k_als_fused2<RT>, grid, 1, 256, smem, fa, tm);
   return DFM_OK;
+}
+template <int RT>
+static int launch_als_masked(dfm_handle* h, const AlsMaskedArgs& fa, int B, int T, int N) {
+  size_t smem = als_masked_smem_doubles<RT>(T, N) * 8;
+  int grid = std::min(B, 148 * 2);
+#ifndef DFM_EMU
+  DFM_SET_SMEM(k_als_masked<RT>, smem);
+  int dev = 0, nsm = 148, occ = 1;
+  cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_als_masked<RT>, 256, smem);
+  if (occ < 1) occ = 1;
+  grid = std::min(B, nsm * occ);
+#endif
+  L(k_als_masked<RT>, grid, 1, 256, smem, fa);
+  return DFM_OK;
+}
+static bool als_masked_shape_ok(int T, int N, int r) {
+  if (r < 1 || r > 8) return false;
+  return ((size_t)r * (T | 1) + (size_t)r * (N | 1) + 5 * (size_t)r * r + 48) * 8 <= 100 * 1024;
 }
 static bool als_fused2_shape_ok(int T, int N, int r) {
   if (r < 1 || r > 8 || T < 4 || (T & 1)) return false;
@@ -533,6 +553,19 @@ int dfm_estimate_factor(dfm_handle* h, const double* X, const dfm_factor_opts* o
         h_active = 0;
       }
     }
+    // panels with missing data, no constraints: all sweeps in ONE launch as well (thread-per-series / thread-per-period
+    // masked normal equations, no host synchronisation in the sweep loop)
+    if (h_active > 0 && nc == 0 && als_masked_shape_ok(T, N, r) && !getenv("DFM_ALS_GENERAL")) {
+      AlsMaskedArgs fa{}; fa.Xs = dXs; fa.F = dF; fa.Lam = dLam; fa.st = st; fa.B = batch; fa.T = T; fa.N = N; fa.nt_min = o->nt_min;
+      fa.tol = o->tol; fa.max_iter = o->max_iter;
+      switch (r) {
+#define DFM_CASEA(RT) case RT: rc = launch_als_masked<RT>(h, fa, batch, T, N); break;
+        DFM_CASEA(1) DFM_CASEA(2) DFM_CASEA(3) DFM_CASEA(4) DFM_CASEA(5) DFM_CASEA(6) DFM_CASEA(7) DFM_CASEA(8)
+#undef DFM_CASEA
+      }
+      if (rc) return rc;
+      h_active = 0;
+    }
     while (it < o->max_iter && h_active > 0) {                                       // :352
       if (nc > 0) L(k_gram_small, batch, 1, 128, 0, dF, T, r, FtF, st);
       L(k_als_lambda, N, batch, 64, smL, dXs, dF, T, N, r, o->nt_min, 0, dLam, (double*)nullptr, FtF, nc, cidx, cR, cr, ds, st);   // :355-362
@@ -566,6 +599,11 @@ int dfm_estimate_factor(dfm_handle* h, const double* X, const dfm_factor_opts* o
 // ------------------------------------------------------------------------------------ a9
 int dfm_estimate_loading(dfm_handle* h, const double* data, const double* F, const dfm_loading_opts* o, double* lambda,
                          double* r2, double* uar_coef, double* uar_ser) {
+  return dfm_estimate_loading_ex(h, data, F, o, lambda, r2, uar_coef, uar_ser, nullptr, nullptr, nullptr);
+}
+
+int dfm_estimate_loading_ex(dfm_handle* h, const double* data, const double* F, const dfm_loading_opts* o, double* lambda,
+                            double* r2, double* uar_coef, double* uar_ser, double* constant, double* resid, int* status_out) {
   if (!h || !data || !F || !o) return fail(h, DFM_ERR_ARG, "dfm_estimate_loading: null argument");
   int T = o->T, ns = o->ns, r = o->r, batch = o->batch, mem = o->mem, L_ = o->n_uarlag, nc = o->n_constr;
   if (T <= 1 || ns <= 0 || r <= 0 || r > 64 || batch <= 0 || L_ <= 0 || L_ > 16 || nc < 0 || nc > 64 ||
@@ -580,6 +618,8 @@ int dfm_estimate_loading(dfm_handle* h, const double* data, const double* F, con
     double* dl = a.get<double>(B * ns * r); double* dr2 = a.get<double>(B * ns);
     double* dac = a.get<double>(B * ns * L_); double* dser = a.get<double>(B * ns);
     double* scr = a.get<double>(B * ns * T); int* status = a.get<int>(B);
+    double* dcon = constant ? a.get<double>(B * ns) : nullptr;
+    double* dres = resid ? (mem == DFM_MEM_HOST ? a.get<double>(B * ns * T) : resid) : nullptr;
     int* cidx = a.get<int>(nc + 1); double* cR = a.get<double>((size_t)nc * r + 1); double* cr = a.get<double>(nc + 1);
     if (!pass) { int rc = ensure_ws(h, a.off); if (rc) return rc; continue; }
     const double* d; const double* f;
@@ -593,11 +633,19 @@ int dfm_estimate_loading(dfm_handle* h, const double* data, const double* F, con
     CK(cudaMemsetAsync(status, 0, B * sizeof(int), h->stream));
     size_t wk = std::max<size_t>((size_t)K * nc + (size_t)nc * (nc + 1) / 2 + nc, (size_t)L_ * (L_ + 1) / 2 + L_);
     size_t sm = (size_t)(np + K + 8 + wk) * 8;
-    L(k_loading, ns, batch, 64, sm, d, f, T, ns, r, o->nt_min, L_, dl, dr2, dac, dser, scr, nc, cidx, cR, cr, status);
+    L(k_loading, ns, batch, 64, sm, d, f, T, ns, r, o->nt_min, L_, dl, dr2, dac, dser, scr, nc, cidx, cR, cr, status, dcon, dres);
     rc = copy_out(h, lambda, dl, B * ns * r, mem); if (rc) return rc;
     rc = copy_out(h, r2, dr2, B * ns, mem); if (rc) return rc;
     rc = copy_out(h, uar_coef, dac, B * ns * L_, mem); if (rc) return rc;
     rc = copy_out(h, uar_ser, dser, B * ns, mem); if (rc) return rc;
+    if (constant) { rc = copy_out(h, constant, dcon, B * ns, mem); if (rc) return rc; }
+    if (resid && mem == DFM_MEM_HOST) { rc = copy_out(h, resid, dres, B * ns * T, mem); if (rc) return rc; }
+    if (status_out) {
+      // per-panel status (0, or DFM_ERR_NOT_PD when a regression / constraint / AR step of some series was singular;
+      // the affected series carry NaN).  Always a HOST array.
+      CK(cudaMemcpyAsync(status_out, status, B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+    }
   }
   return finish(h, mem);
 }
@@ -608,8 +656,8 @@ int dfm_estimate_var(dfm_handle* h, const double* F, int T, int r, int p, int wi
   if (!h || !F || T <= 0 || r <= 0 || p <= 0 || batch <= 0) return fail(h, DFM_ERR_ARG, "dfm_estimate_var: bad argument");
   int k = r * p, K = k + (withconst ? 1 : 0);
   if (T - p <= K) return fail(h, DFM_ERR_TOO_FEW_OBS, "dfm_estimate_var: T - p <= K");
-  size_t sm = ((size_t)K * K + (size_t)K * r + (size_t)r * r + 16) * 8;
-  if (sm > kMaxSmem) return fail(h, DFM_ERR_UNSUPPORTED, "dfm_estimate_var: r*p too large");
+  size_t sm = ((size_t)K * K + (size_t)K * r + (size_t)r * r + 16) * 8 + (size_t)T + 16;
+  if (sm > kMaxSmem) return fail(h, DFM_ERR_UNSUPPORTED, "dfm_estimate_var: r*p or T too large");
   CK(cudaSetDevice(h->device));
   size_t B = batch;
   for (int pass = 0; pass < 2; ++pass) {
@@ -631,7 +679,12 @@ int dfm_estimate_var(dfm_handle* h, const double* F, int T, int r, int p, int wi
     std::vector<int> hs(B);
     CK(cudaMemcpyAsync(hs.data(), status, B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    for (size_t b = 0; b < B; ++b) if (hs[b]) return fail(h, hs[b], "dfm_estimate_var: regression failed");
+    // a failed panel (too few complete rows / singular regression) has NaN in all of its outputs.  A single-panel call
+    // reports the failure as the return code; a batched call fails only when NO panel could be fitted, so that one
+    // degenerate bootstrap draw does not void the other replications (callers test the outputs for NaN).
+    size_t nfail = 0; int first = 0;
+    for (size_t b = 0; b < B; ++b) if (hs[b]) { if (!nfail) first = hs[b]; ++nfail; }
+    if (nfail == B) return fail(h, first, "dfm_estimate_var: regression failed");
   }
   return finish(h, mem);
 }
@@ -669,7 +722,7 @@ int dfm_em_init_from_factors(dfm_handle* h, const double* Xs, const double* F, i
   if (!h || !Xs || !F || T <= 0 || N <= 0 || r <= 0 || r > 64 || p <= 0 || batch <= 0) return fail(h, DFM_ERR_ARG, "dfm_em_init_from_factors: bad argument");
   int k = r * p;
   if (T - p <= k) return fail(h, DFM_ERR_TOO_FEW_OBS, "dfm_em_init_from_factors: T - p <= r*p");
-  size_t smV = ((size_t)k * k + (size_t)k * r + (size_t)r * r + 16) * 8;
+  size_t smV = ((size_t)k * k + (size_t)k * r + (size_t)r * r + 16) * 8 + (size_t)T + 16;
   if (smV > kMaxSmem) return fail(h, DFM_ERR_UNSUPPORTED, "r*p too large");
   CK(cudaSetDevice(h->device));
   size_t B = batch, TN = (size_t)T * N; int np = r * (r + 1) / 2;
@@ -761,7 +814,11 @@ int dfm_em_kalman(dfm_handle* h, const double* X, const dfm_em_opts* o, const df
     // (Not under a CUDA injection profiler or CUDA_LAUNCH_BLOCKING=1: launches are synchronous there, so a kernel that waits for copies
     //  enqueued after its launch would never finish.  DFM_NO_PIPELINE=1 forces the upload-then-compute path too.)
     const char* clb = getenv("CUDA_LAUNCH_BLOCKING");
-    const bool profiler = getenv("CUDA_INJECTION64_PATH") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") || (clb && clb[0] == '1');
+    const char* cdmc = getenv("CUDA_DEVICE_MAX_CONNECTIONS");
+    // ... nor with CUDA_DEVICE_MAX_CONNECTIONS=1 (common in torch.distributed set-ups): all streams then share one hardware
+    // queue, so the uploads could be queued BEHIND the kernel that waits for them.
+    const bool profiler = getenv("CUDA_INJECTION64_PATH") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") || (clb && clb[0] == '1') ||
+                          (cdmc && atoi(cdmc) == 1);
     if (mem == DFM_MEM_HOST && fused && use2 && !getenv("DFM_NO_PIPELINE") && !profiler) {
       const int cap = fused2_capacity(r, T, N);
       if (batch > cap) {
@@ -769,11 +826,18 @@ int dfm_em_kalman(dfm_handle* h, const double* X, const dfm_em_opts* o, const df
         while ((batch + chunk - 1) / chunk > kMaxReadyChunks) chunk *= 2;
         const int nch = (batch + chunk - 1) / chunk;
         cudaStream_t cs = h->copy_stream;
-        cudaEvent_t ev0, ev_k;
-        cudaEventCreateWithFlags(&ev0, cudaEventDisableTiming); cudaEventCreateWithFlags(&ev_k, cudaEventDisableTiming);
-        CK(cudaMemsetAsync(dready, 0, (size_t)nch * sizeof(int), cs));
-        cudaEventRecord(ev0, cs);
-        cudaStreamWaitEvent(h->stream, ev0, 0);                        // flags are zero before the kernel can read them
+        cudaEvent_t ev0 = nullptr, ev_k = nullptr;
+        CK(cudaEventCreateWithFlags(&ev0, cudaEventDisableTiming));
+        { cudaError_t e_ = cudaEventCreateWithFlags(&ev_k, cudaEventDisableTiming); if (e_ != cudaSuccess) { cudaEventDestroy(ev0); CK(e_); } }
+#define CKE(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cudaEventDestroy(ev0); cudaEventDestroy(ev_k); CK(e_); } } while (0)
+        // the workspace is shared with whatever the previous call on this handle left in flight on h->stream (a
+        // DFM_MEM_DEVICE call returns before completion): the copy stream must not touch it before that work is done
+        CKE(cudaEventRecord(ev_k, h->stream));
+        CKE(cudaStreamWaitEvent(cs, ev_k, 0));
+        CKE(cudaStreamWaitEvent(h->d2h_stream, ev_k, 0));
+        CKE(cudaMemsetAsync(dready, 0, (size_t)nch * sizeof(int), cs));
+        CKE(cudaEventRecord(ev0, cs));
+        CKE(cudaStreamWaitEvent(h->stream, ev0, 0));                   // flags are zero before the kernel can read them
         FusedArgs fa{};
         fa.X = dXb; fa.Lam = dL; fa.R = dR; fa.A = dA; fa.Q = dQ; fa.P0 = dP0; fa.Fs = dFs; fa.PsF = dPsF; fa.loglik = dll;
         fa.iters = dit; fa.status = dstat; fa.B = batch; fa.T = T; fa.N = N; fa.max_iter = mi; fa.tol = o->tol; fa.phase_cycles = nullptr;
@@ -781,10 +845,11 @@ int dfm_em_kalman(dfm_handle* h, const double* X, const dfm_em_opts* o, const df
         if (h->done_cap < B) {                                        // completion flags the kernel writes straight into host memory
           if (h->done_host) cudaFreeHost(h->done_host);
           h->done_host = nullptr; h->done_cap = 0;
-          CK(cudaHostAlloc((void**)&h->done_host, B * sizeof(int), cudaHostAllocMapped));
-          CK(cudaHostGetDevicePointer((void**)&h->done_dev, h->done_host, 0));
+          CKE(cudaHostAlloc((void**)&h->done_host, B * sizeof(int), cudaHostAllocMapped));
+          CKE(cudaHostGetDevicePointer((void**)&h->done_dev, h->done_host, 0));
           h->done_cap = B;
         }
+#undef CKE
         memset(h->done_host, 0, B * sizeof(int));
         fa.done = h->done_dev;
         fa.P0out = init->P0 ? nullptr : dP0; fa.p0_steps = 12;        // P0 in the kernel unless the caller gave one (the loglik rows are pre-filled there too)
@@ -916,7 +981,8 @@ int dfm_em_kalman(dfm_handle* h, const double* X, const dfm_em_opts* o, const df
 #ifndef DFM_EMU
       if (const char* sg = getenv("DFM_FUSED_STAGGER")) fa.stagger = atoi(sg);
       if (getenv("DFM_FUSED_PHASES")) {            // diagnostics: per-phase clock64 totals printed to stderr
-        static long long* dph = nullptr;
+        static long long* dph_dev[64] = {nullptr};                    // one diagnostics buffer per device
+        long long*& dph = dph_dev[h->device & 63];
         if (!dph) cudaMalloc((void**)&dph, 148 * 8 * DFM_PH * sizeof(long long));
         cudaMemsetAsync(dph, 0, 148 * 8 * DFM_PH * sizeof(long long), h->stream);
         fa.phase_cycles = dph;

@@ -33,11 +33,12 @@ namespace dfm {
 #define F2_TC 132       // periods per stage == row pitch in the ring; must be == 4 or 12 (mod 16) so that the
 #endif                  // DMMA fragment loads are bank-conflict free, and <= 256 (TMA box limit)
 #define F2_TS F2_TC     // (box width == chunk stride: no re-read of periods; T = 500 -> 4 chunks)
+#ifndef F2_PIPE
+#define F2_PIPE 1       // consumers: 1 = software-pipelined fragment refills, 0 = wait / load all / DMMA per stage
+#endif
 #define F2_NCW 6        // consumer warps (warps 1..6; warp 0 = producer, warp 7 = chain / solves)
 #define F2_GPARTS_S 4                                    // scalar Gram path: time slices per matrix entry
 #define F2_GPARTS ((R == 8) ? (F2_NCW + 1) : F2_GPARTS_S)   // partial Gram matrices (tensor path: one per warp of P3-P5)
-#define F2_NRB (((F2_TC + 7) / 8 + F2_NCW - 1) / F2_NCW)   // 8-period DMMA row blocks per consumer warp and stage (E pass)
-#define F2_NKC (((F2_TC + 3) / 4 + F2_NCW - 1) / F2_NCW)   // 4-period DMMA k-chunks per consumer warp and stage (M pass)
 static_assert(F2_TC % 16 == 4 || F2_TC % 16 == 12, "ring pitch must be 4 or 12 mod 16");
 static_assert(F2_TC <= 256 && (F2_TC * 64) % 128 == 0, "TMA box / stage alignment");
 #define F2_NEXS(R_) ((F2_S * 8 * F2_TS - 4 * (R_) * (R_)) / FUSED_SCR(R_))   // the last 4 R^2 doubles of the idle ring hold scan matrices
@@ -91,123 +92,266 @@ __device__ __forceinline__ void f2_produce(F2Ring& rg, const CUtensorMap* tmap, 
     }
 }
 
-// E pass, consumer warp cw (0..F2_NCW-1):  Z[t][:] = sum_n x[t,n] w_n Lam[n][:]  (w = rinv or 1), returns this
-// thread's share of sum x^2 w.  Period-chunk outer / series-block inner; each warp keeps the 8x8 DMMA
-// accumulators of its two row blocks in registers across all series blocks.
-template <int R>
-__device__ __forceinline__ double f2_consume_E(F2Ring& rg, int cw, int T, int N, int Tp, int Np, double* Z, const double* Lam,
-                                               const double* rinv) {
+// ---- consumer side of the two panel passes ------------------------------------------------------------------
+// A stage's DMMA units (8-period row blocks in the E pass, 4-period k-chunks in the M pass) are dealt round-robin to
+// the F2_NCW consumer warps: warp cw owns units cw, cw + F2_NCW, ...  Each consumer is SOFTWARE-PIPELINED over the
+// stages: while the DMMAs of stage i issue from one register buffer, the fragments of stage i + 1 are already being
+// loaded into the other (wait full[i+1] -> LDS -> DMMA(i)).  A warp issues in order, so without this every stage cost
+// a serial  mbarrier wait (~60-90 cycles) + LDS latency (~30) + DMMA issue (16 each)  chain per warp (measured:
+// 620-720 cycles per stage); pipelined, the wait and the loads hide behind the previous stage's DMMAs.  A stage is
+// released (empty barrier) as soon as its fragments are in registers, i.e. one iteration before its DMMAs.
+#define F2_NBE ((F2_TC + 7) / 8)          // row blocks of a full stage (E pass)
+#define F2_NKM (F2_TC / 4)                // k-chunks of a full stage (M pass; F2_TC % 4 == 0)
+#define F2_CNT(D, cw) (((D) - (cw) + F2_NCW - 1) / F2_NCW)     // units of consumer cw in a full stage
+#define F2_CNT_HI(D) (((D) + F2_NCW - 1) / F2_NCW)
+#define F2_CNT_LO(D) ((D) / F2_NCW)
+#define F2_DMMA(d_, a_, b_) asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"((d_)[0]), "+d"((d_)[1]) : "d"(a_), "d"(b_))
+static_assert(F2_CNT_LO(F2_NBE) >= 1 && F2_CNT_LO(F2_NKM) >= 2, "every consumer warp needs work in a full stage");
+
+// The consumers are separate (non-inlined) functions so that their register allocation is independent of the ~40 live
+// pointers of the kernel body; they address shared memory explicitly (32-bit shared-window addresses, ld.shared /
+// st.shared / mbarrier PTX), because a pointer that crosses a call boundary would otherwise be treated as generic.
+// The loads are volatile asm: they keep their program order relative to the (volatile) mbarrier waits and DMMAs.
+__device__ __forceinline__ double f2_lds(uint32_t a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void f2_sts(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ void f2_wait_s(uint32_t bar, uint32_t phase) {
+  asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(bar), "r"(phase) : "memory");
+}
+__device__ __forceinline__ void f2_arrive_s(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+#define F2_STAGE_BYTES (8 * F2_TS * 8)
+
+// fragments of the stage at ring slot `ra` are in registers: free the slot
+#define F2_RELEASE() do { __syncwarp(); if (lane == 0) f2_arrive_s(q.empty + ra * 8); if (++ra == F2_S) ra = 0; } while (0)
+// shared-window view of the ring position (consumer side)
+struct F2RingS {
+  uint32_t ring, full, empty; int rs; uint32_t rph;
+  __device__ __forceinline__ void load(const F2Ring& rg) { ring = f2_smem_u32(rg.ring); full = f2_smem_u32(rg.full); empty = f2_smem_u32(rg.empty); rs = rg.rs; rph = rg.rph; }
+  __device__ __forceinline__ void store(F2Ring& rg, long long nst) const { if (nst > 0) { if (rg.rs + nst >= F2_S) rg.wrap = true; rg.rs = rs; rg.rph = rph; } }
+  __device__ __forceinline__ void advance() { if (++rs == F2_S) { rs = 0; rph ^= 1; } }
+};
+
+// E pass, consumer warp cw (0..F2_NCW-1):  Z[t][:] = sum_n x[t,n] LamW[n][:], LamW = Lam already scaled by the series
+// weights (1/R_n, or 1).  Period-chunk outer / series-block inner; the warp keeps the 8x8 accumulators of its CNT row
+// blocks in registers across all series blocks of a chunk (the two k-half DMMAs of a row block chain, CNT >= 2 issue
+// slots apart).  When F2_TC is not a multiple of 8, the last row block of a full chunk is shifted back to F2_TC - 8 (it
+// overlaps its neighbour; only its new rows are stored) so that no fragment load leaves the box.  QACC (first EM
+// iteration / first ALS sweep only; the quantity is data-only): returns this thread's share of sum x^2 w.
+template <int R, int CNT, bool QACC>
+__device__ __noinline__ double f2_consume_E(F2Ring& rg, int cw, int T, int N, int Tp, int Np, double* Z, const double* LamW, const double* rinv) {
   const int lane = threadIdx.x & 31, lr = lane >> 2, lc = lane & 3;
-  const int nsb = (N + 7) / 8, nck = (T + F2_TC - 1) / F2_TC;
+  const int nsb = (N + 7) / 8, nck = (T + F2_TC - 1) / F2_TC, nst = nsb * nck;
+  const int tail_len = T - (nck - 1) * F2_TC;                 // length of the last chunk (== F2_TC when T is a multiple)
+  const bool nedge = (N & 7) != 0, lrok = (R == 8) || lr < R;
+  F2RingS q; q.load(rg);
+  int ra = q.rs;                                              // ring slot of the stage whose DMMAs issue next (release cursor)
+  const uint32_t z_s = f2_smem_u32(Z), rinv_s = rinv ? f2_smem_u32(rinv) : 0u;
+  const uint32_t lam_s = f2_smem_u32(LamW) + (uint32_t)((lrok ? lr : 0) * Np + lc) * 8u;
+  const uint32_t lane_off = (uint32_t)(lc * F2_TS + lr) * 8u;
+  uint32_t offF[CNT];                                         // byte offsets of my row blocks in a full chunk
+#pragma unroll
+  for (int j = 0; j < CNT; ++j) { const int t0 = (cw + F2_NCW * j) * 8; offF[j] = (uint32_t)((t0 > F2_TC - 8) ? F2_TC - 8 : t0) * 8u; }
   double qacc = 0.0;
-  for (int c = 0; c < nck; ++c) {
-    const int len = (T - c * F2_TC < F2_TC) ? T - c * F2_TC : F2_TC;
-    // row blocks cw, cw + NCW, ...: one independent accumulator pair per (row block, k half) so that no
-    // two DMMAs of a stage depend on each other (the chains only link consecutive stages)
-    double d[F2_NRB][2][2];
+  double d[CNT][2];
 #pragma unroll
-    for (int j = 0; j < F2_NRB; ++j) { d[j][0][0] = 0.0; d[j][0][1] = 0.0; d[j][1][0] = 0.0; d[j][1][1] = 0.0; }
-    for (int sb = 0; sb < nsb; ++sb) {
-      f2_mbar_wait(&rg.full[rg.rs], rg.rph);
-      const double* tile = rg.ring + (size_t)rg.rs * 8 * F2_TS;
-      // all fragment loads of the stage first (no branches in between: the warp issues in order, so a
-      // load placed after a DMMA would only start once that DMMA's operands had arrived), then the math
-      double rn[2], lm[2], av[2][F2_NRB];
+  for (int j = 0; j < CNT; ++j) { d[j][0] = 0.0; d[j][1] = 0.0; }
+  double a0[CNT], a1[CNT], l0 = 0.0, l1 = 0.0;                // fragments of the stage whose DMMAs issue next
+  int cl = 0, sbl = 0;                                        // (chunk, series block) of the next stage to LOAD
+  int cc = 0, sbc = 0;                                        // ... of the next stage to COMPUTE
+  // One register buffer: each fragment register is refilled for stage i + 1 right behind the DMMA of stage i that
+  // consumed it (the hardware orders the write after the read), so the loads of the next stage are in flight while
+  // the DMMAs of this one issue.  (Macros, not lambdas: register arrays captured by reference go to local memory.)
+  // F2E_ADDR: addresses / masks of the stage to load; F2E_LDA(j, h): fragment of row block j, k-half h.
+#define F2E_ADDR()                                                                                                          \
+    const bool fullL = (cl < nck - 1) || tail_len == F2_TC;                                                                 \
+    const bool fastL = fullL && !(nedge && sbl == nsb - 1);                                                                 \
+    const int lenL = fullL ? F2_TC : tail_len;                                                                              \
+    const uint32_t tileL = q.ring + (uint32_t)q.rs * F2_STAGE_BYTES + lane_off;                                             \
+    const uint32_t laL = lam_s + (uint32_t)sbl * 64u;                                                                       \
+    const bool n0L = sbl * 8 + lc < N, n1L = sbl * 8 + 4 + lc < N;
+#define F2E_OFF(j) (fullL ? offF[j] : (uint32_t)(cw + F2_NCW * (j)) * 64u)
+#define F2E_LDA(j, h) (fastL ? f2_lds(tileL + offF[j] + (h) * (4 * F2_TS * 8))                                              \
+                             : ((((h) ? n1L : n0L) && (int)(F2E_OFF(j) >> 3) + lr < lenL) ? f2_lds(tileL + F2E_OFF(j) + (h) * (4 * F2_TS * 8)) : 0.0))
+#define F2E_LDL(h) (fastL ? (lrok ? f2_lds(laL + (h) * 32) : 0.0) : ((lrok && ((h) ? n1L : n0L)) ? f2_lds(laL + (h) * 32) : 0.0))
+#define F2E_ADVANCE() do { q.advance(); if (++sbl == nsb) { sbl = 0; ++cl; } } while (0)
+#define F2E_LOAD_ALL() do {                                                                                                 \
+    f2_wait_s(q.full + q.rs * 8, q.rph);                                                                                    \
+    F2E_ADDR()                                                                                                              \
+    l0 = F2E_LDL(0); l1 = F2E_LDL(1);                                                                                       \
+    _Pragma("unroll") for (int j = 0; j < CNT; ++j) { a0[j] = F2E_LDA(j, 0); a1[j] = F2E_LDA(j, 1); }                       \
+    F2E_ADVANCE();                                                                                                          \
+  } while (0)
+#if F2_PIPE
+  if (nst > 0) F2E_LOAD_ALL();
+#endif
+  for (int i = 0; i < nst; ++i) {
+#if F2_PIPE
+    F2_RELEASE();                                             // stage i is in registers
+    const bool more = i + 1 < nst;
+    if (more) f2_wait_s(q.full + q.rs * 8, q.rph);
+#else
+    F2E_LOAD_ALL();                                           // plain variant: wait, load everything, then the DMMAs
+    const bool more = false;
+#endif
+    F2E_ADDR()
+    const bool fullC = (cc < nck - 1) || tail_len == F2_TC;
+    const int lenC = fullC ? F2_TC : tail_len;
+    if (QACC) {
+      const int n0_ = sbc * 8 + lc, n1_ = n0_ + 4;
+      const double r0 = (n0_ < N) ? (rinv_s ? f2_lds(rinv_s + n0_ * 8) : 1.0) : 0.0, r1 = (n1_ < N) ? (rinv_s ? f2_lds(rinv_s + n1_ * 8) : 1.0) : 0.0;
 #pragma unroll
-      for (int kc = 0; kc < 2; ++kc) {
-        const int n = sb * 8 + kc * 4 + lc;
-        const bool nok = n < N;
-        rn[kc] = nok ? (rinv ? rinv[n] : 1.0) : 0.0;
-        lm[kc] = (nok && lr < R) ? Lam[LI(n, lr)] : 0.0;
-        const double* trow = tile + (kc * 4 + lc) * F2_TS + lr;
-#pragma unroll
-        for (int j = 0; j < F2_NRB; ++j) {
-          const int t0 = (cw + j * F2_NCW) * 8;
-          av[kc][j] = (nok && t0 + lr < len) ? trow[t0] : 0.0;
-        }
+      for (int j = 0; j < CNT; ++j) {
+        const int rb8 = (cw + F2_NCW * j) * 8, row = (fullC ? (int)(offF[j] >> 3) : rb8) + lr;
+        if (row >= rb8 && row < lenC) { qacc += a0[j] * a0[j] * r0; qacc += a1[j] * a1[j] * r1; }
       }
-#pragma unroll
-      for (int kc = 0; kc < 2; ++kc)
-#pragma unroll
-        for (int j = 0; j < F2_NRB; ++j) {
-          const double ar = av[kc][j] * rn[kc];
-          qacc += av[kc][j] * ar;
-          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                       : "+d"(d[j][kc][0]), "+d"(d[j][kc][1]) : "d"(ar), "d"(lm[kc]));
-        }
-      __syncwarp();
-      if (lane == 0) f2_mbar_arrive(&rg.empty[rg.rs]);
-      rg.advance();
     }
+    if (more && fastL) {                                       // the common case: unmasked refills
 #pragma unroll
-    for (int j = 0; j < F2_NRB; ++j) {
-      const int tl = (cw + j * F2_NCW) * 8 + lr;
-      if (tl < len) { const int t = c * F2_TC + tl; Z[ZI(t, 2 * lc)] = d[j][0][0] + d[j][1][0]; Z[ZI(t, 2 * lc + 1)] = d[j][0][1] + d[j][1][1]; }
+      for (int j = 0; j < CNT; ++j) { F2_DMMA(d[j], a0[j], l0); a0[j] = f2_lds(tileL + offF[j]); }
+      l0 = f2_lds(laL);
+#pragma unroll
+      for (int j = 0; j < CNT; ++j) { F2_DMMA(d[j], a1[j], l1); a1[j] = f2_lds(tileL + offF[j] + 4 * F2_TS * 8); }
+      l1 = f2_lds(laL + 32);
+      if (!lrok) { l0 = 0.0; l1 = 0.0; }
+    } else {
+#pragma unroll
+      for (int j = 0; j < CNT; ++j) { F2_DMMA(d[j], a0[j], l0); if (more) a0[j] = F2E_LDA(j, 0); }
+      if (more) l0 = F2E_LDL(0);
+#pragma unroll
+      for (int j = 0; j < CNT; ++j) { F2_DMMA(d[j], a1[j], l1); if (more) a1[j] = F2E_LDA(j, 1); }
+      if (more) l1 = F2E_LDL(1);
+    }
+    if (more) F2E_ADVANCE();
+#if !F2_PIPE
+    F2_RELEASE();
+#endif
+    if (++sbc == nsb) {                                        // chunk complete: store my rows of Z
+#pragma unroll
+      for (int j = 0; j < CNT; ++j) {
+        const int rb8 = (cw + F2_NCW * j) * 8, row = (fullC ? (int)(offF[j] >> 3) : rb8) + lr;
+        if (row >= rb8 && row < lenC) {
+          const int t = cc * F2_TC + row;
+          f2_sts(z_s + (uint32_t)((2 * lc) * Tp + t) * 8u, d[j][0]); f2_sts(z_s + (uint32_t)((2 * lc + 1) * Tp + t) * 8u, d[j][1]);
+        }
+        d[j][0] = 0.0; d[j][1] = 0.0;
+      }
+      sbc = 0; ++cc;
     }
   }
+#undef F2E_LOAD_ALL
+#undef F2E_ADDR
+#undef F2E_OFF
+#undef F2E_LDA
+#undef F2E_LDL
+#undef F2E_ADVANCE
+  q.store(rg, nst);
   return qacc;
 }
 
-// M pass, consumer warp cw:  Lam[n][:] <- sum_t x[t,n] Z[t][:]  (S_xf) and sxx[n] <- sum_t x[t,n]^2.
-// Series-block outer / period-chunk inner; two accumulator pairs per warp; deterministic cross-warp
-// reduction of the F2_NCW partial tiles at the end of every series block (named barrier 1).
-template <int R>
-__device__ __forceinline__ void f2_consume_M(F2Ring& rg, int cw, int T, int N, int Tp, int Np, const double* Z, double* Lam,
-                                             double* sxx, double* part) {
+// end of a series block in the M pass: deterministic cross-warp reduction of the F2_NCW partial 8x8 tiles (+ sxx)
+template <int R, bool SXX>
+__device__ __forceinline__ void f2_m_reduce(double (&d)[2][2], double& s2, int sb, int cw, int N, int Np, uint32_t part_s, double* Lam, double* sxx) {
   const int lane = threadIdx.x & 31, lr = lane >> 2, lc = lane & 3;
-  const int nsb = (N + 7) / 8, nck = (T + F2_TC - 1) / F2_TC;
-  double d[F2_NKC][2], s2 = 0.0;                                  // one accumulator pair per k-chunk slot: independent DMMAs
+  const uint32_t pb = part_s + (uint32_t)((sb & 1) * F2_NCW * 72 + cw * 72) * 8u;
+  f2_sts(pb + 16 * lane, d[0][0] + d[1][0]); f2_sts(pb + 16 * lane + 8, d[0][1] + d[1][1]);
+  d[0][0] = 0.0; d[0][1] = 0.0; d[1][0] = 0.0; d[1][1] = 0.0;
+  if (SXX) {
+    s2 += __shfl_xor_sync(0xffffffffu, s2, 1); s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+    if (lc == 0) f2_sts(pb + (64 + lr) * 8, s2);
+    s2 = 0.0;
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(F2_NCW * 32) : "memory");
+  const int ct = cw * 32 + lane;                          // 0 .. F2_NCW*32-1
+  if (ct < (SXX ? 72 : 64)) {
+    const uint32_t pp_ = part_s + (uint32_t)((sb & 1) * F2_NCW * 72 + ct) * 8u;
+    double tot_ = 0.0;
 #pragma unroll
-  for (int j = 0; j < F2_NKC; ++j) { d[j][0] = 0.0; d[j][1] = 0.0; }
-  for (int sb = 0; sb < nsb; ++sb)
-    for (int c = 0; c < nck; ++c) {
-      f2_mbar_wait(&rg.full[rg.rs], rg.rph);
-      const double* tile = rg.ring + (size_t)rg.rs * 8 * F2_TS;
-      const int len = (T - c * F2_TC < F2_TC) ? T - c * F2_TC : F2_TC;
-      const bool nok = sb * 8 + lr < N;
-      const double* zc = Z + (size_t)lr * Tp + c * F2_TC + lc;
-      const double* trow = tile + lr * F2_TS + lc;
-      double av[F2_NKC], bv[F2_NKC];                            // k-chunks cw, cw + NCW, ...: loads first, then the math
+    for (int w_ = 0; w_ < F2_NCW; ++w_) tot_ += f2_lds(pp_ + w_ * 72 * 8);
+    if (ct < 64) {
+      const int l_ = ct >> 1, h_ = ct & 1, row = l_ >> 2, col = 2 * (l_ & 3) + h_, n = sb * 8 + row;
+      if (n < N && col < R) Lam[LI(n, col)] = tot_;
+    } else { const int n = sb * 8 + (ct - 64); if (n < N) sxx[n] = tot_; }
+  }
+}
+
+// M pass, consumer warp cw:  Lam[n][:] <- sum_t x[t,n] Z[t][:]  (S_xf) and, with SXX (first iteration only: data-only),
+// sxx[n] <- sum_t x[t,n]^2.  Series-block outer / period-chunk inner, same software pipeline; the k-chunks of a warp
+// alternate between two accumulator pairs; deterministic cross-warp reduction of the F2_NCW partial tiles at the end of
+// every series block (named barrier 1) -- the first stage of the next series block is already in flight then.  Rows
+// of a ragged last series block (n >= N) only reach output rows that are discarded; periods beyond T inside the box
+// are zero-filled by the tensor-map copy (Z is masked there).
+template <int R, int CNT, bool SXX>
+__device__ __noinline__ void f2_consume_M(F2Ring& rg, int cw, int T, int N, int Tp, int Np, const double* Z, double* Lam, double* sxx, double* part) {
+  const int lane = threadIdx.x & 31, lr = lane >> 2, lc = lane & 3;
+  const int nsb = (N + 7) / 8, nck = (T + F2_TC - 1) / F2_TC, nst = nsb * nck;
+  const int tail_len = T - (nck - 1) * F2_TC;
+  F2RingS q; q.load(rg);
+  int ra = q.rs;
+  const uint32_t zrow = f2_smem_u32(Z) + (uint32_t)(lr * Tp + lc + 4 * cw) * 8u, part_s = f2_smem_u32(part);
+  const uint32_t lane_off = (uint32_t)(lr * F2_TS + lc + 4 * cw) * 8u;
+  double d[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, s2 = 0.0;
+  double av[CNT], bv[CNT];                                    // fragments of the stage whose DMMAs issue next
+  int cl = 0;                                                 // chunk of the next stage to LOAD
+  int cc = 0, sbc = 0;                                        // (chunk, series block) of the next stage to COMPUTE
+  // one register buffer, refilled slot by slot behind the DMMA that consumed it (see f2_consume_E)
+#define F2M_ADDR()                                                                                                          \
+    const bool fastL = (cl < nck - 1) || tail_len == F2_TC;                                                                 \
+    const uint32_t trowL = q.ring + (uint32_t)q.rs * F2_STAGE_BYTES + lane_off;                                             \
+    const uint32_t zcL = zrow + (uint32_t)(cl * F2_TC) * 8u;
+#define F2M_TOK(j) (fastL || 4 * (cw + F2_NCW * (j)) + lc < tail_len)
+#define F2M_ADVANCE() do { q.advance(); if (++cl == nck) cl = 0; } while (0)
+#define F2M_LOAD_ALL() do {                                                                                                 \
+    f2_wait_s(q.full + q.rs * 8, q.rph);                                                                                    \
+    F2M_ADDR()                                                                                                              \
+    if (fastL) {                                                                                                            \
+      _Pragma("unroll") for (int j = 0; j < CNT; ++j) { av[j] = f2_lds(trowL + j * (F2_NCW * 32)); bv[j] = f2_lds(zcL + j * (F2_NCW * 32)); } \
+    } else {                                                                                                                \
+      _Pragma("unroll") for (int j = 0; j < CNT; ++j) { const bool tok = F2M_TOK(j); av[j] = tok ? f2_lds(trowL + j * (F2_NCW * 32)) : 0.0; bv[j] = tok ? f2_lds(zcL + j * (F2_NCW * 32)) : 0.0; } \
+    }                                                                                                                       \
+    F2M_ADVANCE();                                                                                                          \
+  } while (0)
+#if F2_PIPE
+  if (nst > 0) F2M_LOAD_ALL();
+#endif
+  for (int i = 0; i < nst; ++i) {
+#if F2_PIPE
+    F2_RELEASE();                                             // stage i is in registers
+    const bool more = i + 1 < nst;
+    if (more) f2_wait_s(q.full + q.rs * 8, q.rph);
+#else
+    F2M_LOAD_ALL();
+    const bool more = false;
+#endif
+    F2M_ADDR()
+    if (more && fastL) {
 #pragma unroll
-      for (int j = 0; j < F2_NKC; ++j) {
-        const int t0 = (cw + j * F2_NCW) * 4;
-        const bool tok = t0 + lc < len;
-        av[j] = (nok && tok) ? trow[t0] : 0.0;
-        bv[j] = tok ? zc[t0] : 0.0;
+      for (int j = 0; j < CNT; ++j) {
+        if (SXX) s2 += av[j] * av[j];
+        F2_DMMA(d[j & 1], av[j], bv[j]);
+        av[j] = f2_lds(trowL + j * (F2_NCW * 32)); bv[j] = f2_lds(zcL + j * (F2_NCW * 32));
       }
+    } else {
 #pragma unroll
-      for (int j = 0; j < F2_NKC; ++j) {
-        s2 += av[j] * av[j];
-        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                     : "+d"(d[j][0]), "+d"(d[j][1]) : "d"(av[j]), "d"(bv[j]));
-      }
-      __syncwarp();
-      if (lane == 0) f2_mbar_arrive(&rg.empty[rg.rs]);
-      rg.advance();
-      if (c == nck - 1) {
-        s2 += __shfl_xor_sync(0xffffffffu, s2, 1); s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
-        double* pb = part + (size_t)(sb & 1) * F2_NCW * 72 + cw * 72;
-        double t0_ = 0.0, t1_ = 0.0;
-#pragma unroll
-        for (int j = 0; j < F2_NKC; ++j) { t0_ += d[j][0]; t1_ += d[j][1]; d[j][0] = 0.0; d[j][1] = 0.0; }
-        pb[2 * lane] = t0_; pb[2 * lane + 1] = t1_;
-        if (lc == 0) pb[64 + lr] = s2;
-        asm volatile("bar.sync 1, %0;" ::"n"(F2_NCW * 32) : "memory");
-        const int ct = cw * 32 + lane;                          // 0 .. F2_NCW*32-1
-        if (ct < 72) {
-          const double* pp_ = part + (size_t)(sb & 1) * F2_NCW * 72 + ct;
-          double tot_ = 0.0;
-#pragma unroll
-          for (int w_ = 0; w_ < F2_NCW; ++w_) tot_ += pp_[w_ * 72];
-          if (ct < 64) {
-            const int l_ = ct >> 1, h_ = ct & 1, row = l_ >> 2, col = 2 * (l_ & 3) + h_, n = sb * 8 + row;
-            if (n < N && col < R) Lam[LI(n, col)] = tot_;
-          } else { const int n = sb * 8 + (ct - 64); if (n < N) sxx[n] = tot_; }
-        }
-        s2 = 0.0;
+      for (int j = 0; j < CNT; ++j) {
+        if (SXX) s2 += av[j] * av[j];
+        F2_DMMA(d[j & 1], av[j], bv[j]);
+        if (more) { const bool tok = F2M_TOK(j); av[j] = tok ? f2_lds(trowL + j * (F2_NCW * 32)) : 0.0; bv[j] = tok ? f2_lds(zcL + j * (F2_NCW * 32)) : 0.0; }
       }
     }
+    if (more) F2M_ADVANCE();
+#if !F2_PIPE
+    F2_RELEASE();
+#endif
+    if (++cc == nck) { cc = 0; f2_m_reduce<R, SXX>(d, s2, sbc, cw, N, Np, part_s, Lam, sxx); ++sbc; }
+  }
+#undef F2M_LOAD_ALL
+#undef F2M_ADDR
+#undef F2M_TOK
+#undef F2M_ADVANCE
+  q.store(rg, nst);
 }
+// dispatch on the warp's unit count in a full stage (two possible values)
+#define F2_RUN_E(R_, Q_, cw_, ...) ((F2_CNT(F2_NBE, cw_) == F2_CNT_HI(F2_NBE)) ? f2_consume_E<R_, F2_CNT_HI(F2_NBE), Q_>(__VA_ARGS__) : f2_consume_E<R_, F2_CNT_LO(F2_NBE), Q_>(__VA_ARGS__))
+#define F2_RUN_M(R_, S_, cw_, ...) do { if (F2_CNT(F2_NKM, cw_) == F2_CNT_HI(F2_NKM)) f2_consume_M<R_, F2_CNT_HI(F2_NKM), S_>(__VA_ARGS__); else f2_consume_M<R_, F2_CNT_LO(F2_NKM), S_>(__VA_ARGS__); } while (0)
 #endif  // !DFM_EMU
 
 #ifdef DFM_EMU
@@ -378,6 +522,14 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
         DFM_SYNC();
         for (int e = DFM_TID; e < RR; e += DFM_NT) { double s = 0.0; for (int sl = 0; sl < nsl; ++sl) s += T1[sl * RR + e]; C[e] = s; }
       }
+      // sum_t x_t' R^-1 x_t = sum_n sxx_n / R_n: sxx is data-only (M pass of the first iteration), so only the first
+      // E pass accumulates the term itself
+      double qs_p = 0.0;
+      if (it > 0) for (int i = DFM_TID; i < N; i += DFM_NT) qs_p += sxx[i] * rinv[i];
+      qs_p = block_sum(qs_p, red);
+      if (DFM_TID == 0) scal[2] = qs_p;
+      // the E pass contracts with LamW = R^-1 Lam: scale Lam in place (the M pass overwrites it with S_xf anyway)
+      for (int e = DFM_TID; e < N * R; e += DFM_NT) { const int i = e % N, c = e / N; Lam[LI(i, c)] *= rinv[i]; }
       DFM_SYNC();
       DFM_TICK(1);
       // ---- covariance chain (data independent).  Forward part: on the chain warp concurrently with the E pass;
@@ -539,9 +691,9 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
       for (int t = 0; t < T; ++t) {
         for (int c = 0; c < FZ; ++c) Z[ZI(t, c)] = 0.0;
         for (int n = 0; n < N; ++n) {
-          double x = X[(size_t)n * T + t], xr = x * rinv[n];
-          qacc += x * xr;
-          for (int c = 0; c < R; ++c) Z[ZI(t, c)] += xr * Lam[LI(n, c)];
+          double x = X[(size_t)n * T + t];
+          if (it == 0) qacc += x * x * rinv[n];
+          for (int c = 0; c < R; ++c) Z[ZI(t, c)] += x * Lam[LI(n, c)];
         }
       }
 #else
@@ -551,7 +703,12 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
         const long long nitems = (long long)((N + 7) / 8) * ((T + F2_TC - 1) / F2_TC);
         F2_ROLE_T0();
         if (DFM_WARP == 0) { f2_produce(rg, &tmap, b * N, T, N, /*c_outer=*/true); F2_ROLE_T1(14); }
-        else if (DFM_WARP <= F2_NCW) { qacc += f2_consume_E<R>(rg, DFM_WARP - 1, T, N, Tp, Np, Z, Lam, rinv); if (DFM_WARP == 1) F2_ROLE_T1(15); }
+        else if (DFM_WARP <= F2_NCW) {
+          const int cw_ = DFM_WARP - 1;
+          if (it == 0) qacc += F2_RUN_E(R, true, cw_, rg, cw_, T, N, Tp, Np, Z, Lam, rinv);
+          else F2_RUN_E(R, false, cw_, rg, cw_, T, N, Tp, Np, Z, Lam, rinv);
+          if (DFM_WARP == 1) F2_ROLE_T1(15);
+        }
         else {
           rg.skip(nitems);                                                   // keep the ring position in step
           chain_fwd();
@@ -621,7 +778,8 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
       // which collapses to  quad_t = zf_{t-1}' K zf_{t-1} - zf_t' W zf_t  with K = M'(W - C) M.  Over the frozen
       // range (W, K constant) the sum only needs the second-moment matrix of the filtered means:
       //   sum_t quad_t = tr(K (Gf + z_{nE-1} z_{nE-1}' - z_{T-1} z_{T-1}')) - tr(W Gf),   Gf = sum_{t>=nE} zf_t zf_t'.
-      double llp = -0.5 * qacc;                              // this thread's share of -1/2 sum x' R^-1 x (E pass)
+      double llp = -0.5 * qacc;                              // this thread's share of -1/2 sum x' R^-1 x (first E pass; else scal[2])
+      if (F2_PTID == 0) llp += -0.5 * scal[2];
       const bool gram = frozen && nE >= 1 && nE < T;
       // explicit periods t < nE: one thread per (t, component) in two stages when their (zp, d) vectors fit
       // in the idle scan workspace; otherwise (and for a chain that never froze) one thread per period
@@ -773,6 +931,25 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
       auto mstep_small = [&]() {
         int* bad = &ctl[2];
         // mean parts of the moment sums (needs only the smoothed means in Z)
+#ifndef DFM_EMU
+        if (R == 8) {
+          // Sm = sum_t z_t z_t' and S11m = sum_{t>=1} z_t z_{t-1}' as DMMA.8x8x4 Gram products over 4-period chunks: the A
+          // fragment (z_i(t0 + k)) doubles as the B fragment of Sm; S11m takes z_j(t0 + k - 1) as B.  Two accumulator
+          // pairs each (chunks alternate), ~2 x 125 DMMAs instead of 2 x 64 x T scalar multiply-adds on 32 lanes.
+          const int lr = DFM_LANE >> 2, lc = DFM_LANE & 3;
+          const double* zr = Z + (size_t)lr * Tp;
+          double g[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, h[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+          for (int t0 = 0; t0 < T; t0 += 8) {
+            const int ta = t0 + lc, tb_ = t0 + 4 + lc;
+            const double va = (ta < T) ? zr[ta] : 0.0, vb = (tb_ < T) ? zr[tb_] : 0.0;
+            const double pa = (ta >= 1 && ta < T) ? zr[ta - 1] : 0.0, pb = (tb_ < T) ? zr[tb_ - 1] : 0.0;
+            F2_DMMA(g[0], va, va); F2_DMMA(h[0], va, pa);
+            F2_DMMA(g[1], vb, vb); F2_DMMA(h[1], vb, pb);
+          }
+          Sm[lr * 8 + 2 * lc] = g[0][0] + g[1][0]; Sm[lr * 8 + 2 * lc + 1] = g[0][1] + g[1][1];
+          S11m[lr * 8 + 2 * lc] = h[0][0] + h[1][0]; S11m[lr * 8 + 2 * lc + 1] = h[0][1] + h[1][1];
+        } else
+#endif
         for (int e = DFM_LANE; e < 2 * RR; e += DFM_WSZ) {
           int which = e / RR, ee = e % RR, i = ee / R, j = ee % R;
           double s0 = 0.0, s1 = 0.0;
@@ -811,7 +988,7 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
         for (int c = 0; c < R; ++c) acc[c] = 0.0;
         for (int t = 0; t < T; ++t) { double x = X[(size_t)n * T + t]; s2 += x * x; for (int c = 0; c < R; ++c) acc[c] += x * Z[ZI(t, c)]; }
         for (int c = 0; c < R; ++c) Lam[LI(n, c)] = acc[c];
-        sxx[n] = s2;
+        if (it == 0) sxx[n] = s2;
       }
 #else
       {
@@ -822,7 +999,12 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
         const long long nitems = (long long)((N + 7) / 8) * ((T + F2_TC - 1) / F2_TC);
         F2_ROLE_T0();
         if (DFM_WARP == 0) { f2_produce(rg, &tmap, b * N, T, N, /*c_outer=*/false); F2_ROLE_T1(17); }
-        else if (DFM_WARP <= F2_NCW) { f2_consume_M<R>(rg, DFM_WARP - 1, T, N, Tp, Np, Z, Lam, sxx, part); if (DFM_WARP == 1) F2_ROLE_T1(18); }
+        else if (DFM_WARP <= F2_NCW) {
+          const int cw_ = DFM_WARP - 1;
+          if (it == 0) F2_RUN_M(R, true, cw_, rg, cw_, T, N, Tp, Np, Z, Lam, sxx, part);
+          else F2_RUN_M(R, false, cw_, rg, cw_, T, N, Tp, Np, Z, Lam, sxx, part);
+          if (DFM_WARP == 1) F2_ROLE_T1(18);
+        }
         else {
           rg.skip(nitems);
           mstep_small();
@@ -950,7 +1132,7 @@ __global__ void DFM_FUSED2_BOUNDS k_als_fused2(AlsFusedArgs a, const DFM_GRID_CO
     for (int e = DFM_TID; e < T * R; e += DFM_NT) { int t = e % T, c = e / T; Z[ZI(t, c)] = a.F[(size_t)b * T * R + e]; }
     if (DFM_TID == 0) ctl[0] = 0;
     DFM_SYNC();
-    double ssr = 0.0, ssr_old = 0.0;
+    double ssr = 0.0, ssr_old = 0.0, tss_all = 0.0;
     long long it = 0;
     int status = 0;
     while (it < a.max_iter) {
@@ -972,7 +1154,7 @@ __global__ void DFM_FUSED2_BOUNDS k_als_fused2(AlsFusedArgs a, const DFM_GRID_CO
       }
 #else
       if (DFM_WARP == 0) f2_produce(rg, &tmap, b * N, T, N, /*c_outer=*/false);
-      else if (DFM_WARP <= F2_NCW) f2_consume_M<R>(rg, DFM_WARP - 1, T, N, Tp, Np, Z, Lam, sxx, part);
+      else if (DFM_WARP <= F2_NCW) { const int cw_ = DFM_WARP - 1; F2_RUN_M(R, false, cw_, rg, cw_, T, N, Tp, Np, Z, Lam, sxx, part); }
       else rg.skip(nitems);
 #endif
       DFM_SYNC();
@@ -996,15 +1178,19 @@ __global__ void DFM_FUSED2_BOUNDS k_als_fused2(AlsFusedArgs a, const DFM_GRID_CO
       }
       DFM_SYNC();
       if (DFM_WARP == 0) w_inv<R>(Hi, LtL, tmp, &ctl[0]);
-      double tssp = 0.0;
+      double tssp = 0.0;                                       // sum x^2: data-only, accumulated in the first sweep only
 #ifdef DFM_EMU
       for (int t = 0; t < T; ++t) {
         for (int c = 0; c < FZ; ++c) Z[ZI(t, c)] = 0.0;
-        for (int n = 0; n < N; ++n) { double x = X[(size_t)n * T + t]; tssp += x * x; for (int c = 0; c < R; ++c) Z[ZI(t, c)] += x * Lam[LI(n, c)]; }
+        for (int n = 0; n < N; ++n) { double x = X[(size_t)n * T + t]; if (it == 0) tssp += x * x; for (int c = 0; c < R; ++c) Z[ZI(t, c)] += x * Lam[LI(n, c)]; }
       }
 #else
       if (DFM_WARP == 0) f2_produce(rg, &tmap, b * N, T, N, /*c_outer=*/true);
-      else if (DFM_WARP <= F2_NCW) tssp += f2_consume_E<R>(rg, DFM_WARP - 1, T, N, Tp, Np, Z, Lam, nullptr);
+      else if (DFM_WARP <= F2_NCW) {
+        const int cw_ = DFM_WARP - 1;
+        if (it == 0) tssp += F2_RUN_E(R, true, cw_, rg, cw_, T, N, Tp, Np, Z, Lam, nullptr);
+        else F2_RUN_E(R, false, cw_, rg, cw_, T, N, Tp, Np, Z, Lam, nullptr);
+      }
       else rg.skip(nitems);
 #endif
       DFM_SYNC();
@@ -1021,8 +1207,8 @@ __global__ void DFM_FUSED2_BOUNDS k_als_fused2(AlsFusedArgs a, const DFM_GRID_CO
         for (int i = 0; i < R; ++i) Z[ZI(t, i)] = f[i];
       }
       bf = block_sum(bf, red);
-      tssp = block_sum(tssp, red);
-      ssr_old = ssr; ssr = tssp - bf;
+      if (it == 0) tss_all = block_sum(tssp, red);
+      ssr_old = ssr; ssr = tss_all - bf;
       ++it;
       if (ctl[0]) { status = 3; break; }
       if (!(fabs(ssr_old - ssr) >= a.tol * (double)T * (double)N)) break;            // :367-368

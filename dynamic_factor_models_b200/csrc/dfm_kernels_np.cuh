@@ -572,7 +572,8 @@ __global__ void k_loading(const double* __restrict__ dataAll, const double* __re
                           int nt_min, int n_uarlag, double* __restrict__ lambda, double* __restrict__ r2out,
                           double* __restrict__ uar_coef, double* __restrict__ uar_ser, double* __restrict__ scratch,
                           int n_constr, const int* __restrict__ c_index, const double* __restrict__ c_R,
-                          const double* __restrict__ c_r, int* __restrict__ status) {
+                          const double* __restrict__ c_r, int* __restrict__ status, double* __restrict__ constant,
+                          double* __restrict__ resid) {
   DFM_SMEM(sm);
   int s_ = DFM_BX, b = DFM_BY;
   const double* y = dataAll + ((size_t)b * ns + s_) * T;
@@ -608,15 +609,21 @@ __global__ void k_loading(const double* __restrict__ dataAll, const double* __re
   double* lam = lambda + (size_t)b * ns * r;
   double* ac = uar_coef + (size_t)b * ns * n_uarlag;
   int cnt = (int)sc[0];
+  // every early exit leaves NaN in ALL outputs of this series (never stale workspace contents)
+#define LOAD_NAN_ALL() do {                                                                       \
+    for (int a = 0; a < r; ++a) lam[s_ + (size_t)ns * a] = DFM_NAN;                               \
+    r2out[o] = DFM_NAN; uar_ser[o] = DFM_NAN;                                                     \
+    for (int l = 0; l < n_uarlag; ++l) ac[s_ + (size_t)ns * l] = DFM_NAN;                         \
+    if (constant) constant[o] = DFM_NAN;                                                          \
+    if (resid) for (int t = 0; t < T; ++t) resid[o * T + t] = DFM_NAN;                            \
+  } while (0)
   if (cnt < nt_min) {            // reference leaves these undefined (SURVEY 'bugs'): NaN
-    for (int a = 0; a < r; ++a) lam[s_ + (size_t)ns * a] = DFM_NAN;
-    r2out[o] = DFM_NAN; uar_ser[o] = DFM_NAN;
-    for (int l = 0; l < n_uarlag; ++l) ac[s_ + (size_t)ns * l] = DFM_NAN;
+    LOAD_NAN_ALL();
     return;
   }
   bool constrained = false;
   for (int q = 0; q < n_constr; ++q) if (c_index[q] == s_) constrained = true;
-  if (chol_solve_packed(A, c, K, 1)) { status[b] = 3; r2out[o] = DFM_NAN; return; }
+  if (chol_solve_packed(A, c, K, 1)) { status[b] = 3; LOAD_NAN_ALL(); return; }
   if (constrained) {             // :loading constraint: R_tmp = [R 0], r unstandardized (:1147-1148)
     int nc = 0;
     for (int q = 0; q < n_constr; ++q) if (c_index[q] == s_) ++nc;
@@ -644,17 +651,19 @@ __global__ void k_loading(const double* __restrict__ dataAll, const double* __re
       }
       ++row;
     }
-    if (chol_solve_packed(S, res, nc, 1)) { status[b] = 3; return; }
+    if (chol_solve_packed(S, res, nc, 1)) { status[b] = 3; LOAD_NAN_ALL(); return; }
     for (int a = 0; a < K; ++a) { double s = 0.0; for (int cc = 0; cc < nc; ++cc) s += tmp[a + K * cc] * res[cc]; c[a] -= s; }
   }
   for (int a = 0; a < r; ++a) lam[s_ + (size_t)ns * a] = c[a];
+  if (constant) constant[o] = c[r];
   // gap-free residuals (:400), R2 (:404 via compute_r2 :565-569)
   int n = 0; double ssr = 0.0;
   for (int t = 0; t < T; ++t) {
     double v = y[t];
-    if (is_nan(v)) continue;
+    if (is_nan(v)) { if (resid) resid[o * T + t] = DFM_NAN; continue; }
     double e = v - c[r];
     for (int a = 0; a < r; ++a) e -= c[a] * F[t + (size_t)T * a];
+    if (resid) resid[o * T + t] = e;
     u[n++] = e; ssr += e * e;
   }
   double tss = sc[1] - sc[2] * sc[2] / cnt;
@@ -675,11 +684,16 @@ __global__ void k_loading(const double* __restrict__ dataAll, const double* __re
       cc2[a] += ua * u[j];
       for (int q = 0; q <= a; ++q) AA[pidx(a, q)] += ua * u[j - 1 - q];
     }
-  if (n - L < L || chol_solve_packed(AA, cc2, L, 1)) { status[b] = 3; uar_ser[o] = DFM_NAN; return; }
+  if (n - L < L || chol_solve_packed(AA, cc2, L, 1)) {
+    status[b] = 3; uar_ser[o] = DFM_NAN;
+    for (int l = 0; l < L; ++l) ac[s_ + (size_t)ns * l] = DFM_NAN;
+    return;
+  }
   double ssr2 = 0.0;
   for (int j = L; j < n; ++j) { double e = u[j]; for (int a = 0; a < L; ++a) e -= cc2[a] * u[j - 1 - a]; ssr2 += e * e; }
   for (int l = 0; l < L; ++l) ac[s_ + (size_t)ns * l] = cc2[l];
   uar_ser[o] = sqrt(ssr2 / (double)(n - L));
+#undef LOAD_NAN_ALL
 }
 
 // ---------------------------------------------------------------- a10 factor VAR (:444-492)
@@ -697,35 +711,62 @@ __global__ void k_var(const double* __restrict__ Fall, int T, int r, int p, int 
   double* ZZ = sm;                 // K x K
   double* ZY = ZZ + K * K;         // K x r  -> beta
   double* Se = ZY + K * r;         // r x r
-  int* info = (int*)(Se + r * r);
-  if (DFM_TID == 0) *info = 0;
-  if (Tu <= K) { if (DFM_TID == 0) status[b] = 2; return; }
+  int* info = (int*)(Se + r * r);       // [0] = Cholesky flag, [1] = number of rows kept
+  unsigned char* keep = (unsigned char*)(info + 4);      // [T]: row t enters the regression
+  if (DFM_TID == 0) { info[0] = 0; info[1] = 0; }
+  DFM_SYNC();
+  // estimate_var! regresses with ols_skipmissing(..., Balanced()) (dfm_functions.ipynb:242-252, 452): every row with a
+  // missing y_t or a missing lag is dropped; rows t < p have no lags and are always dropped
+  {
+    int cnt = 0;
+    for (int t = DFM_TID; t < T; t += DFM_NT) {
+      bool ok = t >= p;
+      for (int l = 0; ok && l <= p; ++l) for (int c = 0; c < r; ++c) if (is_nan(F[(t - l) + (size_t)T * c])) { ok = false; break; }
+      keep[t] = ok ? 1 : 0; cnt += ok ? 1 : 0;
+    }
+    if (cnt) atomicAdd(&info[1], cnt);
+  }
+  DFM_SYNC();
+  Tu = info[1];
+  // a failed panel leaves NaN in every output (so that a batched caller can drop it) and its code in status[b]
+#define VAR_FAIL(code_) do {                                                                                        \
+    if (DFM_TID == 0) status[b] = (code_);                                                                          \
+    for (int e = DFM_TID; e < T * r; e += DFM_NT) resid[(size_t)b * T * r + e] = DFM_NAN;                           \
+    if (betahat) for (int e = DFM_TID; e < K * r; e += DFM_NT) betahat[(size_t)b * K * r + e] = DFM_NAN;            \
+    if (seps) for (int e = DFM_TID; e < r * r; e += DFM_NT) seps[(size_t)b * r * r + e] = DFM_NAN;                  \
+    if (Mo) for (int e = DFM_TID; e < k * k; e += DFM_NT) Mo[(size_t)b * k * k + e] = DFM_NAN;                      \
+    if (Ao) for (int e = DFM_TID; e < r * k; e += DFM_NT) Ao[(size_t)b * r * k + e] = DFM_NAN;                      \
+    if (Qo) for (int e = DFM_TID; e < r * k; e += DFM_NT) Qo[(size_t)b * r * k + e] = DFM_NAN;                      \
+    if (Go) for (int e = DFM_TID; e < k * r; e += DFM_NT) Go[(size_t)b * k * r + e] = DFM_NAN;                      \
+    return;                                                                                                         \
+  } while (0)
+  if (Tu <= K) VAR_FAIL(2);
   // regressor j at time t (t = p..T-1): j==0&&const -> 1 ; else lag l = (j-c)/r + 1, var = (j-c)%r
 #define ZREG(t, j) ((withconst && (j) == 0) ? 1.0 : F[((t) - (((j) - (withconst ? 1 : 0)) / r + 1)) + (size_t)T * (((j) - (withconst ? 1 : 0)) % r)])
   for (int e = DFM_TID; e < K * K; e += DFM_NT) {
     int a = e % K, c = e / K;
     if (a < c) continue;
     double s = 0.0;
-    for (int t = p; t < T; ++t) s += ZREG(t, a) * ZREG(t, c);
+    for (int t = p; t < T; ++t) if (keep[t]) s += ZREG(t, a) * ZREG(t, c);
     ZZ[a + K * c] = s; ZZ[c + K * a] = s;
   }
   for (int e = DFM_TID; e < K * r; e += DFM_NT) {
     int a = e % K, c = e / K;
     double s = 0.0;
-    for (int t = p; t < T; ++t) s += ZREG(t, a) * F[t + (size_t)T * c];
+    for (int t = p; t < T; ++t) if (keep[t]) s += ZREG(t, a) * F[t + (size_t)T * c];
     ZY[a + K * c] = s;
   }
   DFM_SYNC();
   bm_chol(ZZ, K, K, info);
   bm_trsm_lower(ZZ, K, K, ZY, K, r);
   bm_trsm_lowerT(ZZ, K, K, ZY, K, r);          // ZY = betahat (K x r)
-  if (*info) { if (DFM_TID == 0) status[b] = 3; return; }
-  // residuals -> global (needed for seps); rows < p are NaN (:464 leaves them missing)
   double* res = resid + (size_t)b * T * r;
+  if (*info) VAR_FAIL(3);
+  // residuals -> global (needed for seps); dropped rows are NaN (:464 writes the kept rows only)
   for (int e = DFM_TID; e < T * r; e += DFM_NT) {
     int t = e % T, c = e / T;
     double v = DFM_NAN;
-    if (t >= p) { v = F[t + (size_t)T * c]; for (int a = 0; a < K; ++a) v -= ZREG(t, a) * ZY[a + K * c]; }
+    if (keep[t]) { v = F[t + (size_t)T * c]; for (int a = 0; a < K; ++a) v -= ZREG(t, a) * ZY[a + K * c]; }
     res[t + (size_t)T * c] = v;
   }
   DFM_SYNC();
@@ -734,7 +775,7 @@ __global__ void k_var(const double* __restrict__ Fall, int T, int r, int p, int 
   for (int e = DFM_TID; e < r * r; e += DFM_NT) {
     int a = e % r, c = e / r;
     double s = 0.0;
-    for (int t = p; t < T; ++t) s += res[t + (size_t)T * a] * res[t + (size_t)T * c];
+    for (int t = p; t < T; ++t) if (keep[t]) s += res[t + (size_t)T * a] * res[t + (size_t)T * c];
     Se[a + r * c] = s / ndf;
   }
   DFM_SYNC();
@@ -754,9 +795,10 @@ __global__ void k_var(const double* __restrict__ Fall, int T, int r, int p, int 
   DFM_SYNC();
   if (Go) {
     bm_chol(Se, r, r, info);                           // lower factor = cholesky(seps).U'
-    if (*info && DFM_TID == 0) status[b] = 3;
+    if (*info) VAR_FAIL(3);
     for (int e = DFM_TID; e < k * r; e += DFM_NT) { int i = e % k, j = e / k; Go[(size_t)b * k * r + e] = (i < r) ? Se[i + r * j] : 0.0; }
   }
+#undef VAR_FAIL
 }
 
 // ---------------------------------------------------------------- a11 IRF (:793-816)

@@ -120,11 +120,23 @@ typedef struct {
  * uar_ser ns.  Series with < nt_min usable rows get NaN (the reference leaves them undefined). */
 int dfm_estimate_loading(dfm_handle* h, const double* data, const double* F, const dfm_loading_opts* opts,
                          double* lambda, double* r2, double* uar_coef, double* uar_ser);
+/* Same regression, plus what the reference keeps in locals: `constant` ns (the intercept b[end] of :399-401) and
+ * `resid` T x ns (the residuals `ehat` of :400, NaN where the observation is missing or the series was not fitted) --
+ * amengual_watson_test (:741-752) residualises the panel with exactly this regression.  `status` (HOST int[batch], may
+ * be NULL): 0, or DFM_ERR_NOT_PD if some series' regression / constraint / AR step was singular (those series are NaN).
+ * constant / resid / status may be NULL. */
+int dfm_estimate_loading_ex(dfm_handle* h, const double* data, const double* F, const dfm_loading_opts* opts,
+                            double* lambda, double* r2, double* uar_coef, double* uar_ser, double* constant,
+                            double* resid, int* status);
 
 /* ---- a10: estimate_var! + fill_matrices!, :444-492 ------------------------------------ */
-/* F: T x r (rows initperiod..lastperiod, no missing).  K = r*p + withconst.
- * betahat K x r; resid T x r (first p rows NaN); seps r x r (= e'e/(T-p-K)); M k x k, Q r x k,
- * G k x r with chol(seps) lower in its top block (k = r*p).  Any output may be NULL. */
+/* F: T x r (rows initperiod..lastperiod; NaN = missing).  K = r*p + withconst.  As estimate_var! does through
+ * ols_skipmissing(..., Balanced()) (:242-252, :452), every row t whose y_t or one of its p lags is missing is dropped;
+ * T_used = number of rows kept.
+ * betahat K x r; resid T x r (NaN on dropped rows, incl. the first p); seps r x r (= e'e/(T_used-K)); M k x k, Q r x k,
+ * G k x r with chol(seps) lower in its top block (k = r*p).  Any output may be NULL.
+ * A panel that cannot be fitted (T_used <= K, singular regression, seps not PD) has NaN in all of its outputs; the call
+ * returns that panel's error code when batch == 1 or when NO panel of the batch could be fitted, DFM_OK otherwise. */
 int dfm_estimate_var(dfm_handle* h, const double* F, int T, int r, int p, int withconst, int batch, int mem,
                      double* betahat, double* resid, double* seps, double* M, double* Q, double* G);
 

@@ -13,6 +13,7 @@ module DFMB200
 
 const LIB = get(ENV, "DFM_B200_LIB", joinpath(@__DIR__, "..", "dynamic_factor_models_b200", "lib", "libdfm_b200.so"))
 const MEM_HOST = Cint(0)
+const LAST_ALS = Ref{Any}((iters = 0, status = 0, lambda = zeros(0, 0)))   # stats of the last estimate_factor! call
 
 struct FactorOpts
     T::Cint; N::Cint; r::Cint; nt_min::Cint
@@ -70,10 +71,14 @@ function estimate_factor!(m, max_iter::Integer = 100000000, computeR2::Bool = tr
                      Ptr{Cdouble}, Ptr{Cdouble}, Ref{FactorStats}),
                     h, X, opts, C_NULL, F, Lam, R2, C_NULL, C_NULL, stats), "dfm_estimate_factor")
     end
-    m.factor[m.initperiod:m.lastperiod, :] = F                              # :371
     s = stats[]
+    # status 2 / 3 = a period with fewer than r observations / a singular normal-equation system: the factors are NaN
+    # (same rule as api.estimate_factor in the Python mirror); 4 = max_iter reached, which the reference accepts silently
+    (s.status == 2 || s.status == 3) && error("dfm_estimate_factor: ALS failed (status $(s.status))")
+    m.factor[m.initperiod:m.lastperiod, :] = F                              # :371
     m.fes.ssr, m.fes.tss, m.fes.nobs = s.ssr, s.tss, s.nobs                # :342-343, :366
     computeR2 && (m.fes.R2 .= frommissing(R2))
+    LAST_ALS[] = (iters = Int(s.iters), status = Int(s.status), lambda = Lam)   # the reference discards these (:381)
     return nothing
 end
 
@@ -138,6 +143,12 @@ function estimate!(m, method = Main.NonParametric(); lam_constr_f = nothing, lam
     Xs = similar(X); mu = Vector{Float64}(undef, N); sd = Vector{Float64}(undef, N)
     check(ccall((:dfm_standardize, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Cint, Cint, Cint, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
                 h, X, T, N, 1, MEM_HOST, Xs, mu, sd), "dfm_standardize")
+    # series dropped by nt_min in the ALS step (NaN row of its Lambda) stay out of the state-space model as well --
+    # the same masking as api._estimate_parametric, so that both host mirrors fit the same model
+    lam_als = LAST_ALS[].lambda
+    for i in 1:N
+        isnan(lam_als[i, 1]) && (Xs[:, i] .= NaN)
+    end
     F0 = tonan(m.factor[m.initperiod:m.lastperiod, :])
     Lam = Matrix{Float64}(undef, N, r); R = Vector{Float64}(undef, N); A = Matrix{Float64}(undef, r, k); Q = Matrix{Float64}(undef, r, r)
     check(ccall((:dfm_em_init_from_factors, LIB), Cint,

@@ -163,11 +163,26 @@ def check_var_irf(lib, r=3, p=2, T=120):
     np.testing.assert_allclose(irf, irf_ref, rtol=1e-9, atol=1e-12)
 
 
-def _em_compare(lib, X, p, iters, tol_par=1e-8, path=0):
-    r_ = None
-    xs = X
-    F0 = R.pca_score(np.nan_to_num(xs), r_ or 0) if False else None
-    return F0
+def check_var_missing_rows(lib, r=3, p=2, T=120):
+    """estimate_var! drops every row with a missing y_t or lag (ols_skipmissing Balanced, dfm_functions.ipynb:242-252,
+    452): NaNs INSIDE [initperiod, lastperiod] must give the oracle's fit, NaN residuals on the dropped rows."""
+    _, tr = simulate_panel(10, r, T, rep=8)
+    Fm = tr["F"].copy()
+    Fm[17, 1] = np.nan; Fm[60:62, :] = np.nan; Fm[T - 1, 0] = np.nan
+    v = R.VARModel(Fm.copy(), p, True, 1, T); R.estimate_var(v)
+    out = lib.estimate_var(Fm, p, True)
+    np.testing.assert_allclose(out["betahat"], v.betahat, rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(out["seps"], v.seps, rtol=1e-9)
+    np.testing.assert_allclose(out["G"], v.G, rtol=1e-9, atol=1e-12)
+    assert np.array_equal(np.isnan(out["resid"]), np.isnan(v.resid))
+    ok = ~np.isnan(v.resid)
+    np.testing.assert_allclose(out["resid"][ok], v.resid[ok], rtol=1e-8, atol=1e-10)
+    # batched call: a panel without enough complete rows comes back as NaN, the others are fitted
+    Fb = np.stack([tr["F"], np.full_like(tr["F"], np.nan), Fm])
+    ob = lib.estimate_var(Fb, p, True)
+    assert np.isnan(ob["betahat"][1]).all() and np.isnan(ob["M"][1]).all()
+    np.testing.assert_allclose(ob["betahat"][2], v.betahat, rtol=1e-9, atol=1e-11)
+    assert np.isfinite(ob["betahat"][0]).all()
 
 
 def check_em(lib, N=24, r=3, T=70, p=1, miss=0.0, iters=6, path=0, rep=9):
@@ -287,3 +302,20 @@ def check_parametric_c1(lib, panels, iters=3):
     np.testing.assert_allclose(got["loglik"], ref["loglik"], rtol=1e-9)
     assert rmse(got["F"], ref["F"]) < 1e-7
     np.testing.assert_allclose(got["A"], ref["A"], rtol=1e-5, atol=1e-7)
+
+
+def check_nile_published(lib, path=0):
+    """The product's filter / smoother on the published local-level example (Durbin & Koopman 2012, ch. 2; see
+    tests/test_oracle_kalman_published.py): diffuse log-likelihood -632.54 at the published ML estimates."""
+    import json
+    import os
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "nile_local_level.json")))
+    y = np.array(g["nile"], float)[:, None]; pub = g["published"]; P1 = 1e7
+    s2e, s2n = pub["sigma2_eps"], pub["sigma2_eta"]
+    out = lib.em_kalman(y, np.ones((1, 1)), np.array([s2e]), np.ones((1, 1)), np.array([[s2n]]), p=1, P0=np.array([[P1]]), max_iter=1,
+                        path=path)
+    first = -0.5 * np.log(2 * np.pi) - 0.5 * np.log(P1 + s2e) - 0.5 * y[0, 0] ** 2 / (P1 + s2e)
+    assert abs((out["loglik"][0] - first) - pub["loglik_diffuse"]) < 0.01
+    es = K.e_step(y, np.ones((1, 1)), np.array([s2e]), np.ones((1, 1)), np.array([[s2n]]), np.array([[P1]]), 1)
+    np.testing.assert_allclose(out["F"][:, 0], es["zs"][:, 0], rtol=1e-9)
+    np.testing.assert_allclose(out["loglik"][0], es["loglik"], rtol=1e-11)

@@ -29,6 +29,7 @@ def test_estimate_factor_c1(lib, panels): P.check_estimate_factor_c1(lib, panels
 def test_constraint(lib, panels): P.check_constraint(lib, panels)
 def test_full_nonparametric_c1(lib, panels): P.check_full_nonparametric_c1(lib, panels)
 def test_var_irf(lib): P.check_var_irf(lib)
+def test_var_missing_rows(lib): P.check_var_missing_rows(lib)
 def test_em_p1_balanced(lib): P.check_em(lib, p=1, miss=0.0)
 def test_em_p2_missing(lib): P.check_em(lib, p=2, miss=0.12)
 def test_em_convergence_rule(lib): P.check_em_convergence_rule(lib)
@@ -37,6 +38,9 @@ def test_als_batch(lib): P.check_als_batch(lib)
 def test_als_balanced_fused(lib): P.check_als_balanced(lib)
 def test_als_balanced_fused_r8(lib): P.check_als_balanced(lib, N=48, r=8, T=120, B=2)
 def test_parametric_c1(lib, panels): P.check_parametric_c1(lib, panels, iters=2)
+def test_nile_published_general(lib): P.check_nile_published(lib, path=1)
+def test_nile_published_fused(lib): P.check_nile_published(lib, path=2)
+def test_nile_published_fused2(lib): P.check_nile_published(lib, path=3)
 
 
 # ---- fused per-panel EM kernel (path=2): same source under emulation (DMMA loops have a plain twin)
@@ -89,3 +93,15 @@ def test_fused2_em_ragged_shapes(lib, N, r, T):
     """Shapes that are not multiples of the 8-series / 132-period stage geometry or of the scan chunking, and the
     template instantiations the other tests do not touch (r = 2, 5, 6, 7)."""
     P.check_em(lib, N=N, r=r, T=T, p=1, miss=0.0, path=3, iters=4)
+
+
+def test_amengual_watson_table2C_corner(lib, panels, notebook_tables):
+    """estimate_factor_numbers through the C ABI (device residuals from dfm_estimate_loading_ex): the 3 x 3 corner of
+    golden Table 2C (Stock_Watson.ipynb:669-683); the full table runs in the -m gpu tier."""
+    import dynamic_factor_models_b200 as D
+    g = P.gpu_model(panels["all_bpdata"], panels["all_inclcode"], 1)
+    out = D.estimate_factor_numbers(g, 3, lib=lib)
+    gold = np.array(notebook_tables["table2C"])[:3, 1:4]
+    mask = ~np.isnan(gold)
+    assert (np.isnan(out["aw_icp"]) == np.isnan(gold)).all()
+    np.testing.assert_allclose(out["aw_icp"][mask], gold[mask], atol=6e-4)

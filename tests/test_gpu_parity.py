@@ -28,6 +28,7 @@ def test_estimate_factor_c1_r1(lib, panels): P.check_estimate_factor_c1(lib, pan
 def test_constraint(lib, panels): P.check_constraint(lib, panels)
 def test_full_nonparametric_c1(lib, panels): P.check_full_nonparametric_c1(lib, panels)
 def test_var_irf(lib): P.check_var_irf(lib)
+def test_var_missing_rows(lib): P.check_var_missing_rows(lib)
 def test_em_p1_balanced(lib): P.check_em(lib, p=1, miss=0.0, path=1)
 def test_em_p2_missing(lib): P.check_em(lib, p=2, miss=0.12, path=1)
 def test_em_p1_missing(lib): P.check_em(lib, p=1, miss=0.1, path=1, rep=10)
@@ -38,6 +39,9 @@ def test_als_batch(lib): P.check_als_batch(lib)
 def test_als_balanced_fused(lib): P.check_als_balanced(lib)
 def test_als_balanced_fused_r8(lib): P.check_als_balanced(lib, N=48, r=8, T=120, B=2)
 def test_parametric_c1(lib, panels): P.check_parametric_c1(lib, panels, iters=3)
+def test_nile_published_general(lib): P.check_nile_published(lib, path=1)
+def test_nile_published_fused(lib): P.check_nile_published(lib, path=2)
+def test_nile_published_fused2(lib): P.check_nile_published(lib, path=3)
 
 
 def test_table2B_through_gpu(lib, panels, notebook_tables):
@@ -49,6 +53,37 @@ def test_table2B_through_gpu(lib, panels, notebook_tables):
         D.estimate_factor(g, computeR2=False, lib=lib)
         assert abs((1 - g.fes.ssr / g.fes.tss) - gold[r - 1, 1]) < 6e-4
         assert abs(D.bai_ng_criterion(g) - gold[r - 1, 3]) < 6e-4
+
+
+def test_table2A_through_gpu(lib, panels, notebook_tables):
+    """Golden Table 2A (Stock_Watson.ipynb:569-577; Real panel, N = 58 estimation series, r = 1..5): trace R2, marginal
+    R2, Bai-Ng ICp2 and the Ahn-Horenstein eigenvalue ratio, all from the CUDA path."""
+    import dynamic_factor_models_b200 as D
+    gold = np.array(notebook_tables["table2A"])
+    tr, bn = [], []
+    for r in range(1, 7):
+        g = P.gpu_model(panels["real_bpdata"], panels["real_inclcode"], r)
+        D.estimate_factor(g, computeR2=False, lib=lib)
+        tr.append(1 - g.fes.ssr / g.fes.tss); bn.append(D.bai_ng_criterion(g))
+    tr = np.array(tr); marg = np.diff(np.concatenate([[0], tr])); ah = marg[:-1] / marg[1:]
+    got = np.column_stack([np.arange(1, 6), tr[:5], marg[:5], bn[:5], ah[:5]])
+    np.testing.assert_allclose(got, gold, atol=6e-4)
+
+
+def test_table2C_amengual_watson_through_gpu(lib, panels, notebook_tables):
+    """Golden Table 2C (Stock_Watson.ipynb:669-683): Amengual-Watson ICp for 1..10 static x 1..10 dynamic factors --
+    estimate_factor_numbers (dfm_functions.ipynb:698-768) on the device: 10 static fits, 10 residualising regressions
+    (dfm_estimate_loading_ex returns the residuals) and 55 ALS fits of the residual panels."""
+    import dynamic_factor_models_b200 as D
+    gold = np.array(notebook_tables["table2C"])[:, 1:]
+    g = P.gpu_model(panels["all_bpdata"], panels["all_inclcode"], 1)
+    out = D.estimate_factor_numbers(g, 10, lib=lib)
+    got = out["aw_icp"]
+    mask = ~np.isnan(gold)
+    assert (np.isnan(got) == np.isnan(gold)).all()
+    np.testing.assert_allclose(got[mask], gold[mask], atol=6e-4)
+    gold2b = np.array(notebook_tables["table2B"])
+    np.testing.assert_allclose(out["bn_icp"], gold2b[:, 3], atol=6e-4)
 
 
 def test_c2_full_size_vs_oracle(lib):
@@ -112,6 +147,8 @@ def test_fused2_em_r8(lib): P.check_em(lib, N=40, r=8, T=90, p=1, miss=0.0, path
 def test_fused2_em_r1(lib): P.check_em(lib, N=12, r=1, T=50, p=1, miss=0.0, path=3, iters=4)
 def test_fused2_em_r5_ragged(lib): P.check_em(lib, N=37, r=5, T=102, p=1, miss=0.0, path=3, iters=4)   # N % 8 != 0, short chunks
 def test_fused2_em_long(lib): P.check_em(lib, N=24, r=4, T=300, p=1, miss=0.0, path=3, iters=3)        # several ring wraps, 3 period chunks
+def test_fused2_em_ragged_long(lib): P.check_em(lib, N=45, r=8, T=278, p=1, miss=0.0, path=3, iters=3)   # tail chunk 14 periods (len % 4 == 2), N % 8 == 5
+def test_fused2_em_exact_chunks(lib): P.check_em(lib, N=16, r=8, T=264, p=1, miss=0.0, path=3, iters=3)   # T == 2 full chunks: overlapped last row block everywhere
 def test_fused2_em_convergence_rule(lib): P.check_em_convergence_rule(lib, path=3)
 def test_fused2_em_batch(lib): P.check_em_batch_balanced(lib, B=7, path=3)
 def test_fused2_matches_general_c2(lib):
