@@ -37,6 +37,11 @@ class LoadingOpts(C.Structure):
                 ("batch", C.c_int), ("mem", C.c_int)]
 
 
+class BootOpts(C.Structure):
+    _fields_ = [("T", C.c_int), ("ns", C.c_int), ("r", C.c_int), ("p", C.c_int), ("n_uarlag", C.c_int), ("n_resid", C.c_int),
+                ("burn", C.c_int), ("batch", C.c_int), ("mem", C.c_int), ("seed", C.c_ulonglong), ("rep0", C.c_longlong)]
+
+
 class EmOpts(C.Structure):
     _fields_ = [("T", C.c_int), ("N", C.c_int), ("r", C.c_int), ("p", C.c_int), ("max_iter", C.c_int),
                 ("tol", C.c_double), ("batch", C.c_int), ("mem", C.c_int), ("path", C.c_int)]
@@ -59,7 +64,7 @@ EXPORTS = ["dfm_version", "dfm_status_string", "dfm_create", "dfm_create_on_stre
            "dfm_launch_count", "dfm_last_error", "dfm_profile_enable", "dfm_profile_query", "dfm_profile_reset",
            "dfm_profile_kernel_name", "dfm_standardize", "dfm_pca_score", "dfm_estimate_factor",
            "dfm_estimate_loading", "dfm_estimate_loading_ex", "dfm_estimate_var", "dfm_irf", "dfm_em_kalman", "dfm_em_init_from_factors",
-           "dfm_allgather_results", "dfm_shard_range"]
+           "dfm_simulate_panels", "dfm_bootstrap_panels", "dfm_percentiles", "dfm_allgather_results", "dfm_shard_range"]
 
 
 def _ptr(a):
@@ -125,6 +130,10 @@ class Library:
         L.dfm_irf.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_ip,
                               C.c_int, C.c_int, C.c_void_p]
         L.dfm_em_kalman.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(EmOpts), C.POINTER(EmInit), C.POINTER(EmOut)]
+        L.dfm_simulate_panels.argtypes = [C.c_void_p, C.c_ulonglong, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.c_void_p, C.c_void_p]
+        L.dfm_bootstrap_panels.argtypes = [C.c_void_p, C.POINTER(BootOpts)] + [C.c_void_p] * 8
+        L.dfm_percentiles.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.dfm_em_init_from_factors.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                                C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.dfm_allgather_results.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong]
@@ -265,6 +274,36 @@ class Library:
                                              _ptr(seps), _ptr(M), _ptr(Q), _ptr(G)), "dfm_estimate_var")
         return dict(betahat=from_cm(beta, K, r, b), resid=from_cm(res, T, r, b), seps=from_cm(seps, r, r, b),
                     M=from_cm(M, k, k, b), Q=from_cm(Q, r, k, b), G=from_cm(G, k, r, b))
+
+    # ------------------------------------------------------------ replication generators / bands
+    def simulate_panels(self, rep0, B, N, r, T, seed, want_F=False):
+        """(B, T, N) standardised panels of replication ids rep0 .. rep0+B-1 (and the true factors (B, T, r))."""
+        X = np.empty(B * T * N); F = np.empty(B * T * r) if want_F else None
+        self.check(self.lib.dfm_simulate_panels(self.h, seed, rep0, B, T, N, r, MEM_HOST, _ptr(X), _ptr(F)), "dfm_simulate_panels")
+        Xo = from_cm(X, T, N, B)
+        return (Xo, from_cm(F, T, r, B)) if want_F else Xo
+
+    def simulate_panels_raw(self, rep0, B, N, r, T, seed, X, F=0, mem=MEM_DEVICE):
+        self.check(self.lib.dfm_simulate_panels(self.h, seed, rep0, B, T, N, r, mem, C.c_void_p(X), C.c_void_p(F) if F else None),
+                   "dfm_simulate_panels")
+
+    def bootstrap_panels(self, F0, resid, beta, lam, uar_coef, uar_ser, data, rep0, B, seed, burn=50):
+        """(B, Tw, ns) residual-bootstrap draws of replication ids rep0 .. rep0+B-1."""
+        F0 = np.asarray(F0, float); Tw, r = F0.shape; ns, Lg = np.asarray(uar_coef).shape; K = np.asarray(beta).shape[0]
+        o = BootOpts(T=Tw, ns=ns, r=r, p=(K - 1) // r, n_uarlag=Lg, n_resid=np.asarray(resid).shape[0], burn=burn, batch=B, mem=MEM_HOST,
+                     seed=seed, rep0=rep0)
+        X = np.empty(B * ns * Tw)
+        bufs = [to_cm(np.asarray(a_, float)) for a_ in (F0, resid, beta, lam, uar_coef)] + [np.ascontiguousarray(uar_ser, dtype=float),
+                                                                                               to_cm(np.asarray(data, float))]
+        self.check(self.lib.dfm_bootstrap_panels(self.h, C.byref(o), *[_ptr(b_) for b_ in bufs], _ptr(X)), "dfm_bootstrap_panels")
+        return from_cm(X, Tw, ns, B)
+
+    def percentiles(self, recs, q):
+        """recs (n, d) -> (len(q), d): numpy.percentile(recs, q, axis=0) on the device, NaN records ignored."""
+        recs = np.ascontiguousarray(recs, dtype=float); n, d = recs.shape
+        qq = np.ascontiguousarray(q, dtype=float); out = np.empty(len(qq) * d)
+        self.check(self.lib.dfm_percentiles(self.h, _ptr(recs), n, d, _ptr(qq), len(qq), MEM_HOST, _ptr(out)), "dfm_percentiles")
+        return out.reshape(len(qq), d)
 
     def irf(self, M, Q, G, H, shock_ids):
         M = np.asarray(M, float); b = M.shape[0] if M.ndim == 3 else None; B = b or 1

@@ -8,6 +8,7 @@
 #include "dfm_kernels_fused.cuh"
 #include "dfm_kernels_fused2.cuh"
 #include "dfm_kernels_als_masked.cuh"
+#include "dfm_kernels_rep.cuh"
 #include <algorithm>
 #include <new>
 #include <thread>
@@ -1047,6 +1048,87 @@ int dfm_em_kalman(dfm_handle* h, const double* X, const dfm_em_opts* o, const df
 }
 
 // ------------------------------------------------------------------------------------ (e)
+// ------------------------------------------------------------------------------------ K9: replication generators
+int dfm_simulate_panels(dfm_handle* h, unsigned long long seed, long long rep0, int batch, int T, int N, int r, int mem,
+                        double* X, double* F_true) {
+  if (!h || !X || batch <= 0 || T <= 1 || N <= 0 || r <= 0 || r > 64 || rep0 < 0) return fail(h, DFM_ERR_ARG, "dfm_simulate_panels: bad argument");
+  CK(cudaSetDevice(h->device));
+  size_t B = batch;
+  for (int pass = 0; pass < 2; ++pass) {
+    Arena a(pass ? h->ws : nullptr);
+    double* dX = mem == DFM_MEM_HOST ? a.get<double>(B * T * N) : X;
+    double* dF = (mem == DFM_MEM_HOST || !F_true) ? a.get<double>(B * T * r) : F_true;
+    if (!pass) { int rc = ensure_ws(h, a.off); if (rc) return rc; continue; }
+    L(k_simulate_panels, batch, 1, 256, 0, seed, rep0, T, N, r, dX, dF);
+    if (mem == DFM_MEM_HOST) { int rc = copy_out(h, X, dX, B * T * N, mem); if (rc) return rc; }
+    if (F_true) { int rc = copy_out(h, F_true, dF, B * T * r, mem); if (rc) return rc; }
+  }
+  return finish(h, mem);
+}
+
+int dfm_bootstrap_panels(dfm_handle* h, const dfm_boot_opts* o, const double* F0, const double* resid, const double* beta,
+                         const double* lam, const double* uar_coef, const double* uar_ser, const double* data, double* X) {
+  if (!h || !o || !F0 || !resid || !beta || !lam || !uar_coef || !uar_ser || !data || !X)
+    return fail(h, DFM_ERR_ARG, "dfm_bootstrap_panels: null argument");
+  int Tw = o->T, ns = o->ns, r = o->r, p = o->p, Lg = o->n_uarlag, nres = o->n_resid, batch = o->batch, mem = o->mem;
+  if (Tw <= p || ns <= 0 || r <= 0 || p <= 0 || Lg <= 0 || Lg > 16 || nres <= 0 || batch <= 0 || o->burn < 0 || o->rep0 < 0)
+    return fail(h, DFM_ERR_ARG, "dfm_bootstrap_panels: bad shape/options");
+  size_t smem = (size_t)Tw * r * 8;
+  if (smem > kMaxSmem) return fail(h, DFM_ERR_UNSUPPORTED, "dfm_bootstrap_panels: T*r too large");
+  CK(cudaSetDevice(h->device));
+  size_t B = batch; int K = 1 + r * p;
+  for (int pass = 0; pass < 2; ++pass) {
+    Arena a(pass ? h->ws : nullptr);
+    const bool hst = mem == DFM_MEM_HOST;
+    double* dF0 = hst ? a.get<double>((size_t)Tw * r) : nullptr; double* dre = hst ? a.get<double>((size_t)nres * r) : nullptr;
+    double* dbe = hst ? a.get<double>((size_t)K * r) : nullptr; double* dla = hst ? a.get<double>((size_t)ns * r) : nullptr;
+    double* dac = hst ? a.get<double>((size_t)ns * Lg) : nullptr; double* dse = hst ? a.get<double>(ns) : nullptr;
+    double* dda = hst ? a.get<double>((size_t)Tw * ns) : nullptr;
+    double* dX = hst ? a.get<double>(B * ns * Tw) : X;
+    if (!pass) { int rc = ensure_ws(h, a.off); if (rc) return rc; continue; }
+    BootArgs ba{};
+    int rc = stage_in(h, F0, dF0, (size_t)Tw * r, mem, &ba.F0); if (rc) return rc;
+    rc = stage_in(h, resid, dre, (size_t)nres * r, mem, &ba.resid); if (rc) return rc;
+    rc = stage_in(h, beta, dbe, (size_t)K * r, mem, &ba.beta); if (rc) return rc;
+    rc = stage_in(h, lam, dla, (size_t)ns * r, mem, &ba.lam); if (rc) return rc;
+    rc = stage_in(h, uar_coef, dac, (size_t)ns * Lg, mem, &ba.uar_coef); if (rc) return rc;
+    rc = stage_in(h, uar_ser, dse, (size_t)ns, mem, &ba.uar_ser); if (rc) return rc;
+    rc = stage_in(h, data, dda, (size_t)Tw * ns, mem, &ba.data); if (rc) return rc;
+    ba.X = dX; ba.Tw = Tw; ba.ns = ns; ba.r = r; ba.p = p; ba.L = Lg; ba.nres = nres; ba.burn = o->burn; ba.seed = o->seed; ba.rep0 = o->rep0;
+#ifndef DFM_EMU
+    DFM_SET_SMEM(k_bootstrap_panels, smem);
+#endif
+    L(k_bootstrap_panels, batch, 1, 256, smem, ba);
+    if (hst) { rc = copy_out(h, X, dX, B * ns * Tw, mem); if (rc) return rc; }
+  }
+  return finish(h, mem);
+}
+
+// ------------------------------------------------------------------------------------ (f)3: percentile bands
+int dfm_percentiles(dfm_handle* h, const double* recs, long long n, int d, const double* q, int nq, int mem, double* out) {
+  if (!h || !recs || !q || !out || n <= 0 || d <= 0 || nq <= 0 || nq > 64) return fail(h, DFM_ERR_ARG, "dfm_percentiles: bad argument");
+  for (int k = 0; k < nq; ++k) if (!(q[k] >= 0.0 && q[k] <= 100.0)) return fail(h, DFM_ERR_ARG, "dfm_percentiles: q outside [0, 100]");
+  long long npad = 2; while (npad < n) npad <<= 1;
+  size_t smem = (size_t)(npad + 2) * 8;
+  if (smem > kMaxSmem) return fail(h, DFM_ERR_UNSUPPORTED, "dfm_percentiles: more than 16384 replications");
+  CK(cudaSetDevice(h->device));
+  for (int pass = 0; pass < 2; ++pass) {
+    Arena a(pass ? h->ws : nullptr);
+    double* dr = mem == DFM_MEM_HOST ? a.get<double>((size_t)n * d) : nullptr;
+    double* dq = a.get<double>(nq); double* dout = mem == DFM_MEM_HOST ? a.get<double>((size_t)nq * d) : out;
+    if (!pass) { int rc = ensure_ws(h, a.off); if (rc) return rc; continue; }
+    const double* r_; int rc = stage_in(h, recs, dr, (size_t)n * d, mem, &r_); if (rc) return rc;
+    CK(cudaMemcpyAsync(dq, q, nq * sizeof(double), cudaMemcpyHostToDevice, h->stream));      // q is always a host array
+#ifndef DFM_EMU
+    DFM_SET_SMEM(k_percentiles, smem);
+#endif
+    L(k_percentiles, d, 1, 256, smem, r_, (int)n, d, dq, nq, (int)npad, dout);
+    if (mem == DFM_MEM_HOST) { rc = copy_out(h, out, dout, (size_t)nq * d, mem); if (rc) return rc; }
+    else CK(cudaStreamSynchronize(h->stream));                                               // (dq lives in the shared workspace)
+  }
+  return finish(h, mem);
+}
+
 int dfm_allgather_results(dfm_handle* h, void* nccl_comm, const double* send, double* recv, long long count) {
   if (!h || !nccl_comm || !send || !recv || count <= 0) return fail(h, DFM_ERR_ARG, "dfm_allgather_results: bad argument");
 #ifdef DFM_EMU

@@ -191,6 +191,39 @@ int dfm_em_kalman(dfm_handle* h, const double* X, const dfm_em_opts* opts, const
 int dfm_em_init_from_factors(dfm_handle* h, const double* Xs, const double* F, int T, int N, int r, int p,
                              int batch, int mem, double* Lam, double* R, double* A, double* Q);
 
+/* ---- K9: replication generators.  The reference has no Monte-Carlo / bootstrap / RNG code (its
+ * notebook never draws a random number); SURVEY.md 8d freezes the definitions these entry points implement.  Draws come
+ * from a counter-based Philox4x32-10 stream that is a pure function of (seed, replication id, stream, element): panel
+ * `rep0 + b` is bit-identical whatever the batch split or the number of GPUs.  oracle/dgp.py restates the stream. */
+/* Synthetic DGP (C2 / C3 / C5): Lam ~ N(0,1); f_t = diag(a) f_{t-1} + eta_t, a ~ U(.2,.8), burn-in 100; e_it ~ N(0, s2_i),
+ * s2_i ~ U(.5,1.5); x = Lam f + e, column-standardised as standardize_data (:501-509).
+ * X: batch panels T x N column-major; F_true (may be NULL): the simulated factors, T x r column-major per panel. */
+int dfm_simulate_panels(dfm_handle* h, unsigned long long seed, long long rep0, int batch, int T, int N, int r, int mem,
+                        double* X, double* F_true);
+
+/* Residual bootstrap of a fitted non-parametric model (C4): resample the factor-VAR residuals (`varm.resid`, :464) with
+ * replacement, rebuild f* through `betahat` (:463; the first p rows of the fitted factors start the recursion), draw the
+ * idiosyncratic AR(n_uarlag) processes from (uar_coef, uar_ser) (:405-412) after `burn` periods, x* = Lam f* + u*, and
+ * re-impose the NaN pattern of `data`.  Series whose lam row / uar_ser is NaN come back as NaN columns. */
+typedef struct {
+  int T, ns, r, p;          /* window length (rows initperiod..lastperiod), series, factors, VAR lags */
+  int n_uarlag;             /* <= 16 */
+  int n_resid;              /* rows of `resid` */
+  int burn;                 /* burn-in periods of the idiosyncratic processes */
+  int batch; int mem;
+  unsigned long long seed; long long rep0;     /* replication ids rep0 .. rep0 + batch - 1 */
+} dfm_boot_opts;
+/* F0 T x r; resid n_resid x r; beta (1 + r p) x r = [const; lag 1; ...; lag p]; lam ns x r; uar_coef ns x n_uarlag;
+ * uar_ser ns; data T x ns (only its NaN pattern is read); all column-major.  X: batch panels T x ns column-major. */
+int dfm_bootstrap_panels(dfm_handle* h, const dfm_boot_opts* opts, const double* F0, const double* resid, const double* beta,
+                         const double* lam, const double* uar_coef, const double* uar_ser, const double* data, double* X);
+
+/* ---- (f)3: percentile bands over the replication axis (the post-processing step behind impulse_response, :793-825).
+ * recs: n x d ROW-major (one record of d statistics per replication, as gathered by dfm_allgather_results); q: nq
+ * percentiles in [0, 100] (HOST array); out: nq x d row-major.  numpy.percentile's default (linear) interpolation; NaN
+ * records (failed replications) are ignored.  n <= 16384. */
+int dfm_percentiles(dfm_handle* h, const double* recs, long long n, int d, const double* q, int nq, int mem, double* out);
+
 /* ---- (e): the single collective of the multi-GPU path ---------------------------------- */
 /* AllGather `count` doubles per rank of per-replication result records (device pointers on the
  * handle's device) with ncclAllGather on the handle's stream.  `nccl_comm` is an ncclComm_t

@@ -319,3 +319,61 @@ def check_nile_published(lib, path=0):
     es = K.e_step(y, np.ones((1, 1)), np.array([s2e]), np.ones((1, 1)), np.array([[s2n]]), np.array([[P1]]), 1)
     np.testing.assert_allclose(out["F"][:, 0], es["zs"][:, 0], rtol=1e-9)
     np.testing.assert_allclose(out["loglik"][0], es["loglik"], rtol=1e-11)
+
+
+def check_simulate_panels(lib, N=24, r=3, T=70, B=3, rep0=5):
+    """Device generator (K9) vs its numpy restatement: same counter-based Philox stream, same DGP; panels are a function
+    of the replication id only (any batch split gives the same bits)."""
+    from oracle import dgp
+    X, F = lib.simulate_panels(rep0, B, N, r, T, dgp.SEED, want_F=True)
+    for b in range(B):
+        Xr, tr = dgp.simulate_panel_device_stream(N, r, T, rep=rep0 + b)
+        np.testing.assert_allclose(F[b], tr["F"], rtol=1e-12, atol=1e-13)
+        np.testing.assert_allclose(X[b], Xr, rtol=1e-10, atol=1e-12)
+    assert abs(X.mean(axis=1)).max() < 1e-12 and abs(X.std(axis=1) - 1).max() < 1e-12      # standardised columns
+    X2 = lib.simulate_panels(rep0 + 1, 1, N, r, T, dgp.SEED)
+    assert np.array_equal(X2[0], X[1])                                                     # independent of the batch split
+    assert not np.allclose(lib.simulate_panels(rep0, 1, N, r, T, dgp.SEED + 1)[0], X[0])
+
+
+def check_simulate_panels_statistics(lib, N=60, r=4, T=400, B=8):
+    """The device DGP has the frozen distributions: factor AR(1) coefficients in [.2,.8], unit innovation variance,
+    and a dominant r-factor structure (moments over B panels)."""
+    from oracle import dgp
+    X, F = lib.simulate_panels(100, B, N, r, T, dgp.SEED, want_F=True)
+    a_hat = np.array([[np.dot(F[b, 1:, j], F[b, :-1, j]) / np.dot(F[b, :-1, j], F[b, :-1, j]) for j in range(r)] for b in range(B)])
+    assert a_hat.min() > 0.05 and a_hat.max() < 0.92
+    innov = F[:, 1:, :] - a_hat[:, None, :] * F[:, :-1, :]
+    assert abs(innov.var() - 1.0) < 0.05
+    # common component share: var(Lam f) / var(x) with E|lam|^2 = r, var f_j = 1/(1-a^2) >= 1, s2 ~ 1  ->  well above 1/2
+    ev = np.linalg.eigvalsh(np.corrcoef(X[0].T))[::-1]
+    assert ev[:r].sum() / N > 0.5 and ev[r] < ev[r - 1]
+
+
+def check_bootstrap_panels(lib, panels, B=2):
+    """Device residual bootstrap (C4) vs its numpy restatement on the fitted C1 model."""
+    from oracle import dgp
+    m = ref_model(panels["all_bpdata"], panels["all_inclcode"], 4)
+    R.estimate(m)
+    i0, i1 = m.initperiod, m.lastperiod
+    v = m.factor_var_model; p = v.nlag
+    F0 = m.factor[i0 - 1:i1]; resid = v.resid[i0 - 1:i1][p:]
+    data = m.data[i0 - 1:i1]
+    X = lib.bootstrap_panels(F0, resid, v.betahat, m.lambda_, m.uar_coef, m.uar_ser, data, 7, B, dgp.SEED, burn=50)
+    for b in range(B):
+        Xr = dgp.bootstrap_panel_device_stream(F0, resid, v.betahat, m.lambda_, m.uar_coef, m.uar_ser, data, 7 + b, burn=50)
+        assert np.array_equal(np.isnan(X[b]), np.isnan(Xr))
+        ok = ~np.isnan(Xr)
+        np.testing.assert_allclose(X[b][ok], Xr[ok], rtol=1e-9, atol=1e-10)
+    assert np.array_equal(np.isnan(X[0]) | np.isnan(data), np.isnan(X[0]))                 # original missing pattern re-imposed
+
+
+def check_percentiles(lib, n=37, d=11):
+    rng = np.random.default_rng(3)
+    recs = rng.standard_normal((n, d)); recs[5] = np.nan; recs[20] = np.nan             # two failed replications
+    q = [5, 16, 50, 84, 95, 0, 100]
+    got = lib.percentiles(recs, q)
+    ref = np.nanpercentile(recs, q, axis=0)
+    np.testing.assert_allclose(got, ref, rtol=1e-12, atol=1e-14)
+    got1 = lib.percentiles(recs[:1], [50.0])
+    np.testing.assert_allclose(got1[0], recs[0])

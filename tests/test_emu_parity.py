@@ -29,6 +29,10 @@ def test_estimate_factor_c1(lib, panels): P.check_estimate_factor_c1(lib, panels
 def test_constraint(lib, panels): P.check_constraint(lib, panels)
 def test_full_nonparametric_c1(lib, panels): P.check_full_nonparametric_c1(lib, panels)
 def test_var_irf(lib): P.check_var_irf(lib)
+def test_simulate_panels(lib): P.check_simulate_panels(lib)
+def test_simulate_panels_statistics(lib): P.check_simulate_panels_statistics(lib)
+def test_bootstrap_panels(lib, panels): P.check_bootstrap_panels(lib, panels)
+def test_percentiles(lib): P.check_percentiles(lib)
 def test_var_missing_rows(lib): P.check_var_missing_rows(lib)
 def test_em_p1_balanced(lib): P.check_em(lib, p=1, miss=0.0)
 def test_em_p2_missing(lib): P.check_em(lib, p=2, miss=0.12)

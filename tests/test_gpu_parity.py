@@ -28,6 +28,12 @@ def test_estimate_factor_c1_r1(lib, panels): P.check_estimate_factor_c1(lib, pan
 def test_constraint(lib, panels): P.check_constraint(lib, panels)
 def test_full_nonparametric_c1(lib, panels): P.check_full_nonparametric_c1(lib, panels)
 def test_var_irf(lib): P.check_var_irf(lib)
+def test_simulate_panels(lib): P.check_simulate_panels(lib)
+def test_simulate_panels_c2_shape(lib): P.check_simulate_panels(lib, N=200, r=8, T=500, B=2, rep0=1249)
+def test_simulate_panels_statistics(lib): P.check_simulate_panels_statistics(lib)
+def test_bootstrap_panels(lib, panels): P.check_bootstrap_panels(lib, panels)
+def test_percentiles(lib): P.check_percentiles(lib)
+def test_percentiles_1000(lib): P.check_percentiles(lib, n=1000, d=1536)
 def test_var_missing_rows(lib): P.check_var_missing_rows(lib)
 def test_em_p1_balanced(lib): P.check_em(lib, p=1, miss=0.0, path=1)
 def test_em_p2_missing(lib): P.check_em(lib, p=2, miss=0.12, path=1)

@@ -22,7 +22,7 @@ def test_monte_carlo_em_matches_oracle(lib):
     rec = replicate.monte_carlo_em(lib, n_rep, N, r, T, em_iters=iters)
     assert rec.shape == (n_rep, 4) and (rec[:, 2] == 0).all() and (rec[:, 1] == iters).all()
     for b in (0, n_rep - 1):
-        X = replicate.simulate_panel(N, r, T, rep=b)
+        X = replicate.simulate_panel(N, r, T, rep=b, lib=lib)
         m = R.DFMModel(X, np.ones(N, int), 20, 40, 1, T, 0, r, 1e-8, 4, 1)
         R.estimate_factor(m, max_iter=1, computeR2=False)
         Lam, Rv, A, Q = K.init_from_factors(m.xs, m.factor, 1)
@@ -41,8 +41,10 @@ def test_bootstrap_irf_c1(lib, panels):
     irfs, bands = replicate.bootstrap_irf(lib, g, 4, H=8)
     assert irfs.shape == (4, 4, 8, 4) and np.isfinite(irfs).all()
     assert (bands[5] <= bands[95] + 1e-12).all()
+    for q in (5, 50, 95):                                        # device percentile kernel == numpy.percentile
+        np.testing.assert_allclose(bands[q], np.percentile(irfs, q, axis=0), rtol=1e-12, atol=1e-14)
     # oracle re-estimation of replication 2
-    Xs = replicate.bootstrap_panels(g, [2])[0]
+    Xs = replicate.bootstrap_panels(g, [2], lib=lib)[0]
     full = np.full_like(panels["all_bpdata"], np.nan); full[2:224] = Xs
     m = P.ref_model(full, panels["all_inclcode"], 4)
     R.estimate_factor(m, computeR2=False); R.estimate_var(m.factor_var_model)
@@ -50,3 +52,14 @@ def test_bootstrap_irf_c1(lib, panels):
     s = np.sign((m.factor[2:224] * F0).sum(0)); s[s == 0] = 1
     ref = R.impulse_response(m.factor_var_model, [0, 1, 2, 3], 8) * s[:, None, None] * s[None, None, :]
     np.testing.assert_allclose(irfs[2], ref, rtol=1e-5, atol=1e-8)
+
+
+def test_generators_are_shard_invariant_on_device(lib):
+    """Panel b is bit-identical for world = 1 and 8 (device-resident generation, shards of dfm_shard_range)."""
+    from dynamic_factor_models_b200 import replicate
+    whole = lib.simulate_panels(0, 24, 40, 4, 100, replicate.SEED)
+    parts = []
+    for rank in range(8):
+        b, e = lib.shard_range(24, rank, 8)
+        parts.append(lib.simulate_panels(b, e - b, 40, 4, 100, replicate.SEED))
+    assert np.array_equal(np.concatenate(parts), whole)

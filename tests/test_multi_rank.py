@@ -34,7 +34,7 @@ def _worker(rank, world, port, tmp, what):
 def _fitted_model(lib):
     import dynamic_factor_models_b200 as D
     from dynamic_factor_models_b200 import replicate
-    X = replicate.simulate_panel(14, 2, 70, rep=7)
+    X = replicate.simulate_panel(14, 2, 70, rep=7, lib=lib)
     X[3:9, 2] = np.nan
     m = D.DFMModel(X, np.r_[np.ones(12, int), np.zeros(2, int)], 20, 20, 1, 70, 0, 2, 1e-8, 2, 2)
     D.estimate(m, lib=lib)
@@ -60,10 +60,19 @@ def test_two_ranks_match_one(tmp_path, what):
 
 
 def test_shards_cover_and_are_gpu_count_independent():
-    """Replication b's panel depends on b only."""
-    from dynamic_factor_models_b200 import replicate
-    a = replicate.simulate_panel(8, 2, 20, rep=3)
-    b = replicate.simulate_panel(8, 2, 20, rep=3)
-    assert (a == b).all()
-    from oracle.dgp import simulate_panel
-    np.testing.assert_allclose(a, simulate_panel(8, 2, 20, rep=3)[0], rtol=0, atol=0)
+    """Replication b's panel depends on b only: any batch split / shard gives the same bits, and the device stream is
+    the one oracle/dgp.py restates."""
+    import build_emu
+    from dynamic_factor_models_b200 import Library, replicate
+    lib = Library(build_emu.build())
+    whole = lib.simulate_panels(0, 6, 8, 2, 20, replicate.SEED)
+    for world in (2, 3):
+        parts = []
+        for rank in range(world):
+            b, e = lib.shard_range(6, rank, world)
+            parts.append(lib.simulate_panels(b, e - b, 8, 2, 20, replicate.SEED))
+        assert np.array_equal(np.concatenate(parts), whole)
+    from oracle.dgp import simulate_panel_device_stream
+    np.testing.assert_allclose(replicate.simulate_panel(8, 2, 20, rep=3, lib=lib), simulate_panel_device_stream(8, 2, 20, rep=3)[0],
+                               rtol=1e-10, atol=1e-12)
+    lib.close()
