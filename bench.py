@@ -34,20 +34,14 @@ METRIC = "EM iters/sec (N=200,r=8,T=500)"
 UNIT = "panel-EM-iterations/s"
 
 
-def make_panels(B, rep0):
-    """Frozen DGP of SURVEY.md 8d (dynamic_factor_models_b200/replicate.py::simulate_panel; the same definition the
-    oracle freezes in oracle/dgp.py), vectorised AR recursion.  (B, T, N) float64."""
-    from scipy.signal import lfilter
-    from dynamic_factor_models_b200.replicate import SEED
-    out = np.empty((B, T_, NS))
-    for b in range(B):
-        rng = np.random.Generator(np.random.Philox(key=[SEED, rep0 + b]))
-        Lam = rng.standard_normal((NS, R_)); a = rng.uniform(0.2, 0.8, R_); s2 = rng.uniform(0.5, 1.5, NS)
-        eta = rng.standard_normal((T_ + 100, R_)); e = rng.standard_normal((T_, NS)) * np.sqrt(s2)
-        F = np.stack([lfilter([1.0], [1.0, -a[j]], eta[:, j]) for j in range(R_)], axis=1)[100:]
-        X = F @ Lam.T + e
-        out[b] = (X - X.mean(0)) / X.std(0)
-    return out
+SEED = 20260922            # dynamic_factor_models_b200.replicate.SEED == oracle.dgp.SEED (frozen)
+
+
+def make_panels_host(B, rep0):
+    """CPU arm only: the numpy restatement (oracle/dgp.py) of the DEVICE generator's Philox stream -- the same
+    replication ids give the same panels (to libm rounding) as dfm_simulate_panels.  (B, T, N) float64."""
+    from oracle.dgp import simulate_panel_device_stream
+    return np.stack([simulate_panel_device_stream(NS, R_, T_, rep=rep0 + b, seed=SEED)[0] for b in range(B)])
 
 
 class ClockSampler:
@@ -153,7 +147,7 @@ def cpu_sample(iters, steps=1, warmup=1, Xs=None, init=None):
     hc = host_cores()
     n = hc["threads"]
     if Xs is None:
-        Xs = make_panels(CPU_SAMPLE_PANELS, 0)
+        Xs = make_panels_host(CPU_SAMPLE_PANELS, 0)
         init = host_init(Xs)
     for _ in range(warmup):
         cpu_em(Xs[:2 * n], tuple(a[:2 * n] for a in init), 2, nthreads=n)
@@ -221,10 +215,13 @@ def main():
 
     B, iters, K_, W_ = args.panels, args.em_iters, args.steps, args.warmup
     k = R_ * P_; np_ = R_ * (R_ + 1) // 2
-    # ---- inputs: this rank's replication shard (ids rank*B .. rank*B+B-1: identical whatever the GPU count)
-    Xh = make_panels(B, rank * B)                                  # (B, T, N)
-    X_cm = torch.from_numpy(np.ascontiguousarray(Xh.transpose(0, 2, 1)))   # column-major panels
-    dX = X_cm.to(dev)
+    # ---- inputs: this rank's replication shard (ids rank*B .. rank*B+B-1: identical whatever the GPU count), generated
+    # on the device (dfm_simulate_panels: counter-based Philox keyed by the replication id)
+    dX = torch.empty(B * T_ * NS, dtype=torch.float64, device=dev)
+    t_gen = time.perf_counter()
+    lib.simulate_panels_raw(rank * B, B, NS, R_, T_, SEED, dX.data_ptr())
+    lib.sync(); t_gen = time.perf_counter() - t_gen
+    X_cm = dX.cpu()                                                # column-major panels on the host (e2e leg, CPU baseline)
     # initial parameters on the device: one ALS sweep from PCA (reference path) -> init_from_factors
     dF0 = torch.empty(B * T_ * R_, dtype=torch.float64, device=dev)
     lib.estimate_factor_raw(dX.data_ptr(), T_, NS, R_, B, MEM_DEVICE, F=dF0.data_ptr(), max_iter=1)
@@ -350,7 +347,7 @@ def main():
                "note": "includes standardisation; starts from given factors (F_init)"}
         if not args.no_cpu:
             from oracle import dfm_ref as Rf
-            m_ = Rf.DFMModel(Xh[0], np.ones(NS, int), 20, 40, 1, T_, 0, R_, 0.0, 4, 1)
+            m_ = Rf.DFMModel(np.ascontiguousarray(X_cm[:T_ * NS].numpy().reshape(NS, T_).T), np.ones(NS, int), 20, 40, 1, T_, 0, R_, 0.0, 4, 1)
             t0 = time.perf_counter(); Rf.estimate_factor(m_, max_iter=3, computeR2=False); dtc = time.perf_counter() - t0
             als["cpu_restated_reference"] = {"value": 3 / dtc, "unit": "panel-ALS-sweeps/s", "cores": 1, "kind": "port",
                                              "sample": "1 panel x 3 sweeps, oracle/dfm_ref.py (numpy/scipy pivoted-QR loops mirroring the reference's control flow; includes one PCA/SVD)"}
@@ -362,14 +359,15 @@ def main():
         Bs = min(B, CPU_SAMPLE_PANELS)
         Lh = lambda t, rows, cols: np.ascontiguousarray(t[:Bs * rows * cols].cpu().numpy().reshape(Bs, cols, rows).transpose(0, 2, 1))
         init = (Lh(dLam0, NS, R_), dR0[:Bs * NS].cpu().numpy().reshape(Bs, NS), Lh(dA0, R_, k), Lh(dQ0, R_, R_))
-        cpu, _, out = cpu_sample(iters, steps=1, warmup=1, Xs=Xh[:Bs], init=init)
+        Xh = np.ascontiguousarray(X_cm[:Bs * T_ * NS].numpy().reshape(Bs, NS, T_).transpose(0, 2, 1))     # (Bs, T, N)
+        cpu, _, out = cpu_sample(iters, steps=1, warmup=1, Xs=Xh, init=init)
         Fg = dout["F"][:Bs * T_ * R_].cpu().numpy().reshape(Bs, R_, T_).transpose(0, 2, 1)
         rmse = float(np.sqrt(np.mean((Fg - out["F"]) ** 2)))
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K_, "warmup": W_,
                 "ms_per_step": ms / K_, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic",
+                "data": "synthetic (device-generated frozen DGP, SURVEY.md 8d)",
                 "config": {"workload": f"C5 shard of C2-shaped Monte-Carlo panels: {B} panels/GPU, N={NS} r={R_} T={T_} p={P_}, "
                                        f"{iters} EM iterations (Kalman filter + RTS smoother + M-step) per step, then one all-gather",
                            "panels_per_gpu": B, "em_iters_per_step": iters, "parallelism": f"replications x{world}",
@@ -377,7 +375,9 @@ def main():
                            "path": args.path, "all_status_ok": status_ok},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / Ke},
                 "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
-                "factor_rmse_vs_oracle": rmse, "als": als, "timing": {"cuda_event_ms": ms_dev, "wall_ms": ms_wall}}
+                "factor_rmse_vs_oracle": rmse, "als": als, "timing": {"cuda_event_ms": ms_dev, "wall_ms": ms_wall},
+                "generator": {"where": "device (dfm_simulate_panels, Philox4x32-10 keyed by replication id)", "panels": B,
+                              "seconds": t_gen}}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
