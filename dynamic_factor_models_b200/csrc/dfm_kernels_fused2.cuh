@@ -34,7 +34,7 @@ namespace dfm {
 #endif                  // DMMA fragment loads are bank-conflict free, and <= 256 (TMA box limit)
 #define F2_TS F2_TC     // (box width == chunk stride: no re-read of periods; T = 500 -> 4 chunks)
 #ifndef F2_PIPE
-#define F2_PIPE 1       // consumers: 1 = software-pipelined fragment refills, 0 = wait / load all / DMMA per stage
+#define F2_PIPE 0       // consumers: 1 = software-pipelined fragment refills, 0 = wait / load all / DMMA per stage (measured: 0 is 10 % faster)
 #endif
 #define F2_NCW 6        // consumer warps (warps 1..6; warp 0 = producer, warp 7 = chain / solves)
 #define F2_GPARTS_S 4                                    // scalar Gram path: time slices per matrix entry
@@ -151,9 +151,9 @@ __device__ __noinline__ double f2_consume_E(F2Ring& rg, int cw, int T, int N, in
 #pragma unroll
   for (int j = 0; j < CNT; ++j) { const int t0 = (cw + F2_NCW * j) * 8; offF[j] = (uint32_t)((t0 > F2_TC - 8) ? F2_TC - 8 : t0) * 8u; }
   double qacc = 0.0;
-  double d[CNT][2];
-#pragma unroll
-  for (int j = 0; j < CNT; ++j) { d[j][0] = 0.0; d[j][1] = 0.0; }
+  double d[CNT][2][2];                                        // one accumulator pair per (row block, k half): no two DMMAs of a
+#pragma unroll                                                // stage depend on each other (a dependent DMMA stalls the in-order warp)
+  for (int j = 0; j < CNT; ++j) { d[j][0][0] = 0.0; d[j][0][1] = 0.0; d[j][1][0] = 0.0; d[j][1][1] = 0.0; }
   double a0[CNT], a1[CNT], l0 = 0.0, l1 = 0.0;                // fragments of the stage whose DMMAs issue next
   int cl = 0, sbl = 0;                                        // (chunk, series block) of the next stage to LOAD
   int cc = 0, sbc = 0;                                        // ... of the next stage to COMPUTE
@@ -206,18 +206,18 @@ __device__ __noinline__ double f2_consume_E(F2Ring& rg, int cw, int T, int N, in
     }
     if (more && fastL) {                                       // the common case: unmasked refills
 #pragma unroll
-      for (int j = 0; j < CNT; ++j) { F2_DMMA(d[j], a0[j], l0); a0[j] = f2_lds(tileL + offF[j]); }
+      for (int j = 0; j < CNT; ++j) { F2_DMMA(d[j][0], a0[j], l0); a0[j] = f2_lds(tileL + offF[j]); }
       l0 = f2_lds(laL);
 #pragma unroll
-      for (int j = 0; j < CNT; ++j) { F2_DMMA(d[j], a1[j], l1); a1[j] = f2_lds(tileL + offF[j] + 4 * F2_TS * 8); }
+      for (int j = 0; j < CNT; ++j) { F2_DMMA(d[j][1], a1[j], l1); a1[j] = f2_lds(tileL + offF[j] + 4 * F2_TS * 8); }
       l1 = f2_lds(laL + 32);
       if (!lrok) { l0 = 0.0; l1 = 0.0; }
     } else {
 #pragma unroll
-      for (int j = 0; j < CNT; ++j) { F2_DMMA(d[j], a0[j], l0); if (more) a0[j] = F2E_LDA(j, 0); }
+      for (int j = 0; j < CNT; ++j) { F2_DMMA(d[j][0], a0[j], l0); if (more) a0[j] = F2E_LDA(j, 0); }
       if (more) l0 = F2E_LDL(0);
 #pragma unroll
-      for (int j = 0; j < CNT; ++j) { F2_DMMA(d[j], a1[j], l1); if (more) a1[j] = F2E_LDA(j, 1); }
+      for (int j = 0; j < CNT; ++j) { F2_DMMA(d[j][1], a1[j], l1); if (more) a1[j] = F2E_LDA(j, 1); }
       if (more) l1 = F2E_LDL(1);
     }
     if (more) F2E_ADVANCE();
@@ -230,9 +230,9 @@ __device__ __noinline__ double f2_consume_E(F2Ring& rg, int cw, int T, int N, in
         const int rb8 = (cw + F2_NCW * j) * 8, row = (fullC ? (int)(offF[j] >> 3) : rb8) + lr;
         if (row >= rb8 && row < lenC) {
           const int t = cc * F2_TC + row;
-          f2_sts(z_s + (uint32_t)((2 * lc) * Tp + t) * 8u, d[j][0]); f2_sts(z_s + (uint32_t)((2 * lc + 1) * Tp + t) * 8u, d[j][1]);
+          f2_sts(z_s + (uint32_t)((2 * lc) * Tp + t) * 8u, d[j][0][0] + d[j][1][0]); f2_sts(z_s + (uint32_t)((2 * lc + 1) * Tp + t) * 8u, d[j][0][1] + d[j][1][1]);
         }
-        d[j][0] = 0.0; d[j][1] = 0.0;
+        d[j][0][0] = 0.0; d[j][0][1] = 0.0; d[j][1][0] = 0.0; d[j][1][1] = 0.0;
       }
       sbc = 0; ++cc;
     }
@@ -249,11 +249,10 @@ __device__ __noinline__ double f2_consume_E(F2Ring& rg, int cw, int T, int N, in
 
 // end of a series block in the M pass: deterministic cross-warp reduction of the F2_NCW partial 8x8 tiles (+ sxx)
 template <int R, bool SXX>
-__device__ __forceinline__ void f2_m_reduce(double (&d)[2][2], double& s2, int sb, int cw, int N, int Np, uint32_t part_s, double* Lam, double* sxx) {
+__device__ __forceinline__ void f2_m_reduce(double t0, double t1, double& s2, int sb, int cw, int N, int Np, uint32_t part_s, double* Lam, double* sxx) {
   const int lane = threadIdx.x & 31, lr = lane >> 2, lc = lane & 3;
   const uint32_t pb = part_s + (uint32_t)((sb & 1) * F2_NCW * 72 + cw * 72) * 8u;
-  f2_sts(pb + 16 * lane, d[0][0] + d[1][0]); f2_sts(pb + 16 * lane + 8, d[0][1] + d[1][1]);
-  d[0][0] = 0.0; d[0][1] = 0.0; d[1][0] = 0.0; d[1][1] = 0.0;
+  f2_sts(pb + 16 * lane, t0); f2_sts(pb + 16 * lane + 8, t1);
   if (SXX) {
     s2 += __shfl_xor_sync(0xffffffffu, s2, 1); s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
     if (lc == 0) f2_sts(pb + (64 + lr) * 8, s2);
@@ -288,7 +287,9 @@ __device__ __noinline__ void f2_consume_M(F2Ring& rg, int cw, int T, int N, int 
   int ra = q.rs;
   const uint32_t zrow = f2_smem_u32(Z) + (uint32_t)(lr * Tp + lc + 4 * cw) * 8u, part_s = f2_smem_u32(part);
   const uint32_t lane_off = (uint32_t)(lr * F2_TS + lc + 4 * cw) * 8u;
-  double d[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, s2 = 0.0;
+  double d[CNT][2], s2 = 0.0;                                 // one accumulator pair per k-chunk slot: independent DMMAs within a stage
+#pragma unroll
+  for (int j = 0; j < CNT; ++j) { d[j][0] = 0.0; d[j][1] = 0.0; }
   double av[CNT], bv[CNT];                                    // fragments of the stage whose DMMAs issue next
   int cl = 0;                                                 // chunk of the next stage to LOAD
   int cc = 0, sbc = 0;                                        // (chunk, series block) of the next stage to COMPUTE
@@ -326,14 +327,14 @@ __device__ __noinline__ void f2_consume_M(F2Ring& rg, int cw, int T, int N, int 
 #pragma unroll
       for (int j = 0; j < CNT; ++j) {
         if (SXX) s2 += av[j] * av[j];
-        F2_DMMA(d[j & 1], av[j], bv[j]);
+        F2_DMMA(d[j], av[j], bv[j]);
         av[j] = f2_lds(trowL + j * (F2_NCW * 32)); bv[j] = f2_lds(zcL + j * (F2_NCW * 32));
       }
     } else {
 #pragma unroll
       for (int j = 0; j < CNT; ++j) {
         if (SXX) s2 += av[j] * av[j];
-        F2_DMMA(d[j & 1], av[j], bv[j]);
+        F2_DMMA(d[j], av[j], bv[j]);
         if (more) { const bool tok = F2M_TOK(j); av[j] = tok ? f2_lds(trowL + j * (F2_NCW * 32)) : 0.0; bv[j] = tok ? f2_lds(zcL + j * (F2_NCW * 32)) : 0.0; }
       }
     }
@@ -341,7 +342,12 @@ __device__ __noinline__ void f2_consume_M(F2Ring& rg, int cw, int T, int N, int 
 #if !F2_PIPE
     F2_RELEASE();
 #endif
-    if (++cc == nck) { cc = 0; f2_m_reduce<R, SXX>(d, s2, sbc, cw, N, Np, part_s, Lam, sxx); ++sbc; }
+    if (++cc == nck) {
+      double t0_ = 0.0, t1_ = 0.0;
+#pragma unroll
+      for (int j = 0; j < CNT; ++j) { t0_ += d[j][0]; t1_ += d[j][1]; d[j][0] = 0.0; d[j][1] = 0.0; }
+      cc = 0; f2_m_reduce<R, SXX>(t0_, t1_, s2, sbc, cw, N, Np, part_s, Lam, sxx); ++sbc;
+    }
   }
 #undef F2M_LOAD_ALL
 #undef F2M_ADDR
