@@ -180,6 +180,261 @@ def run_reference(args):
                       "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+def _peak():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    if os.path.exists(peaks_path):
+        try:
+            pk = json.load(open(peaks_path)); peak = float(pk.get("hbm_gbs", peak)); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return peak, peak_src
+
+
+def _dist_setup():
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        sys.stdout.flush(); saved_fd = os.dup(1); os.dup2(2, 1)
+        dist.init_process_group("nccl", device_id=dev)
+        dist.barrier(); torch.cuda.synchronize()
+        sys.stdout.flush(); os.dup2(saved_fd, 1); os.close(saved_fd)
+    return torch, dist, world, rank, local, dev
+
+
+def _timed(torch, dist, world, dev, fn, nsteps):
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(nsteps):
+        fn()
+    torch.cuda.synchronize()
+    tt = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    return float(tt[0])
+
+
+def run_c4(args):
+    """Config C4: bootstrap confidence bands of the factor-VAR impulse responses of the hom_fac_1 model (T = 222, N = 139
+    estimation series, r = 8, VAR(4), 5.7 % missing).  A step = one full bootstrap of `--panels` replications per GPU:
+    device resampler (dfm_bootstrap_panels) -> standardise + PCA + masked fused ALS (dfm_estimate_factor) -> factor VAR
+    (dfm_estimate_var) -> IRF (dfm_irf) -> one all-gather of the per-replication records -> percentile bands
+    (dfm_percentiles).  `value` keeps everything device-resident; `e2e` is replicate.bootstrap_irf (host arrays)."""
+    torch, dist, world, rank, local, dev = _dist_setup()
+    import dynamic_factor_models_b200 as D
+    from dynamic_factor_models_b200 import Library, replicate
+    from dynamic_factor_models_b200._lib import MEM_DEVICE
+    lib = Library(path=os.environ.get("DFM_BENCH_LIB"), device=local)
+    z = np.load(os.path.join(ROOT, "tests", "golden", "hom_fac_1_panels.npz"))
+    r, p, L, H, burn = 8, 4, 4, 24, 50
+    m = D.DFMModel(z["all_bpdata"], z["all_inclcode"], 20, 40, 3, 224, 0, r, 1e-8, L, p)
+    D.estimate(m, lib=lib)                                         # the fitted C1 model (estimate!(::NonParametric), :530-543)
+    B = args.panels if args.panels != 1250 else 1000 // world      # C4 = 1000 replications, sharded
+    K_, W_ = args.steps, args.warmup
+    i0, i1 = m.initperiod, m.lastperiod
+    incl = m.inclcode == 1
+    v = m.factor_var_model
+    F0 = m.factor[i0 - 1:i1]; Tw = F0.shape[0]; ns = int(incl.sum()); k = r * p
+    resid = v.resid[i0 - 1:i1][p:]
+    cm = lambda a: torch.from_numpy(np.ascontiguousarray(np.asarray(a, float).T)).to(dev)      # column-major device copy
+    dins = [cm(F0), cm(resid), cm(v.betahat), cm(m.lambda_[incl]), cm(m.uar_coef[incl]),
+            torch.from_numpy(np.ascontiguousarray(m.uar_ser[incl])).to(dev), cm(m.data[i0 - 1:i1][:, incl])]
+    f0v = dins[0].view(1, r, Tw)
+    f64 = lambda n: torch.empty(n, dtype=torch.float64, device=dev)
+    dX, dF, dM, dQ, dG, dirf = f64(B * ns * Tw), f64(B * Tw * r), f64(B * k * k), f64(B * r * k), f64(B * k * r), f64(B * r * H * r)
+    gathered = f64(world * B * r * H * r) if world > 1 else dirf
+    qs = list(replicate.BAND_PERCENTILES); dband = f64(len(qs) * r * H * r)
+    sweeps = [0]
+
+    def step_device():
+        lib.bootstrap_panels_raw(Tw, ns, r, p, L, resid.shape[0], burn, B, SEED, rank * B, [t.data_ptr() for t in dins], dX.data_ptr())
+        st = lib.estimate_factor_raw(dX.data_ptr(), Tw, ns, r, B, MEM_DEVICE, F=dF.data_ptr(), nt_min=m.nt_min_factor_estimation, tol=m.tol)
+        sweeps[0] = sum(s_["iters"] for s_ in st)
+        lib.sync()
+        Fv = dF.view(B, r, Tw)
+        sg = torch.sign((Fv * f0v).sum(2)); sg[sg == 0] = 1.0
+        Fv.mul_(sg[:, :, None])                                    # factor signs aligned with the original estimate
+        torch.cuda.synchronize()
+        lib.estimate_var_raw(dF.data_ptr(), Tw, r, p, True, B, MEM_DEVICE, M=dM.data_ptr(), Q=dQ.data_ptr(), G=dG.data_ptr())
+        lib.irf_raw(dM.data_ptr(), dQ.data_ptr(), dG.data_ptr(), k, r, H, list(range(r)), B, MEM_DEVICE, dirf.data_ptr())
+        lib.sync()
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, dirf)            # the path's single collective
+        lib.percentiles_raw(gathered.data_ptr(), world * B, r * H * r, qs, dband.data_ptr())
+        lib.sync()
+
+    for _ in range(W_):
+        step_device()
+    clocks = ClockSampler(local); clocks.start()
+    l0 = lib.launches
+    ms = _timed(torch, dist, world, dev, step_device, K_)
+    launches = lib.launches - l0
+    clk = clocks.stop()
+    value = world * B * K_ / (ms * 1e-3)
+    nfail = int(torch.isnan(dirf.view(B, -1)).any(1).sum().item())
+
+    def step_e2e():
+        replicate.bootstrap_irf(lib, m, world * B, H=H, rank=rank, world=world, seed=SEED)
+
+    step_e2e()
+    Ke = 2
+    ms_e = _timed(torch, dist, world, dev, step_e2e, Ke)
+    nsall = m.ns
+    h2d = 8 * B * (Tw * ns + Tw * r + k * k + 2 * r * k)           # panels of the estimation series, factors, M, Q, G
+    d2h = 8 * B * (Tw * nsall + Tw * r + ns * r + 2 * ns + (1 + k) * r + Tw * r + r * r + k * k + 2 * r * k + r * H * r)
+
+    # ---- roofline of the dominant kernel (masked fused ALS): X is read twice per sweep (Lambda-step and F-step)
+    lib.profile(True); step_device(); prof = lib.profile_report(); lib.profile(False)
+    tot = sum(v_[0] for v_ in prof.values()) or 1.0
+    dom = max(prof, key=lambda n: prof[n][0])
+    peak, peak_src = _peak()
+    d_ms, d_cnt = prof[dom]
+    alg = 2.0 * Tw * ns * 8 * sweeps[0] if "als_masked" in dom else None
+    roof = {"bound": "hbm", "kernel": dom, "achieved": (alg / (d_ms * 1e-3) / 1e9) if alg else None, "peak": peak, "unit": "GB/s",
+            "frac": (alg / (d_ms * 1e-3) / 1e9 / peak) if alg else None, "traffic": None, "peak_source": peak_src,
+            "kernel_share_of_step": d_ms / tot, "avg_launch_ms": d_ms / d_cnt, "algorithmic_bytes_per_launch": alg,
+            "note": "2*T*N*8 bytes per ALS sweep and panel (SURVEY 8d); the 296 resident panels (73 MB) are re-read from L2, so the "
+                    "kernel is latency / issue bound, not HBM bound",
+            "kernel_ms": {n: round(v_[0], 3) for n, v_ in sorted(prof.items(), key=lambda kv: -kv[1][0])}}
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import dfm_ref as Rf
+        nb = 2
+        Xb = replicate.bootstrap_panels(m, range(nb), SEED, lib=lib)
+        t0 = time.perf_counter()
+        for b in range(nb):
+            full = np.full_like(z["all_bpdata"], np.nan); full[i0 - 1:i1] = Xb[b]
+            mo = Rf.DFMModel(full, z["all_inclcode"], 20, 40, 3, 224, 0, r, 1e-8, L, p)
+            Rf.estimate_factor(mo, computeR2=False); Rf.estimate_var(mo.factor_var_model)
+            Rf.impulse_response(mo.factor_var_model, list(range(r)), H)
+        dt = time.perf_counter() - t0
+        cpu = {"value": nb / dt, "unit": "bootstrap replications/s", "cores": 1, "kind": "port",
+               "sample": f"{nb} replications re-estimated by oracle/dfm_ref.py (numpy/scipy restatement of estimate_factor!, estimate_var!, "
+                         f"impulse_response), {dt:.1f} s"}
+    if rank == 0:
+        print(json.dumps({"metric": "bootstrap replications/sec (C4: hom_fac_1 model, r=8, VAR(4), IRF H=24)", "value": value,
+                          "unit": "bootstrap replications/s", "n_gpus": world, "steps": K_, "warmup": W_, "ms_per_step": ms / K_,
+                          "higher_is_better": True, "scaling": "strong" if args.panels == 1250 else "weak", "vs_baseline": None, "dtype": "f64",
+                          "data": "residual bootstrap of the hom_fac_1 panel (device resampler)",
+                          "config": {"workload": f"C4: {world * B} bootstrap replications of the Stock-Watson panel (T={Tw}, N={ns} estimation "
+                                                 f"series, r={r}, VAR({p}), 5.7 % missing): resample -> ALS -> VAR -> IRF(H={H}) -> bands",
+                                     "replications_per_gpu": B, "als_sweeps_per_step": sweeps[0], "failed_replications": nfail,
+                                     "l2": "panels are regenerated every step; 296 resident panels = 73 MB < L2 (stated, not flushed)"},
+                          "e2e": {"value": world * B * Ke / (ms_e * 1e-3), "unit": "bootstrap replications/s", "h2d_bytes_per_step": h2d,
+                                  "d2h_bytes_per_step": d2h, "ms_per_step": ms_e / Ke},
+                          "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+                          "als": {"value": sweeps[0] * world / (prof[dom][0] * 1e-3) if "als_masked" in dom else None,
+                                  "unit": "panel-ALS-sweeps/s (masked fused kernel)"}}))
+    if world > 1:
+        dist.destroy_process_group()
+    lib.close()
+
+
+def run_single_panel(args):
+    """Configs C2-single (N=200, r=8, T=500: fused kernel, one CTA, latency bound) and C3 (N=2000, r=20, T=2000: general
+    multi-kernel path): ONE panel, Kalman-EM; replicas only across GPUs (a single panel does not shard).
+    c2-single runs to convergence (relative log-likelihood change 1e-7); c3 runs a fixed 10 iterations."""
+    torch, dist, world, rank, local, dev = _dist_setup()
+    from dynamic_factor_models_b200 import Library
+    from dynamic_factor_models_b200._lib import MEM_DEVICE, MEM_HOST
+    import ctypes as C
+    lib = Library(path=os.environ.get("DFM_BENCH_LIB"), device=local)
+    c3 = args.config == "c3"
+    N, r, T, p = (2000, 20, 2000, 1) if c3 else (NS, R_, T_, P_)
+    mi, tol = (10, 0.0) if c3 else (500, 1e-7)
+    K_, W_ = args.steps, args.warmup
+    k = r * p
+    f64 = lambda n: torch.empty(n, dtype=torch.float64, device=dev)
+    dX, dF0 = f64(T * N), f64(T * r)
+    lib.simulate_panels_raw(rank, 1, N, r, T, SEED, dX.data_ptr())
+    lib.estimate_factor_raw(dX.data_ptr(), T, N, r, 1, MEM_DEVICE, F=dF0.data_ptr(), max_iter=1)          # PCA + one ALS sweep
+    dL0, dR0, dA0, dQ0 = f64(N * r), f64(N), f64(r * k), f64(r * r)
+    lib.check(lib.lib.dfm_em_init_from_factors(lib.h, C.c_void_p(dX.data_ptr()), C.c_void_p(dF0.data_ptr()), T, N, r, p, 1, MEM_DEVICE,
+                                               C.c_void_p(dL0.data_ptr()), C.c_void_p(dR0.data_ptr()), C.c_void_p(dA0.data_ptr()),
+                                               C.c_void_p(dQ0.data_ptr())), "em_init")
+    lib.sync()
+    dout = {n: f64(sz) for n, sz in dict(Lam=N * r, R=N, A=r * k, Q=r * r, F=T * r, loglik=mi).items()}
+    dit = torch.empty(1, dtype=torch.int32, device=dev); dst = torch.empty(1, dtype=torch.int32, device=dev)
+    init_d = dict(Lam=dL0.data_ptr(), R=dR0.data_ptr(), A=dA0.data_ptr(), Q=dQ0.data_ptr(), P0=0)
+    out_d = dict(Lam=dout["Lam"].data_ptr(), R=dout["R"].data_ptr(), A=dout["A"].data_ptr(), Q=dout["Q"].data_ptr(), P0=0,
+                 F=dout["F"].data_ptr(), PF=0, loglik=dout["loglik"].data_ptr(), iters=dit.data_ptr(), status=dst.data_ptr())
+
+    def step_device():
+        lib.em_kalman_raw(dX.data_ptr(), T, N, r, p, 1, mi, tol, init_d, out_d, MEM_DEVICE, args.path)
+        lib.sync()
+
+    for _ in range(W_):
+        step_device()
+    clocks = ClockSampler(local); clocks.start()
+    l0 = lib.launches
+    ms = _timed(torch, dist, world, dev, step_device, K_)
+    launches = lib.launches - l0
+    clk = clocks.stop()
+    iters = int(dit.item())
+    value = world * iters * K_ / (ms * 1e-3)
+    hX = dX.cpu().pin_memory()
+    hin = {n: t.cpu().pin_memory() for n, t in dict(Lam=dL0, R=dR0, A=dA0, Q=dQ0).items()}
+    hout = {n: torch.empty(t.numel(), dtype=torch.float64).pin_memory() for n, t in dout.items()}
+    hit = torch.empty(1, dtype=torch.int32).pin_memory(); hst = torch.empty(1, dtype=torch.int32).pin_memory()
+    init_h = dict(Lam=hin["Lam"].data_ptr(), R=hin["R"].data_ptr(), A=hin["A"].data_ptr(), Q=hin["Q"].data_ptr(), P0=0)
+    out_h = dict(Lam=hout["Lam"].data_ptr(), R=hout["R"].data_ptr(), A=hout["A"].data_ptr(), Q=hout["Q"].data_ptr(), P0=0,
+                 F=hout["F"].data_ptr(), PF=0, loglik=hout["loglik"].data_ptr(), iters=hit.data_ptr(), status=hst.data_ptr())
+
+    def step_e2e():
+        lib.em_kalman_raw(hX.data_ptr(), T, N, r, p, 1, mi, tol, init_h, out_h, MEM_HOST, args.path)
+
+    step_e2e()
+    Ke = max(2, min(K_, 3))
+    ms_e = _timed(torch, dist, world, dev, step_e2e, Ke)
+    lib.profile(True); step_device(); prof = lib.profile_report(); lib.profile(False)
+    tot = sum(v_[0] for v_ in prof.values()) or 1.0
+    dom = max(prof, key=lambda n: prof[n][0])
+    peak, peak_src = _peak()
+    alg = 2.0 * T * N * 8 * iters
+    roof = {"bound": "hbm", "kernel": dom, "achieved": alg / (tot * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (tot * 1e-3) / 1e9 / peak,
+            "traffic": None, "peak_source": peak_src, "kernel_share_of_step": prof[dom][0] / tot,
+            "algorithmic_bytes_per_step": alg,
+            "note": ("one panel: the T-step Kalman / smoother recursions are a serial dependency chain -- latency bound, the HBM fraction "
+                     "is reported for completeness (SURVEY.md 8d: do not quote an HBM fraction for B = 1)"),
+            "kernel_ms": {n: round(v_[0], 3) for n, v_ in sorted(prof.items(), key=lambda kv: -kv[1][0])}}
+    us_per_iter = ms * 1e3 / (K_ * iters)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu and not c3:
+        from oracle.c import kem
+        Xh = np.ascontiguousarray(hX.numpy().reshape(1, N, T).transpose(0, 2, 1))
+        Lh = lambda t, rows, cols: np.ascontiguousarray(t.cpu().numpy().reshape(1, cols, rows).transpose(0, 2, 1))
+        ini = (Lh(dL0, N, r), dR0.cpu().numpy().reshape(1, N), Lh(dA0, r, k), Lh(dQ0, r, r))
+        _omp_env()
+        t0 = time.perf_counter()
+        o = kem.em_kalman_batch(Xh, *ini, p=p, max_iter=mi, tol=tol, nthreads=1)
+        dt = time.perf_counter() - t0
+        cpu = {"value": int(o["iters"][0]) / dt, "unit": "EM iterations/s", "cores": 1, "kind": "port",
+               "sample": f"the same panel to the same convergence rule, oracle C port, 1 thread, {int(o['iters'][0])} iterations in {dt:.2f} s"}
+    if rank == 0:
+        name = "C3 (N=2000, r=20, T=2000)" if c3 else "C2 (N=200, r=8, T=500), EM to convergence"
+        print(json.dumps({"metric": f"EM iters/sec, single panel {name}", "value": value, "unit": "EM iterations/s", "n_gpus": world,
+                          "steps": K_, "warmup": W_, "ms_per_step": ms / K_, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "f64", "data": "synthetic (device-generated frozen DGP, SURVEY.md 8d)",
+                          "config": {"workload": f"one panel N={N} r={r} T={T} p={p}; " + ("10 EM iterations" if c3 else f"EM to convergence (rel. loglik change {tol}): {iters} iterations"),
+                                     "parallelism": f"replicas x{world} (a single panel does not shard)", "iterations": iters,
+                                     "status_ok": bool((dst == 0).all().item()), "l2": "panel fits L2 (stated; latency-bound configuration)"},
+                          "critical_path": {"us_per_em_iteration": us_per_iter, "us_per_time_step": us_per_iter / T,
+                                            "note": "E-step + M-step of one iteration / T periods"},
+                          "e2e": {"value": world * int(hit.item()) * Ke / (ms_e * 1e-3), "unit": "EM iterations/s",
+                                  "h2d_bytes_per_step": 8 * (T * N + N * r + N + r * k + r * r), "d2h_bytes_per_step": 8 * (T * r + N * r + N + r * k + r * r + mi) + 8,
+                                  "ms_per_step": ms_e / Ke},
+                          "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu}))
+    if world > 1:
+        dist.destroy_process_group()
+    lib.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -190,9 +445,14 @@ def main():
     ap.add_argument("--em-iters", type=int, default=50, help="EM iterations per step (SURVEY 8d: fixed 50)")
     ap.add_argument("--path", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--config", default="c5", choices=["c5", "c4", "c3", "c2-single"],
+                    help="c5 (default, the headline metric): Monte-Carlo shard of C2-shaped panels; c4: bootstrap IRF bands of the "
+                         "hom_fac_1 model; c3: one large panel N=2000 r=20 T=2000; c2-single: one C2 panel, EM to convergence")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.config != "c5":
+        return {"c4": run_c4, "c3": run_single_panel, "c2-single": run_single_panel}[args.config](args)
 
     import torch
     import torch.distributed as dist

@@ -199,6 +199,26 @@ class Library:
                    "dfm_estimate_factor")
         return [dict(ssr=s.ssr, tss=s.tss, nobs=s.nobs, iters=s.iters, status=s.status) for s in st]
 
+    # pointer-level wrappers of the replication pipeline (device-resident C4 step: addresses are ints)
+    def bootstrap_panels_raw(self, T, ns, r, p, L, n_resid, burn, B, seed, rep0, ptrs, X, mem=MEM_DEVICE):
+        """ptrs = (F0, resid, beta, lam, uar_coef, uar_ser, data) addresses."""
+        o = BootOpts(T=T, ns=ns, r=r, p=p, n_uarlag=L, n_resid=n_resid, burn=burn, batch=B, mem=mem, seed=seed, rep0=rep0)
+        self.check(self.lib.dfm_bootstrap_panels(self.h, C.byref(o), *[C.c_void_p(a_) for a_ in ptrs], C.c_void_p(X)), "dfm_bootstrap_panels")
+
+    def estimate_var_raw(self, F, T, r, p, withconst, B, mem, betahat=0, resid=0, seps=0, M=0, Q=0, G=0):
+        vp = lambda a: C.c_void_p(a) if a else None
+        self.check(self.lib.dfm_estimate_var(self.h, C.c_void_p(F), T, r, p, int(withconst), B, mem, vp(betahat), vp(resid), vp(seps),
+                                             vp(M), vp(Q), vp(G)), "dfm_estimate_var")
+
+    def irf_raw(self, M, Q, G, k, r, H, shock_ids, B, mem, out):
+        ids = np.ascontiguousarray(shock_ids, dtype=np.int32)
+        self.check(self.lib.dfm_irf(self.h, C.c_void_p(M), C.c_void_p(Q), C.c_void_p(G), k, r, H, len(ids), ids.ctypes.data_as(c_ip), B, mem,
+                                    C.c_void_p(out)), "dfm_irf")
+
+    def percentiles_raw(self, recs, n, d, q, out, mem=MEM_DEVICE):
+        qq = np.ascontiguousarray(q, dtype=float)
+        self.check(self.lib.dfm_percentiles(self.h, C.c_void_p(recs), n, d, _ptr(qq), len(qq), mem, C.c_void_p(out)), "dfm_percentiles")
+
     def shard_range(self, n_rep, rank, world):
         b, e = C.c_longlong(), C.c_longlong()
         rc = self.lib.dfm_shard_range(n_rep, rank, world, C.byref(b), C.byref(e))
