@@ -1137,15 +1137,21 @@ int dfm_allgather_results(dfm_handle* h, void* nccl_comm, const double* send, do
   typedef int (*allgather_fn)(const void*, void*, size_t, int, void*, cudaStream_t);
   static allgather_fn fn = nullptr;
   if (!fn) {
-    const char* names[] = {"libnccl.so.2", "libnccl.so"};
-    void* lib = nullptr;
-    for (const char* n : names) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
-    if (!lib) return fail(h, DFM_ERR_NCCL, "libnccl not found");
-    fn = (allgather_fn)dlsym(lib, "ncclAllGather");
+    // the communicator was created by the NCCL the caller already loaded (NCCL.jl, torch's bundled copy, ...): use THAT
+    // library's ncclAllGather when it is visible in the process, and only otherwise load one by name
+    fn = (allgather_fn)dlsym(RTLD_DEFAULT, "ncclAllGather");
+    if (!fn) {
+      const char* names[] = {"libnccl.so.2", "libnccl.so"};
+      void* lib = nullptr;
+      for (const char* n : names) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+      if (!lib) return fail(h, DFM_ERR_NCCL, "libnccl not found");
+      fn = (allgather_fn)dlsym(lib, "ncclAllGather");
+    }
     if (!fn) return fail(h, DFM_ERR_NCCL, "ncclAllGather not found");
   }
   CK(cudaSetDevice(h->device));
-  int rc = fn(send, recv, (size_t)count, /*ncclFloat64*/ 8, nccl_comm, h->stream);
+  const int kNcclFloat64 = 8;      // ncclDataType_t: ncclFloat64 = ncclDouble = 8 in every NCCL 2.x release (nccl.h)
+  int rc = fn(send, recv, (size_t)count, kNcclFloat64, nccl_comm, h->stream);
   if (rc != 0) return fail(h, DFM_ERR_NCCL, "ncclAllGather failed");
   return DFM_OK;
 #endif
