@@ -176,8 +176,14 @@ __device__ __noinline__ double f2_consume_E(F2Ring& rg, int cw, int T, int N, in
 #define F2E_LOAD_ALL() do {                                                                                                 \
     f2_wait_s(q.full + q.rs * 8, q.rph);                                                                                    \
     F2E_ADDR()                                                                                                              \
-    l0 = F2E_LDL(0); l1 = F2E_LDL(1);                                                                                       \
-    _Pragma("unroll") for (int j = 0; j < CNT; ++j) { a0[j] = F2E_LDA(j, 0); a1[j] = F2E_LDA(j, 1); }                       \
+    if (fastL) {                       /* the common case: straight-line unmasked loads */                                  \
+      l0 = f2_lds(laL); l1 = f2_lds(laL + 32);                                                                              \
+      _Pragma("unroll") for (int j = 0; j < CNT; ++j) { a0[j] = f2_lds(tileL + offF[j]); a1[j] = f2_lds(tileL + offF[j] + 4 * F2_TS * 8); } \
+      if (!lrok) { l0 = 0.0; l1 = 0.0; }                                                                                    \
+    } else {                                                                                                                \
+      l0 = F2E_LDL(0); l1 = F2E_LDL(1);                                                                                     \
+      _Pragma("unroll") for (int j = 0; j < CNT; ++j) { a0[j] = F2E_LDA(j, 0); a1[j] = F2E_LDA(j, 1); }                     \
+    }                                                                                                                       \
     F2E_ADVANCE();                                                                                                          \
   } while (0)
 #if F2_PIPE
