@@ -64,7 +64,7 @@ EXPORTS = ["dfm_version", "dfm_status_string", "dfm_create", "dfm_create_on_stre
            "dfm_launch_count", "dfm_last_error", "dfm_profile_enable", "dfm_profile_query", "dfm_profile_reset",
            "dfm_profile_kernel_name", "dfm_standardize", "dfm_pca_score", "dfm_estimate_factor",
            "dfm_estimate_loading", "dfm_estimate_loading_ex", "dfm_estimate_var", "dfm_irf", "dfm_em_kalman", "dfm_em_init_from_factors",
-           "dfm_simulate_panels", "dfm_bootstrap_panels", "dfm_percentiles", "dfm_allgather_results", "dfm_shard_range"]
+           "dfm_simulate_panels", "dfm_bootstrap_panels", "dfm_bootstrap_irf", "dfm_percentiles", "dfm_allgather_results", "dfm_shard_range"]
 
 
 def _ptr(a):
@@ -133,6 +133,8 @@ class Library:
         L.dfm_simulate_panels.argtypes = [C.c_void_p, C.c_ulonglong, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                           C.c_void_p, C.c_void_p]
         L.dfm_bootstrap_panels.argtypes = [C.c_void_p, C.POINTER(BootOpts)] + [C.c_void_p] * 8
+        L.dfm_bootstrap_irf.argtypes = [C.c_void_p, C.POINTER(BootOpts)] + [C.c_void_p] * 7 + [C.c_int, C.c_double, C.c_int, C.c_void_p,
+                                                                                               C.c_void_p, C.c_void_p]
         L.dfm_percentiles.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.dfm_em_init_from_factors.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                                C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -317,6 +319,19 @@ class Library:
                                                                                                to_cm(np.asarray(data, float))]
         self.check(self.lib.dfm_bootstrap_panels(self.h, C.byref(o), *[_ptr(b_) for b_ in bufs], _ptr(X)), "dfm_bootstrap_panels")
         return from_cm(X, Tw, ns, B)
+
+    def bootstrap_irf(self, F0, resid, beta, lam, uar_coef, uar_ser, data, rep0, B, seed, H, nt_min=20, tol=1e-8, burn=50):
+        """The whole C4 replication step on the device: (B, r, H, r) impulse responses [variable, horizon, shock] of the
+        re-estimated models of bootstrap draws rep0 .. rep0+B-1, plus the ALS iteration counts / statuses."""
+        F0 = np.asarray(F0, float); Tw, r = F0.shape; ns, Lg = np.asarray(uar_coef).shape; K = np.asarray(beta).shape[0]
+        o = BootOpts(T=Tw, ns=ns, r=r, p=(K - 1) // r, n_uarlag=Lg, n_resid=np.asarray(resid).shape[0], burn=burn, batch=B, mem=MEM_HOST,
+                     seed=seed, rep0=rep0)
+        bufs = [to_cm(np.asarray(a_, float)) for a_ in (F0, resid, beta, lam, uar_coef)] + [np.ascontiguousarray(uar_ser, dtype=float),
+                                                                                               to_cm(np.asarray(data, float))]
+        out = np.empty(B * r * H * r); it = np.zeros(B, np.int32); st = np.zeros(B, np.int32)
+        self.check(self.lib.dfm_bootstrap_irf(self.h, C.byref(o), *[_ptr(b_) for b_ in bufs], nt_min, tol, H, _ptr(out), _ptr(it), _ptr(st)),
+                   "dfm_bootstrap_irf")
+        return np.ascontiguousarray(out.reshape(B, r, H, r).transpose(0, 3, 2, 1)), it, st
 
     def percentiles(self, recs, q):
         """recs (n, d) -> (len(q), d): numpy.percentile(recs, q, axis=0) on the device, NaN records ignored."""

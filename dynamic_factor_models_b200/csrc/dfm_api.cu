@@ -1104,6 +1104,59 @@ int dfm_bootstrap_panels(dfm_handle* h, const dfm_boot_opts* o, const double* F0
   return finish(h, mem);
 }
 
+// One call for the whole C4 replication step ("one panel + B bootstrap seeds"): resample -> standardise + PCA
+// + ALS (estimate_factor!, :328-382) -> sign alignment -> factor VAR (:444-492) -> IRF (:793-825), device resident between
+// the stages.  The stages are the public entry points above run on temporaries of this call.
+int dfm_bootstrap_irf(dfm_handle* h, const dfm_boot_opts* o, const double* F0, const double* resid, const double* beta,
+                      const double* lam, const double* uar_coef, const double* uar_ser, const double* data, int nt_min,
+                      double tol, int H, double* irf, int* als_iters, int* als_status) {
+  if (!h || !o || !F0 || !resid || !beta || !lam || !uar_coef || !uar_ser || !data || !irf || H <= 0)
+    return fail(h, DFM_ERR_ARG, "dfm_bootstrap_irf: bad argument");
+  const int Tw = o->T, ns = o->ns, r = o->r, p = o->p, Lg = o->n_uarlag, nres = o->n_resid, batch = o->batch, mem = o->mem;
+  if (Tw <= p || ns <= 0 || r <= 0 || p <= 0 || Lg <= 0 || nres <= 0 || batch <= 0) return fail(h, DFM_ERR_ARG, "dfm_bootstrap_irf: bad shape");
+  CK(cudaSetDevice(h->device));
+  const size_t B = batch; const int k = r * p, K = 1 + k;
+  // temporaries of this call (the stages' own scratch lives in the handle's workspace)
+  const size_t nin[7] = {(size_t)Tw * r, (size_t)nres * r, (size_t)K * r, (size_t)ns * r, (size_t)ns * Lg, (size_t)ns, (size_t)Tw * ns};
+  const double* hin[7] = {F0, resid, beta, lam, uar_coef, uar_ser, data};
+  size_t tot = 0, off[16];
+  auto take = [&](size_t n) { size_t o_ = tot; tot += (n * 8 + 255) & ~(size_t)255; return o_; };
+  for (int i = 0; i < 7; ++i) off[i] = take(nin[i]);
+  const size_t oX = take(B * ns * Tw), oF = take(B * Tw * r), oM = take(B * k * k), oQ = take(B * r * k), oG = take(B * k * r),
+               oI = take(B * (size_t)r * H * r);
+  char* base = nullptr;
+  CK(cudaMalloc((void**)&base, tot));
+  auto D = [&](size_t o_) { return reinterpret_cast<double*>(base + o_); };
+#define BI_FAIL(rc_) do { int r__ = (rc_); if (r__) { cudaStreamSynchronize(h->stream); cudaFree(base); return r__; } } while (0)
+  const double* din[7];
+  for (int i = 0; i < 7; ++i) {
+    if (mem == DFM_MEM_HOST) {
+      if (cudaMemcpyAsync(D(off[i]), hin[i], nin[i] * 8, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) BI_FAIL(fail(h, DFM_ERR_CUDA, "dfm_bootstrap_irf: upload failed"));
+      din[i] = D(off[i]);
+    } else din[i] = hin[i];
+  }
+  dfm_boot_opts ob = *o; ob.mem = DFM_MEM_DEVICE;
+  BI_FAIL(dfm_bootstrap_panels(h, &ob, din[0], din[1], din[2], din[3], din[4], din[5], din[6], D(oX)));
+  dfm_factor_opts fo{}; fo.T = Tw; fo.N = ns; fo.r = r; fo.nt_min = nt_min; fo.tol = tol; fo.max_iter = 100000000; fo.compute_r2 = 0;
+  fo.n_constr = 0; fo.batch = batch; fo.mem = DFM_MEM_DEVICE;
+  std::vector<dfm_factor_stats> fs(B);
+  BI_FAIL(dfm_estimate_factor(h, D(oX), &fo, nullptr, D(oF), nullptr, nullptr, nullptr, nullptr, fs.data()));
+  for (size_t b = 0; b < B; ++b) { if (als_iters) als_iters[b] = fs[b].iters; if (als_status) als_status[b] = fs[b].status; }
+  L(k_sign_align, batch, 1, 128, 48 * 8, D(oF), din[0], Tw, r);
+  int rc = dfm_estimate_var(h, D(oF), Tw, r, p, 1, batch, DFM_MEM_DEVICE, nullptr, nullptr, nullptr, D(oM), D(oQ), D(oG));
+  if (rc != DFM_OK && rc != DFM_ERR_NOT_PD && rc != DFM_ERR_TOO_FEW_OBS) BI_FAIL(rc);       // (all panels failed: records stay NaN)
+  std::vector<int> ids(r); for (int j = 0; j < r; ++j) ids[j] = j;
+  double* dI = mem == DFM_MEM_HOST ? D(oI) : irf;
+  BI_FAIL(dfm_irf(h, D(oM), D(oQ), D(oG), k, r, H, r, ids.data(), batch, DFM_MEM_DEVICE, dI));
+  if (mem == DFM_MEM_HOST && cudaMemcpyAsync(irf, dI, B * (size_t)r * H * r * 8, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess)
+    BI_FAIL(fail(h, DFM_ERR_CUDA, "dfm_bootstrap_irf: download failed"));
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  cudaFree(base);
+#undef BI_FAIL
+  CK(e);
+  return DFM_OK;
+}
+
 // ------------------------------------------------------------------------------------ (f)3: percentile bands
 int dfm_percentiles(dfm_handle* h, const double* recs, long long n, int d, const double* q, int nq, int mem, double* out) {
   if (!h || !recs || !q || !out || n <= 0 || d <= 0 || nq <= 0 || nq > 64) return fail(h, DFM_ERR_ARG, "dfm_percentiles: bad argument");

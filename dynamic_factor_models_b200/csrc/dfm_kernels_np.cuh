@@ -282,9 +282,29 @@ __global__ void k_subspace_eig(double* __restrict__ Gall, double* __restrict__ V
     }
     res = rmax / fabs(theta[0]);
     if (res <= tol) { ++it; break; }
-    // next iterate: V <- Y (= G V, to be orthonormalised)
+    // next iterate: V <- G^q V (q = 3 products per orthonormalisation + Rayleigh-Ritz cycle: the cycle -- CholQR2 and a
+    // Jacobi eigen-solve of the m x m projected matrix -- costs far more than a product, and the error of the wanted
+    // pairs contracts by (lambda_{m+1} / lambda_r)^q per cycle; Y = G V of the rotated basis is already there)
     for (int e = DFM_TID; e < n * m; e += DFM_NT) V[e] = Y[e];
     DFM_SYNC();
+    for (int q_ = 1; q_ < 3; ++q_) {
+      for (int e = DFM_TID; e < n * m; e += DFM_NT) {
+        int i = e % n, j = e / n;
+        double s = 0.0;
+        for (int l = 0; l < n; ++l) s += G[i + (size_t)n * l] * V[l + (size_t)n * j];
+        Y[e] = s;
+      }
+      DFM_SYNC();
+      // rescale the columns (plain power steps grow like lambda^q): keeps the Gram matrix of CholQR well scaled
+      for (int j = 0; j < m; ++j) {
+        double s = 0.0;
+        for (int i = DFM_TID; i < n; i += DFM_NT) s += Y[i + (size_t)n * j] * Y[i + (size_t)n * j];
+        s = block_sum(s, red);
+        const double sc_ = (s > 0.0) ? 1.0 / sqrt(s) : 1.0;
+        for (int i = DFM_TID; i < n; i += DFM_NT) V[i + (size_t)n * j] = Y[i + (size_t)n * j] * sc_;
+      }
+      DFM_SYNC();
+    }
   }
   // ---- leave results where k_pca_finish looks for them
   for (int i = DFM_TID; i < n; i += DFM_NT) G[i + (size_t)n * i] = (i < m) ? theta[i] : -1e300;

@@ -154,6 +154,20 @@ __global__ void k_bootstrap_panels(BootArgs a) {
   }
 }
 
+// Sign convention of re-estimated factors: column j of every panel's F is flipped when it correlates negatively with
+// the reference factors F0 (PCA / ALS factors are identified up to sign).  grid (B).  NaN factors stay NaN.
+__global__ void k_sign_align(double* __restrict__ Fall, const double* __restrict__ F0, int T, int r) {
+  DFM_SMEM(red);
+  double* F = Fall + (size_t)DFM_BX * T * r;
+  for (int j = 0; j < r; ++j) {
+    double s = 0.0;
+    for (int t = DFM_TID; t < T; t += DFM_NT) s += F[t + (size_t)T * j] * F0[t + (size_t)T * j];
+    s = block_sum(s, red);
+    if (s < 0.0) for (int t = DFM_TID; t < T; t += DFM_NT) F[t + (size_t)T * j] = -F[t + (size_t)T * j];
+    DFM_SYNC();
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Percentile bands over the replication axis (numpy.percentile's default linear interpolation: position q/100 (n-1)).
 // recs: [n][d] row-major (replication-major records);  grid = d statistics, one bitonic sort of <= npad values in shared

@@ -77,28 +77,20 @@ BAND_PERCENTILES = (5, 16, 50, 84, 95)
 
 def bootstrap_irf(lib, m, n_rep, H=24, rank=0, world=1, seed=SEED):
     """C4: bootstrap distribution of the factor-VAR impulse responses.  Every replication is
-    re-estimated with the full non-parametric pipeline (ALS factors -> VAR -> IRF), all batched on the
-    device; factor signs are aligned with the original estimate; replications whose re-estimation fails
-    (ALS status 2/3, singular VAR) are NaN records and are ignored by the bands.  Returns
+    re-estimated with the full non-parametric pipeline (ALS factors -> VAR -> IRF) inside ONE device-resident
+    call (dfm_bootstrap_irf); factor signs are aligned with the original estimate; replications whose
+    re-estimation fails (ALS status 2/3, singular VAR) are NaN records and are ignored by the bands.  Returns
     (irfs (n_rep, r, H, r), bands dict of 5/16/50/84/95 percentiles)."""
     b, e = lib.shard_range(n_rep, rank, world)
     r = m.nfac_t; p = m.factor_var_model.nlag
     rec = np.full((e - b, r * H * r), np.nan)
     if e > b:
-        Xs = bootstrap_panels(m, range(b, e), seed, lib=lib)
-        incl = m.inclcode == 1
-        als = lib.estimate_factor(Xs[:, :, incl], r, nt_min=m.nt_min_factor_estimation, tol=m.tol, compute_r2=False)
-        Fb = als["F"]                                                        # (n, Tw, r)
-        st = als["stats"] if isinstance(als["stats"], list) else [als["stats"]]
-        good = np.array([s["status"] in (0, 4) for s in st]) & np.isfinite(Fb).all(axis=(1, 2))
-        Fb = np.where(good[:, None, None], Fb, np.nan)                       # failed draws: NaN factors -> NaN VAR -> NaN record
-        F0 = m.factor[m.initperiod - 1:m.lastperiod]
-        sg = np.sign(np.einsum("btr,tr->br", np.nan_to_num(Fb), F0)); sg[sg == 0] = 1.0
-        Fb = Fb * sg[:, None, :]
-        if good.any():
-            var = lib.estimate_var(Fb, p, True)                              # failed panels come back as NaN
-            irf = lib.irf(var["M"], var["Q"], var["G"], H, list(range(r)))   # (n, r, H, r)
-            rec[:] = irf.reshape(e - b, -1)
+        i0, i1 = m.initperiod, m.lastperiod
+        v = m.factor_var_model; incl = m.inclcode == 1
+        irf, _, _ = lib.bootstrap_irf(m.factor[i0 - 1:i1], v.resid[i0 - 1:i1][p:], v.betahat, m.lambda_[incl], m.uar_coef[incl],
+                                      m.uar_ser[incl], m.data[i0 - 1:i1][:, incl], b, e - b, seed, H,
+                                      nt_min=m.nt_min_factor_estimation, tol=m.tol)
+        rec[:] = irf.reshape(e - b, -1)                                      # one device-resident call per shard
     allrec = gather_records(rec, n_rep, rank, world, lib)
     irfs = allrec.reshape(n_rep, r, H, r)
     pb = lib.percentiles(allrec, BAND_PERCENTILES)                           # device sort per statistic

@@ -218,6 +218,16 @@ typedef struct {
 int dfm_bootstrap_panels(dfm_handle* h, const dfm_boot_opts* opts, const double* F0, const double* resid, const double* beta,
                          const double* lam, const double* uar_coef, const double* uar_ser, const double* data, double* X);
 
+/* The whole C4 replication step in one call ("one panel + B bootstrap seeds"): dfm_bootstrap_panels ->
+ * dfm_estimate_factor (standardise, PCA start, ALS with nt_min / tol as estimate_factor!) -> factor signs aligned with F0 ->
+ * dfm_estimate_var (VAR(p) with constant) -> dfm_irf for all r shocks, device resident between the stages.  Inputs as
+ * dfm_bootstrap_panels (pass the ESTIMATION series only: lam, uar_*, data restricted to inclcode == 1).
+ * irf: batch records [shock j][horizon h][variable i] = r*H*r doubles each (NaN record = failed replication);
+ * als_iters / als_status: HOST int[batch] or NULL.  Synchronous. */
+int dfm_bootstrap_irf(dfm_handle* h, const dfm_boot_opts* opts, const double* F0, const double* resid, const double* beta,
+                      const double* lam, const double* uar_coef, const double* uar_ser, const double* data, int nt_min,
+                      double tol, int H, double* irf, int* als_iters, int* als_status);
+
 /* ---- (f)3: percentile bands over the replication axis (the post-processing step behind impulse_response, :793-825).
  * recs: n x d ROW-major (one record of d statistics per replication, as gathered by dfm_allgather_results); q: nq
  * percentiles in [0, 100] (HOST array); out: nq x d row-major.  numpy.percentile's default (linear) interpolation; NaN

@@ -43,15 +43,22 @@ def test_bootstrap_irf_c1(lib, panels):
     assert (bands[5] <= bands[95] + 1e-12).all()
     for q in (5, 50, 95):                                        # device percentile kernel == numpy.percentile
         np.testing.assert_allclose(bands[q], np.percentile(irfs, q, axis=0), rtol=1e-12, atol=1e-14)
-    # oracle re-estimation of replication 2
-    Xs = replicate.bootstrap_panels(g, [2], lib=lib)[0]
-    full = np.full_like(panels["all_bpdata"], np.nan); full[2:224] = Xs
-    m = P.ref_model(full, panels["all_inclcode"], 4)
+    # oracle re-estimation of replication 2 (the fused call resamples the ESTIMATION series only)
+    check_bootstrap_replication(lib, g, panels, irfs, 2)
+
+
+def check_bootstrap_replication(lib, g, panels, irfs, rep, H=8):
+    i0, i1 = g.initperiod, g.lastperiod
+    v = g.factor_var_model; p = v.nlag; incl = g.inclcode == 1
+    Xs = lib.bootstrap_panels(g.factor[i0 - 1:i1], v.resid[i0 - 1:i1][p:], v.betahat, g.lambda_[incl], g.uar_coef[incl], g.uar_ser[incl],
+                              g.data[i0 - 1:i1][:, incl], rep, 1, 20260922)[0]
+    full = np.full_like(panels["all_bpdata"], np.nan); full[i0 - 1:i1, np.flatnonzero(incl)] = Xs
+    m = P.ref_model(full, panels["all_inclcode"], g.nfac_t)
     R.estimate_factor(m, computeR2=False); R.estimate_var(m.factor_var_model)
-    F0 = g.factor[2:224]
-    s = np.sign((m.factor[2:224] * F0).sum(0)); s[s == 0] = 1
-    ref = R.impulse_response(m.factor_var_model, [0, 1, 2, 3], 8) * s[:, None, None] * s[None, None, :]
-    np.testing.assert_allclose(irfs[2], ref, rtol=1e-5, atol=1e-8)
+    F0 = g.factor[i0 - 1:i1]
+    s = np.sign((m.factor[i0 - 1:i1] * F0).sum(0)); s[s == 0] = 1
+    ref = R.impulse_response(m.factor_var_model, list(range(g.nfac_t)), H) * s[:, None, None] * s[None, None, :]
+    np.testing.assert_allclose(irfs[rep], ref, rtol=1e-5, atol=1e-8)
 
 
 def test_generators_are_shard_invariant_on_device(lib):
