@@ -208,6 +208,7 @@ static int run_em_general(dfm_handle* h, const double* x, const dfm_em_opts* o, 
                           EmState* st, int* dit, int* dstat, int* active, int ntC, int nblkC, size_t smFS) {
   int T = o->T, N = o->N, r = o->r, p = o->p, batch = o->batch, mi = o->max_iter;
   int np = r * (r + 1) / 2;
+  int* dsrc = dnt + (size_t)batch * T;
   L(k_em_state_init, batch, 1, 1, 0, st);
   L(k_em_scan, N, batch, 64, 0, x, dL, T, N, r, st);
   L(k_em_prep, batch, 1, 128, 0, dL, dR, N, r, p, dW, dlogR, dC, dA, dAn, dQ, dQn, st, mi, 0);
@@ -215,7 +216,7 @@ static int run_em_general(dfm_handle* h, const double* x, const dfm_em_opts* o, 
   for (int it = 0; it < mi && h_active > 0; ++it) {
     L(k_em_contract, nblkC, batch, ntC, ((size_t)(np + r) * ntC + 8) * 8, x, dL, dW, dR, dlogR, dC, T, N, r, dBt, dqt, dslr, dnt, dCt, st);
     L(k_em_filter_smooth, batch, 1, 128, smFS, dA, dQ, dP0, dC, dBt, dqt, dslr, dnt, dCt, T, r, p, dzp, dzf, dPp, dPf,
-      dFs, dPsF, dSff, dAn, dQn, dll, mi, o->tol, st);
+      dFs, dPsF, dSff, dAn, dQn, dll, mi, o->tol, st, dsrc);
     L(k_em_mstep_series, N, batch, 64, (size_t)(2 * np + r + 8) * 8, x, dFs, dPsF, dSff, T, N, r, dL, dR, st);
     L(k_em_prep, batch, 1, 128, 0, dL, dR, N, r, p, dW, dlogR, dC, dA, dAn, dQ, dQn, st, mi, 1);
     if (o->tol > 0 && ((it & 3) == 3)) {
@@ -797,7 +798,7 @@ int dfm_em_kalman(dfm_handle* h, const double* X, const dfm_em_opts* o, const df
     {   // general-path buffers (also the fallback when the scan finds missing data)
       dAn = a.get<double>(B * rk); dQn = a.get<double>(B * rr); dW = a.get<double>(B * N * r); dlogR = a.get<double>(B * N);
       dC = a.get<double>(B * rr); dBt = a.get<double>(B * T * r); dqt = a.get<double>(B * T); dslr = a.get<double>(B * T);
-      dnt = a.get<int>(B * T); dCt = a.get<double>(B * T * np); dzp = a.get<double>(B * T * k); dzf = a.get<double>(B * T * k);
+      dnt = a.get<int>(2 * B * T) /* n_t, then src_t of the frozen-step logic */; dCt = a.get<double>(B * T * np); dzp = a.get<double>(B * T * k); dzf = a.get<double>(B * T * k);
       dPp = a.get<double>(B * T * kk); dPf = a.get<double>(B * T * kk); dSff = a.get<double>(B * rr);
     }
     if (!pass) { int rc = ensure_ws(h, a.off); if (rc) return rc; continue; }

@@ -136,10 +136,26 @@ __global__ void k_em_contract(const double* __restrict__ Xall, const double* __r
   }
 }
 
+// max over the block of two values at once.  red: >= 80 doubles of shared scratch.  All threads get the results.
+__device__ __forceinline__ void block_max2(double& a, double& b, double* red) {
+#ifndef DFM_EMU
+  for (int o = 16; o > 0; o >>= 1) { a = fmax(a, __shfl_xor_sync(0xffffffffu, a, o)); b = fmax(b, __shfl_xor_sync(0xffffffffu, b, o)); }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  if (lane == 0) { red[w] = a; red[40 + w] = b; }
+  __syncthreads();
+  double x = red[0], y = red[40];
+  for (int i = 1; i < nw; ++i) { x = fmax(x, red[i]); y = fmax(y, red[40 + i]); }
+  __syncthreads();
+  a = x; b = y;
+#else
+  (void)red;
+#endif
+}
+
 // shared-memory footprint (doubles) of k_em_filter_smooth
 __host__ __device__ inline size_t em_fs_smem_doubles(int r, int p) {
   size_t k = (size_t)r * p, kk = k * k, rr = (size_t)r * r, rk = (size_t)r * k;
-  return 9 * kk + 7 * rr + 3 * rk + 6 * k + 2 * r + 64;
+  return 9 * kk + 7 * rr + 3 * rk + 6 * k + 2 * r + 64 + 64;
 }
 
 // Kalman filter + RTS smoother + transition M-step for one panel.  grid (B), one block.
@@ -154,7 +170,14 @@ __global__ void k_em_filter_smooth(const double* __restrict__ Aall, const double
                                    double* __restrict__ zp_, double* __restrict__ zf_, double* __restrict__ Pp_,
                                    double* __restrict__ Pf_, double* __restrict__ Fs_, double* __restrict__ PsF_,
                                    double* __restrict__ SffAll_, double* __restrict__ Anew_, double* __restrict__ Qnew_,
-                                   double* __restrict__ loglik_, int max_iter, double tol, EmState* st) {
+                                   double* __restrict__ loglik_, int max_iter, double tol, EmState* st, int* __restrict__ src_) {
+  // FROZEN STEPS.  Where the information matrix C_t does not change (a balanced panel: everywhere; missing data: between
+  // two changes of the observation pattern) the covariance recursion is data independent and converges to its steady
+  // state; once P_{t|t-1} repeats (relative 1e-14) the factorisations, the gain and P_{t|t} of the following periods
+  // are the ones already in shared memory, and only the r- and k-sized mean updates remain.  src[t] = the period whose
+  // stored covariances period t uses.  The smoother gain J_t depends on (P_{src[t]|src[t]}, P_{src[t+1]|src[t+1]-1})
+  // only and is reused likewise; the smoothed covariance recursion freezes the same way (C3: T = 2000 periods, ~25
+  // explicit steps in each direction).
   DFM_SMEM(sm);
   int b = DFM_BX;
   if (st[b].done) return;
@@ -168,8 +191,10 @@ __global__ void k_em_filter_smooth(const double* __restrict__ Aall, const double
   double* zp = S11 + rk;     double* zf = zp + k;      double* zsn = zf + k;    double* zs = zsn + k;
   double* dv = zs + k;       double* tv = dv + k;
   double* g = tv + k;        double* bt = g + r;
-  double* red = bt + r;      // 40
-  int* info = (int*)(red + 44);
+  double* red = bt + r;      // 40 (+ 80 for block_max2 behind `info`)
+  int* info = (int*)(red + 44);                          // [0] Cholesky flag, [2], [3]: "C changed" flags of even / odd periods
+  double* red2 = red + 48;   // 80
+  int* src = src_ + (size_t)b * T;
   const double* A = Aall + (size_t)b * rk; const double* Qg = Qall + (size_t)b * rr;
   const double* P0 = P0all + (size_t)b * kk; const double* Cg = Call + (size_t)b * rr;
   const double* Bt = Bt_ + (size_t)b * T * r; const double* qt = qt_ + (size_t)b * T;
@@ -179,7 +204,7 @@ __global__ void k_em_filter_smooth(const double* __restrict__ Aall, const double
   double* Ppg = Pp_ + (size_t)b * T * kk; double* Pfg = Pf_ + (size_t)b * T * kk;
   double* Fs = Fs_ + (size_t)b * T * r; double* PsF = PsF_ + (size_t)b * T * np;
   int hm = st[b].has_missing;
-  if (DFM_TID == 0) *info = 0;
+  if (DFM_TID == 0) { info[0] = 0; info[2] = 0; info[3] = 0; }
   for (int e = DFM_TID; e < kk; e += DFM_NT) {
     int i = e % k, j = e / k;
     M[e] = (i < r) ? A[i + r * j] : ((j == i - r) ? 1.0 : 0.0);
@@ -190,12 +215,54 @@ __global__ void k_em_filter_smooth(const double* __restrict__ Aall, const double
   DFM_SYNC();
   double ll = 0.0;
   // ------------------------------------------------------------------ forward: Kalman filter
+  int frozen = 0, last_src = 0;          // (uniform over the block)
+  double ldS = 0.0;                      // thread 0: 2 sum log diag chol(S) of the last explicit step
   for (int t = 0; t < T; ++t) {
+    // information matrix of this period; did it change?  (flag of this period's parity; thread 0 clears the other one)
+    if (DFM_TID == 0) info[2 + ((t + 1) & 1)] = 0;
+    if (hm) {
+      for (int e = DFM_TID; e < rr; e += DFM_NT) {
+        int a = e % r, c = e / r;
+        double cn = (a >= c) ? Ct[t + (size_t)T * pidx(a, c)] : Ct[t + (size_t)T * pidx(c, a)];
+        if (cn != C[e]) info[2 + (t & 1)] = 1;
+        C[e] = cn;
+      }
+    }
+    for (int e = DFM_TID; e < r; e += DFM_NT) bt[e] = Bt[t + (size_t)T * e];
+    DFM_SYNC();
+    const int cchg = (t == 0) ? 1 : info[2 + (t & 1)];
+    if (frozen && !cchg) {
+      // ---- frozen step: same Pp, L, S, Tm, Wm, Pf as period last_src; only the means move
+      for (int i = DFM_TID; i < k; i += DFM_NT) { double s = 0.0; for (int l = 0; l < k; ++l) s += M[i + k * l] * zf[l]; tv[i] = s; }
+      DFM_SYNC();
+      for (int e = DFM_TID; e < k; e += DFM_NT) zp[e] = tv[e];
+      DFM_SYNC();
+      for (int a = DFM_TID; a < r; a += DFM_NT) { double s = bt[a]; for (int c = 0; c < r; ++c) s -= C[a + r * c] * zp[c]; g[a] = s; }
+      DFM_SYNC();
+      for (int i = DFM_TID; i < k; i += DFM_NT) { double s = zp[i]; for (int a = 0; a < r; ++a) s += Pf[i + k * a] * g[a]; zf[i] = s; }
+      if (DFM_TID == 0) {
+        double quad = qt[t];
+        for (int a = 0; a < r; ++a) {
+          quad -= 2.0 * zp[a] * bt[a];
+          double cz = 0.0, pg = 0.0;
+          for (int c = 0; c < r; ++c) { cz += C[a + r * c] * zp[c]; pg += Pf[a + k * c] * g[c]; }
+          quad += zp[a] * cz - g[a] * pg;
+        }
+        ll += -0.5 * ((double)ntv[t] * DFM_LOG2PI + slr[t] + ldS + quad);
+        src[t] = last_src;
+      }
+      DFM_SYNC();
+      for (int e = DFM_TID; e < k; e += DFM_NT) { zpg[(size_t)t * k + e] = zp[e]; zfg[(size_t)t * k + e] = zf[e]; }
+      DFM_SYNC();
+      continue;
+    }
+    frozen = 0;
     if (t == 0) {
       for (int e = DFM_TID; e < kk; e += DFM_NT) Pp[e] = P0[e];
       for (int e = DFM_TID; e < k; e += DFM_NT) zp[e] = 0.0;
       DFM_SYNC();
     } else {
+      for (int e = DFM_TID; e < kk; e += DFM_NT) T3[e] = Pp[e];                 // previous P_{t|t-1}: freeze test below
       bm_gemm(T1, k, M, k, false, Pf, k, false, k, k, k, 1.0, 0.0);            // M Pf
       bm_gemm(Pp, k, T1, k, false, M, k, true, k, k, k, 1.0, 0.0);             // (M Pf) M'
       for (int e = DFM_TID; e < rr; e += DFM_NT) { int i = e % r, j = e / r; Pp[i + k * j] += Q[e]; }
@@ -205,10 +272,6 @@ __global__ void k_em_filter_smooth(const double* __restrict__ Aall, const double
       for (int e = DFM_TID; e < k; e += DFM_NT) zp[e] = tv[e];
       DFM_SYNC();
     }
-    if (hm) {
-      for (int e = DFM_TID; e < rr; e += DFM_NT) { int a = e % r, c = e / r; C[e] = (a >= c) ? Ct[t + (size_t)T * pidx(a, c)] : Ct[t + (size_t)T * pidx(c, a)]; }
-    }
-    for (int e = DFM_TID; e < r; e += DFM_NT) bt[e] = Bt[t + (size_t)T * e];
     for (int e = DFM_TID; e < rr; e += DFM_NT) { int i = e % r, j = e / r; L[e] = Pp[i + k * j]; }
     DFM_SYNC();
     bm_chol(L, r, r, info);                                                     // Pff = L L'
@@ -235,8 +298,8 @@ __global__ void k_em_filter_smooth(const double* __restrict__ Aall, const double
     DFM_SYNC();
     for (int i = DFM_TID; i < k; i += DFM_NT) { double s = zp[i]; for (int a = 0; a < r; ++a) s += Pf[i + k * a] * g[a]; zf[i] = s; }
     if (DFM_TID == 0) {
-      double ld = slr[t];
-      for (int a = 0; a < r; ++a) ld += 2.0 * log(S[a + r * a]);
+      ldS = 0.0;
+      for (int a = 0; a < r; ++a) ldS += 2.0 * log(S[a + r * a]);
       double quad = qt[t];
       for (int a = 0; a < r; ++a) {
         quad -= 2.0 * zp[a] * bt[a];
@@ -244,13 +307,24 @@ __global__ void k_em_filter_smooth(const double* __restrict__ Aall, const double
         for (int c = 0; c < r; ++c) { cz += C[a + r * c] * zp[c]; pg += Pf[a + k * c] * g[c]; }
         quad += zp[a] * cz - g[a] * pg;
       }
-      ll += -0.5 * ((double)ntv[t] * DFM_LOG2PI + ld + quad);
+      ll += -0.5 * ((double)ntv[t] * DFM_LOG2PI + slr[t] + ldS + quad);
+      src[t] = t;
     }
     DFM_SYNC();
     for (int e = DFM_TID; e < kk; e += DFM_NT) { Ppg[(size_t)t * kk + e] = Pp[e]; Pfg[(size_t)t * kk + e] = Pf[e]; }
     for (int e = DFM_TID; e < k; e += DFM_NT) { zpg[(size_t)t * k + e] = zp[e]; zfg[(size_t)t * k + e] = zf[e]; }
+    last_src = t;
+    if (t >= 1 && !cchg) {                                                      // steady state reached?  (T3 = previous Pp)
+      double dm = 0.0, pm = 0.0;
+      for (int e = DFM_TID; e < kk; e += DFM_NT) { dm = fmax(dm, fabs(Pp[e] - T3[e])); pm = fmax(pm, fabs(Pp[e])); }
+      block_max2(dm, pm, red2);
+      frozen = (dm <= 1e-14 * pm) ? 1 : 0;
+    }
     DFM_SYNC();
   }
+#ifdef DFM_EMU
+  if (getenv("DFM_DEBUG_FREEZE")) { int nf = 0; for (int t = 0; t < T; ++t) nf += (src[t] != t); printf("[freeze] b=%d T=%d k=%d frozen forward steps %d\n", b, T, k, nf); }
+#endif
   // ------------------------------------------------------------------ backward: RTS smoother
   for (int e = DFM_TID; e < kk; e += DFM_NT) Psn[e] = Pf[e];
   for (int e = DFM_TID; e < k; e += DFM_NT) zsn[e] = zf[e];
@@ -262,24 +336,39 @@ __global__ void k_em_filter_smooth(const double* __restrict__ Aall, const double
     SffA[e] = zsn[a] * zsn[c] + Psn[a + k * c];
   }
   DFM_SYNC();
+  int jpp = -1, jpf = -1, ps_frozen = 0;           // periods whose covariances built the gain in T3; smoothed covariance frozen?
   for (int t = T - 2; t >= 0; --t) {
-    for (int e = DFM_TID; e < kk; e += DFM_NT) { T1[e] = Ppg[(size_t)(t + 1) * kk + e]; Pf[e] = Pfg[(size_t)t * kk + e]; }
+    const int sp = src[t + 1], sf = src[t];
+    const bool newJ = (sp != jpp) || (sf != jpf);
+    if (newJ) ps_frozen = 0;
     for (int e = DFM_TID; e < k; e += DFM_NT) { zp[e] = zpg[(size_t)(t + 1) * k + e]; zf[e] = zfg[(size_t)t * k + e]; }
+    if (!ps_frozen) for (int e = DFM_TID; e < kk; e += DFM_NT) { T1[e] = Ppg[(size_t)sp * kk + e]; Pf[e] = Pfg[(size_t)sf * kk + e]; }
     DFM_SYNC();
-    bm_copy(T2, k, T1, k, k, k);
-    bm_chol(T2, k, k, info);                                                    // Pp(t+1) = Lp Lp'
-    bm_gemm(T3, k, M, k, false, Pf, k, false, k, k, k, 1.0, 0.0);              // M Pf(t)
-    bm_trsm_lower(T2, k, k, T3, k, k);
-    bm_trsm_lowerT(T2, k, k, T3, k, k);                                         // T3 = J' = Pp^-1 M Pf
+    if (newJ) {
+      bm_copy(T2, k, T1, k, k, k);
+      bm_chol(T2, k, k, info);                                                  // Pp(t+1) = Lp Lp'
+      bm_gemm(T3, k, M, k, false, Pf, k, false, k, k, k, 1.0, 0.0);            // M Pf(t)
+      bm_trsm_lower(T2, k, k, T3, k, k);
+      bm_trsm_lowerT(T2, k, k, T3, k, k);                                       // T3 = J' = Pp^-1 M Pf
+      jpp = sp; jpf = sf;
+    }
     for (int e = DFM_TID; e < k; e += DFM_NT) dv[e] = zsn[e] - zp[e];
-    for (int e = DFM_TID; e < kk; e += DFM_NT) T1[e] = Psn[e] - T1[e];         // D = Ps(t+1) - Pp(t+1)
+    if (!ps_frozen) for (int e = DFM_TID; e < kk; e += DFM_NT) T1[e] = Psn[e] - T1[e];     // D = Ps(t+1) - Pp(t+1)
     DFM_SYNC();
     for (int i = DFM_TID; i < k; i += DFM_NT) { double s = zf[i]; for (int l = 0; l < k; ++l) s += T3[l + k * i] * dv[l]; zs[i] = s; }
-    bm_gemm(T2, k, T1, k, false, T3, k, false, k, k, k, 1.0, 0.0);             // D J'
-    bm_copy(Ps, k, Pf, k, k, k);
-    bm_gemm(Ps, k, T3, k, true, T2, k, false, k, k, k, 1.0, 1.0);              // Pf + J D J'
-    bm_symmetrize(Ps, k, k);
-    bm_gemm(Tm, r, Psn, k, false, T3, k, false, r, k, k, 1.0, 0.0);            // Pc[0:r,:] = Ps(t+1)[0:r,:] J'
+    if (!ps_frozen) {
+      bm_gemm(T2, k, T1, k, false, T3, k, false, k, k, k, 1.0, 0.0);           // D J'
+      bm_copy(Ps, k, Pf, k, k, k);
+      bm_gemm(Ps, k, T3, k, true, T2, k, false, k, k, k, 1.0, 1.0);            // Pf + J D J'
+      bm_symmetrize(Ps, k, k);
+      bm_gemm(Tm, r, Psn, k, false, T3, k, false, r, k, k, 1.0, 0.0);          // Pc[0:r,:] = Ps(t+1)[0:r,:] J'
+      if (!newJ) {                                                              // smoothed covariance at its steady state?
+        double dm = 0.0, pm = 0.0;
+        for (int e = DFM_TID; e < kk; e += DFM_NT) { dm = fmax(dm, fabs(Ps[e] - Psn[e])); pm = fmax(pm, fabs(Ps[e])); }
+        block_max2(dm, pm, red2);
+        ps_frozen = (dm <= 1e-14 * pm) ? 1 : 0;      // from the next period on: Ps = Psn, Tm as they are
+      }
+    } else DFM_SYNC();
     for (int e = DFM_TID; e < rk; e += DFM_NT) { int i = e % r, j = e / r; S11[e] += zsn[i] * zs[j] + Tm[e]; }
     for (int e = DFM_TID; e < kk; e += DFM_NT) { int i = e % k, j = e / k; S00[e] += zs[i] * zs[j] + Ps[e]; }
     for (int e = DFM_TID; e < rr; e += DFM_NT) {

@@ -377,3 +377,19 @@ def check_percentiles(lib, n=37, d=11):
     np.testing.assert_allclose(got, ref, rtol=1e-12, atol=1e-14)
     got1 = lib.percentiles(recs[:1], [50.0])
     np.testing.assert_allclose(got1[0], recs[0])
+
+
+def check_em_block_missing(lib, path=1):
+    """Missing data in BLOCKS (series that start late / end early / have a hole): the observation pattern is constant
+    over long stretches, so the general path freezes its covariance recursion between pattern changes (src[t] logic of
+    k_em_filter_smooth) -- results must still equal the oracle's period-by-period recursion."""
+    X, _ = simulate_panel(20, 2, 260, rep=3)
+    X[:60, 3] = np.nan; X[200:, 7] = np.nan; X[100:140, 11] = np.nan
+    F0 = R.pca_score(np.nan_to_num(X), 2)
+    Lam, Rv, A, Q = K.init_from_factors(X, F0, 2)
+    ref = K.em_kalman(X, Lam, Rv, A, Q, p=2, max_iter=4)
+    got = lib.em_kalman(X, Lam, Rv, A, Q, p=2, max_iter=4, path=path)
+    np.testing.assert_allclose(got["loglik"], ref["loglik"], rtol=1e-11)
+    np.testing.assert_allclose(got["F"], ref["F"], rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(got["Lam"], ref["Lam"], rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(got["A"], ref["A"], rtol=1e-8, atol=1e-10)

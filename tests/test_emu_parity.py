@@ -37,6 +37,8 @@ def test_var_missing_rows(lib): P.check_var_missing_rows(lib)
 def test_em_p1_balanced(lib): P.check_em(lib, p=1, miss=0.0)
 def test_em_p2_missing(lib): P.check_em(lib, p=2, miss=0.12)
 def test_em_convergence_rule(lib): P.check_em_convergence_rule(lib)
+def test_em_p2_long_balanced_frozen(lib): P.check_em(lib, N=30, r=3, T=300, p=2, miss=0.0, iters=3, path=1)
+def test_em_block_missing_frozen(lib): P.check_em_block_missing(lib)
 def test_em_batch(lib): P.check_em_batch(lib)
 def test_als_batch(lib): P.check_als_batch(lib)
 def test_als_balanced_fused(lib): P.check_als_balanced(lib)

@@ -40,6 +40,9 @@ def test_em_p2_missing(lib): P.check_em(lib, p=2, miss=0.12, path=1)
 def test_em_p1_missing(lib): P.check_em(lib, p=1, miss=0.1, path=1, rep=10)
 def test_em_auto_path(lib): P.check_em(lib, N=40, r=8, T=90, p=1, miss=0.0, path=0, iters=5)
 def test_em_convergence_rule(lib): P.check_em_convergence_rule(lib, path=1)
+def test_em_p2_long_balanced_frozen(lib): P.check_em(lib, N=30, r=3, T=300, p=2, miss=0.0, iters=3, path=1)
+def test_em_r12_balanced_frozen(lib): P.check_em(lib, N=60, r=12, T=240, p=1, miss=0.0, iters=3, path=1)
+def test_em_block_missing_frozen(lib): P.check_em_block_missing(lib)
 def test_em_batch(lib): P.check_em_batch(lib, path=1)
 def test_als_batch(lib): P.check_als_batch(lib)
 def test_als_balanced_fused(lib): P.check_als_balanced(lib)
@@ -181,7 +184,7 @@ def test_pca_subspace(lib): P.check_pca(lib, r=5, sizes=((150, 90), (80, 130), (
 
 def test_c3_full_size(lib):
     """BASELINE config C3 (N=2000, r=20, T=2000): PCA by subspace iteration vs LAPACK SVD, one ALS sweep
-    and two EM iterations of the general path vs the oracle's C port."""
+    and ten EM iterations of the general path (frozen-step logic: ~25 explicit covariance steps of 2000) vs the oracle's C port."""
     from oracle.dgp import simulate_panel
     from oracle.c import kem
     from oracle import dfm_ref as R, kalman_em as K
@@ -194,8 +197,8 @@ def test_c3_full_size(lib):
     out = lib.estimate_factor(X, r, max_iter=1, compute_r2=False, F_init=ref)
     assert out["stats"]["status"] in (0, 4)
     Lam, Rv, A, Q = lib.em_init_from_factors(X, out["F"], 1)
-    em = lib.em_kalman(X, Lam, Rv, A, Q, p=1, max_iter=2, want_PF=False)
-    cref = kem.em_kalman_batch(X[None], Lam[None], Rv[None], A[None], Q[None], p=1, max_iter=2)
+    em = lib.em_kalman(X, Lam, Rv, A, Q, p=1, max_iter=10, want_PF=False)
+    cref = kem.em_kalman_batch(X[None], Lam[None], Rv[None], A[None], Q[None], p=1, max_iter=10)
     np.testing.assert_allclose(em["loglik"], cref["loglik"][0], rtol=1e-9)
     assert P.rmse(em["F"], cref["F"][0]) < 1e-8
 
