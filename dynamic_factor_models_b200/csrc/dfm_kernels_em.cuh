@@ -107,7 +107,7 @@ __global__ void k_em_contract(const double* __restrict__ Xall, const double* __r
                               int* __restrict__ nt_, double* __restrict__ Ct, const EmState* st) {
   DFM_SMEM(sm);
   int b = DFM_BY;
-  if (st[b].done) return;
+  if (st[b].done || !st[b].has_missing) return;   // balanced panels: k_em_contract_bal
   int np = r * (r + 1) / 2, nt = DFM_NT;
   double* c = sm + DFM_TID;                       // c[a*nt]
   double* A = sm + (size_t)r * nt + DFM_TID;      // A[e*nt]
@@ -150,6 +150,37 @@ __device__ __forceinline__ void block_max2(double& a, double& b, double* red) {
 #else
   (void)red;
 #endif
+}
+
+// E-step contraction of a BALANCED panel (no NaN among the series in the model): b_t = W' x_t, q_t, sum log R, n_t; the
+// information matrix is the constant C.  32 periods x 8 component groups per block: lane = period (coalesced reads of
+// the column-major panel), warp = component group g (components g, g + 8, ...: the W loads are warp-uniform broadcasts).
+// r <= 64.  grid (ceil(T / 32), B), 256 threads.
+__global__ void k_em_contract_bal(const double* __restrict__ Xall, const double* __restrict__ Wall, const double* __restrict__ Rall,
+                                  const double* __restrict__ logRall, int T, int N, int r, double* __restrict__ Bt,
+                                  double* __restrict__ qt, double* __restrict__ slr, int* __restrict__ nt_, const EmState* st) {
+  int b = DFM_BY;
+  if (st[b].done || st[b].has_missing) return;
+  const double* X = Xall + (size_t)b * T * N; const double* W = Wall + (size_t)b * N * r;
+  const double* R = Rall + (size_t)b * N; const double* logR = logRall + (size_t)b * N;
+  for (int idx = DFM_TID; idx < 256; idx += DFM_NT) {
+    const int tl = idx & 31, g = idx >> 5, t = DFM_BX * 32 + tl;
+    if (t >= T) continue;
+    double acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.0;
+    double q = 0.0, sl = 0.0; int n = 0;
+    for (int i = 0; i < N; ++i) {
+      if (is_nan(W[i])) continue;                 // series excluded from the model (uniform over the block)
+      const double x = X[t + (size_t)T * i];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const int a = g + 8 * j; if (a < r) acc[j] += x * W[i + (size_t)N * a]; }
+      if (g == 0) { ++n; q += x * x / R[i]; sl += logR[i]; }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const int a = g + 8 * j; if (a < r) Bt[(size_t)b * T * r + t + (size_t)T * a] = acc[j]; }
+    if (g == 0) { qt[(size_t)b * T + t] = q; slr[(size_t)b * T + t] = sl; nt_[(size_t)b * T + t] = n; }
+  }
 }
 
 // shared-memory footprint (doubles) of k_em_filter_smooth
