@@ -215,7 +215,7 @@ static int run_em_general(dfm_handle* h, const double* x, const dfm_em_opts* o, 
   int h_active = batch;
   for (int it = 0; it < mi && h_active > 0; ++it) {
     L(k_em_contract, nblkC, batch, ntC, ((size_t)(np + r) * ntC + 8) * 8, x, dL, dW, dR, dlogR, dC, T, N, r, dBt, dqt, dslr, dnt, dCt, st);
-    L(k_em_contract_bal, (T + 31) / 32, batch, 256, 0, x, dW, dR, dlogR, T, N, r, dBt, dqt, dslr, dnt, st);   // (each returns at once for the other kind)
+    L(k_em_contract_bal, (T + 31) / 32, batch, 256, 8 * 32 * 3 * 8, x, dW, dR, dlogR, T, N, r, dBt, dqt, dslr, dnt, st);   // (each returns at once for the other kind)
     L(k_em_filter_smooth, batch, 1, 128, smFS, dA, dQ, dP0, dC, dBt, dqt, dslr, dnt, dCt, T, r, p, dzp, dzf, dPp, dPf,
       dFs, dPsF, dSff, dAn, dQn, dll, mi, o->tol, st, dsrc);
     L(k_em_mstep_series, N, batch, 64, (size_t)(2 * np + r + 8) * 8, x, dFs, dPsF, dSff, T, N, r, dL, dR, st);

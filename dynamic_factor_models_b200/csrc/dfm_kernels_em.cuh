@@ -159,27 +159,38 @@ __device__ __forceinline__ void block_max2(double& a, double& b, double* red) {
 __global__ void k_em_contract_bal(const double* __restrict__ Xall, const double* __restrict__ Wall, const double* __restrict__ Rall,
                                   const double* __restrict__ logRall, int T, int N, int r, double* __restrict__ Bt,
                                   double* __restrict__ qt, double* __restrict__ slr, int* __restrict__ nt_, const EmState* st) {
+  DFM_SMEM(part);                                 // [8][32][3] partial (q, sum log R, n) of the component groups
   int b = DFM_BY;
   if (st[b].done || st[b].has_missing) return;
   const double* X = Xall + (size_t)b * T * N; const double* W = Wall + (size_t)b * N * r;
   const double* R = Rall + (size_t)b * N; const double* logR = logRall + (size_t)b * N;
   for (int idx = DFM_TID; idx < 256; idx += DFM_NT) {
     const int tl = idx & 31, g = idx >> 5, t = DFM_BX * 32 + tl;
-    if (t >= T) continue;
     double acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.0;
-    double q = 0.0, sl = 0.0; int n = 0;
-    for (int i = 0; i < N; ++i) {
-      if (is_nan(W[i])) continue;                 // series excluded from the model (uniform over the block)
-      const double x = X[t + (size_t)T * i];
+    double q = 0.0, sl = 0.0, n = 0.0;
+    if (t < T)
+      for (int i = 0; i < N; ++i) {
+        if (is_nan(W[i])) continue;               // series excluded from the model (uniform over the block)
+        const double x = X[t + (size_t)T * i];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { const int a = g + 8 * j; if (a < r) acc[j] += x * W[i + (size_t)N * a]; }
-      if (g == 0) { ++n; q += x * x / R[i]; sl += logR[i]; }
+        for (int j = 0; j < 8; ++j) { const int a = g + 8 * j; if (a < r) acc[j] += x * W[i + (size_t)N * a]; }
+        if ((i & 7) == g) { n += 1.0; q += x * x / R[i]; sl += logR[i]; }       // the scalar sums are split over the groups
+      }
+    if (t < T) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const int a = g + 8 * j; if (a < r) Bt[(size_t)b * T * r + t + (size_t)T * a] = acc[j]; }
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { const int a = g + 8 * j; if (a < r) Bt[(size_t)b * T * r + t + (size_t)T * a] = acc[j]; }
-    if (g == 0) { qt[(size_t)b * T + t] = q; slr[(size_t)b * T + t] = sl; nt_[(size_t)b * T + t] = n; }
+    part[(g * 32 + tl) * 3] = q; part[(g * 32 + tl) * 3 + 1] = sl; part[(g * 32 + tl) * 3 + 2] = n;
+  }
+  DFM_SYNC();
+  for (int tl = DFM_TID; tl < 32; tl += DFM_NT) {
+    const int t = DFM_BX * 32 + tl;
+    if (t >= T) continue;
+    double q = 0.0, sl = 0.0, n = 0.0;
+    for (int g = 0; g < 8; ++g) { q += part[(g * 32 + tl) * 3]; sl += part[(g * 32 + tl) * 3 + 1]; n += part[(g * 32 + tl) * 3 + 2]; }
+    qt[(size_t)b * T + t] = q; slr[(size_t)b * T + t] = sl; nt_[(size_t)b * T + t] = (int)n;
   }
 }
 
@@ -271,18 +282,14 @@ __global__ void k_em_filter_smooth(const double* __restrict__ Aall, const double
       for (int a = DFM_TID; a < r; a += DFM_NT) { double s = bt[a]; for (int c = 0; c < r; ++c) s -= C[a + r * c] * zp[c]; g[a] = s; }
       DFM_SYNC();
       for (int i = DFM_TID; i < k; i += DFM_NT) { double s = zp[i]; for (int a = 0; a < r; ++a) s += Pf[i + k * a] * g[a]; zf[i] = s; }
+      DFM_SYNC();
       if (DFM_TID == 0) {
+        // quad = q - 2 zp'b + zp'C zp - g'Pff g  with  C zp = b - g  and  Pff g = (zf - zp)[0:r]:  O(r) instead of O(r^2)
         double quad = qt[t];
-        for (int a = 0; a < r; ++a) {
-          quad -= 2.0 * zp[a] * bt[a];
-          double cz = 0.0, pg = 0.0;
-          for (int c = 0; c < r; ++c) { cz += C[a + r * c] * zp[c]; pg += Pf[a + k * c] * g[c]; }
-          quad += zp[a] * cz - g[a] * pg;
-        }
+        for (int a = 0; a < r; ++a) quad += -2.0 * zp[a] * bt[a] + zp[a] * (bt[a] - g[a]) - g[a] * (zf[a] - zp[a]);
         ll += -0.5 * ((double)ntv[t] * DFM_LOG2PI + slr[t] + ldS + quad);
         src[t] = last_src;
       }
-      DFM_SYNC();
       for (int e = DFM_TID; e < k; e += DFM_NT) { zpg[(size_t)t * k + e] = zp[e]; zfg[(size_t)t * k + e] = zf[e]; }
       DFM_SYNC();
       continue;
