@@ -343,6 +343,23 @@ const char* dfm_status_string(int s) {
   return "unknown";
 }
 
+// release everything a handle owns (also the error paths of dfm_create_on_stream: nothing leaks)
+static void handle_teardown(dfm_handle* h) {
+  if (!h) return;
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->ws) cudaFree(h->ws);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+#ifndef DFM_EMU
+  if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+  if (h->pinned_one) cudaFreeHost(h->pinned_one);
+  if (h->d2h_stream) { cudaStreamSynchronize(h->d2h_stream); cudaStreamDestroy(h->d2h_stream); }
+  if (h->done_host) cudaFreeHost(h->done_host);
+  if (h->prof) for (auto& r : *h->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }       // events of profiled launches
+#endif
+  delete h->prof;
+  delete h;
+}
+
 int dfm_create_on_stream(int device, void* cuda_stream, dfm_handle** out) {
   if (!out) return DFM_ERR_ARG;
   *out = nullptr;
@@ -353,19 +370,20 @@ int dfm_create_on_stream(int device, void* cuda_stream, dfm_handle** out) {
   if (!h) return DFM_ERR_CUDA;
   h->device = device; h->ws = nullptr; h->ws_bytes = 0; h->launches = 0; h->err[0] = 0;
   h->profile = 0; h->prof = new std::vector<ProfRec>();
+  h->stream = nullptr; h->own_stream = false;
   h->copy_stream = nullptr; h->pinned_one = nullptr; h->d2h_stream = nullptr; h->done_host = nullptr; h->done_dev = nullptr; h->done_cap = 0;
 #ifndef DFM_EMU
-  if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete h->prof; delete h; return DFM_ERR_CUDA; }
-  if (cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking) != cudaSuccess) { delete h->prof; delete h; return DFM_ERR_CUDA; }
-  if (cudaHostAlloc((void**)&h->pinned_one, sizeof(int), cudaHostAllocDefault) != cudaSuccess) { delete h->prof; delete h; return DFM_ERR_CUDA; }
+  if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { h->copy_stream = nullptr; handle_teardown(h); return DFM_ERR_CUDA; }
+  if (cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking) != cudaSuccess) { h->d2h_stream = nullptr; handle_teardown(h); return DFM_ERR_CUDA; }
+  if (cudaHostAlloc((void**)&h->pinned_one, sizeof(int), cudaHostAllocDefault) != cudaSuccess) { h->pinned_one = nullptr; handle_teardown(h); return DFM_ERR_CUDA; }
   *h->pinned_one = 1;
 #endif
   if (cuda_stream) { h->stream = (cudaStream_t)cuda_stream; h->own_stream = false; }
-  else { if (cudaStreamCreate(&h->stream) != cudaSuccess) { delete h; return DFM_ERR_CUDA; } h->own_stream = true; }
+  else { if (cudaStreamCreate(&h->stream) != cudaSuccess) { h->stream = nullptr; handle_teardown(h); return DFM_ERR_CUDA; } h->own_stream = true; }
   DFM_SET_SMEM(k_em_filter_smooth, kMaxSmem); DFM_SET_SMEM(k_als_factor, kMaxSmem); DFM_SET_SMEM(k_em_contract, kMaxSmem);
   DFM_SET_SMEM(k_lyapunov, kMaxSmem); DFM_SET_SMEM(k_var, kMaxSmem); DFM_SET_SMEM(k_pca_finish, kMaxSmem);
   DFM_SET_SMEM(k_jacobi, kMaxSmem); DFM_SET_SMEM(k_subspace_eig, kMaxSmem); DFM_SET_SMEM(k_loading, kMaxSmem); DFM_SET_SMEM(k_als_lambda, kMaxSmem);
-  if (cudaGetLastError() != cudaSuccess) { delete h; return DFM_ERR_CUDA; }
+  if (cudaGetLastError() != cudaSuccess) { handle_teardown(h); return DFM_ERR_CUDA; }
   *out = h;
   return DFM_OK;
 }
@@ -374,17 +392,7 @@ int dfm_create(int device, dfm_handle** out) { return dfm_create_on_stream(devic
 int dfm_destroy(dfm_handle* h) {
   if (!h) return DFM_ERR_ARG;
   cudaSetDevice(h->device);
-  cudaStreamSynchronize(h->stream);
-  if (h->ws) cudaFree(h->ws);
-  if (h->own_stream) cudaStreamDestroy(h->stream);
-#ifndef DFM_EMU
-  if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
-  if (h->pinned_one) cudaFreeHost(h->pinned_one);
-  if (h->d2h_stream) { cudaStreamSynchronize(h->d2h_stream); cudaStreamDestroy(h->d2h_stream); }
-  if (h->done_host) cudaFreeHost(h->done_host);
-#endif
-  delete h->prof;
-  delete h;
+  handle_teardown(h);
   return DFM_OK;
 }
 int dfm_sync(dfm_handle* h) { if (!h) return DFM_ERR_ARG; CK(cudaStreamSynchronize(h->stream)); return DFM_OK; }
