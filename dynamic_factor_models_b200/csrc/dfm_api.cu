@@ -5,6 +5,7 @@
 #include "dfm_common.cuh"
 #include "dfm_kernels_np.cuh"
 #include "dfm_kernels_em.cuh"
+#include "dfm_kernels_emb.cuh"
 #include "dfm_kernels_fused.cuh"
 #include "dfm_kernels_fused2.cuh"
 #include "dfm_kernels_als_masked.cuh"
@@ -201,25 +202,96 @@ static int launch_fused(dfm_handle* h, const FusedArgs& fa, int B, int T, int N,
   return DFM_OK;
 }
 
+// Multi-CTA contraction kernels of the general path for balanced panels (dfm_kernels_emb.cuh): split factors and buffers.
+struct EmbPlan {
+  bool on; int ncb, ntE, nsE, nper, ntM, tsM, tper;
+  double *Bpart, *qpart, *Spart, *sxxpart, *Cpart; int* counters;
+  size_t smE, smM;
+};
+static EmbPlan emb_plan(int T, int N, int r, int batch) {
+  EmbPlan e{};
+  e.on = r <= 32 && !getenv("DFM_NO_EMB");
+  if (!e.on) return e;
+  e.ncb = (r + 7) / 8;
+  const int target = 2 * 148;
+  e.ntE = (T + EMB_TILE - 1) / EMB_TILE;
+  int want = (target + e.ntE * batch - 1) / (e.ntE * batch);
+  int ns = std::max((N + EMB_MAXSPLIT - 1) / EMB_MAXSPLIT, std::min(want, (N + 31) / 32));
+  e.nper = (((N + ns - 1) / ns) + 3) & ~3;
+  e.nsE = (N + e.nper - 1) / e.nper;
+  e.ntM = (N + EMB_TILE - 1) / EMB_TILE;
+  want = (target + e.ntM * batch - 1) / (e.ntM * batch);
+  int ts = std::max(1, std::min(want, (T + 31) / 32));
+  e.tper = (((T + ts - 1) / ts) + 3) & ~3;
+  e.tsM = (T + e.tper - 1) / e.tper;
+  if ((long long)e.nsE * batch > 65535 || (long long)e.tsM * batch > 65535) { e.on = false; return e; }
+  e.smE = ((size_t)e.ncb * 8 * emb_pad(e.nper) + e.nper + 48) * 8;
+  e.smM = ((size_t)2 * r * r + (size_t)EMB_TILE * (r + 1) + 48) * 8;
+  return e;
+}
+template <int NCB>
+static int emb_launch_E(dfm_handle* h, const EmbPlan& e, const double* x, const double* dW, const double* dR, const double* dlogR, int T, int N,
+                        int r, int batch, double* dBt, double* dqt, double* dslr, int* dnt, EmState* st) {
+  DFM_SET_SMEM(k_emb_contract<NCB>, e.smE);
+  L(k_emb_contract<NCB>, e.ntE, e.nsE * batch, 256, e.smE, x, dW, dR, dlogR, T, N, r, e.nsE, e.nper, batch, e.Bpart, e.qpart, e.counters,
+    dBt, dqt, dslr, dnt, st);
+  return DFM_OK;
+}
+template <int NCB>
+static int emb_launch_M(dfm_handle* h, const EmbPlan& e, const double* x, const double* dFs, const double* dSff, int T, int N, int r, int batch,
+                        double* dL, double* dR, double* dW, double* dlogR, EmState* st) {
+  L(k_emb_mstep<NCB>, e.ntM, e.tsM * batch, 256, e.smM, x, dFs, dSff, T, N, r, e.tsM, e.tper, batch, e.Spart, e.sxxpart,
+    e.counters + (size_t)batch * e.ntE, dL, dR, dW, dlogR, e.Cpart, st);
+  return DFM_OK;
+}
+
 // General multi-kernel EM path on device-resident data (any r, p, missing data).
 static int run_em_general(dfm_handle* h, const double* x, const dfm_em_opts* o, double* dL, double* dR, double* dA, double* dQ, double* dP0,
                           double* dAn, double* dQn, double* dW, double* dlogR, double* dC, double* dBt, double* dqt, double* dslr, int* dnt,
                           double* dCt, double* dzp, double* dzf, double* dPp, double* dPf, double* dFs, double* dPsF, double* dSff, double* dll,
-                          EmState* st, int* dit, int* dstat, int* active, int ntC, int nblkC, size_t smFS) {
+                          EmState* st, int* dit, int* dstat, int* active, int ntC, int nblkC, size_t smFS, int stgT, const EmbPlan& emb) {
   int T = o->T, N = o->N, r = o->r, p = o->p, batch = o->batch, mi = o->max_iter;
   int np = r * (r + 1) / 2;
   int* dsrc = dnt + (size_t)batch * T;
+  const int ntFS = (batch <= 296) ? 512 : 256;     // few panels: more warps for the parallel frozen runs; many: two CTAs per SM
   L(k_em_state_init, batch, 1, 1, 0, st);
   L(k_em_scan, N, batch, 64, 0, x, dL, T, N, r, st);
-  L(k_em_prep, batch, 1, 128, 0, dL, dR, N, r, p, dW, dlogR, dC, dA, dAn, dQ, dQn, st, mi, 0);
+  L(k_em_prep, batch, 1, 128, 0, dL, dR, N, r, p, dW, dlogR, dC, dA, dAn, dQ, dQn, st, mi, 0, 0);
+  // how many panels have missing data?  (decides which contraction kernels are launched at all: one sync, before the loop)
+  int n_missing = batch;
+  if (emb.on) {
+    L(k_em_count_missing, 1, 1, 128, 48 * 8, st, batch, active);
+    CK(cudaMemcpyAsync(&n_missing, active, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemsetAsync(emb.counters, 0, sizeof(int) * (size_t)batch * (emb.ntE + emb.ntM), h->stream));
+  }
+  const bool any_missing = n_missing > 0, any_bal = emb.on ? (n_missing < batch) : true;
+  const int emb_on = emb.on ? 1 : 0;
   int h_active = batch;
   for (int it = 0; it < mi && h_active > 0; ++it) {
-    L(k_em_contract, nblkC, batch, ntC, ((size_t)(np + r) * ntC + 8) * 8, x, dL, dW, dR, dlogR, dC, T, N, r, dBt, dqt, dslr, dnt, dCt, st);
-    L(k_em_contract_bal, (T + 31) / 32, batch, 256, 8 * 32 * 3 * 8, x, dW, dR, dlogR, T, N, r, dBt, dqt, dslr, dnt, st);   // (each returns at once for the other kind)
-    L(k_em_filter_smooth, batch, 1, 128, smFS, dA, dQ, dP0, dC, dBt, dqt, dslr, dnt, dCt, T, r, p, dzp, dzf, dPp, dPf,
-      dFs, dPsF, dSff, dAn, dQn, dll, mi, o->tol, st, dsrc);
-    L(k_em_mstep_series, N, batch, 64, (size_t)(2 * np + r + 8) * 8, x, dFs, dPsF, dSff, T, N, r, dL, dR, st);
-    L(k_em_prep, batch, 1, 128, 0, dL, dR, N, r, p, dW, dlogR, dC, dA, dAn, dQ, dQn, st, mi, 1);
+    if (any_missing) L(k_em_contract, nblkC, batch, ntC, ((size_t)(np + r) * ntC + 8) * 8, x, dL, dW, dR, dlogR, dC, T, N, r, dBt, dqt, dslr, dnt, dCt, st);
+    if (any_bal) {                                                          // (each returns at once for panels of the other kind)
+      if (!emb.on) L(k_em_contract_bal, (T + 31) / 32, batch, 256, 8 * 32 * 3 * 8, x, dW, dR, dlogR, T, N, r, dBt, dqt, dslr, dnt, st);
+      else switch (emb.ncb) {
+        case 1: emb_launch_E<1>(h, emb, x, dW, dR, dlogR, T, N, r, batch, dBt, dqt, dslr, dnt, st); break;
+        case 2: emb_launch_E<2>(h, emb, x, dW, dR, dlogR, T, N, r, batch, dBt, dqt, dslr, dnt, st); break;
+        case 3: emb_launch_E<3>(h, emb, x, dW, dR, dlogR, T, N, r, batch, dBt, dqt, dslr, dnt, st); break;
+        default: emb_launch_E<4>(h, emb, x, dW, dR, dlogR, T, N, r, batch, dBt, dqt, dslr, dnt, st); break;
+      }
+    }
+    L(k_em_filter_smooth, batch, 1, ntFS, smFS, dA, dQ, dP0, dC, dBt, dqt, dslr, dnt, dCt, T, r, p, dzp, dzf, dPp, dPf,
+      dFs, dPsF, dSff, dAn, dQn, dll, mi, o->tol, st, dsrc, stgT);
+    if (any_missing || !emb.on) L(k_em_mstep_series, N, batch, 64, (size_t)(2 * np + r + 8) * 8, x, dFs, dPsF, dSff, T, N, r, dL, dR, st, emb_on);
+    if (any_bal && emb.on) {
+      switch (emb.ncb) {
+        case 1: emb_launch_M<1>(h, emb, x, dFs, dSff, T, N, r, batch, dL, dR, dW, dlogR, st); break;
+        case 2: emb_launch_M<2>(h, emb, x, dFs, dSff, T, N, r, batch, dL, dR, dW, dlogR, st); break;
+        case 3: emb_launch_M<3>(h, emb, x, dFs, dSff, T, N, r, batch, dL, dR, dW, dlogR, st); break;
+        default: emb_launch_M<4>(h, emb, x, dFs, dSff, T, N, r, batch, dL, dR, dW, dlogR, st); break;
+      }
+      L(k_emb_close, batch, 1, 128, 0, N, r, p, emb.ntM, emb.Cpart, dC, dA, dAn, dQ, dQn, st, mi);
+    }
+    if (any_missing || !emb.on) L(k_em_prep, batch, 1, 128, 0, dL, dR, N, r, p, dW, dlogR, dC, dA, dAn, dQ, dQn, st, mi, 1, emb_on);
     if (o->tol > 0 && ((it & 3) == 3)) {
       L(k_em_count_active, 1, 1, 128, 48 * 8, st, batch, active);
       CK(cudaMemcpyAsync(&h_active, active, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -400,6 +472,22 @@ long long dfm_launch_count(const dfm_handle* h) { return h ? h->launches : -1; }
 const char* dfm_last_error(const dfm_handle* h) { return h ? h->err : "null handle"; }
 
 // ---- per-kernel CUDA-event profiling (bench.py's roofline leg; off by default) -----------------
+// diagnostics: per-section clock64 totals of k_em_filter_smooth (block 0); on = 1 arms and clears, out (16 doubles) reads
+int dfm_debug_fs_prof(dfm_handle* h, int on, double* out) {
+#ifndef DFM_EMU
+  if (!h) return DFM_ERR_ARG;
+  CK(cudaStreamSynchronize(h->stream));
+  long long v[48];
+  if (out) { CK(cudaMemcpyFromSymbol(v, dfm::g_fs_prof, sizeof(v))); for (int i = 0; i < 48; ++i) out[i] = (double)v[i]; }
+  memset(v, 0, sizeof(v));
+  CK(cudaMemcpyToSymbol(dfm::g_fs_prof, v, sizeof(v)));
+  CK(cudaMemcpyToSymbol(dfm::g_fs_prof_on, &on, sizeof(int)));
+#else
+  (void)h; (void)on; (void)out;
+#endif
+  return DFM_OK;
+}
+
 int dfm_profile_enable(dfm_handle* h, int on) {
   if (!h) return DFM_ERR_ARG;
   h->profile = on ? 1 : 0;
@@ -769,7 +857,16 @@ int dfm_em_kalman(dfm_handle* h, const double* X, const dfm_em_opts* o, const df
   int T = o->T, N = o->N, r = o->r, p = o->p, batch = o->batch, mem = o->mem, mi = o->max_iter;
   if (T <= 1 || N <= 0 || r <= 0 || r > 64 || p <= 0 || batch <= 0 || mi <= 0 || o->tol < 0)
     return fail(h, DFM_ERR_ARG, "dfm_em_kalman: bad shape/options");
-  size_t smFS = em_fs_smem_doubles(r, p) * 8;
+  // staging tile of the frozen-run phases of the filter / smoother: few panels -> large tiles (one CTA per SM anyway);
+  // many panels -> the largest tile that still lets two CTAs share an SM, if any does
+  int stgT = (batch <= 148) ? 128 : 16;
+  {
+    const size_t lim2 = 112 * 1024;
+    if (batch <= 148) { while (stgT > 8 && em_fs_smem_doubles(r, p, stgT) * 8 > kMaxSmem) stgT /= 2; }
+    else if (em_fs_smem_doubles(r, p, 4) * 8 <= lim2) { while (stgT > 4 && em_fs_smem_doubles(r, p, stgT) * 8 > lim2) stgT /= 2; }
+    else { while (stgT > 4 && em_fs_smem_doubles(r, p, stgT) * 8 > kMaxSmem) stgT /= 2; }
+  }
+  size_t smFS = em_fs_smem_doubles(r, p, stgT) * 8;
   if (smFS > kMaxSmem) return fail(h, DFM_ERR_UNSUPPORTED, "dfm_em_kalman: state dimension r*p too large for the general path");
   CK(cudaSetDevice(h->device));
   size_t B = batch, TN = (size_t)T * N; int k = r * p, kk = k * k, rr = r * r, rk = r * k, np = r * (r + 1) / 2;
@@ -781,6 +878,7 @@ int dfm_em_kalman(dfm_handle* h, const double* X, const dfm_em_opts* o, const df
   if (o->path == 3 && !fused2_ok) return fail(h, DFM_ERR_UNSUPPORTED, "dfm_em_kalman: TMA fused path needs p = 1, r <= 8, even T and a panel that fits shared memory");
   bool fused = (fused_ok || fused2_ok) && o->path != 1;
   const bool use2 = fused2_ok && (o->path == 0 || o->path == 3);
+  EmbPlan emb = emb_plan(T, N, r, batch);
   for (int pass = 0; pass < 2; ++pass) {
     Arena a(pass ? h->ws : nullptr);
     double* dXb = mem == DFM_MEM_HOST ? a.get<double>(B * TN) : nullptr;
@@ -809,6 +907,11 @@ int dfm_em_kalman(dfm_handle* h, const double* X, const dfm_em_opts* o, const df
       dC = a.get<double>(B * rr); dBt = a.get<double>(B * T * r); dqt = a.get<double>(B * T); dslr = a.get<double>(B * T);
       dnt = a.get<int>(2 * B * T) /* n_t, then src_t of the frozen-step logic */; dCt = a.get<double>(B * T * np); dzp = a.get<double>(B * T * k); dzf = a.get<double>(B * T * k);
       dPp = a.get<double>(B * T * kk); dPf = a.get<double>(B * T * kk); dSff = a.get<double>(B * rr);
+      if (emb.on) {
+        emb.Bpart = a.get<double>((size_t)emb.nsE * B * T * r); emb.qpart = a.get<double>((size_t)emb.nsE * B * T);
+        emb.Spart = a.get<double>((size_t)emb.tsM * B * N * r); emb.sxxpart = a.get<double>((size_t)emb.tsM * B * N);
+        emb.Cpart = a.get<double>(B * emb.ntM * rr); emb.counters = a.get<int>(B * (size_t)(emb.ntE + emb.ntM));
+      }
     }
     if (!pass) { int rc = ensure_ws(h, a.off); if (rc) return rc; continue; }
     int rc = DFM_OK;
@@ -954,7 +1057,7 @@ int dfm_em_kalman(dfm_handle* h, const double* X, const dfm_em_opts* o, const df
         if (!init->P0) L(k_lyapunov, batch, 1, 128, (size_t)(3 * kk + 8) * 8, dA, dQ, r, p, dP0, 12);
         { long long n = (long long)B * mi; L(k_fill, (int)std::min<long long>((n + 255) / 256, 1024), 1, 256, 0, dll, n, DFM_NAN); }
         rc = run_em_general(h, xg, o, dL, dR, dA, dQ, dP0, dAn, dQn, dW, dlogR, dC, dBt, dqt, dslr, dnt, dCt, dzp, dzf, dPp, dPf, dFs, dPsF, dSff, dll, st, dit,
-                            dstat, active, ntC, nblkC, smFS);
+                            dstat, active, ntC, nblkC, smFS, stgT, emb);
         if (rc) return rc;
         computed = true;
       }
@@ -1035,7 +1138,7 @@ int dfm_em_kalman(dfm_handle* h, const double* X, const dfm_em_opts* o, const df
 #endif
     } else {
       rc = run_em_general(h, x, o, dL, dR, dA, dQ, dP0, dAn, dQn, dW, dlogR, dC, dBt, dqt, dslr, dnt, dCt, dzp, dzf, dPp, dPf, dFs, dPsF, dSff, dll, st, dit,
-                          dstat, active, ntC, nblkC, smFS);
+                          dstat, active, ntC, nblkC, smFS, stgT, emb);
       if (rc) return rc;
     }
     }   // !computed

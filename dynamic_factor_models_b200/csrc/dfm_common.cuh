@@ -32,6 +32,7 @@ static thread_local double g_emu_smem[1 << 19];   // 4 MB of "shared memory"
 static inline double atomicAdd(double* p, double v) { double o = *p; *p += v; return o; }
 static inline int atomicAdd(int* p, int v) { int o = *p; *p += v; return o; }
 static inline int atomicMax(int* p, int v) { int o = *p; if (v > o) *p = v; return o; }
+static inline int atomicMin(int* p, int v) { int o = *p; if (v < o) *p = v; return o; }
 typedef void* cudaStream_t;
 #define DFM_LAUNCH(kern, gx_, gy_, nt_, smem_, stream_, ...)                          \
   do {                                                                               \
@@ -54,6 +55,22 @@ typedef void* cudaStream_t;
 #endif
 
 #define DFM_NAN (nan(""))
+
+// warp-level view of the block (the host emulation runs one logical thread per block)
+#ifdef DFM_EMU
+#define DFM_LANE 0
+#define DFM_WSZ 1
+#define DFM_WARP 0
+#define DFM_NWARP 1
+#define DFM_WSYNC() ((void)0)
+#else
+#define DFM_LANE ((int)(threadIdx.x & 31))
+#define DFM_WSZ 32
+#define DFM_WARP ((int)(threadIdx.x >> 5))
+#define DFM_NWARP ((int)(blockDim.x >> 5))
+#define DFM_WSYNC() __syncwarp()
+#endif
+
 
 namespace dfm {
 
@@ -164,51 +181,60 @@ __device__ inline void bm_symmetrize(double* A, int ld, int n) {
 
 // In-place lower Cholesky of the n x n SPD matrix A (upper triangle is ZEROED so A can be used
 // as a full matrix afterwards).  *info (shared int) is set to 1 on a non-positive pivot.
+// Right-looking with ONE barrier per column: the columns stay unscaled during the elimination (the trailing
+// update divides by the pivot d_j instead), and are scaled by 1/sqrt(d_j) in one pass at the end.
 __device__ inline void bm_chol(double* A, int ld, int n, int* info) {
   for (int j = 0; j < n; ++j) {
-    if (DFM_TID == 0) {
-      double d = A[j + ld * j];
-      if (!(d > 0.0)) { *info = 1; d = 1.0; }
-      A[j + ld * j] = sqrt(d);
-    }
-    DFM_SYNC();
-    double inv = 1.0 / A[j + ld * j];
-    for (int i = j + 1 + DFM_TID; i < n; i += DFM_NT) A[i + ld * j] *= inv;
-    DFM_SYNC();
-    int m = n - j - 1;   // trailing update of the lower triangle, columns j+1..n-1
+    double d = A[j + ld * j];                        // final after the updates of columns < j
+    if (!(d > 0.0)) { if (DFM_TID == 0) *info = 1; d = 1.0; }
+    const double dinv = 1.0 / d;
+    const int m = n - j - 1;                         // trailing update of the lower triangle, columns j+1..n-1
     for (int e = DFM_TID; e < m * m; e += DFM_NT) {
       int i = j + 1 + e % m, c = j + 1 + e / m;
-      if (i >= c) A[i + ld * c] -= A[i + ld * j] * A[c + ld * j];
+      if (i >= c) A[i + ld * c] -= A[i + ld * j] * A[c + ld * j] * dinv;
     }
     DFM_SYNC();
   }
-  for (int e = DFM_TID; e < n * n; e += DFM_NT) { int i = e % n, j = e / n; if (i < j) A[i + ld * j] = 0.0; }
+  for (int e = DFM_TID; e < n * n; e += DFM_NT) {
+    int i = e % n, j = e / n;
+    if (i < j) { A[i + ld * j] = 0.0; continue; }
+    double d = A[j + ld * j];
+    if (!(d > 0.0)) d = 1.0;
+    if (i > j) A[i + ld * j] *= 1.0 / sqrt(d);
+  }
+  DFM_SYNC();
+  for (int j = DFM_TID; j < n; j += DFM_NT) { double d = A[j + ld * j]; if (!(d > 0.0)) d = 1.0; A[j + ld * j] = sqrt(d); }
   DFM_SYNC();
 }
 
-// B (n x m) <- L^-1 B   (L lower, n x n); one thread per right-hand-side column.
+// B (n x m) <- L^-1 B   (L lower, n x n).  Right-looking, all threads on the rank-one update of the rows below the
+// pivot row, ONE barrier per row: rows stay unscaled during the elimination (x_i = B_i / L_ii is formed on the fly)
+// and are divided by the diagonal in one pass at the end.
 __device__ inline void bm_trsm_lower(const double* L, int ldl, int n, double* B, int ldb, int m) {
-  for (int c = DFM_TID; c < m; c += DFM_NT) {
-    double* x = B + (size_t)ldb * c;
-    for (int i = 0; i < n; ++i) {
-      double s = x[i];
-      for (int l = 0; l < i; ++l) s -= L[i + ldl * l] * x[l];
-      x[i] = s / L[i + ldl * i];
+  for (int i = 0; i + 1 < n; ++i) {
+    const double inv = 1.0 / L[i + ldl * i];
+    const int nr = n - i - 1;
+    for (int e = DFM_TID; e < nr * m; e += DFM_NT) {
+      int i2 = i + 1 + e % nr, c = e / nr;
+      B[i2 + ldb * c] -= L[i2 + ldl * i] * (B[i + ldb * c] * inv);
     }
+    DFM_SYNC();
   }
+  for (int e = DFM_TID; e < n * m; e += DFM_NT) { int i = e % n, c = e / n; B[i + ldb * c] /= L[i + ldl * i]; }
   DFM_SYNC();
 }
 
 // B (n x m) <- L^-T B
 __device__ inline void bm_trsm_lowerT(const double* L, int ldl, int n, double* B, int ldb, int m) {
-  for (int c = DFM_TID; c < m; c += DFM_NT) {
-    double* x = B + (size_t)ldb * c;
-    for (int i = n - 1; i >= 0; --i) {
-      double s = x[i];
-      for (int l = i + 1; l < n; ++l) s -= L[l + ldl * i] * x[l];
-      x[i] = s / L[i + ldl * i];
+  for (int i = n - 1; i > 0; --i) {
+    const double inv = 1.0 / L[i + ldl * i];
+    for (int e = DFM_TID; e < i * m; e += DFM_NT) {
+      int i2 = e % i, c = e / i;
+      B[i2 + ldb * c] -= L[i + ldl * i2] * (B[i + ldb * c] * inv);
     }
+    DFM_SYNC();
   }
+  for (int e = DFM_TID; e < n * m; e += DFM_NT) { int i = e % n, c = e / n; B[i + ldb * c] /= L[i + ldl * i]; }
   DFM_SYNC();
 }
 

@@ -62,8 +62,9 @@ __global__ void k_lyapunov(const double* __restrict__ Aall, const double* __rest
 __global__ void k_em_prep(const double* __restrict__ LamAll, const double* __restrict__ Rall, int N, int r, int p,
                           double* __restrict__ Wall, double* __restrict__ logRall, double* __restrict__ Call,
                           double* __restrict__ A, const double* __restrict__ Anew, double* __restrict__ Q,
-                          const double* __restrict__ Qnew, EmState* st, int max_iter, int closing) {
+                          const double* __restrict__ Qnew, EmState* st, int max_iter, int closing, int skip_bal) {
   int b = DFM_BX;
+  if (closing && skip_bal && !st[b].has_missing) return;      // balanced panels are closed by k_emb_close
   int was_done = st[b].done;
   DFM_SYNC();
   if (closing && !was_done) {
@@ -194,17 +195,386 @@ __global__ void k_em_contract_bal(const double* __restrict__ Xall, const double*
   }
 }
 
-// shared-memory footprint (doubles) of k_em_filter_smooth
-__host__ __device__ inline size_t em_fs_smem_doubles(int r, int p) {
-  size_t k = (size_t)r * p, kk = k * k, rr = (size_t)r * r, rk = (size_t)r * k;
-  return 9 * kk + 7 * rr + 3 * rk + 6 * k + 2 * r + 64 + 64;
+// diagnostics (dfm_debug_fs_prof): clock64 totals of block 0, thread 0, per section
+#ifndef DFM_EMU
+__device__ long long g_fs_prof[48];
+__device__ int g_fs_prof_on;
+#define FS_T0() long long fs_t_ = (g_fs_prof_on && blockIdx.x == 0 && threadIdx.x == 0) ? clock64() : 0
+#define FS_T(k_) do { if (g_fs_prof_on && blockIdx.x == 0 && threadIdx.x == 0) { long long n_ = clock64(); g_fs_prof[k_] += n_ - fs_t_; fs_t_ = n_; } } while (0)
+#define FS_CNT(k_) do { if (g_fs_prof_on && blockIdx.x == 0 && threadIdx.x == 0) g_fs_prof[k_] += 1; } while (0)
+#else
+#define FS_T0() ((void)0)
+#define FS_T(k_) ((void)0)
+#define FS_CNT(k_) ((void)0)
+#endif
+
+// ---- small dense helpers of the filter / smoother steps ------------------------------------------------------------
+// Reciprocal and reciprocal square root from the hardware seed (MUFU, ~2^-23) + two Newton steps: ~1 ulp, a fraction of
+// the latency of the correctly rounded division / sqrt sequences, which sit on the serial path of every Cholesky column.
+__device__ __forceinline__ double fast_rcp(double d) {
+#ifdef DFM_EMU
+  return 1.0 / d;
+#else
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  double e = fma(-d, y, 1.0); y = fma(y, e, y);
+  e = fma(-d, y, 1.0); y = fma(y, e, y);
+  e = fma(-d, y, 1.0); y = fma(y, e, y);
+  return y;
+#endif
+}
+__device__ __forceinline__ double fast_rsqrt(double d) {
+#ifdef DFM_EMU
+  return 1.0 / sqrt(d);
+#else
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  const double hd = 0.5 * d;
+  double e = fma(-hd * y, y, 0.5); y = fma(y, e, y);
+  e = fma(-hd * y, y, 0.5); y = fma(y, e, y);
+  e = fma(-hd * y, y, 0.5); y = fma(y, e, y);
+  return y;
+#endif
 }
 
-// Kalman filter + RTS smoother + transition M-step for one panel.  grid (B), one block.
+// Lower Cholesky of the n x n SPD matrix A (shared, column-major), block-cooperative, ONE barrier per column: columns stay
+// unscaled during the elimination (the trailing update multiplies by 1/d_j), warps take the trailing columns, lanes the
+// rows (conflict-free, no index arithmetic); one final pass scales column j by d_j^-1/2 and zeroes the upper triangle.
+// dinv (n doubles, shared) receives 1 / L_jj for the triangular solves.  *info = 1 on a non-positive pivot.
+__device__ inline void bc_chol(double* A, int ld, int n, double* dinv, int* info) {
+  for (int j = 0; j < n; ++j) {
+    double d = A[j + ld * j];                          // final after the updates of columns < j
+    if (!(d > 0.0)) { if (DFM_TID == 0) *info = 1; d = 1.0; }
+    const double di = fast_rcp(d);
+    if (DFM_TID == 0) dinv[j] = d;                     // (pivot; turned into 1 / L_jj below)
+    for (int c = j + 1 + DFM_WARP; c < n; c += DFM_NWARP) {
+      const double lc = A[c + ld * j] * di;
+      for (int i = c + DFM_LANE; i < n; i += DFM_WSZ) A[i + ld * c] -= A[i + ld * j] * lc;
+    }
+    DFM_SYNC();
+  }
+  for (int j = DFM_WARP; j < n; j += DFM_NWARP) {
+    const double rs = fast_rsqrt(dinv[j]);
+    for (int i = DFM_LANE; i < n; i += DFM_WSZ) {
+      if (i < j) A[i + ld * j] = 0.0;
+      else if (i == j) A[i + ld * j] = dinv[j] * rs;
+      else A[i + ld * j] *= rs;
+    }
+  }
+  DFM_SYNC();
+  for (int j = DFM_TID; j < n; j += DFM_NT) dinv[j] = fast_rsqrt(dinv[j]);
+  DFM_SYNC();
+}
+
+// Triangular solves on TRANSPOSED right-hand sides: XT is m x n (leading dimension ldx), ROW j of XT is the j-th right-hand
+// side and is overwritten by its solution.  One thread per row, no barriers inside: consecutive threads touch consecutive
+// addresses (conflict-free), the entries of L and 1 / L_aa (dinv) are warp-uniform broadcasts.
+__device__ inline void bt_trsm_lower(const double* L, int ldl, int n, const double* dinv, double* XT, int ldx, int m) {      // L y = x
+  for (int j = DFM_TID; j < m; j += DFM_NT)
+    for (int a = 0; a < n; ++a) {
+      double s0 = XT[j + ldx * a], s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      int c = 0;
+      for (; c + 3 < a; c += 4) {
+        s0 -= L[a + ldl * c] * XT[j + ldx * c]; s1 -= L[a + ldl * (c + 1)] * XT[j + ldx * (c + 1)];
+        s2 -= L[a + ldl * (c + 2)] * XT[j + ldx * (c + 2)]; s3 -= L[a + ldl * (c + 3)] * XT[j + ldx * (c + 3)];
+      }
+      for (; c < a; ++c) s0 -= L[a + ldl * c] * XT[j + ldx * c];
+      XT[j + ldx * a] = ((s0 + s1) + (s2 + s3)) * dinv[a];
+    }
+  DFM_SYNC();
+}
+__device__ inline void bt_trsm_lowerT(const double* L, int ldl, int n, const double* dinv, double* XT, int ldx, int m) {     // L' y = x
+  for (int j = DFM_TID; j < m; j += DFM_NT)
+    for (int a = n - 1; a >= 0; --a) {
+      double s0 = XT[j + ldx * a], s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      int c = a + 1;
+      for (; c + 3 < n; c += 4) {
+        s0 -= L[c + ldl * a] * XT[j + ldx * c]; s1 -= L[c + 1 + ldl * a] * XT[j + ldx * (c + 1)];
+        s2 -= L[c + 2 + ldl * a] * XT[j + ldx * (c + 2)]; s3 -= L[c + 3 + ldl * a] * XT[j + ldx * (c + 3)];
+      }
+      for (; c < n; ++c) s0 -= L[c + ldl * a] * XT[j + ldx * c];
+      XT[j + ldx * a] = ((s0 + s1) + (s2 + s3)) * dinv[a];
+    }
+  DFM_SYNC();
+}
+
+// Warp-tiled FP64 tensor-core product on shared-memory operands (mma.sync.m8n8k4.f64 -> DMMA.8x8x4):
+//   D(m, n) = sum_l A(m, l) B(n, l),   A(m, l) = As[m * sam + l * sal],   B(n, l) = Bs[n * sbn + l * sbl],   m < Mr, n < Nn, l < K.
+// The 8 x 8 output tiles are dealt to the warps round-robin; epi(m, n, value) is called once for every valid element.
+// A dot-product loop on shared-memory operands needs two 8-byte operand reads per multiply-add and is bound by the
+// shared-memory pipe (measured: the k x k products of the frozen-run phases); a DMMA needs two reads per 256 of them.
+#ifndef DFM_EMU
+#define EM_DMMA(d_, a_, b_) asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"((d_)[0]), "+d"((d_)[1]) : "d"(a_), "d"(b_))
+#endif
+template <class Epi>
+__device__ __forceinline__ void wt_gemm(const double* As, int sam, int sal, const double* Bs, int sbn, int sbl, int Mr, int Nn, int K, Epi epi) {
+#ifndef DFM_EMU
+  const int lr = DFM_LANE >> 2, lc = DFM_LANE & 3;
+  const int mt = (Mr + 7) >> 3, ntl = (Nn + 7) >> 3;
+  for (int tile = DFM_WARP; tile < mt * ntl; tile += DFM_NWARP) {
+    const int mb = tile % mt, nb = tile / mt;
+    const int m = mb * 8 + lr, n = nb * 8 + lr;
+    const bool mok = m < Mr, nok = n < Nn;
+    const double* ap = As + (size_t)(mok ? m : 0) * sam + (size_t)lc * sal;
+    const double* bp = Bs + (size_t)(nok ? n : 0) * sbn + (size_t)lc * sbl;
+    double d0[2] = {0.0, 0.0}, d1[2] = {0.0, 0.0};
+    int l0 = 0;
+    for (; l0 + 8 <= K; l0 += 8) {
+      const double a0 = mok ? ap[(size_t)l0 * sal] : 0.0, b0 = nok ? bp[(size_t)l0 * sbl] : 0.0;
+      const double a1 = mok ? ap[(size_t)(l0 + 4) * sal] : 0.0, b1 = nok ? bp[(size_t)(l0 + 4) * sbl] : 0.0;
+      EM_DMMA(d0, a0, b0); EM_DMMA(d1, a1, b1);
+    }
+    for (; l0 < K; l0 += 4) {
+      const bool lok = l0 + lc < K;
+      const double a0 = (mok && lok) ? ap[(size_t)l0 * sal] : 0.0, b0 = (nok && lok) ? bp[(size_t)l0 * sbl] : 0.0;
+      EM_DMMA(d0, a0, b0);
+    }
+    const int mo = mb * 8 + lr, no = nb * 8 + 2 * lc;
+    if (mo < Mr) { if (no < Nn) epi(mo, no, d0[0] + d1[0]); if (no + 1 < Nn) epi(mo, no + 1, d0[1] + d1[1]); }
+  }
+#else
+  for (int n = 0; n < Nn; ++n)
+    for (int m = 0; m < Mr; ++m) {
+      double v = 0.0;
+      for (int l = 0; l < K; ++l) v += As[(size_t)m * sam + (size_t)l * sal] * Bs[(size_t)n * sbn + (size_t)l * sbl];
+      epi(m, n, v);
+    }
+#endif
+}
+// Same product accumulated into per-warp register tiles that persist over several calls (the reduction dimension arrives
+// in pieces): tile index = warp + q * (number of warps), q < EM_TQ; acc[q] is the lane's pair of the tile's 8 x 8 block.
+#define EM_TQ 6
+__device__ __forceinline__ void wt_gemm_acc(const double* As, int sam, int sal, const double* Bs, int sbn, int sbl, int Mr, int Nn, int K,
+                                            int tile0, double (*acc)[2]) {
+#ifndef DFM_EMU
+  const int lr = DFM_LANE >> 2, lc = DFM_LANE & 3;
+  const int mt = (Mr + 7) >> 3, ntl = (Nn + 7) >> 3;
+#pragma unroll
+  for (int q = 0; q < EM_TQ; ++q) {
+    const int tile = DFM_WARP + q * DFM_NWARP - tile0;
+    if (tile >= 0 && tile < mt * ntl) {
+      const int mb = tile % mt, nb = tile / mt;
+      const int m = mb * 8 + lr, n = nb * 8 + lr;
+      const bool mok = m < Mr, nok = n < Nn;
+      const double* ap = As + (size_t)(mok ? m : 0) * sam + (size_t)lc * sal;
+      const double* bp = Bs + (size_t)(nok ? n : 0) * sbn + (size_t)lc * sbl;
+      for (int l0 = 0; l0 < K; l0 += 4) {
+        const bool lok = l0 + lc < K;
+        const double a0 = (mok && lok) ? ap[(size_t)l0 * sal] : 0.0, b0 = (nok && lok) ? bp[(size_t)l0 * sbl] : 0.0;
+        EM_DMMA(acc[q], a0, b0);
+      }
+    }
+  }
+#else
+  (void)As; (void)sam; (void)sal; (void)Bs; (void)sbn; (void)sbl; (void)Mr; (void)Nn; (void)K; (void)tile0; (void)acc;
+#endif
+}
+// visit the elements of the register tiles: f(q-th tile's (m, n), value)
+template <class F>
+__device__ __forceinline__ void wt_acc_visit(int Mr, int Nn, int tile0, double (*acc)[2], F f) {
+#ifndef DFM_EMU
+  const int lr = DFM_LANE >> 2, lc = DFM_LANE & 3;
+  const int mt = (Mr + 7) >> 3, ntl = (Nn + 7) >> 3;
+#pragma unroll
+  for (int q = 0; q < EM_TQ; ++q) {
+    const int tile = DFM_WARP + q * DFM_NWARP - tile0;
+    if (tile >= 0 && tile < mt * ntl) {
+      const int mo = (tile % mt) * 8 + lr, no = (tile / mt) * 8 + 2 * lc;
+      if (mo < Mr) { if (no < Nn) f(mo, no, acc[q][0]); if (no + 1 < Nn) f(mo, no + 1, acc[q][1]); }
+    }
+  }
+#else
+  (void)Mr; (void)Nn; (void)tile0; (void)acc; (void)f;
+#endif
+}
+__host__ __device__ inline int em_lds(int k) { return k + ((12 - k % 8) % 8); }      // row stride == 4 (mod 8): conflict-free fragments
+
+// ---- parallel-in-time treatment of FROZEN RUNS (consecutive periods whose covariances are the stored steady state):
+// the mean recursion  z_t = Phi z_{t -+ 1} + u_t  with a constant k x k matrix is a linear scan.  The run is cut into
+// EM_RUN_NCH chunks, one per warp: pass 1 = chunk-local recursion from a zero state (keeps only the end state),
+// boundary propagation with Phi^Lc (binary powering, block-cooperative), pass 2 = the recursion again from the true
+// incoming state, writing z_t over u_t in place.  The u_t of the next four steps are prefetched into registers (they
+// come from L2; the recursion itself runs out of shared memory).  C3 (T = 2000, k = 20): 2 x 2000 serial steps -> 2 x 2 x 125.
+#define EM_RUN_NCH 16          // chunks per run (= warps used by the scan)
+#define EM_RUN_MIN 32          // shorter runs take the serial frozen steps
+
+// zg: global [T][k] (u_t in, z_t out) ; the run covers L periods starting at t_first and moving in direction dir (+1 / -1);
+// Phi: k x k column-major (shared) ; z_in: state entering the run (k) ; Rp, base, tmp: k x k shared temporaries ;
+// wb: 3 * k * EM_RUN_NCH doubles of shared workspace.  k <= 64.  Ends with a block barrier.
+#ifdef DFM_EMU
+#define EM_NOINLINE
+#else
+#define EM_NOINLINE __noinline__
+#endif
+__device__ EM_NOINLINE void em_run_scan(double* __restrict__ zg, int k, int t_first, int L, int dir, const double* Phi,
+                                   const double* z_in, double* Rp, double* base, double* tmp, double* wb) {
+  const int Lc = (L + EM_RUN_NCH - 1) / EM_RUN_NCH;
+  FS_T0();
+  // Rp = Phi^Lc
+  for (int e = DFM_TID; e < k * k; e += DFM_NT) { int i = e % k, j = e / k; Rp[e] = (i == j) ? 1.0 : 0.0; base[e] = Phi[e]; }
+  DFM_SYNC();
+  for (int ex = Lc; ex > 0; ex >>= 1) {
+    if (ex & 1) { bm_gemm(tmp, k, Rp, k, false, base, k, false, k, k, k, 1.0, 0.0); bm_copy(Rp, k, tmp, k, k, k); }
+    if (ex > 1) { bm_gemm(tmp, k, base, k, false, base, k, false, k, k, k, 1.0, 0.0); bm_copy(base, k, tmp, k, k, k); }
+  }
+  FS_T(27);
+  for (int pass = 1; pass <= 2; ++pass) {
+    for (int c = DFM_WARP; c < EM_RUN_NCH; c += DFM_NWARP) {
+      double* cur = wb + (size_t)c * 3 * k; double* nxt = cur + k; double* bnd = cur + 2 * k;
+      const int s0 = c * Lc, len = (L - s0 < Lc) ? ((L - s0 > 0) ? L - s0 : 0) : Lc;
+      for (int i = DFM_LANE; i < k; i += DFM_WSZ) cur[i] = (pass == 1) ? 0.0 : bnd[i];
+      DFM_WSYNC();
+      // rows of this lane: i0 = lane, i1 = lane + warp size (k <= 2 warp sizes on the GPU; the emulation loops over rows)
+#ifndef DFM_EMU
+      const int i0 = DFM_LANE, i1 = DFM_LANE + 32;
+      const bool r0 = i0 < k, r1 = i1 < k;
+      if (k <= 32) {
+        // row i0 of Phi in registers: a step costs k broadcast reads of the state instead of 2 k^2 / 32 operand reads per lane
+        // (16 warps running this from shared-memory operands alone saturate the shared-memory pipe)
+        double ph[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) ph[j] = (r0 && j < k) ? Phi[i0 + k * j] : 0.0;
+        double ub[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const long long tt = t_first + (long long)dir * (s0 + q); ub[q] = (q < len && r0) ? zg[tt * k + i0] : 0.0; }
+        for (int sg = 0; sg < len; sg += 4) {
+          double un[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int sn = sg + 4 + q;
+            const long long tt = t_first + (long long)dir * (s0 + sn);
+            un[q] = (sn < len && r0) ? zg[tt * k + i0] : 0.0;
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (sg + q < len) {
+              const long long tt = t_first + (long long)dir * (s0 + sg + q);
+              double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                if (j < k) {
+                  a0 += ph[j] * cur[j];
+                  if (j + 1 < k) a1 += ph[j + 1] * cur[j + 1];
+                  if (j + 2 < k) a2 += ph[j + 2] * cur[j + 2];
+                  if (j + 3 < k) a3 += ph[j + 3] * cur[j + 3];
+                }
+              }
+              if (r0) { const double v = ((a0 + a1) + (a2 + a3)) + ub[q]; nxt[i0] = v; if (pass == 2) zg[tt * k + i0] = v; }
+              __syncwarp();
+              double* sw = cur; cur = nxt; nxt = sw;
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) ub[q] = un[q];
+        }
+      } else {
+      double ub0[4], ub1[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const long long tt = t_first + (long long)dir * (s0 + q);
+        ub0[q] = (q < len && r0) ? zg[tt * k + i0] : 0.0; ub1[q] = (q < len && r1) ? zg[tt * k + i1] : 0.0;
+      }
+      for (int sg = 0; sg < len; sg += 4) {
+        double un0[4], un1[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int sn = sg + 4 + q;
+          const long long tt = t_first + (long long)dir * (s0 + sn);
+          un0[q] = (sn < len && r0) ? zg[tt * k + i0] : 0.0; un1[q] = (sn < len && r1) ? zg[tt * k + i1] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (sg + q < len) {
+            const long long tt = t_first + (long long)dir * (s0 + sg + q);
+            double a0 = 0.0, a1 = 0.0, c0 = 0.0, c1 = 0.0;
+            int j = 0;
+            for (; j + 1 < k; j += 2) {
+              const double z0 = cur[j], z1 = cur[j + 1];
+              if (r0) { a0 += Phi[i0 + k * j] * z0; a1 += Phi[i0 + k * (j + 1)] * z1; }
+              if (r1) { c0 += Phi[i1 + k * j] * z0; c1 += Phi[i1 + k * (j + 1)] * z1; }
+            }
+            if (j < k) { const double z0 = cur[j]; if (r0) a0 += Phi[i0 + k * j] * z0; if (r1) c0 += Phi[i1 + k * j] * z0; }
+            if (r0) { const double v = (a0 + a1) + ub0[q]; nxt[i0] = v; if (pass == 2) zg[tt * k + i0] = v; }
+            if (r1) { const double v = (c0 + c1) + ub1[q]; nxt[i1] = v; if (pass == 2) zg[tt * k + i1] = v; }
+            __syncwarp();
+            double* sw = cur; cur = nxt; nxt = sw;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { ub0[q] = un0[q]; ub1[q] = un1[q]; }
+      }
+      }
+#else
+      for (int s_ = 0; s_ < len; ++s_) {
+        const int tt = t_first + dir * (s0 + s_);
+        for (int i = 0; i < k; ++i) {
+          double a0 = 0.0;
+          for (int j = 0; j < k; ++j) a0 += Phi[i + k * j] * cur[j];
+          const double v = a0 + zg[(size_t)tt * k + i];
+          nxt[i] = v;
+          if (pass == 2) zg[(size_t)tt * k + i] = v;
+        }
+        double* sw = cur; cur = nxt; nxt = sw;
+      }
+#endif
+      if (pass == 1) {                                  // end state of the zero-start recursion -> bnd (cur may be either buffer)
+        double* b0 = wb + (size_t)c * 3 * k + 2 * k;
+        for (int i = DFM_LANE; i < k; i += DFM_WSZ) b0[i] = cur[i];
+      }
+    }
+    DFM_SYNC();
+    FS_T(27 + pass);
+    if (pass == 1) {
+      // incoming states: in_0 = z_in, in_{c+1} = Phi^Lc in_c + e_c ; bnd[c] holds e_c and is overwritten by in_c
+      double* inc = wb;                                  // 2k doubles (chunk 0's idle cur/nxt buffers): current in_c, next in_c
+      for (int i = DFM_TID; i < k; i += DFM_NT) inc[i] = z_in[i];
+      DFM_SYNC();
+      for (int c = 0; c + 1 < EM_RUN_NCH; ++c) {
+        double* ec = wb + (size_t)c * 3 * k + 2 * k;
+        for (int i = DFM_TID; i < k; i += DFM_NT) { double s = ec[i]; for (int j = 0; j < k; ++j) s += Rp[i + k * j] * inc[j]; inc[k + i] = s; }
+        DFM_SYNC();
+        for (int i = DFM_TID; i < k; i += DFM_NT) { ec[i] = inc[i]; inc[i] = inc[k + i]; }      // bnd[c] <- in_c
+        DFM_SYNC();
+      }
+      double* el = wb + (size_t)(EM_RUN_NCH - 1) * 3 * k + 2 * k;
+      for (int i = DFM_TID; i < k; i += DFM_NT) el[i] = inc[i];
+      DFM_SYNC();
+      FS_T(30);
+    }
+  }
+}
+
+// shared-memory footprint (doubles) of k_em_filter_smooth; stg_T = periods per staging tile of the frozen-run phases
+__host__ __device__ inline size_t em_fs_smem_doubles(int r, int p, int stg_T = 16) {
+  size_t k = (size_t)r * p, kk = k * k, rr = (size_t)r * r, rk = (size_t)r * k;
+  return 9 * kk + 7 * rr + 3 * rk + 6 * k + 2 * r + 64 + 64 + 3 * k * EM_RUN_NCH + (size_t)r * (stg_T + 4) + (size_t)(2 * stg_T + 1) * em_lds((int)k) + 8 + 3 * 64;
+}
+
+#ifdef DFM_EMU
+#define EM_FS_BOUNDS
+#else
+#define EM_FS_BOUNDS __launch_bounds__(512, 1)
+#endif
+#define EM_ACC_MAX 8           // Gram-sum outputs per thread held in registers by the backward frozen runs
+
+// Kalman filter + RTS smoother + transition M-step for one panel.  grid (B), one block (256 or 512 threads).
 // Scratch (global, per panel): zp, zf [T x k]; Pp, Pf [T x k x k].
 // Outputs: Fs [T x r], PsF packed [T x np] (smoothed Var f_t), SffAll [r x r] = sum_t E f f',
 // Anew [r x k], Qnew [r x r], loglik path.
-__global__ void k_em_filter_smooth(const double* __restrict__ Aall, const double* __restrict__ Qall,
+//
+// EXPLICIT STEPS (covariances move).  Forward, information form: P_{t|t-1} from the companion structure of M (rows >= r
+// of M are a shift: only A P_f, r k^2 flops, is a product), Cholesky factors of P_ff and S = I + L'C L on warp 0 with
+// warp barriers, the two triangular solves on transposed right-hand sides (thread per row, no barriers, conflict-free).
+// Backward: J = P_f M' P_p^-1 is obtained row-wise the same way (right-hand sides = rows of P_f M'), so only J -- never
+// J' -- is needed: zs = zf + J dv, Ps = Pf + (J D) J', Pc = Ps(t+1)[0:r,:] J' are all conflict-free products.
+// FROZEN STEPS.  Where the information matrix C_t does not change (a balanced panel: everywhere; missing data: between
+// two changes of the observation pattern) the covariance recursion is data independent and converges to its steady
+// state; once P_{t|t-1} repeats (relative 1e-14) the factorisations, the gain and P_{t|t} of the following periods
+// are the ones already in shared memory, and only the mean updates remain: serial steps for short runs, the parallel
+// scan above for runs of >= EM_RUN_MIN periods (inputs and outputs of the element-wise phases staged through shared
+// memory in tiles of stg_T periods).  src[t] = the period whose stored covariances period t uses.  The smoother gain
+// and the smoothed covariance freeze the same way.
+__global__ void EM_FS_BOUNDS k_em_filter_smooth(const double* __restrict__ Aall, const double* __restrict__ Qall,
                                    const double* __restrict__ P0all, const double* __restrict__ Call,
                                    const double* __restrict__ Bt_, const double* __restrict__ qt_,
                                    const double* __restrict__ slr_, const int* __restrict__ nt__,
@@ -212,14 +582,8 @@ __global__ void k_em_filter_smooth(const double* __restrict__ Aall, const double
                                    double* __restrict__ zp_, double* __restrict__ zf_, double* __restrict__ Pp_,
                                    double* __restrict__ Pf_, double* __restrict__ Fs_, double* __restrict__ PsF_,
                                    double* __restrict__ SffAll_, double* __restrict__ Anew_, double* __restrict__ Qnew_,
-                                   double* __restrict__ loglik_, int max_iter, double tol, EmState* st, int* __restrict__ src_) {
-  // FROZEN STEPS.  Where the information matrix C_t does not change (a balanced panel: everywhere; missing data: between
-  // two changes of the observation pattern) the covariance recursion is data independent and converges to its steady
-  // state; once P_{t|t-1} repeats (relative 1e-14) the factorisations, the gain and P_{t|t} of the following periods
-  // are the ones already in shared memory, and only the r- and k-sized mean updates remain.  src[t] = the period whose
-  // stored covariances period t uses.  The smoother gain J_t depends on (P_{src[t]|src[t]}, P_{src[t+1]|src[t+1]-1})
-  // only and is reused likewise; the smoothed covariance recursion freezes the same way (C3: T = 2000 periods, ~25
-  // explicit steps in each direction).
+                                   double* __restrict__ loglik_, int max_iter, double tol, EmState* st, int* __restrict__ src_,
+                                   int stg_T) {
   DFM_SMEM(sm);
   int b = DFM_BX;
   if (st[b].done) return;
@@ -234,8 +598,13 @@ __global__ void k_em_filter_smooth(const double* __restrict__ Aall, const double
   double* dv = zs + k;       double* tv = dv + k;
   double* g = tv + k;        double* bt = g + r;
   double* red = bt + r;      // 40 (+ 80 for block_max2 behind `info`)
-  int* info = (int*)(red + 44);                          // [0] Cholesky flag, [2], [3]: "C changed" flags of even / odd periods
+  int* info = (int*)(red + 44);                          // [0] Cholesky flag, [1] run search, [2], [3]: "C changed" flags of even / odd periods
   double* red2 = red + 48;   // 80
+  double* wb = red2 + 80;    // 3 * k * EM_RUN_NCH: scan workspace of the frozen runs
+  double* stg = wb + 3 * k * EM_RUN_NCH;   // stg_T * (2k + r) + 2k: staging tiles of the frozen-run phases
+  double* dvL = stg + (size_t)r * (stg_T + 4) + (size_t)(2 * stg_T + 1) * em_lds(k) + 8;   // 1 / diag of the Cholesky factors: L (or Pp), S
+  double* dvS = dvL + 64;
+  double* ldS_sh = red + 40; // log det of the last explicit step, for all threads
   int* src = src_ + (size_t)b * T;
   const double* A = Aall + (size_t)b * rk; const double* Qg = Qall + (size_t)b * rr;
   const double* P0 = P0all + (size_t)b * kk; const double* Cg = Call + (size_t)b * rr;
@@ -246,7 +615,8 @@ __global__ void k_em_filter_smooth(const double* __restrict__ Aall, const double
   double* Ppg = Pp_ + (size_t)b * T * kk; double* Pfg = Pf_ + (size_t)b * T * kk;
   double* Fs = Fs_ + (size_t)b * T * r; double* PsF = PsF_ + (size_t)b * T * np;
   int hm = st[b].has_missing;
-  if (DFM_TID == 0) { info[0] = 0; info[2] = 0; info[3] = 0; }
+  const int TT = stg_T;
+  if (DFM_TID == 0) { info[0] = 0; info[1] = 0; info[2] = 0; info[3] = 0; }
   for (int e = DFM_TID; e < kk; e += DFM_NT) {
     int i = e % k, j = e / k;
     M[e] = (i < r) ? A[i + r * j] : ((j == i - r) ? 1.0 : 0.0);
@@ -256,8 +626,9 @@ __global__ void k_em_filter_smooth(const double* __restrict__ Aall, const double
   for (int e = DFM_TID; e < rk; e += DFM_NT) S11[e] = 0.0;
   DFM_SYNC();
   double ll = 0.0;
+  FS_T0();
   // ------------------------------------------------------------------ forward: Kalman filter
-  int frozen = 0, last_src = 0;          // (uniform over the block)
+  int frozen = 0, last_src = 0, run_known = 0;   // (uniform over the block; run_known: the frozen run in progress ends there)
   double ldS = 0.0;                      // thread 0: 2 sum log diag chol(S) of the last explicit step
   for (int t = 0; t < T; ++t) {
     // information matrix of this period; did it change?  (flag of this period's parity; thread 0 clears the other one)
@@ -273,6 +644,85 @@ __global__ void k_em_filter_smooth(const double* __restrict__ Aall, const double
     for (int e = DFM_TID; e < r; e += DFM_NT) bt[e] = Bt[t + (size_t)T * e];
     DFM_SYNC();
     const int cchg = (t == 0) ? 1 : info[2 + (t & 1)];
+    if (frozen && !cchg && t >= run_known) {
+      // ---- how far does this frozen run reach?  (next change of the information matrix, or T)
+      int t1 = T;
+      if (hm) {
+        if (DFM_TID == 0) info[1] = T;
+        DFM_SYNC();
+        for (int base_ = t + 1; base_ < T; base_ += DFM_NT) {
+          const int tp = base_ + DFM_TID;
+          if (tp < T) {
+            bool ch = false;
+            for (int e = 0; e < np; ++e) ch = ch || (Ct[tp + (size_t)T * e] != Ct[tp - 1 + (size_t)T * e]);
+            if (ch) atomicMin(&info[1], tp);
+          }
+          DFM_SYNC();
+          const int v = info[1];
+          DFM_SYNC();
+          if (v < T) break;
+        }
+        t1 = info[1];
+      }
+      run_known = t1;
+      const int Lr = t1 - t;
+#ifdef DFM_EMU
+      if (getenv("DFM_DEBUG_FREEZE")) printf("[run fwd] b=%d t=%d t1=%d\n", b, t, t1);
+#endif
+      if (Lr >= EM_RUN_MIN) {
+        // ---- parallel frozen run [t, t1):  zf_t = Phi zf_{t-1} + Kb b_t,  Phi = M - Kb C M[0:r,:],  Kb = Pf[:, 0:r]
+        bm_gemm(Tm, r, C, r, false, M, k, false, r, k, r, 1.0, 0.0);             // C M[0:r,:]   (Tm, Wm: rebuilt by the next explicit step)
+        bm_gemm(T1, k, Pf, k, false, Tm, r, false, k, k, r, 1.0, 0.0);           // Kb (C M[0:r,:])
+        for (int e = DFM_TID; e < kk; e += DFM_NT) T1[e] = M[e] - T1[e];
+        const int TTp = TT + 4, lds = em_lds(k);
+        double* Bs = stg;                           // [r][TTp]        b_t of the tile (component-major)
+        double* Zs = Bs + (size_t)r * TTp;          // [TT + 1][lds]   zf_{t0-1} .. zf_{t0+len-1}
+        double* Zq = Zs + (size_t)(TT + 1) * lds;   // [TT][lds]       zp of the tile
+        for (int t0 = t; t0 < t1; t0 += TT) {                                    // u_t = Kb b_t  -> zfg
+          const int len = (t1 - t0 < TT) ? t1 - t0 : TT;
+          DFM_SYNC();
+#pragma unroll 4
+          for (int e = DFM_TID; e < r * len; e += DFM_NT) { const int a = e / len, tt = e - a * len; Bs[a * TTp + tt] = Bt[t0 + tt + (size_t)T * a]; }
+          DFM_SYNC();
+          wt_gemm(Bs, 1, TTp, Pf, 1, k, len, k, r, [&](int m, int n, double v) { zfg[(size_t)(t0 + m) * k + n] = v; });
+        }
+        DFM_SYNC();
+        FS_T(22);
+        em_run_scan(zfg, k, t, Lr, +1, T1, zf, T2, T3, Psn, wb);                  // (T2, T3, Psn are free between explicit steps)
+        FS_T(23);
+        double llp = 0.0;
+        const double ldS_ = *ldS_sh;
+        for (int t0 = t; t0 < t1; t0 += TT) {                                    // zp_t = M zf_{t-1}, likelihood terms
+          const int len = (t1 - t0 < TT) ? t1 - t0 : TT;
+          DFM_SYNC();
+#pragma unroll 4
+          for (int e = DFM_TID; e < r * len; e += DFM_NT) { const int a = e / len, tt = e - a * len; Bs[a * TTp + tt] = Bt[t0 + tt + (size_t)T * a]; }
+          {
+            const double* g0 = zfg + (size_t)(t0 - 1) * k;                      // rows t0-1 .. t0+len-1 are contiguous
+#pragma unroll 4
+            for (int e = DFM_TID; e < (len + 1) * k; e += DFM_NT) {
+              const int tt = e / k, i = e - tt * k;
+              Zs[tt * lds + i] = (t0 == t && tt == 0) ? zf[i] : g0[e];
+            }
+          }
+          DFM_SYNC();
+          wt_gemm(Zs, lds, 1, M, 1, k, len, k, k, [&](int m, int n, double v) { Zq[m * lds + n] = v; zpg[(size_t)(t0 + m) * k + n] = v; });
+          DFM_SYNC();
+          wt_gemm(Zq, lds, 1, C, 1, r, len, r, r, [&](int m, int a, double cz) {
+            const double ba = Bs[a * TTp + m], ga = ba - cz, zpa = Zq[m * lds + a], zfa = Zs[(m + 1) * lds + a];
+            double term = -2.0 * zpa * ba + zpa * (ba - ga) - ga * (zfa - zpa);
+            if (a == 0) { term += (double)ntv[t0 + m] * DFM_LOG2PI + slr[t0 + m] + ldS_ + qt[t0 + m]; src[t0 + m] = last_src; }
+            llp += -0.5 * term;
+          });
+        }
+        ll += block_sum(llp, red);
+        for (int e = DFM_TID; e < k; e += DFM_NT) zf[e] = zfg[(size_t)(t1 - 1) * k + e];
+        DFM_SYNC();
+        t = t1 - 1;
+        FS_T(1);
+        continue;
+      }
+    }
     if (frozen && !cchg) {
       // ---- frozen step: same Pp, L, S, Tm, Wm, Pf as period last_src; only the means move
       for (int i = DFM_TID; i < k; i += DFM_NT) { double s = 0.0; for (int l = 0; l < k; ++l) s += M[i + k * l] * zf[l]; tv[i] = s; }
@@ -292,6 +742,7 @@ __global__ void k_em_filter_smooth(const double* __restrict__ Aall, const double
       }
       for (int e = DFM_TID; e < k; e += DFM_NT) { zpg[(size_t)t * k + e] = zp[e]; zfg[(size_t)t * k + e] = zf[e]; }
       DFM_SYNC();
+      FS_T(2);
       continue;
     }
     frozen = 0;
@@ -300,55 +751,66 @@ __global__ void k_em_filter_smooth(const double* __restrict__ Aall, const double
       for (int e = DFM_TID; e < k; e += DFM_NT) zp[e] = 0.0;
       DFM_SYNC();
     } else {
+      // P_{t|t-1} = M Pf M' + Q through the companion structure:  AP = M[0:r,:] Pf  (r x k, in Wm), then
+      //   [0:r,0:r] = AP M[0:r,:]' + Q,  [0:r, r:] = AP[:, 0:k-r],  [r:, r:] = Pf[0:k-r, 0:k-r]
       for (int e = DFM_TID; e < kk; e += DFM_NT) T3[e] = Pp[e];                 // previous P_{t|t-1}: freeze test below
-      bm_gemm(T1, k, M, k, false, Pf, k, false, k, k, k, 1.0, 0.0);            // M Pf
-      bm_gemm(Pp, k, T1, k, false, M, k, true, k, k, k, 1.0, 0.0);             // (M Pf) M'
-      for (int e = DFM_TID; e < rr; e += DFM_NT) { int i = e % r, j = e / r; Pp[i + k * j] += Q[e]; }
+      wt_gemm(M, 1, k, Pf, k, 1, r, k, k, [&](int a, int j, double v) { Wm[a + r * j] = v; });        // AP = M[0:r,:] Pf
       for (int i = DFM_TID; i < k; i += DFM_NT) { double s = 0.0; for (int l = 0; l < k; ++l) s += M[i + k * l] * zf[l]; tv[i] = s; }
       DFM_SYNC();
-      bm_symmetrize(Pp, k, k);
+      wt_gemm(Wm, 1, r, M, 1, k, r, r, k, [&](int i, int j, double v) { T1[i + k * j] = v + Q[i + r * j]; });   // AP M[0:r,:]' + Q
+      for (int e = DFM_TID; e < kk; e += DFM_NT) {
+        const int i = e % k, j = e / k;
+        if (i < j || i < r) continue;                                           // lower triangle below the top-left block
+        T1[e] = (j >= r) ? Pf[(i - r) + k * (j - r)] : Wm[j + r * (i - r)];
+      }
+      DFM_SYNC();
+      // (only the lower triangle was formed; mirror it)
+      for (int e = DFM_TID; e < kk; e += DFM_NT) {
+        const int i = e % k, j = e / k;
+        Pp[e] = (i >= j) ? T1[e] : T1[j + k * i];
+      }
       for (int e = DFM_TID; e < k; e += DFM_NT) zp[e] = tv[e];
       DFM_SYNC();
     }
+    FS_T(10);
     for (int e = DFM_TID; e < rr; e += DFM_NT) { int i = e % r, j = e / r; L[e] = Pp[i + k * j]; }
+    for (int e = DFM_TID; e < rk; e += DFM_NT) { int j = e % k, a = e / k; Tm[e] = Pp[a + k * j]; }       // TmT[j + k a] = Pp[a, j]
     DFM_SYNC();
-    bm_chol(L, r, r, info);                                                     // Pff = L L'
+    FS_T(16);
+    bc_chol(L, r, r, dvL, info);                                                // Pff = L L'
+    FS_T(17);
     bm_gemm(T4, r, C, r, false, L, r, false, r, r, r, 1.0, 0.0);               // C L
     bm_gemm(S, r, L, r, true, T4, r, false, r, r, r, 1.0, 0.0);                // L' C L
     for (int e = DFM_TID; e < r; e += DFM_NT) S[e + r * e] += 1.0;
     DFM_SYNC();
     bm_symmetrize(S, r, r);
-    bm_chol(S, r, r, info);                                                     // S = Ls Ls'
-    for (int e = DFM_TID; e < rk; e += DFM_NT) { int i = e % r, j = e / r; Tm[e] = Pp[i + k * j]; }
+    FS_T(18);
+    bc_chol(S, r, r, dvS, info);                                                // S = Ls Ls'
+    bt_trsm_lower(L, r, r, dvL, Tm, k, k);                                      // TmT = (L^-1 Pp[0:r,:])'
+    FS_T(19);
+    for (int e = DFM_TID; e < rk; e += DFM_NT) Wm[e] = Tm[e];
     DFM_SYNC();
-    bm_trsm_lower(L, r, r, Tm, r, k);                                           // Tm = L^-1 Pp[0:r,:]
-    bm_copy(Wm, r, Tm, r, r, k);
-    bm_trsm_lower(S, r, r, Wm, r, k);                                           // Wm = Ls^-1 Tm
-    for (int e = DFM_TID; e < kk; e += DFM_NT) {                                // Pf = Pp - Tm'Tm + Wm'Wm
-      int i = e % k, j = e / k;
-      if (i < j) continue;
-      double s = 0.0;
-      for (int a = 0; a < r; ++a) s += Wm[a + r * i] * Wm[a + r * j] - Tm[a + r * i] * Tm[a + r * j];
-      double v = Pp[i + k * j] + s;
-      Pf[i + k * j] = v; Pf[j + k * i] = v;
-    }
+    bt_trsm_lower(S, r, r, dvS, Wm, k, k);                                      // WmT = (Ls^-1 Tm)'
+    FS_T(11);
+    // Pf = Pp - Tm'Tm + Wm'Wm  (both products on the same tile -> lane mapping: an element stays with one thread)
+    wt_gemm(Wm, 1, k, Wm, 1, k, k, k, r, [&](int i, int j, double v) { Pf[i + k * j] = Pp[i + k * j] + v; });
+    wt_gemm(Tm, 1, k, Tm, 1, k, k, k, r, [&](int i, int j, double v) { Pf[i + k * j] -= v; });
+    DFM_SYNC();
+    for (int e = DFM_TID; e < kk; e += DFM_NT) { int i = e % k, j = e / k; if (i < j) Pf[e] = Pf[j + k * i]; }
     for (int a = DFM_TID; a < r; a += DFM_NT) { double s = bt[a]; for (int c = 0; c < r; ++c) s -= C[a + r * c] * zp[c]; g[a] = s; }
     DFM_SYNC();
     for (int i = DFM_TID; i < k; i += DFM_NT) { double s = zp[i]; for (int a = 0; a < r; ++a) s += Pf[i + k * a] * g[a]; zf[i] = s; }
+    DFM_SYNC();
+    FS_T(12);
     if (DFM_TID == 0) {
       ldS = 0.0;
-      for (int a = 0; a < r; ++a) ldS += 2.0 * log(S[a + r * a]);
-      double quad = qt[t];
-      for (int a = 0; a < r; ++a) {
-        quad -= 2.0 * zp[a] * bt[a];
-        double cz = 0.0, pg = 0.0;
-        for (int c = 0; c < r; ++c) { cz += C[a + r * c] * zp[c]; pg += Pf[a + k * c] * g[c]; }
-        quad += zp[a] * cz - g[a] * pg;
-      }
+      for (int a = 0; a < r; ++a) ldS -= 2.0 * log(dvS[a]);
+      *ldS_sh = ldS;
+      double quad = qt[t];             // C zp = b - g and Pff g = (zf - zp)[0:r]: O(r), as in the frozen steps
+      for (int a = 0; a < r; ++a) quad += -2.0 * zp[a] * bt[a] + zp[a] * (bt[a] - g[a]) - g[a] * (zf[a] - zp[a]);
       ll += -0.5 * ((double)ntv[t] * DFM_LOG2PI + slr[t] + ldS + quad);
       src[t] = t;
     }
-    DFM_SYNC();
     for (int e = DFM_TID; e < kk; e += DFM_NT) { Ppg[(size_t)t * kk + e] = Pp[e]; Pfg[(size_t)t * kk + e] = Pf[e]; }
     for (int e = DFM_TID; e < k; e += DFM_NT) { zpg[(size_t)t * k + e] = zp[e]; zfg[(size_t)t * k + e] = zf[e]; }
     last_src = t;
@@ -359,6 +821,7 @@ __global__ void k_em_filter_smooth(const double* __restrict__ Aall, const double
       frozen = (dm <= 1e-14 * pm) ? 1 : 0;
     }
     DFM_SYNC();
+    FS_T(13); FS_CNT(8);
   }
 #ifdef DFM_EMU
   if (getenv("DFM_DEBUG_FREEZE")) { int nf = 0; for (int t = 0; t < T; ++t) nf += (src[t] != t); printf("[freeze] b=%d T=%d k=%d frozen forward steps %d\n", b, T, k, nf); }
@@ -374,32 +837,155 @@ __global__ void k_em_filter_smooth(const double* __restrict__ Aall, const double
     SffA[e] = zsn[a] * zsn[c] + Psn[a + k * c];
   }
   DFM_SYNC();
-  int jpp = -1, jpf = -1, ps_frozen = 0;           // periods whose covariances built the gain in T3; smoothed covariance frozen?
+  int jpp = -1, jpf = -1, ps_frozen = 0;           // periods whose covariances built the gain J in T3; smoothed covariance frozen?
+  int brun_known = T;                              // backward runs: no search above this period (a shorter run is in progress)
   for (int t = T - 2; t >= 0; --t) {
     const int sp = src[t + 1], sf = src[t];
     const bool newJ = (sp != jpp) || (sf != jpf);
     if (newJ) ps_frozen = 0;
+    if (!newJ && ps_frozen && jpp == jpf && t <= brun_known) {
+      // ---- frozen backward run: every period down to tl uses the gain in T3 and the smoothed covariance in Ps
+      if (DFM_TID == 0) info[1] = -1;
+      DFM_SYNC();
+      for (int base_ = t - 1; base_ >= 0; base_ -= DFM_NT) {
+        const int tp = base_ - DFM_TID;
+        if (tp >= 0 && src[tp] != jpf) atomicMax(&info[1], tp);
+        DFM_SYNC();
+        const int v = info[1];
+        DFM_SYNC();
+        if (v >= 0) break;
+      }
+      const int tl = info[1] + 1, Lr = t - tl + 1;
+      brun_known = tl - 1;
+#ifdef DFM_EMU
+      if (getenv("DFM_DEBUG_FREEZE")) printf("[run bwd] b=%d t=%d tl=%d\n", b, t, tl);
+#endif
+      if (Lr >= EM_RUN_MIN) {
+        // zs_t = J zs_{t+1} + v_t,  v_t = zf_t - J zp_{t+1}   (J is in T3)
+        const int lds = em_lds(k);
+        double* Zq = stg;                              // [TT][lds]      zp_{t0+1} .. zp_{t0+len}
+        for (int t0 = tl; t0 <= t; t0 += TT) {
+          const int len = (t - t0 + 1 < TT) ? t - t0 + 1 : TT;
+          DFM_SYNC();
+          {
+            const double* g0 = zpg + (size_t)(t0 + 1) * k;
+#pragma unroll 4
+            for (int e = DFM_TID; e < len * k; e += DFM_NT) { const int tt = e / k, i = e - tt * k; Zq[tt * lds + i] = g0[e]; }
+          }
+          DFM_SYNC();
+          wt_gemm(Zq, lds, 1, T3, 1, k, len, k, k, [&](int m, int n, double v) { zfg[(size_t)(t0 + m) * k + n] -= v; });
+        }
+        DFM_SYNC();
+        FS_T(24);
+        em_run_scan(zfg, k, t, Lr, -1, T3, zsn, T1, Pf, T2, wb);                 // (T1, Pf, T2 are free here; zfg now holds zs_t)
+        FS_T(25);
+        // Gram sums of the smoothed means: S00 (k x k), S11 (r x k) as DMMA products over tiles of zs rows staged in shared
+        // memory; a warp's output tiles stay in registers over the tiles of the run
+        const double cnt = (double)Lr;
+        const int nt00 = ((k + 7) >> 3) * ((k + 7) >> 3), nt11 = ((r + 7) >> 3) * ((k + 7) >> 3);
+        double acc[EM_TQ][2];
+#pragma unroll
+        for (int q = 0; q < EM_TQ; ++q) { acc[q][0] = 0.0; acc[q][1] = 0.0; }
+#ifndef DFM_EMU
+        const bool in_regs = nt00 + nt11 <= EM_TQ * DFM_NWARP;
+#else
+        const bool in_regs = false;
+#endif
+        double* Zs = stg;                              // [TT + 1][lds]   zs_{t0} .. zs_{t0+len}
+        for (int t0 = tl; t0 <= t; t0 += TT) {
+          const int len = (t - t0 + 1 < TT) ? t - t0 + 1 : TT;
+          DFM_SYNC();
+          {
+            const double* g0 = zfg + (size_t)t0 * k;
+#pragma unroll 4
+            for (int e = DFM_TID; e < (len + 1) * k; e += DFM_NT) {
+              const int tt = e / k, i = e - tt * k;
+              Zs[tt * lds + i] = (t0 + tt > t) ? zsn[i] : g0[e];
+            }
+          }
+          DFM_SYNC();
+          for (int e = DFM_TID; e < r * len; e += DFM_NT) { const int a = e / len, tt = e - a * len; Fs[t0 + tt + (size_t)T * a] = Zs[tt * lds + a]; }
+          if (in_regs) {
+            wt_gemm_acc(Zs, 1, lds, Zs, 1, lds, k, k, len, 0, acc);                    // sum_t zs_t zs_t'
+            wt_gemm_acc(Zs + lds, 1, lds, Zs, 1, lds, r, k, len, nt00, acc);           // sum_t zs_{t+1}[0:r] zs_t'
+          } else {
+            for (int e = DFM_TID; e < kk + rk; e += DFM_NT) {                   // (emulation / very large k: plain sums)
+              double g0 = 0.0;
+              if (e < kk) {
+                const int i = e % k, j = e / k;
+                for (int tt = 0; tt < len; ++tt) g0 += Zs[tt * lds + i] * Zs[tt * lds + j];
+                S00[e] += g0;
+                if (i < r && j < r) { SffA[i + r * j] += g0; Sff2[i + r * j] += g0; }
+              } else { const int e2 = e - kk, i = e2 % r, j = e2 / r; for (int tt = 0; tt < len; ++tt) g0 += Zs[(tt + 1) * lds + i] * Zs[tt * lds + j]; S11[e2] += g0; }
+            }
+          }
+        }
+        DFM_SYNC();
+        FS_T(26);
+        // zs_tl (k) -> tv for the Sff2 correction; fold the register sums into the shared accumulators
+        for (int e = DFM_TID; e < k; e += DFM_NT) tv[e] = zfg[(size_t)tl * k + e];
+        if (in_regs) {
+          wt_acc_visit(k, k, 0, acc, [&](int i, int j, double v) {
+            S00[i + k * j] += v;
+            if (i < r && j < r) { SffA[i + r * j] += v; Sff2[i + r * j] += v; }            // r x r block of the same Gram sum
+          });
+          wt_acc_visit(r, k, nt00, acc, [&](int i, int j, double v) { S11[i + r * j] += v; });
+        }
+        DFM_SYNC();
+        for (int e = DFM_TID; e < rr; e += DFM_NT) {                            // (zsn: still the state that entered the run)
+          const int i = e % r, j = e / r;
+          SffA[e] += cnt * Ps[i + k * j];
+          Sff2[e] += cnt * Ps[i + k * j] - tv[i] * tv[j] + zsn[i] * zsn[j];
+        }
+        for (int e = DFM_TID; e < kk; e += DFM_NT) S00[e] += cnt * Ps[e];
+        for (int e = DFM_TID; e < rk; e += DFM_NT) S11[e] += cnt * Tm[e];
+        for (int a = 0, pe = 0; a < r; ++a)
+          for (int c = 0; c <= a; ++c, ++pe) {
+            const double v = Ps[a + k * c];
+            double* dst = PsF + (size_t)T * pe;
+            for (int tt = tl + DFM_TID; tt <= t; tt += DFM_NT) dst[tt] = v;
+          }
+        DFM_SYNC();
+        for (int e = DFM_TID; e < k; e += DFM_NT) zsn[e] = tv[e];
+        DFM_SYNC();
+        t = tl;
+        FS_T(4);
+        continue;
+      }
+    }
     for (int e = DFM_TID; e < k; e += DFM_NT) { zp[e] = zpg[(size_t)(t + 1) * k + e]; zf[e] = zfg[(size_t)t * k + e]; }
     if (!ps_frozen) for (int e = DFM_TID; e < kk; e += DFM_NT) { T1[e] = Ppg[(size_t)sp * kk + e]; Pf[e] = Pfg[(size_t)sf * kk + e]; }
     DFM_SYNC();
+    FS_T(14);
     if (newJ) {
-      bm_copy(T2, k, T1, k, k, k);
-      bm_chol(T2, k, k, info);                                                  // Pp(t+1) = Lp Lp'
-      bm_gemm(T3, k, M, k, false, Pf, k, false, k, k, k, 1.0, 0.0);            // M Pf(t)
-      bm_trsm_lower(T2, k, k, T3, k, k);
-      bm_trsm_lowerT(T2, k, k, T3, k, k);                                       // T3 = J' = Pp^-1 M Pf
+      // J = Pf M' Pp^-1, row by row:  T3 <- Pf M' (companion structure: columns >= r are a shift of Pf), T2 = chol(Pp) on
+      // warp 0 meanwhile, then  L y = x, L' z = y  on the rows of T3 (thread per row)
+      for (int e = DFM_TID; e < kk; e += DFM_NT) {
+        T2[e] = T1[e];
+        const int i = e % k, j = e / k;
+        if (j >= r) T3[e] = Pf[i + k * (j - r)];
+      }
+      wt_gemm(Pf, 1, k, M, 1, k, k, r, k, [&](int i, int j, double v) { T3[i + k * j] = v; });
+      DFM_SYNC();
+      bc_chol(T2, k, k, dvL, info);
+      FS_T(20);
+      bt_trsm_lower(T2, k, k, dvL, T3, k, k);
+      FS_T(21);
+      bt_trsm_lowerT(T2, k, k, dvL, T3, k, k);                                  // T3 = J
       jpp = sp; jpf = sf;
     }
+    FS_T(15);
     for (int e = DFM_TID; e < k; e += DFM_NT) dv[e] = zsn[e] - zp[e];
     if (!ps_frozen) for (int e = DFM_TID; e < kk; e += DFM_NT) T1[e] = Psn[e] - T1[e];     // D = Ps(t+1) - Pp(t+1)
     DFM_SYNC();
-    for (int i = DFM_TID; i < k; i += DFM_NT) { double s = zf[i]; for (int l = 0; l < k; ++l) s += T3[l + k * i] * dv[l]; zs[i] = s; }
+    for (int i = DFM_TID; i < k; i += DFM_NT) { double s = zf[i]; for (int l = 0; l < k; ++l) s += T3[i + k * l] * dv[l]; zs[i] = s; }
     if (!ps_frozen) {
-      bm_gemm(T2, k, T1, k, false, T3, k, false, k, k, k, 1.0, 0.0);           // D J'
-      bm_copy(Ps, k, Pf, k, k, k);
-      bm_gemm(Ps, k, T3, k, true, T2, k, false, k, k, k, 1.0, 1.0);            // Pf + J D J'
+      wt_gemm(T3, 1, k, T1, k, 1, k, k, k, [&](int i, int j, double v) { T2[i + k * j] = v; });           // J D
+      wt_gemm(Psn, 1, k, T3, 1, k, r, k, k, [&](int i, int j, double v) { Tm[i + r * j] = v; });          // Pc[0:r,:] = Ps(t+1)[0:r,:] J'
+      DFM_SYNC();
+      wt_gemm(T2, 1, k, T3, 1, k, k, k, k, [&](int i, int j, double v) { Ps[i + k * j] = Pf[i + k * j] + v; });   // Pf + (J D) J'
+      DFM_SYNC();
       bm_symmetrize(Ps, k, k);
-      bm_gemm(Tm, r, Psn, k, false, T3, k, false, r, k, k, 1.0, 0.0);          // Pc[0:r,:] = Ps(t+1)[0:r,:] J'
       if (!newJ) {                                                              // smoothed covariance at its steady state?
         double dm = 0.0, pm = 0.0;
         for (int e = DFM_TID; e < kk; e += DFM_NT) { dm = fmax(dm, fabs(Ps[e] - Psn[e])); pm = fmax(pm, fabs(Ps[e])); }
@@ -407,6 +993,7 @@ __global__ void k_em_filter_smooth(const double* __restrict__ Aall, const double
         ps_frozen = (dm <= 1e-14 * pm) ? 1 : 0;      // from the next period on: Ps = Psn, Tm as they are
       }
     } else DFM_SYNC();
+    FS_T(7);
     for (int e = DFM_TID; e < rk; e += DFM_NT) { int i = e % r, j = e / r; S11[e] += zsn[i] * zs[j] + Tm[e]; }
     for (int e = DFM_TID; e < kk; e += DFM_NT) { int i = e % k, j = e / k; S00[e] += zs[i] * zs[j] + Ps[e]; }
     for (int e = DFM_TID; e < rr; e += DFM_NT) {
@@ -420,25 +1007,27 @@ __global__ void k_em_filter_smooth(const double* __restrict__ Aall, const double
     for (int e = DFM_TID; e < kk; e += DFM_NT) Psn[e] = Ps[e];
     for (int e = DFM_TID; e < k; e += DFM_NT) zsn[e] = zs[e];
     DFM_SYNC();
+    FS_T(3); FS_CNT(9);
   }
   // ------------------------------------------------------------------ transition M-step
-  // A = S11 S00^-1 ;  Q = (Sff2 - A S11') / (T-1)
+  // A = S11 S00^-1 (row by row: S00 A[i,:]' = S11[i,:]') ;  Q = (Sff2 - A S11') / (T-1)
   bm_copy(T2, k, S00, k, k, k);
-  bm_chol(T2, k, k, info);
-  for (int e = DFM_TID; e < rk; e += DFM_NT) { int i = e % r, j = e / r; T3[j + k * i] = S11[e]; }   // S11' (k x r)
+  bc_chol(T2, k, k, dvL, info);
+  for (int e = DFM_TID; e < rk; e += DFM_NT) Wm[e] = S11[e];
   DFM_SYNC();
-  bm_trsm_lower(T2, k, k, T3, k, r);
-  bm_trsm_lowerT(T2, k, k, T3, k, r);                                           // T3 = A' (k x r)
+  bt_trsm_lower(T2, k, k, dvL, Wm, r, r);
+  bt_trsm_lowerT(T2, k, k, dvL, Wm, r, r);                                           // Wm = A (r x k)
   for (int e = DFM_TID; e < rr; e += DFM_NT) {
     int a = e % r, c = e / r;
     double s = Sff2[e];
-    for (int l = 0; l < k; ++l) s -= T3[l + k * a] * S11[c + r * l];           // (A S11')[a,c]
+    for (int l = 0; l < k; ++l) s -= Wm[a + r * l] * S11[c + r * l];           // (A S11')[a,c]
     T4[e] = s / (double)(T - 1);
   }
   DFM_SYNC();
   bm_symmetrize(T4, r, r);
-  for (int e = DFM_TID; e < rk; e += DFM_NT) { int i = e % r, j = e / r; Anew_[(size_t)b * rk + e] = T3[j + k * i]; }
+  for (int e = DFM_TID; e < rk; e += DFM_NT) Anew_[(size_t)b * rk + e] = Wm[e];
   for (int e = DFM_TID; e < rr; e += DFM_NT) { Qnew_[(size_t)b * rr + e] = T4[e]; SffAll_[(size_t)b * rr + e] = SffA[e]; }
+  FS_T(6);
   if (DFM_TID == 0) {
     int it = st[b].iters;
     loglik_[(size_t)b * max_iter + it] = ll;
@@ -452,10 +1041,11 @@ __global__ void k_em_filter_smooth(const double* __restrict__ Aall, const double
 // Lam_i = S_ff^(i)^-1 S_xf^(i);  R_i = (S_xx - 2 lam'S_xf + lam' S_ff lam) / T_i.   grid (N, B).
 __global__ void k_em_mstep_series(const double* __restrict__ Xall, const double* __restrict__ Fs_,
                                   const double* __restrict__ PsF_, const double* __restrict__ SffAll_, int T, int N,
-                                  int r, double* __restrict__ LamAll, double* __restrict__ Rall, EmState* st) {
+                                  int r, double* __restrict__ LamAll, double* __restrict__ Rall, EmState* st, int skip_bal) {
   DFM_SMEM(sm);
   int i = DFM_BX, b = DFM_BY;
   if (st[b].done) return;
+  if (skip_bal && !st[b].has_missing) return;                 // balanced panels: k_emb_mstep
   int np = r * (r + 1) / 2;
   double* Lam = LamAll + (size_t)b * N * r; double* R = Rall + (size_t)b * N;
   if (is_nan(Lam[i]) || is_nan(R[i])) return;         // excluded series stay excluded
@@ -509,6 +1099,14 @@ __global__ void k_em_count_active(const EmState* st, int B, int* out) {
   DFM_SMEM(sm);
   double n = 0.0;
   for (int b = DFM_TID; b < B; b += DFM_NT) n += st[b].done ? 0.0 : 1.0;
+  n = block_sum(n, sm);
+  if (DFM_TID == 0) *out = (int)n;
+}
+
+__global__ void k_em_count_missing(const EmState* st, int B, int* out) {
+  DFM_SMEM(sm);
+  double n = 0.0;
+  for (int b = DFM_TID; b < B; b += DFM_NT) n += st[b].has_missing ? 1.0 : 0.0;
   n = block_sum(n, sm);
   if (DFM_TID == 0) *out = (int)n;
 }

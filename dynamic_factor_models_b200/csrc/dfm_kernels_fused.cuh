@@ -18,20 +18,6 @@
 #pragma once
 #include "dfm_common.cuh"
 
-#ifdef DFM_EMU
-#define DFM_LANE 0
-#define DFM_WSZ 1
-#define DFM_WARP 0
-#define DFM_NWARP 1
-#define DFM_WSYNC() ((void)0)
-#else
-#define DFM_LANE ((int)(threadIdx.x & 31))
-#define DFM_WSZ 32
-#define DFM_WARP ((int)(threadIdx.x >> 5))
-#define DFM_NWARP ((int)(blockDim.x >> 5))
-#define DFM_WSYNC() __syncwarp()
-#endif
-
 namespace dfm {
 
 #define FZ 8   // number of state components kept in Z (= DMMA tile width)
