@@ -172,7 +172,7 @@ static int make_panel_tmap(dfm_handle* h, const double* X, int T, long long rows
   }
   cuuint64_t dims[2] = {(cuuint64_t)T, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)T * 8};
-  cuuint32_t box[2] = {F2_TS, 8}, es[2] = {1, 1};
+  cuuint32_t box[2] = {F2_TS, 8 * F2_SBS}, es[2] = {1, 1};
   CUresult rc = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)X, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (rc != CUDA_SUCCESS) { snprintf(h->err, sizeof(h->err), "cuTensorMapEncodeTiled failed (%d)", (int)rc); return DFM_ERR_CUDA; }
@@ -249,7 +249,7 @@ static int emb_launch_M(dfm_handle* h, const EmbPlan& e, const double* x, const 
 static int run_em_general(dfm_handle* h, const double* x, const dfm_em_opts* o, double* dL, double* dR, double* dA, double* dQ, double* dP0,
                           double* dAn, double* dQn, double* dW, double* dlogR, double* dC, double* dBt, double* dqt, double* dslr, int* dnt,
                           double* dCt, double* dzp, double* dzf, double* dPp, double* dPf, double* dFs, double* dPsF, double* dSff, double* dll,
-                          EmState* st, int* dit, int* dstat, int* active, int ntC, int nblkC, size_t smFS, int stgT, const EmbPlan& emb) {
+                          EmState* st, int* dit, int* dstat, int* active, int ntC, int nblkC, size_t smFS, int stgT, int want_psf, const EmbPlan& emb) {
   int T = o->T, N = o->N, r = o->r, p = o->p, batch = o->batch, mi = o->max_iter;
   int np = r * (r + 1) / 2;
   int* dsrc = dnt + (size_t)batch * T;
@@ -280,7 +280,7 @@ static int run_em_general(dfm_handle* h, const double* x, const dfm_em_opts* o, 
       }
     }
     L(k_em_filter_smooth, batch, 1, ntFS, smFS, dA, dQ, dP0, dC, dBt, dqt, dslr, dnt, dCt, T, r, p, dzp, dzf, dPp, dPf,
-      dFs, dPsF, dSff, dAn, dQn, dll, mi, o->tol, st, dsrc, stgT);
+      dFs, dPsF, dSff, dAn, dQn, dll, mi, o->tol, st, dsrc, stgT, want_psf);
     if (any_missing || !emb.on) L(k_em_mstep_series, N, batch, 64, (size_t)(2 * np + r + 8) * 8, x, dFs, dPsF, dSff, T, N, r, dL, dR, st, emb_on);
     if (any_bal && emb.on) {
       switch (emb.ncb) {
@@ -360,7 +360,7 @@ static bool als_masked_shape_ok(int T, int N, int r) {
 static bool als_fused2_shape_ok(int T, int N, int r) {
   if (r < 1 || r > 8 || T < 4 || (T & 1)) return false;
   return ((size_t)FZ * pad4mod16(T) + (size_t)r * pad4mod16(N) + (size_t)N + 4 * (size_t)r * r + 2 * r + 48 +
-          2 * F2_NCW * 72 + (size_t)F2_S * 8 * F2_TS + 32) * 8 <= 113 * 1024;
+          2 * F2_NCW * 72 + (size_t)F2_S * F2_STG + 32) * 8 <= 113 * 1024;
 }
 
 // resident CTAs (= panels processed concurrently) of the TMA fused EM kernel
@@ -388,7 +388,7 @@ static int fused2_capacity(int r, int T, int N) {
 static bool fused2_shape_ok(int T, int N, int r, int p) {
   if (p != 1 || r < 1 || r > 8 || T < 4 || (T & 1)) return false;
   size_t need = ((size_t)FZ * pad4mod16(T) + (size_t)r * pad4mod16(N) + 3 * (size_t)N + 30 * (size_t)r * r + 2 * (size_t)r +
-                 std::max((size_t)97 * r + (size_t)r * r, (size_t)2 * F2_NCW * 72) + (size_t)F2_S * 8 * F2_TS + 106) * 8;
+                 std::max((size_t)97 * r + (size_t)r * r, (size_t)2 * F2_NCW * 72) + (size_t)F2_S * F2_STG + 106) * 8;
   return need <= 113 * 1024;          // two CTAs per SM
 }
 
@@ -859,7 +859,7 @@ int dfm_em_kalman(dfm_handle* h, const double* X, const dfm_em_opts* o, const df
     return fail(h, DFM_ERR_ARG, "dfm_em_kalman: bad shape/options");
   // staging tile of the frozen-run phases of the filter / smoother: few panels -> large tiles (one CTA per SM anyway);
   // many panels -> the largest tile that still lets two CTAs share an SM, if any does
-  int stgT = (batch <= 148) ? 128 : 16;
+  int stgT = (batch <= 148) ? 256 : 16;
   {
     const size_t lim2 = 112 * 1024;
     if (batch <= 148) { while (stgT > 8 && em_fs_smem_doubles(r, p, stgT) * 8 > kMaxSmem) stgT /= 2; }
@@ -1057,7 +1057,7 @@ int dfm_em_kalman(dfm_handle* h, const double* X, const dfm_em_opts* o, const df
         if (!init->P0) L(k_lyapunov, batch, 1, 128, (size_t)(3 * kk + 8) * 8, dA, dQ, r, p, dP0, 12);
         { long long n = (long long)B * mi; L(k_fill, (int)std::min<long long>((n + 255) / 256, 1024), 1, 256, 0, dll, n, DFM_NAN); }
         rc = run_em_general(h, xg, o, dL, dR, dA, dQ, dP0, dAn, dQn, dW, dlogR, dC, dBt, dqt, dslr, dnt, dCt, dzp, dzf, dPp, dPf, dFs, dPsF, dSff, dll, st, dit,
-                            dstat, active, ntC, nblkC, smFS, stgT, emb);
+                            dstat, active, ntC, nblkC, smFS, stgT, out->PF ? 1 : 0, emb);
         if (rc) return rc;
         computed = true;
       }
@@ -1138,7 +1138,7 @@ int dfm_em_kalman(dfm_handle* h, const double* X, const dfm_em_opts* o, const df
 #endif
     } else {
       rc = run_em_general(h, x, o, dL, dR, dA, dQ, dP0, dAn, dQn, dW, dlogR, dC, dBt, dqt, dslr, dnt, dCt, dzp, dzf, dPp, dPf, dFs, dPsF, dSff, dll, st, dit,
-                          dstat, active, ntC, nblkC, smFS, stgT, emb);
+                          dstat, active, ntC, nblkC, smFS, stgT, out->PF ? 1 : 0, emb);
       if (rc) return rc;
     }
     }   // !computed

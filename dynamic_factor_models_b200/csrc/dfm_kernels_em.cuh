@@ -406,8 +406,164 @@ __host__ __device__ inline int em_lds(int k) { return k + ((12 - k % 8) % 8); } 
 #else
 #define EM_NOINLINE __noinline__
 #endif
+#ifndef DFM_EMU
+// Tensor-core variant of the run scan for k <= 32 and a large workspace (one CTA per SM configurations): 64 chunks, 8 per warp
+// on warps 0..7.  A warp advances its 8 chunk recursions together: the step  Z <- Phi Z + U  with Z = [k x 8 chunks] is
+// ceil(k/8) x ceil(k/4) DMMA.8x8x4 with the Phi fragments in registers and Z as the B operand from a [k][12] shared tile
+// (conflict-free); the u_t of later steps are pulled into L1 four steps ahead (prefetch.global.L1).  A step costs one
+// dependent DMMA chain (~ceil(k/4) x 26 cycles) instead of ~100 instructions per chunk, and the chains are 4x shorter
+// (64 chunks).  ws: >= 256 k doubles of shared workspace.
+#define EM_SC_NW 8
+#define EM_SC_ZS 12
+template <int MB>
+__device__ EM_NOINLINE void em_run_scan_tc(double* __restrict__ zg, int k, int t_first, int L, int dir, const double* Phi,
+                                           const double* z_in, double* Rp, double* base, double* tmp, double* ws) {
+  constexpr int KBX = 2 * MB, KR = 8 * MB;             // k-chunks and (zero padded) state rows of a warp's tile
+  const int NCH = 8 * EM_SC_NW;
+  const int Lc = (L + NCH - 1) / NCH;
+  FS_T0();
+  // Rp = Phi^Lc (binary powering on the tensor path; the three buffers rotate)
+  for (int e = DFM_TID; e < k * k; e += DFM_NT) { int i = e % k, j = e / k; Rp[e] = (i == j) ? 1.0 : 0.0; base[e] = Phi[e]; }
+  DFM_SYNC();
+  for (int ex = Lc; ex > 0; ex >>= 1) {
+    if (ex & 1) {
+      wt_gemm(Rp, 1, k, base, k, 1, k, k, k, [&](int i, int j, double v) { tmp[i + k * j] = v; });
+      DFM_SYNC();
+      double* sw = Rp; Rp = tmp; tmp = sw;
+    }
+    if (ex > 1) {
+      wt_gemm(base, 1, k, base, k, 1, k, k, k, [&](int i, int j, double v) { tmp[i + k * j] = v; });
+      DFM_SYNC();
+      double* sw = base; base = tmp; tmp = sw;
+    }
+  }
+  FS_T(27);
+  double* bnd = ws + (size_t)EM_SC_NW * 2 * KR * EM_SC_ZS;             // [64][k]: e_c, then in_c
+  const int lr = DFM_LANE >> 2, lc = DFM_LANE & 3, w = DFM_WARP;
+  for (int pass = 1; pass <= 2; ++pass) {
+    if (w < EM_SC_NW) {
+      double* cur = ws + (size_t)w * 2 * KR * EM_SC_ZS; double* nxt = cur + (size_t)KR * EM_SC_ZS;
+      double aP[MB][KBX];
+#pragma unroll
+      for (int mb = 0; mb < MB; ++mb)
+#pragma unroll
+        for (int kb = 0; kb < KBX; ++kb) {
+          const int i = mb * 8 + lr, l = kb * 4 + lc;
+          aP[mb][kb] = (i < k && l < k) ? Phi[i + k * l] : 0.0;
+        }
+      // this lane's two chunks (columns 2 lc, 2 lc + 1 of the warp's tile) and their first periods
+      const int cA = 8 * w + 2 * lc, cB = cA + 1;
+      const long long tA = (long long)t_first + (long long)dir * cA * Lc, tB = (long long)t_first + (long long)dir * cB * Lc;
+      const int lenA = (L - cA * Lc < Lc) ? ((L - cA * Lc > 0) ? L - cA * Lc : 0) : Lc;
+      const int lenB = (L - cB * Lc < Lc) ? ((L - cB * Lc > 0) ? L - cB * Lc : 0) : Lc;
+      const long long dk = (long long)dir * k;
+      bool rok[MB];
+#pragma unroll
+      for (int mb = 0; mb < MB; ++mb) rok[mb] = mb * 8 + lr < k;
+      for (int e = DFM_LANE; e < KR * 8; e += 32) {     // (rows >= k stay zero in both buffers: no bounds tests in the step)
+        const int i = e >> 3, n = e & 7;
+        cur[i * EM_SC_ZS + n] = (pass == 1 || i >= k) ? 0.0 : bnd[(size_t)(8 * w + n) * k + i];
+        nxt[i * EM_SC_ZS + n] = 0.0;
+      }
+      __syncwarp();
+      const double* pA = zg + tA * k + lr; const double* pB = zg + tB * k + lr;
+      for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int mb = 0; mb < MB; ++mb) {
+          if (rok[mb] && q < lenA) asm volatile("prefetch.global.L1 [%0];" ::"l"(pA + q * dk + mb * 8));
+          if (rok[mb] && q < lenB) asm volatile("prefetch.global.L1 [%0];" ::"l"(pB + q * dk + mb * 8));
+        }
+      }
+      for (int s_ = 0; s_ < Lc; ++s_) {
+        const bool okA = s_ < lenA, okB = s_ < lenB;
+        double* gA = const_cast<double*>(pA) + s_ * dk; double* gB = const_cast<double*>(pB) + s_ * dk;
+        double uA[MB], uB[MB];
+#pragma unroll
+        for (int mb = 0; mb < MB; ++mb) {
+          uA[mb] = (rok[mb] && okA) ? gA[mb * 8] : 0.0;
+          uB[mb] = (rok[mb] && okB) ? gB[mb * 8] : 0.0;
+        }
+        if (s_ + 4 < lenA) {
+#pragma unroll
+          for (int mb = 0; mb < MB; ++mb) if (rok[mb]) asm volatile("prefetch.global.L1 [%0];" ::"l"(gA + 4 * dk + mb * 8));
+        }
+        if (s_ + 4 < lenB) {
+#pragma unroll
+          for (int mb = 0; mb < MB; ++mb) if (rok[mb]) asm volatile("prefetch.global.L1 [%0];" ::"l"(gB + 4 * dk + mb * 8));
+        }
+        double d[MB][2];
+#pragma unroll
+        for (int mb = 0; mb < MB; ++mb) { d[mb][0] = 0.0; d[mb][1] = 0.0; }
+        double bz[KBX];
+#pragma unroll
+        for (int kb = 0; kb < KBX; ++kb) bz[kb] = cur[(kb * 4 + lc) * EM_SC_ZS + lr];
+#pragma unroll
+        for (int kb = 0; kb < KBX; ++kb)
+#pragma unroll
+          for (int mb = 0; mb < MB; ++mb) EM_DMMA(d[mb], aP[mb][kb], bz[kb]);
+#pragma unroll
+        for (int mb = 0; mb < MB; ++mb) {
+          const int i = mb * 8 + lr;
+          const double vA = d[mb][0] + uA[mb], vB = d[mb][1] + uB[mb];
+          nxt[i * EM_SC_ZS + 2 * lc] = vA; nxt[i * EM_SC_ZS + 2 * lc + 1] = vB;       // (rows >= k: 0 + 0)
+          if (pass == 2 && rok[mb]) {
+            if (okA) gA[mb * 8] = vA;
+            if (okB) gB[mb * 8] = vB;
+          }
+        }
+        __syncwarp();
+        double* sw = cur; cur = nxt; nxt = sw;
+      }
+      if (pass == 1)
+        for (int e = DFM_LANE; e < k * 8; e += 32) { const int i = e >> 3, n = e & 7; bnd[(size_t)(8 * w + n) * k + i] = cur[i * EM_SC_ZS + n]; }
+    }
+    DFM_SYNC();
+    FS_T(27 + pass);
+    if (pass == 1) {
+      // incoming states on warp 0: in_0 = z_in, in_{c+1} = Phi^Lc in_c + e_c  (row i of Phi^Lc in the registers of lane i,
+      // zero padded to 32 x 32 so that the step has no bounds tests; bnd[c] is overwritten by in_c)
+      if (w == 0) {
+        double* inc = ws;                               // 32 doubles (warp 0's idle tile)
+        const int i = DFM_LANE;
+        const bool iok = i < k;
+        double rw[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) rw[j] = (iok && j < k) ? Rp[i + k * j] : 0.0;
+        inc[i] = iok ? z_in[i] : 0.0;
+        __syncwarp();
+        for (int c = 0; c < NCH; ++c) {
+          double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) { a0 += rw[j] * inc[j]; a1 += rw[j + 1] * inc[j + 1]; a2 += rw[j + 2] * inc[j + 2]; a3 += rw[j + 3] * inc[j + 3]; }
+          const double ec = iok ? bnd[(size_t)c * k + i] : 0.0, ic = inc[i];
+          __syncwarp();
+          if (iok) bnd[(size_t)c * k + i] = ic;
+          inc[i] = ((a0 + a1) + (a2 + a3)) + ec;        // (lanes >= k: 0)
+          __syncwarp();
+        }
+      }
+      DFM_SYNC();
+      FS_T(30);
+    }
+  }
+}
+#endif
+
 __device__ EM_NOINLINE void em_run_scan(double* __restrict__ zg, int k, int t_first, int L, int dir, const double* Phi,
-                                   const double* z_in, double* Rp, double* base, double* tmp, double* wb) {
+                                   const double* z_in, double* Rp, double* base, double* tmp, double* wb, double* ws, int ws_doubles) {
+#ifndef DFM_EMU
+  if (k <= 32 && DFM_NWARP >= EM_SC_NW && ws_doubles >= EM_SC_NW * 2 * 8 * ((k + 7) >> 3) * EM_SC_ZS + 8 * EM_SC_NW * k && L >= 256) {
+    switch ((k + 7) >> 3) {
+      case 1: em_run_scan_tc<1>(zg, k, t_first, L, dir, Phi, z_in, Rp, base, tmp, ws); break;
+      case 2: em_run_scan_tc<2>(zg, k, t_first, L, dir, Phi, z_in, Rp, base, tmp, ws); break;
+      case 3: em_run_scan_tc<3>(zg, k, t_first, L, dir, Phi, z_in, Rp, base, tmp, ws); break;
+      default: em_run_scan_tc<4>(zg, k, t_first, L, dir, Phi, z_in, Rp, base, tmp, ws); break;
+    }
+    return;
+  }
+#else
+  (void)ws; (void)ws_doubles;
+#endif
   const int Lc = (L + EM_RUN_NCH - 1) / EM_RUN_NCH;
   FS_T0();
   // Rp = Phi^Lc
@@ -583,7 +739,7 @@ __global__ void EM_FS_BOUNDS k_em_filter_smooth(const double* __restrict__ Aall,
                                    double* __restrict__ Pf_, double* __restrict__ Fs_, double* __restrict__ PsF_,
                                    double* __restrict__ SffAll_, double* __restrict__ Anew_, double* __restrict__ Qnew_,
                                    double* __restrict__ loglik_, int max_iter, double tol, EmState* st, int* __restrict__ src_,
-                                   int stg_T) {
+                                   int stg_T, int want_psf) {
   DFM_SMEM(sm);
   int b = DFM_BX;
   if (st[b].done) return;
@@ -602,7 +758,8 @@ __global__ void EM_FS_BOUNDS k_em_filter_smooth(const double* __restrict__ Aall,
   double* red2 = red + 48;   // 80
   double* wb = red2 + 80;    // 3 * k * EM_RUN_NCH: scan workspace of the frozen runs
   double* stg = wb + 3 * k * EM_RUN_NCH;   // stg_T * (2k + r) + 2k: staging tiles of the frozen-run phases
-  double* dvL = stg + (size_t)r * (stg_T + 4) + (size_t)(2 * stg_T + 1) * em_lds(k) + 8;   // 1 / diag of the Cholesky factors: L (or Pp), S
+  const int stg_doubles = r * (stg_T + 4) + (2 * stg_T + 1) * em_lds(k) + 8;
+  double* dvL = stg + stg_doubles;   // 1 / diag of the Cholesky factors: L (or Pp), S
   double* dvS = dvL + 64;
   double* ldS_sh = red + 40; // log det of the last explicit step, for all threads
   int* src = src_ + (size_t)b * T;
@@ -616,6 +773,7 @@ __global__ void EM_FS_BOUNDS k_em_filter_smooth(const double* __restrict__ Aall,
   double* Fs = Fs_ + (size_t)b * T * r; double* PsF = PsF_ + (size_t)b * T * np;
   int hm = st[b].has_missing;
   const int TT = stg_T;
+  const bool psf = hm || want_psf;       // the smoothed covariances leave the kernel only if the M-step (missing data) or the caller needs them
   if (DFM_TID == 0) { info[0] = 0; info[1] = 0; info[2] = 0; info[3] = 0; }
   for (int e = DFM_TID; e < kk; e += DFM_NT) {
     int i = e % k, j = e / k;
@@ -688,7 +846,7 @@ __global__ void EM_FS_BOUNDS k_em_filter_smooth(const double* __restrict__ Aall,
         }
         DFM_SYNC();
         FS_T(22);
-        em_run_scan(zfg, k, t, Lr, +1, T1, zf, T2, T3, Psn, wb);                  // (T2, T3, Psn are free between explicit steps)
+        em_run_scan(zfg, k, t, Lr, +1, T1, zf, T2, T3, Psn, wb, stg, stg_doubles);                  // (T2, T3, Psn are free between explicit steps)
         FS_T(23);
         double llp = 0.0;
         const double ldS_ = *ldS_sh;
@@ -833,7 +991,7 @@ __global__ void EM_FS_BOUNDS k_em_filter_smooth(const double* __restrict__ Aall,
   for (int e = DFM_TID; e < r; e += DFM_NT) Fs[(T - 1) + (size_t)T * e] = zsn[e];
   for (int e = DFM_TID; e < rr; e += DFM_NT) {
     int a = e % r, c = e / r;
-    if (a >= c) PsF[(T - 1) + (size_t)T * pidx(a, c)] = Psn[a + k * c];
+    if (psf && a >= c) PsF[(T - 1) + (size_t)T * pidx(a, c)] = Psn[a + k * c];
     SffA[e] = zsn[a] * zsn[c] + Psn[a + k * c];
   }
   DFM_SYNC();
@@ -877,7 +1035,7 @@ __global__ void EM_FS_BOUNDS k_em_filter_smooth(const double* __restrict__ Aall,
         }
         DFM_SYNC();
         FS_T(24);
-        em_run_scan(zfg, k, t, Lr, -1, T3, zsn, T1, Pf, T2, wb);                 // (T1, Pf, T2 are free here; zfg now holds zs_t)
+        em_run_scan(zfg, k, t, Lr, -1, T3, zsn, T1, Pf, T2, wb, stg, stg_doubles);                 // (T1, Pf, T2 are free here; zfg now holds zs_t)
         FS_T(25);
         // Gram sums of the smoothed means: S00 (k x k), S11 (r x k) as DMMA products over tiles of zs rows staged in shared
         // memory; a warp's output tiles stay in registers over the tiles of the run
@@ -939,7 +1097,7 @@ __global__ void EM_FS_BOUNDS k_em_filter_smooth(const double* __restrict__ Aall,
         }
         for (int e = DFM_TID; e < kk; e += DFM_NT) S00[e] += cnt * Ps[e];
         for (int e = DFM_TID; e < rk; e += DFM_NT) S11[e] += cnt * Tm[e];
-        for (int a = 0, pe = 0; a < r; ++a)
+        if (psf) for (int a = 0, pe = 0; a < r; ++a)
           for (int c = 0; c <= a; ++c, ++pe) {
             const double v = Ps[a + k * c];
             double* dst = PsF + (size_t)T * pe;
@@ -1000,7 +1158,7 @@ __global__ void EM_FS_BOUNDS k_em_filter_smooth(const double* __restrict__ Aall,
       int a = e % r, c = e / r;
       Sff2[e] += zsn[a] * zsn[c] + Psn[a + k * c];
       SffA[e] += zs[a] * zs[c] + Ps[a + k * c];
-      if (a >= c) PsF[t + (size_t)T * pidx(a, c)] = Ps[a + k * c];
+      if (psf && a >= c) PsF[t + (size_t)T * pidx(a, c)] = Ps[a + k * c];
     }
     for (int e = DFM_TID; e < r; e += DFM_NT) Fs[t + (size_t)T * e] = zs[e];
     DFM_SYNC();

@@ -26,9 +26,13 @@ struct CUtensorMap { char opaque[128]; };
 
 namespace dfm {
 
+#ifndef F2_SBS
+#define F2_SBS 1        // 8-series blocks per stage (= per tensor-map copy): a copy costs ~400 cycles + bytes / 27 per CTA whatever
+#endif                  // its size (tools/bench_tma2d.cu), so wider stages raise the rate a single CTA can stream at
 #ifndef F2_S
-#define F2_S 4          // ring stages
+#define F2_S (4 / F2_SBS)   // ring stages (the ring keeps its size: F2_S * F2_SBS * 8 * F2_TS doubles)
 #endif
+#define F2_STG (F2_SBS * 8 * F2_TS)   // doubles per stage
 #ifndef F2_TC
 #define F2_TC 132       // periods per stage == row pitch in the ring; must be == 4 or 12 (mod 16) so that the
 #endif                  // DMMA fragment loads are bank-conflict free, and <= 256 (TMA box limit)
@@ -40,8 +44,8 @@ namespace dfm {
 #define F2_NKC (((F2_TC + 3) / 4 + F2_NCW - 1) / F2_NCW)   // 4-period DMMA k-chunks per consumer warp and stage (M pass)
 static_assert(F2_TC % 16 == 4 || F2_TC % 16 == 12, "ring pitch must be 4 or 12 mod 16");
 static_assert(F2_TC <= 256 && (F2_TC * 64) % 128 == 0, "TMA box / stage alignment");
-#define F2_NEXS(R_) ((F2_S * 8 * F2_TS - 4 * (R_) * (R_)) / FUSED_SCR(R_))   // the last 4 R^2 doubles of the idle ring hold scan matrices
-#define F2_RTAIL(R_) (F2_S * 8 * F2_TS - 4 * (R_) * (R_))
+#define F2_NEXS(R_) ((F2_S * F2_STG - 4 * (R_) * (R_)) / FUSED_SCR(R_))   // the last 4 R^2 doubles of the idle ring hold scan matrices
+#define F2_RTAIL(R_) (F2_S * F2_STG - 4 * (R_) * (R_))
 
 #ifndef DFM_EMU
 __device__ __forceinline__ uint32_t f2_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -76,15 +80,15 @@ struct F2Ring {
 // issue-bound (~115 cycles per request, serialised over the lanes of a warp: tools/bench_stream.cu).
 __device__ __forceinline__ void f2_produce(F2Ring& rg, const CUtensorMap* tmap, int row0, int T, int N, bool c_outer) {
   const int lane = threadIdx.x & 31;
-  const int nsb = (N + 7) / 8, nck = (T + F2_TC - 1) / F2_TC;
+  const int nsb = (N + 8 * F2_SBS - 1) / (8 * F2_SBS), nck = (T + F2_TC - 1) / F2_TC;      // (stages per pass: series-block groups x chunks)
   const int n_out = c_outer ? nck : nsb, n_in = c_outer ? nsb : nck;
   for (int o = 0; o < n_out; ++o)
     for (int i = 0; i < n_in; ++i) {
       const int c = c_outer ? o : i, sb = c_outer ? i : o;
       if (rg.wrap) f2_mbar_wait(&rg.empty[rg.rs], rg.rph ^ 1);
       if (lane == 0) {
-        f2_mbar_expect(&rg.full[rg.rs], (uint32_t)(8 * F2_TS * 8));
-        f2_tma_2d(rg.ring + (size_t)rg.rs * 8 * F2_TS, tmap, c * F2_TC, row0 + sb * 8, &rg.full[rg.rs]);
+        f2_mbar_expect(&rg.full[rg.rs], (uint32_t)(F2_STG * 8));
+        f2_tma_2d(rg.ring + (size_t)rg.rs * F2_STG, tmap, c * F2_TC, row0 + sb * 8 * F2_SBS, &rg.full[rg.rs]);
       }
       __syncwarp();
       rg.advance();
@@ -98,43 +102,48 @@ template <int R>
 __device__ __forceinline__ double f2_consume_E(F2Ring& rg, int cw, int T, int N, int Tp, int Np, double* Z, const double* Lam,
                                                const double* rinv) {
   const int lane = threadIdx.x & 31, lr = lane >> 2, lc = lane & 3;
-  const int nsb = (N + 7) / 8, nck = (T + F2_TC - 1) / F2_TC;
+  const int nsg = (N + 8 * F2_SBS - 1) / (8 * F2_SBS), nck = (T + F2_TC - 1) / F2_TC;
   double qacc = 0.0;
   for (int c = 0; c < nck; ++c) {
     const int len = (T - c * F2_TC < F2_TC) ? T - c * F2_TC : F2_TC;
     // row blocks cw, cw + NCW, ...: one independent accumulator pair per (row block, k half) so that no
-    // two DMMAs of a stage depend on each other (the chains only link consecutive stages)
+    // two DMMAs of a series block depend on each other (the chains only link consecutive series blocks)
     double d[F2_NRB][2][2];
 #pragma unroll
     for (int j = 0; j < F2_NRB; ++j) { d[j][0][0] = 0.0; d[j][0][1] = 0.0; d[j][1][0] = 0.0; d[j][1][1] = 0.0; }
-    for (int sb = 0; sb < nsb; ++sb) {
+    for (int sg = 0; sg < nsg; ++sg) {
       f2_mbar_wait(&rg.full[rg.rs], rg.rph);
-      const double* tile = rg.ring + (size_t)rg.rs * 8 * F2_TS;
-      // all fragment loads of the stage first (no branches in between: the warp issues in order, so a
-      // load placed after a DMMA would only start once that DMMA's operands had arrived), then the math
-      double rn[2], lm[2], av[2][F2_NRB];
+      const double* stage = rg.ring + (size_t)rg.rs * F2_STG;
 #pragma unroll
-      for (int kc = 0; kc < 2; ++kc) {
-        const int n = sb * 8 + kc * 4 + lc;
-        const bool nok = n < N;
-        rn[kc] = nok ? (rinv ? rinv[n] : 1.0) : 0.0;
-        lm[kc] = (nok && lr < R) ? Lam[LI(n, lr)] : 0.0;
-        const double* trow = tile + (kc * 4 + lc) * F2_TS + lr;
+      for (int sub = 0; sub < F2_SBS; ++sub) {
+        const double* tile = stage + (size_t)sub * 8 * F2_TS;
+        const int sb = sg * F2_SBS + sub;
+        // all fragment loads of the series block first (no branches in between: the warp issues in order, so a
+        // load placed after a DMMA would only start once that DMMA's operands had arrived), then the math
+        double rn[2], lm[2], av[2][F2_NRB];
 #pragma unroll
-        for (int j = 0; j < F2_NRB; ++j) {
-          const int t0 = (cw + j * F2_NCW) * 8;
-          av[kc][j] = (nok && t0 + lr < len) ? trow[t0] : 0.0;
+        for (int kc = 0; kc < 2; ++kc) {
+          const int n = sb * 8 + kc * 4 + lc;
+          const bool nok = n < N;
+          rn[kc] = nok ? (rinv ? rinv[n] : 1.0) : 0.0;
+          lm[kc] = (nok && lr < R) ? Lam[LI(n, lr)] : 0.0;
+          const double* trow = tile + (kc * 4 + lc) * F2_TS + lr;
+#pragma unroll
+          for (int j = 0; j < F2_NRB; ++j) {
+            const int t0 = (cw + j * F2_NCW) * 8;
+            av[kc][j] = (nok && t0 + lr < len) ? trow[t0] : 0.0;
+          }
         }
+#pragma unroll
+        for (int kc = 0; kc < 2; ++kc)
+#pragma unroll
+          for (int j = 0; j < F2_NRB; ++j) {
+            const double ar = av[kc][j] * rn[kc];
+            qacc += av[kc][j] * ar;
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                         : "+d"(d[j][kc][0]), "+d"(d[j][kc][1]) : "d"(ar), "d"(lm[kc]));
+          }
       }
-#pragma unroll
-      for (int kc = 0; kc < 2; ++kc)
-#pragma unroll
-        for (int j = 0; j < F2_NRB; ++j) {
-          const double ar = av[kc][j] * rn[kc];
-          qacc += av[kc][j] * ar;
-          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                       : "+d"(d[j][kc][0]), "+d"(d[j][kc][1]) : "d"(ar), "d"(lm[kc]));
-        }
       __syncwarp();
       if (lane == 0) f2_mbar_arrive(&rg.empty[rg.rs]);
       rg.advance();
@@ -155,56 +164,69 @@ template <int R>
 __device__ __forceinline__ void f2_consume_M(F2Ring& rg, int cw, int T, int N, int Tp, int Np, const double* Z, double* Lam,
                                              double* sxx, double* part) {
   const int lane = threadIdx.x & 31, lr = lane >> 2, lc = lane & 3;
-  const int nsb = (N + 7) / 8, nck = (T + F2_TC - 1) / F2_TC;
-  double d[F2_NKC][2], s2 = 0.0;                                  // one accumulator pair per k-chunk slot: independent DMMAs
+  const int nsg = (N + 8 * F2_SBS - 1) / (8 * F2_SBS), nck = (T + F2_TC - 1) / F2_TC;
+  // one accumulator pair per (series block of the stage, k-chunk slot): independent DMMAs
+  double d[F2_SBS][F2_NKC][2], s2[F2_SBS];
 #pragma unroll
-  for (int j = 0; j < F2_NKC; ++j) { d[j][0] = 0.0; d[j][1] = 0.0; }
-  for (int sb = 0; sb < nsb; ++sb)
+  for (int sub = 0; sub < F2_SBS; ++sub) {
+    s2[sub] = 0.0;
+#pragma unroll
+    for (int j = 0; j < F2_NKC; ++j) { d[sub][j][0] = 0.0; d[sub][j][1] = 0.0; }
+  }
+  for (int sg = 0; sg < nsg; ++sg)
     for (int c = 0; c < nck; ++c) {
       f2_mbar_wait(&rg.full[rg.rs], rg.rph);
-      const double* tile = rg.ring + (size_t)rg.rs * 8 * F2_TS;
+      const double* stage = rg.ring + (size_t)rg.rs * F2_STG;
       const int len = (T - c * F2_TC < F2_TC) ? T - c * F2_TC : F2_TC;
-      const bool nok = sb * 8 + lr < N;
       const double* zc = Z + (size_t)lr * Tp + c * F2_TC + lc;
-      const double* trow = tile + lr * F2_TS + lc;
-      double av[F2_NKC], bv[F2_NKC];                            // k-chunks cw, cw + NCW, ...: loads first, then the math
+      double bv[F2_NKC];                                         // Z fragments: shared by the series blocks of the stage
 #pragma unroll
-      for (int j = 0; j < F2_NKC; ++j) {
-        const int t0 = (cw + j * F2_NCW) * 4;
-        const bool tok = t0 + lc < len;
-        av[j] = (nok && tok) ? trow[t0] : 0.0;
-        bv[j] = tok ? zc[t0] : 0.0;
-      }
+      for (int j = 0; j < F2_NKC; ++j) { const int t0 = (cw + j * F2_NCW) * 4; bv[j] = (t0 + lc < len) ? zc[t0] : 0.0; }
 #pragma unroll
-      for (int j = 0; j < F2_NKC; ++j) {
-        s2 += av[j] * av[j];
-        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                     : "+d"(d[j][0]), "+d"(d[j][1]) : "d"(av[j]), "d"(bv[j]));
+      for (int sub = 0; sub < F2_SBS; ++sub) {
+        const bool nok = (sg * F2_SBS + sub) * 8 + lr < N;
+        const double* trow = stage + (size_t)sub * 8 * F2_TS + lr * F2_TS + lc;
+        double av[F2_NKC];                                       // k-chunks cw, cw + NCW, ...: loads first, then the math
+#pragma unroll
+        for (int j = 0; j < F2_NKC; ++j) { const int t0 = (cw + j * F2_NCW) * 4; av[j] = (nok && t0 + lc < len) ? trow[t0] : 0.0; }
+#pragma unroll
+        for (int j = 0; j < F2_NKC; ++j) {
+          s2[sub] += av[j] * av[j];
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                       : "+d"(d[sub][j][0]), "+d"(d[sub][j][1]) : "d"(av[j]), "d"(bv[j]));
+        }
       }
       __syncwarp();
       if (lane == 0) f2_mbar_arrive(&rg.empty[rg.rs]);
       rg.advance();
       if (c == nck - 1) {
-        s2 += __shfl_xor_sync(0xffffffffu, s2, 1); s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
-        double* pb = part + (size_t)(sb & 1) * F2_NCW * 72 + cw * 72;
-        double t0_ = 0.0, t1_ = 0.0;
+        // cross-warp reduction of the F2_NCW partial tiles, one series block after the other; buffer = block parity
+        // (a block's partials are rewritten two barriers later at the earliest)
 #pragma unroll
-        for (int j = 0; j < F2_NKC; ++j) { t0_ += d[j][0]; t1_ += d[j][1]; d[j][0] = 0.0; d[j][1] = 0.0; }
-        pb[2 * lane] = t0_; pb[2 * lane + 1] = t1_;
-        if (lc == 0) pb[64 + lr] = s2;
-        asm volatile("bar.sync 1, %0;" ::"n"(F2_NCW * 32) : "memory");
-        const int ct = cw * 32 + lane;                          // 0 .. F2_NCW*32-1
-        if (ct < 72) {
-          const double* pp_ = part + (size_t)(sb & 1) * F2_NCW * 72 + ct;
-          double tot_ = 0.0;
+        for (int sub = 0; sub < F2_SBS; ++sub) {
+          const int sb = sg * F2_SBS + sub;
+          double sq = s2[sub];
+          sq += __shfl_xor_sync(0xffffffffu, sq, 1); sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+          double* pb = part + (size_t)(sb & 1) * F2_NCW * 72 + cw * 72;
+          double t0_ = 0.0, t1_ = 0.0;
 #pragma unroll
-          for (int w_ = 0; w_ < F2_NCW; ++w_) tot_ += pp_[w_ * 72];
-          if (ct < 64) {
-            const int l_ = ct >> 1, h_ = ct & 1, row = l_ >> 2, col = 2 * (l_ & 3) + h_, n = sb * 8 + row;
-            if (n < N && col < R) Lam[LI(n, col)] = tot_;
-          } else { const int n = sb * 8 + (ct - 64); if (n < N) sxx[n] = tot_; }
+          for (int j = 0; j < F2_NKC; ++j) { t0_ += d[sub][j][0]; t1_ += d[sub][j][1]; d[sub][j][0] = 0.0; d[sub][j][1] = 0.0; }
+          pb[2 * lane] = t0_; pb[2 * lane + 1] = t1_;
+          if (lc == 0) pb[64 + lr] = sq;
+          asm volatile("bar.sync 1, %0;" ::"n"(F2_NCW * 32) : "memory");
+          const int ct = cw * 32 + lane;                          // 0 .. F2_NCW*32-1
+          if (ct < 72) {
+            const double* pp_ = part + (size_t)(sb & 1) * F2_NCW * 72 + ct;
+            double tot_ = 0.0;
+#pragma unroll
+            for (int w_ = 0; w_ < F2_NCW; ++w_) tot_ += pp_[w_ * 72];
+            if (ct < 64) {
+              const int l_ = ct >> 1, h_ = ct & 1, row = l_ >> 2, col = 2 * (l_ & 3) + h_, n = sb * 8 + row;
+              if (n < N && col < R) Lam[LI(n, col)] = tot_;
+            } else { const int n = sb * 8 + (ct - 64); if (n < N) sxx[n] = tot_; }
+          }
+          s2[sub] = 0.0;
         }
-        s2 = 0.0;
       }
     }
 }
@@ -548,7 +570,7 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
       {
         // TMA pass (see f2_produce / f2_consume_E): warp 0 produces, warps 1..6 consume, warp 7 runs the
         // data-independent covariance chain concurrently
-        const long long nitems = (long long)((N + 7) / 8) * ((T + F2_TC - 1) / F2_TC);
+        const long long nitems = (long long)((N + 8 * F2_SBS - 1) / (8 * F2_SBS)) * ((T + F2_TC - 1) / F2_TC);
         F2_ROLE_T0();
         if (DFM_WARP == 0) { f2_produce(rg, &tmap, b * N, T, N, /*c_outer=*/true); F2_ROLE_T1(14); }
         else if (DFM_WARP <= F2_NCW) { qacc += f2_consume_E<R>(rg, DFM_WARP - 1, T, N, Tp, Np, Z, Lam, rinv); if (DFM_WARP == 1) F2_ROLE_T1(15); }
@@ -841,7 +863,7 @@ __global__ void DFM_FUSED2_BOUNDS k_em_fused2(FusedArgs a, const DFM_GRID_CONSTA
         // async-proxy writes of the bulk copies
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
-        const long long nitems = (long long)((N + 7) / 8) * ((T + F2_TC - 1) / F2_TC);
+        const long long nitems = (long long)((N + 8 * F2_SBS - 1) / (8 * F2_SBS)) * ((T + F2_TC - 1) / F2_TC);
         F2_ROLE_T0();
         if (DFM_WARP == 0) { f2_produce(rg, &tmap, b * N, T, N, /*c_outer=*/false); F2_ROLE_T1(17); }
         else if (DFM_WARP <= F2_NCW) { f2_consume_M<R>(rg, DFM_WARP - 1, T, N, Tp, Np, Z, Lam, sxx, part); if (DFM_WARP == 1) F2_ROLE_T1(18); }
@@ -963,7 +985,7 @@ __global__ void DFM_FUSED2_BOUNDS k_als_fused2(AlsFusedArgs a, const DFM_GRID_CO
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
   F2Ring rg; rg.ring = ring; rg.full = fullb; rg.empty = emptyb; rg.rs = 0; rg.rph = 0; rg.wrap = false;
-  const long long nitems = (long long)((N + 7) / 8) * ((T + F2_TC - 1) / F2_TC);
+  const long long nitems = (long long)((N + 8 * F2_SBS - 1) / (8 * F2_SBS)) * ((T + F2_TC - 1) / F2_TC);
 #endif
   for (int b = DFM_BX; b < a.B; b += DFM_GX) {
     const double* X = a.Xs + (size_t)b * T * N;
@@ -1060,13 +1082,13 @@ __global__ void DFM_FUSED2_BOUNDS k_als_fused2(AlsFusedArgs a, const DFM_GRID_CO
 template <int R>
 inline size_t als_fused2_smem_doubles(int T, int N) {
   return (size_t)FZ * pad4mod16(T) + (size_t)R * pad4mod16(N) + (size_t)N + 4 * (size_t)R * R + 2 * R + 48 +
-         2 * F2_NCW * 72 + (size_t)F2_S * 8 * F2_TS + 26;
+         2 * F2_NCW * 72 + (size_t)F2_S * F2_STG + 26;
 }
 
 template <int R>
 inline size_t fused2_smem_doubles(int T, int N) {
   return (size_t)FZ * pad4mod16(T) + (size_t)R * pad4mod16(N) + 3 * (size_t)N + 30 * (size_t)R * R + 2 * R + 40 + 8 + 8 +
-         std::max((size_t)97 * R + (size_t)R * R, (size_t)2 * F2_NCW * 72) + (size_t)F2_S * 8 * F2_TS + 26;
+         std::max((size_t)97 * R + (size_t)R * R, (size_t)2 * F2_NCW * 72) + (size_t)F2_S * F2_STG + 26;
 }
 
 }  // namespace dfm
