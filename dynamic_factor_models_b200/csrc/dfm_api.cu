@@ -561,12 +561,21 @@ static int run_pca(dfm_handle* h, const double* dXs, int T, int N, int r, int ba
   int nmax = std::min(N, T);
   if (col_n) L(k_balanced_cols, batch, 1, 1, 0, col_n, T, N, bal_idx, nbal);
   else L(k_all_cols, batch, 1, 128, 0, N, bal_idx, nbal);
-  int gx = (int)std::min<long long>(((long long)nmax * nmax + 255) / 256, 4096);
-  L(k_gram, gx, batch, 256, 0, dXs, T, N, bal_idx, nbal, G, nmax);
-  if (nmax <= 64) L(k_jacobi, batch, 1, 256, (size_t)(nmax + 2 + 48) * 8, G, V, nbal, T, nmax, 60, (int*)nullptr);
+  if (getenv("DFM_OLD_GRAM")) {
+    int gx = (int)std::min<long long>(((long long)nmax * nmax + 255) / 256, 4096);
+    L(k_gram, gx, batch, 256, 0, dXs, T, N, bal_idx, nbal, G, nmax);
+  } else {
+    const int nb16 = (nmax + 15) / 16, nblocks = nb16 * (nb16 + 1) / 2;
+    L(k_gram_tc, (nblocks + 7) / 8, batch, 256, 0, dXs, T, N, bal_idx, nbal, G, nmax);
+  }
+  if (nmax <= 64) L(k_jacobi, batch, 1, 256, (size_t)(2 * nmax * nmax + 2 * (nmax + 3) + 48) * 8, G, V, nbal, T, nmax, 60, (int*)nullptr);
   else {
     int m = std::min(nmax, pca_block(r));
-    L(k_subspace_eig, batch, 1, 256, (size_t)(3 * m * m + 2 * m + 64) * 8, G, V, Ysub, nbal, T, nmax, r, m, 500, 1e-13, (int*)nullptr);
+    const size_t sm2 = subspace2_smem_doubles(nmax, m) * 8;
+    if (sm2 <= 110 * 1024 && !getenv("DFM_OLD_SUBSPACE")) {       // iterate in shared memory, products on the tensor path
+      DFM_SET_SMEM(k_subspace_eig2, sm2);
+      L(k_subspace_eig2, batch, 1, 256, sm2, G, V, nbal, T, nmax, r, m, 500, 1e-13, (int*)nullptr);
+    } else L(k_subspace_eig, batch, 1, 256, (size_t)(3 * m * m + 3 * m + 72) * 8, G, V, Ysub, nbal, T, nmax, r, m, 500, 1e-13, (int*)nullptr);
   }
   L(k_pca_finish, batch, 1, 128, (size_t)(r / 2 + 2 + 48 + N) * 8, dXs, T, N, bal_idx, nbal, G, V, nmax, r, dF, status, st);
   return DFM_OK;
@@ -825,6 +834,7 @@ int dfm_em_init_from_factors(dfm_handle* h, const double* Xs, const double* F, i
   if (smV > kMaxSmem) return fail(h, DFM_ERR_UNSUPPORTED, "r*p too large");
   CK(cudaSetDevice(h->device));
   size_t B = batch, TN = (size_t)T * N; int np = r * (r + 1) / 2;
+  EmbPlan embi = emb_plan(T, N, r, batch);
   for (int pass = 0; pass < 2; ++pass) {
     Arena a(pass ? h->ws : nullptr);
     double* dX = mem == DFM_MEM_HOST ? a.get<double>(B * TN) : nullptr;
@@ -832,14 +842,39 @@ int dfm_em_init_from_factors(dfm_handle* h, const double* Xs, const double* F, i
     double* dL = a.get<double>(B * N * r); double* dR = a.get<double>(B * N);
     double* dA = a.get<double>(B * r * k); double* dQ = a.get<double>(B * r * r); double* dres = a.get<double>(B * T * r);
     int* status = a.get<int>(B);
+    EmState* est = nullptr; int* miss = nullptr; double *dFtF = nullptr, *dWs = nullptr, *dlogRs = nullptr;
+    if (embi.on) {
+      est = a.get<EmState>(B); miss = a.get<int>(B); dFtF = a.get<double>(B * r * r); dWs = a.get<double>(B * N * r); dlogRs = a.get<double>(B * N);
+      embi.Spart = a.get<double>((size_t)embi.tsM * B * N * r); embi.sxxpart = a.get<double>((size_t)embi.tsM * B * N);
+      embi.Cpart = a.get<double>(B * embi.ntM * r * r); embi.counters = a.get<int>(B * (size_t)(embi.ntE + embi.ntM));
+    }
     if (!pass) { int rc = ensure_ws(h, a.off); if (rc) return rc; continue; }
     const double *x, *f;
     int rc = stage_in(h, Xs, dX, B * TN, mem, &x); if (rc) return rc;
     rc = stage_in(h, F, dFb, B * T * r, mem, &f); if (rc) return rc;
     CK(cudaMemsetAsync(status, 0, B * sizeof(int), h->stream));
     size_t smL = (size_t)(2 * np + 2 * r + 8) * 8;
+    if (embi.on) {
+      // balanced panels: Lam = (X'F)(F'F)^-1, R = ssr / T on the tensor-core M-step kernel (S_ff = F'F, no state covariance);
+      // panels with missing data keep the masked per-series regressions
+      CK(cudaMemsetAsync(est, 0, B * sizeof(EmState), h->stream));
+      CK(cudaMemsetAsync(miss, 0, B * sizeof(int), h->stream));
+      CK(cudaMemsetAsync(embi.counters, 0, sizeof(int) * B * (size_t)(embi.ntE + embi.ntM), h->stream));
+      CK(cudaMemsetAsync(dL, 0, B * N * r * sizeof(double), h->stream));
+      CK(cudaMemsetAsync(dR, 0, B * N * sizeof(double), h->stream));
+      L(k_emb_init_flags, N, batch, 64, 0, x, T, N, est, miss);
+      L(k_gram_small, batch, 1, 128, 0, f, T, r, dFtF, (const AlsState*)nullptr);
+      switch (embi.ncb) {
+        case 1: emb_launch_M<1>(h, embi, x, f, dFtF, T, N, r, batch, dL, dR, dWs, dlogRs, est); break;
+        case 2: emb_launch_M<2>(h, embi, x, f, dFtF, T, N, r, batch, dL, dR, dWs, dlogRs, est); break;
+        case 3: emb_launch_M<3>(h, embi, x, f, dFtF, T, N, r, batch, dL, dR, dWs, dlogRs, est); break;
+        default: emb_launch_M<4>(h, embi, x, f, dFtF, T, N, r, batch, dL, dR, dWs, dlogRs, est); break;
+      }
+      L(k_als_lambda, N, batch, 64, smL, x, f, T, N, r, 0, 2, dL, dR, (const double*)nullptr, 0, (const int*)nullptr,
+        (const double*)nullptr, (const double*)nullptr, (const double*)nullptr, (AlsState*)nullptr, (const int*)miss);
+    } else
     L(k_als_lambda, N, batch, 64, smL, x, f, T, N, r, 0, 2, dL, dR, (const double*)nullptr, 0, (const int*)nullptr,
-      (const double*)nullptr, (const double*)nullptr, (const double*)nullptr, (AlsState*)nullptr);
+      (const double*)nullptr, (const double*)nullptr, (const double*)nullptr, (AlsState*)nullptr, (const int*)nullptr);
     L(k_var, batch, 1, 128, smV, f, T, r, p, 0, 1, (double*)nullptr, dres, dQ, (double*)nullptr, (double*)nullptr,
       (double*)nullptr, dA, status);
     rc = copy_out(h, Lam, dL, B * N * r, mem); if (rc) return rc;

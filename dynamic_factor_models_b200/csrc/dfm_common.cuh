@@ -238,4 +238,185 @@ __device__ inline void bm_trsm_lowerT(const double* L, int ldl, int n, double* B
   DFM_SYNC();
 }
 
+// ================= fast reciprocals, block-cooperative Cholesky, transposed solves, tensor-core tile products =========
+// Reciprocal and reciprocal square root from the hardware seed (MUFU, ~2^-23) + two Newton steps: ~1 ulp, a fraction of
+// the latency of the correctly rounded division / sqrt sequences, which sit on the serial path of every Cholesky column.
+__device__ __forceinline__ double fast_rcp(double d) {
+#ifdef DFM_EMU
+  return 1.0 / d;
+#else
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  double e = fma(-d, y, 1.0); y = fma(y, e, y);
+  e = fma(-d, y, 1.0); y = fma(y, e, y);
+  e = fma(-d, y, 1.0); y = fma(y, e, y);
+  return y;
+#endif
+}
+__device__ __forceinline__ double fast_rsqrt(double d) {
+#ifdef DFM_EMU
+  return 1.0 / sqrt(d);
+#else
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  const double hd = 0.5 * d;
+  double e = fma(-hd * y, y, 0.5); y = fma(y, e, y);
+  e = fma(-hd * y, y, 0.5); y = fma(y, e, y);
+  e = fma(-hd * y, y, 0.5); y = fma(y, e, y);
+  return y;
+#endif
+}
+
+// Lower Cholesky of the n x n SPD matrix A (shared, column-major), block-cooperative, ONE barrier per column: columns stay
+// unscaled during the elimination (the trailing update multiplies by 1/d_j), warps take the trailing columns, lanes the
+// rows (conflict-free, no index arithmetic); one final pass scales column j by d_j^-1/2 and zeroes the upper triangle.
+// dinv (n doubles, shared) receives 1 / L_jj for the triangular solves.  *info = 1 on a non-positive pivot.
+__device__ inline void bc_chol(double* A, int ld, int n, double* dinv, int* info) {
+  for (int j = 0; j < n; ++j) {
+    double d = A[j + ld * j];                          // final after the updates of columns < j
+    if (!(d > 0.0)) { if (DFM_TID == 0) *info = 1; d = 1.0; }
+    const double di = fast_rcp(d);
+    if (DFM_TID == 0) dinv[j] = d;                     // (pivot; turned into 1 / L_jj below)
+    for (int c = j + 1 + DFM_WARP; c < n; c += DFM_NWARP) {
+      const double lc = A[c + ld * j] * di;
+      for (int i = c + DFM_LANE; i < n; i += DFM_WSZ) A[i + ld * c] -= A[i + ld * j] * lc;
+    }
+    DFM_SYNC();
+  }
+  for (int j = DFM_WARP; j < n; j += DFM_NWARP) {
+    const double rs = fast_rsqrt(dinv[j]);
+    for (int i = DFM_LANE; i < n; i += DFM_WSZ) {
+      if (i < j) A[i + ld * j] = 0.0;
+      else if (i == j) A[i + ld * j] = dinv[j] * rs;
+      else A[i + ld * j] *= rs;
+    }
+  }
+  DFM_SYNC();
+  for (int j = DFM_TID; j < n; j += DFM_NT) dinv[j] = fast_rsqrt(dinv[j]);
+  DFM_SYNC();
+}
+
+// Triangular solves on TRANSPOSED right-hand sides: XT is m x n (leading dimension ldx), ROW j of XT is the j-th right-hand
+// side and is overwritten by its solution.  One thread per row, no barriers inside: consecutive threads touch consecutive
+// addresses (conflict-free), the entries of L and 1 / L_aa (dinv) are warp-uniform broadcasts.
+__device__ inline void bt_trsm_lower(const double* L, int ldl, int n, const double* dinv, double* XT, int ldx, int m) {      // L y = x
+  for (int j = DFM_TID; j < m; j += DFM_NT)
+    for (int a = 0; a < n; ++a) {
+      double s0 = XT[j + ldx * a], s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      int c = 0;
+      for (; c + 3 < a; c += 4) {
+        s0 -= L[a + ldl * c] * XT[j + ldx * c]; s1 -= L[a + ldl * (c + 1)] * XT[j + ldx * (c + 1)];
+        s2 -= L[a + ldl * (c + 2)] * XT[j + ldx * (c + 2)]; s3 -= L[a + ldl * (c + 3)] * XT[j + ldx * (c + 3)];
+      }
+      for (; c < a; ++c) s0 -= L[a + ldl * c] * XT[j + ldx * c];
+      XT[j + ldx * a] = ((s0 + s1) + (s2 + s3)) * dinv[a];
+    }
+  DFM_SYNC();
+}
+__device__ inline void bt_trsm_lowerT(const double* L, int ldl, int n, const double* dinv, double* XT, int ldx, int m) {     // L' y = x
+  for (int j = DFM_TID; j < m; j += DFM_NT)
+    for (int a = n - 1; a >= 0; --a) {
+      double s0 = XT[j + ldx * a], s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      int c = a + 1;
+      for (; c + 3 < n; c += 4) {
+        s0 -= L[c + ldl * a] * XT[j + ldx * c]; s1 -= L[c + 1 + ldl * a] * XT[j + ldx * (c + 1)];
+        s2 -= L[c + 2 + ldl * a] * XT[j + ldx * (c + 2)]; s3 -= L[c + 3 + ldl * a] * XT[j + ldx * (c + 3)];
+      }
+      for (; c < n; ++c) s0 -= L[c + ldl * a] * XT[j + ldx * c];
+      XT[j + ldx * a] = ((s0 + s1) + (s2 + s3)) * dinv[a];
+    }
+  DFM_SYNC();
+}
+
+// Warp-tiled FP64 tensor-core product on shared-memory operands (mma.sync.m8n8k4.f64 -> DMMA.8x8x4):
+//   D(m, n) = sum_l A(m, l) B(n, l),   A(m, l) = As[m * sam + l * sal],   B(n, l) = Bs[n * sbn + l * sbl],   m < Mr, n < Nn, l < K.
+// The 8 x 8 output tiles are dealt to the warps round-robin; epi(m, n, value) is called once for every valid element.
+// A dot-product loop on shared-memory operands needs two 8-byte operand reads per multiply-add and is bound by the
+// shared-memory pipe (measured: the k x k products of the frozen-run phases); a DMMA needs two reads per 256 of them.
+#ifndef DFM_EMU
+#define EM_DMMA(d_, a_, b_) asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"((d_)[0]), "+d"((d_)[1]) : "d"(a_), "d"(b_))
+#endif
+template <class Epi>
+__device__ __forceinline__ void wt_gemm(const double* As, int sam, int sal, const double* Bs, int sbn, int sbl, int Mr, int Nn, int K, Epi epi) {
+#ifndef DFM_EMU
+  const int lr = DFM_LANE >> 2, lc = DFM_LANE & 3;
+  const int mt = (Mr + 7) >> 3, ntl = (Nn + 7) >> 3;
+  for (int tile = DFM_WARP; tile < mt * ntl; tile += DFM_NWARP) {
+    const int mb = tile % mt, nb = tile / mt;
+    const int m = mb * 8 + lr, n = nb * 8 + lr;
+    const bool mok = m < Mr, nok = n < Nn;
+    const double* ap = As + (size_t)(mok ? m : 0) * sam + (size_t)lc * sal;
+    const double* bp = Bs + (size_t)(nok ? n : 0) * sbn + (size_t)lc * sbl;
+    double d0[2] = {0.0, 0.0}, d1[2] = {0.0, 0.0};
+    int l0 = 0;
+    for (; l0 + 8 <= K; l0 += 8) {
+      const double a0 = mok ? ap[(size_t)l0 * sal] : 0.0, b0 = nok ? bp[(size_t)l0 * sbl] : 0.0;
+      const double a1 = mok ? ap[(size_t)(l0 + 4) * sal] : 0.0, b1 = nok ? bp[(size_t)(l0 + 4) * sbl] : 0.0;
+      EM_DMMA(d0, a0, b0); EM_DMMA(d1, a1, b1);
+    }
+    for (; l0 < K; l0 += 4) {
+      const bool lok = l0 + lc < K;
+      const double a0 = (mok && lok) ? ap[(size_t)l0 * sal] : 0.0, b0 = (nok && lok) ? bp[(size_t)l0 * sbl] : 0.0;
+      EM_DMMA(d0, a0, b0);
+    }
+    const int mo = mb * 8 + lr, no = nb * 8 + 2 * lc;
+    if (mo < Mr) { if (no < Nn) epi(mo, no, d0[0] + d1[0]); if (no + 1 < Nn) epi(mo, no + 1, d0[1] + d1[1]); }
+  }
+#else
+  for (int n = 0; n < Nn; ++n)
+    for (int m = 0; m < Mr; ++m) {
+      double v = 0.0;
+      for (int l = 0; l < K; ++l) v += As[(size_t)m * sam + (size_t)l * sal] * Bs[(size_t)n * sbn + (size_t)l * sbl];
+      epi(m, n, v);
+    }
+#endif
+}
+// Same product accumulated into per-warp register tiles that persist over several calls (the reduction dimension arrives
+// in pieces): tile index = warp + q * (number of warps), q < EM_TQ; acc[q] is the lane's pair of the tile's 8 x 8 block.
+#define EM_TQ 6
+__device__ __forceinline__ void wt_gemm_acc(const double* As, int sam, int sal, const double* Bs, int sbn, int sbl, int Mr, int Nn, int K,
+                                            int tile0, double (*acc)[2]) {
+#ifndef DFM_EMU
+  const int lr = DFM_LANE >> 2, lc = DFM_LANE & 3;
+  const int mt = (Mr + 7) >> 3, ntl = (Nn + 7) >> 3;
+#pragma unroll
+  for (int q = 0; q < EM_TQ; ++q) {
+    const int tile = DFM_WARP + q * DFM_NWARP - tile0;
+    if (tile >= 0 && tile < mt * ntl) {
+      const int mb = tile % mt, nb = tile / mt;
+      const int m = mb * 8 + lr, n = nb * 8 + lr;
+      const bool mok = m < Mr, nok = n < Nn;
+      const double* ap = As + (size_t)(mok ? m : 0) * sam + (size_t)lc * sal;
+      const double* bp = Bs + (size_t)(nok ? n : 0) * sbn + (size_t)lc * sbl;
+      for (int l0 = 0; l0 < K; l0 += 4) {
+        const bool lok = l0 + lc < K;
+        const double a0 = (mok && lok) ? ap[(size_t)l0 * sal] : 0.0, b0 = (nok && lok) ? bp[(size_t)l0 * sbl] : 0.0;
+        EM_DMMA(acc[q], a0, b0);
+      }
+    }
+  }
+#else
+  (void)As; (void)sam; (void)sal; (void)Bs; (void)sbn; (void)sbl; (void)Mr; (void)Nn; (void)K; (void)tile0; (void)acc;
+#endif
+}
+// visit the elements of the register tiles: f(q-th tile's (m, n), value)
+template <class F>
+__device__ __forceinline__ void wt_acc_visit(int Mr, int Nn, int tile0, double (*acc)[2], F f) {
+#ifndef DFM_EMU
+  const int lr = DFM_LANE >> 2, lc = DFM_LANE & 3;
+  const int mt = (Mr + 7) >> 3, ntl = (Nn + 7) >> 3;
+#pragma unroll
+  for (int q = 0; q < EM_TQ; ++q) {
+    const int tile = DFM_WARP + q * DFM_NWARP - tile0;
+    if (tile >= 0 && tile < mt * ntl) {
+      const int mo = (tile % mt) * 8 + lr, no = (tile / mt) * 8 + 2 * lc;
+      if (mo < Mr) { if (no < Nn) f(mo, no, acc[q][0]); if (no + 1 < Nn) f(mo, no + 1, acc[q][1]); }
+    }
+  }
+#else
+  (void)Mr; (void)Nn; (void)tile0; (void)acc; (void)f;
+#endif
+}
+__host__ __device__ inline int em_lds(int k) { return k + ((12 - k % 8) % 8); }      // row stride == 4 (mod 8): conflict-free fragments
+
 }  // namespace dfm

@@ -279,4 +279,13 @@ __global__ void k_emb_close(int N, int r, int p, int ntilesM, const double* __re
   }
 }
 
+// EM initialisation on the same machinery: per-panel flags (any NaN in the panel?) -> EmState.has_missing / an int copy.
+__global__ void k_emb_init_flags(const double* __restrict__ Xall, int T, int N, EmState* st, int* __restrict__ miss) {
+  const int i = DFM_BX, b = DFM_BY;
+  const double* x = Xall + ((size_t)b * N + i) * T;
+  int bad = 0;
+  for (int t = DFM_TID; t < T; t += DFM_NT) if (is_nan(x[t])) bad = 1;
+  if (bad) { st[b].has_missing = 1; miss[b] = 1; }       // benign race: all writers store 1
+}
+
 }  // namespace dfm

@@ -97,25 +97,102 @@ __global__ void k_gram(const double* __restrict__ Xs, int T, int N, const int* _
   }
 }
 
+// Gram matrix on the FP64 tensor path: one WARP per 16 x 16 block of the lower triangle (2 x 2 DMMA tiles: two A and two
+// B fragments per four DMMA.8x8x4), fragments straight from global memory -- a panel (<= 1 MB) is L2 resident and every
+// 32-byte sector a fragment load touches is used completely; the reduction runs over T (mode 0) or over the balanced
+// columns (mode 1).  grid (ceil(nblocks / 8), B), 256 threads, nblocks = nb16 (nb16 + 1) / 2 with nb16 = ceil(nmax / 16).
+// The scalar k_gram (one thread per entry, 2 T loads per entry) took 24.8 ms for the 1250-panel C5 shard.
+__global__ void k_gram_tc(const double* __restrict__ Xs, int T, int N, const int* __restrict__ bal_idx,
+                          const int* __restrict__ nbal, double* __restrict__ G, int nmax) {
+#ifndef DFM_EMU
+  const int b = DFM_BY;
+  const int nb = nbal[b];
+  const int mode = (nb <= T) ? 0 : 1;
+  const int n = mode ? T : nb, K = mode ? nb : T;
+  const int nb16 = (n + 15) >> 4;
+  const int blk = DFM_BX * DFM_NWARP + DFM_WARP;
+  if (blk >= nb16 * (nb16 + 1) / 2) return;
+  int bi = (int)((sqrt(8.0 * blk + 1.0) - 1.0) * 0.5);
+  while ((bi + 1) * (bi + 2) / 2 <= blk) ++bi;
+  while (bi * (bi + 1) / 2 > blk) --bi;
+  const int bj = blk - bi * (bi + 1) / 2;                 // bj <= bi
+  const double* X = Xs + (size_t)b * T * N;
+  const int* idx = bal_idx + (size_t)b * N;
+  double* g = G + (size_t)b * nmax * nmax;
+  const int lr = DFM_LANE >> 2, lc = DFM_LANE & 3;
+  const int r0 = bi * 16 + lr, r1 = r0 + 8, c0 = bj * 16 + lr, c1 = c0 + 8;
+  double d00[2] = {0.0, 0.0}, d01[2] = {0.0, 0.0}, d10[2] = {0.0, 0.0}, d11[2] = {0.0, 0.0};
+#define GR_DMMA(d_, a_, b_) asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"((d_)[0]), "+d"((d_)[1]) : "d"(a_), "d"(b_))
+  if (mode == 0) {
+    const double* pa0 = (r0 < n) ? X + (size_t)T * idx[r0] : nullptr; const double* pa1 = (r1 < n) ? X + (size_t)T * idx[r1] : nullptr;
+    const double* pb0 = (c0 < n) ? X + (size_t)T * idx[c0] : nullptr; const double* pb1 = (c1 < n) ? X + (size_t)T * idx[c1] : nullptr;
+#pragma unroll 4
+    for (int l0 = 0; l0 < K; l0 += 4) {
+      const int l = l0 + lc;
+      const bool lok = l < K;
+      const double a0 = (pa0 && lok) ? pa0[l] : 0.0, a1 = (pa1 && lok) ? pa1[l] : 0.0;
+      const double b0 = (pb0 && lok) ? pb0[l] : 0.0, b1 = (pb1 && lok) ? pb1[l] : 0.0;
+      GR_DMMA(d00, a0, b0); GR_DMMA(d01, a0, b1); GR_DMMA(d10, a1, b0); GR_DMMA(d11, a1, b1);
+    }
+  } else {
+#pragma unroll 4
+    for (int l0 = 0; l0 < K; l0 += 4) {
+      const int l = l0 + lc;
+      const double* col = (l < K) ? X + (size_t)T * idx[l] : nullptr;
+      const double a0 = (col && r0 < n) ? col[r0] : 0.0, a1 = (col && r1 < n) ? col[r1] : 0.0;
+      const double b0 = (col && c0 < n) ? col[c0] : 0.0, b1 = (col && c1 < n) ? col[c1] : 0.0;
+      GR_DMMA(d00, a0, b0); GR_DMMA(d01, a0, b1); GR_DMMA(d10, a1, b0); GR_DMMA(d11, a1, b1);
+    }
+  }
+#undef GR_DMMA
+  // element (row, col) of tile (ti, tj): row = bi*16 + 8 ti + lr, col = bj*16 + 8 tj + 2 lc (+1); lower triangle, mirrored
+  auto put = [&](int row, int col, double v) { if (row < n && col < n && row >= col) { g[row + (size_t)n * col] = v; g[col + (size_t)n * row] = v; } };
+  const int cc = bj * 16 + 2 * lc;
+  put(r0, cc, d00[0]); put(r0, cc + 1, d00[1]); put(r0, cc + 8, d01[0]); put(r0, cc + 9, d01[1]);
+  put(r1, cc, d10[0]); put(r1, cc + 1, d10[1]); put(r1, cc + 8, d11[0]); put(r1, cc + 9, d11[1]);
+#else
+  // emulation: plain sums (same entries)
+  int b = DFM_BY;
+  int nb = nbal[b];
+  int mode = (nb <= T) ? 0 : 1;
+  int n = mode ? T : nb;
+  if (DFM_BX != 0) return;
+  const double* X = Xs + (size_t)b * T * N;
+  const int* idx = bal_idx + (size_t)b * N;
+  double* g = G + (size_t)b * nmax * nmax;
+  for (int c = 0; c < n; ++c)
+    for (int a = c; a < n; ++a) {
+      double s = 0.0;
+      if (mode == 0) { const double* xa = X + (size_t)idx[a] * T; const double* xc = X + (size_t)idx[c] * T; for (int t = 0; t < T; ++t) s += xa[t] * xc[t]; }
+      else for (int j = 0; j < nb; ++j) { const double* col = X + (size_t)idx[j] * T; s += col[a] * col[c]; }
+      g[a + (size_t)n * c] = s; g[c + (size_t)n * a] = s;
+    }
+#endif
+}
+
 // Cyclic Jacobi eigen-solver core (round-robin parallel ordering) on an n x n symmetric matrix G with
 // leading dimension n (shared or global memory).  G is destroyed (diagonal = eigenvalues); V (n x n,
-// ld n) receives the eigenvectors in its columns.  cs: n+2 doubles, red: 40 doubles of shared scratch.
-// Block-cooperative; returns the number of sweeps.
+// ld n) receives the eigenvectors in its columns.  cs: 2 (n + 2) doubles, red: 40 doubles of shared scratch.
+// Block-cooperative; returns the number of sweeps.  Per round: the m/2 disjoint pairs and their rotations are tabulated
+// once (reciprocals / reciprocal square roots from the hardware seed), then applied with warp = pair, lane = column --
+// no index arithmetic in the element loops, three barriers per round.
 __device__ inline int jacobi_core(double* G, double* V, int n, double* cs, double* red, int max_sweeps) {
   int m = (n + 1) & ~1;                  // even number of players
+  int* pq = (int*)(cs + m + 2);          // [m/2][2] pair table of the round
   for (int e = DFM_TID; e < n * n; e += DFM_NT) { int i = e % n, j = e / n; V[i + (size_t)n * j] = (i == j) ? 1.0 : 0.0; }
   DFM_SYNC();
   int sweep = 0;
   for (; sweep < max_sweeps; ++sweep) {
     double off = 0.0, dg = 0.0;
-    for (int e = DFM_TID; e < n * n; e += DFM_NT) {
-      int i = e % n, j = e / n; double v = G[i + (size_t)n * j];
-      if (i > j) off += v * v; else if (i == j) dg += v * v;
-    }
+    for (int j = DFM_WARP; j < n; j += DFM_NWARP)
+      for (int i = DFM_LANE; i < n; i += DFM_WSZ) {
+        double v = G[i + (size_t)n * j];
+        if (i > j) off += v * v; else if (i == j) dg += v * v;
+      }
     off = block_sum(off, red); dg = block_sum(dg, red);
     if (off <= 1e-32 * dg) break;
     for (int s = 0; s < m - 1; ++s) {
-      // phase 1: rotation angles for the m/2 disjoint pairs of this round
+      // phase 1: pairs and rotation angles of this round
       for (int i = DFM_TID; i < m / 2; i += DFM_NT) {
         int j1 = i, j2 = m - 1 - i;
         int p = (j1 == 0) ? 0 : ((j1 - 1 + s) % (m - 1)) + 1;
@@ -124,44 +201,41 @@ __device__ inline int jacobi_core(double* G, double* V, int n, double* cs, doubl
         double c = 1.0, sn = 0.0;
         if (q < n) {
           double app = G[p + (size_t)n * p], aqq = G[q + (size_t)n * q], apq = G[p + (size_t)n * q];
-          if (fabs(apq) > 1e-300 && fabs(apq) > 1e-18 * sqrt(fabs(app * aqq))) {
-            double tau = (aqq - app) / (2.0 * apq);
-            double t = ((tau >= 0.0) ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-            c = 1.0 / sqrt(1.0 + t * t); sn = t * c;
+          if (fabs(apq) > 1e-300 && fabs(apq) * fabs(apq) > 1e-36 * fabs(app * aqq)) {
+            double tau = (aqq - app) * 0.5 * fast_rcp(apq);
+            double h = 1.0 + tau * tau;
+            double t = ((tau >= 0.0) ? 1.0 : -1.0) * fast_rcp(fabs(tau) + h * fast_rsqrt(h));
+            c = fast_rsqrt(1.0 + t * t); sn = t * c;
           }
-        }
-        cs[2 * i] = c; cs[2 * i + 1] = sn;
+        } else q = -1;
+        cs[2 * i] = c; cs[2 * i + 1] = sn; pq[2 * i] = p; pq[2 * i + 1] = q;
       }
       DFM_SYNC();
       // phase 2: G <- J' G  (rows p, q)
-      for (int e = DFM_TID; e < (m / 2) * n; e += DFM_NT) {
-        int i = e / n, j = e % n;
-        int j1 = i, j2 = m - 1 - i;
-        int p = (j1 == 0) ? 0 : ((j1 - 1 + s) % (m - 1)) + 1;
-        int q = (j2 == 0) ? 0 : ((j2 - 1 + s) % (m - 1)) + 1;
-        if (p > q) { int t_ = p; p = q; q = t_; }
-        if (q >= n) continue;
-        double c = cs[2 * i], sn = cs[2 * i + 1];
-        double gp = G[p + (size_t)n * j], gq = G[q + (size_t)n * j];
-        G[p + (size_t)n * j] = c * gp - sn * gq;
-        G[q + (size_t)n * j] = sn * gp + c * gq;
+      for (int i = DFM_WARP; i < m / 2; i += DFM_NWARP) {
+        const int p = pq[2 * i], q = pq[2 * i + 1];
+        if (q < 0) continue;
+        const double c = cs[2 * i], sn = cs[2 * i + 1];
+        for (int j = DFM_LANE; j < n; j += DFM_WSZ) {
+          double gp = G[p + (size_t)n * j], gq = G[q + (size_t)n * j];
+          G[p + (size_t)n * j] = c * gp - sn * gq;
+          G[q + (size_t)n * j] = sn * gp + c * gq;
+        }
       }
       DFM_SYNC();
       // phase 3: G <- G J, V <- V J  (columns p, q)
-      for (int e = DFM_TID; e < (m / 2) * n; e += DFM_NT) {
-        int i = e / n, j = e % n;
-        int j1 = i, j2 = m - 1 - i;
-        int p = (j1 == 0) ? 0 : ((j1 - 1 + s) % (m - 1)) + 1;
-        int q = (j2 == 0) ? 0 : ((j2 - 1 + s) % (m - 1)) + 1;
-        if (p > q) { int t_ = p; p = q; q = t_; }
-        if (q >= n) continue;
-        double c = cs[2 * i], sn = cs[2 * i + 1];
-        double gp = G[j + (size_t)n * p], gq = G[j + (size_t)n * q];
-        G[j + (size_t)n * p] = c * gp - sn * gq;
-        G[j + (size_t)n * q] = sn * gp + c * gq;
-        double vp = V[j + (size_t)n * p], vq = V[j + (size_t)n * q];
-        V[j + (size_t)n * p] = c * vp - sn * vq;
-        V[j + (size_t)n * q] = sn * vp + c * vq;
+      for (int i = DFM_WARP; i < m / 2; i += DFM_NWARP) {
+        const int p = pq[2 * i], q = pq[2 * i + 1];
+        if (q < 0) continue;
+        const double c = cs[2 * i], sn = cs[2 * i + 1];
+        for (int j = DFM_LANE; j < n; j += DFM_WSZ) {
+          double gp = G[j + (size_t)n * p], gq = G[j + (size_t)n * q];
+          G[j + (size_t)n * p] = c * gp - sn * gq;
+          G[j + (size_t)n * q] = sn * gp + c * gq;
+          double vp = V[j + (size_t)n * p], vq = V[j + (size_t)n * q];
+          V[j + (size_t)n * p] = c * vp - sn * vq;
+          V[j + (size_t)n * q] = sn * vp + c * vq;
+        }
       }
       DFM_SYNC();
     }
@@ -169,7 +243,8 @@ __device__ inline int jacobi_core(double* G, double* V, int n, double* cs, doubl
   return sweep;
 }
 
-// Direct Jacobi on the Gram matrix (small n).  grid (B), one block per panel.
+// Direct Jacobi on the Gram matrix (small n <= 64): the matrix and the eigenvector matrix live in shared memory for the
+// sweeps (copy in, rotate, copy out).  grid (B), one block per panel; shared 2 n^2 + 2 (n + 2) + 48 doubles.
 __global__ void k_jacobi(double* __restrict__ Gall, double* __restrict__ Vall, const int* __restrict__ nbal,
                          int T, int nmax, int max_sweeps, int* __restrict__ sweeps_out) {
   DFM_SMEM(sm);
@@ -179,7 +254,12 @@ __global__ void k_jacobi(double* __restrict__ Gall, double* __restrict__ Vall, c
   double* G = Gall + (size_t)b * nmax * nmax;
   double* V = Vall + (size_t)b * nmax * nmax;
   int m = (n + 1) & ~1;
-  int sw = jacobi_core(G, V, n, sm, sm + m + 2, max_sweeps);
+  double* Gs = sm; double* Vs = Gs + (size_t)n * n; double* cs = Vs + (size_t)n * n;
+  for (int e = DFM_TID; e < n * n; e += DFM_NT) Gs[e] = G[e];
+  DFM_SYNC();
+  int sw = jacobi_core(Gs, Vs, n, cs, cs + 2 * (m + 2), max_sweeps);
+  DFM_SYNC();
+  for (int e = DFM_TID; e < n * n; e += DFM_NT) { G[e] = Gs[e]; V[e] = Vs[e]; }
   if (DFM_TID == 0 && sweeps_out) sweeps_out[b] = sw;
 }
 
@@ -200,7 +280,7 @@ __global__ void k_subspace_eig(double* __restrict__ Gall, double* __restrict__ V
   double* G = Gall + (size_t)b * nmax * nmax;
   double* V = Vall + (size_t)b * nmax * nmax;           // n x m in the first m columns
   double* Y = Yall + (size_t)b * nmax * mmax;           // n x m
-  double* H = sm; double* W = H + m * m; double* S = W + m * m; double* cs = S + m * m; double* red = cs + m + 2;
+  double* H = sm; double* W = H + m * m; double* S = W + m * m; double* cs = S + m * m; double* red = cs + 2 * (m + 2);
   int* info = (int*)(red + 40);
   double* theta = red + 44;                              // m
   if (DFM_TID == 0) *info = 0;
@@ -311,6 +391,117 @@ __global__ void k_subspace_eig(double* __restrict__ Gall, double* __restrict__ V
   if (DFM_TID == 0 && iters_out) iters_out[b] = (res <= tol) ? it : -it;
 }
 
+// Shared-memory / tensor-core variant of k_subspace_eig for panels whose iterate fits shared memory (2 n m doubles):
+// the n x m iterate V and the product Y = G V stay in shared memory, every product (G V, V'V, V'Y, V W) is a DMMA tile
+// product (wt_gemm; G is read from L2), CholQR uses the block-cooperative Cholesky + transposed solves, and the
+// Rayleigh-Ritz step (Jacobi on the m x m projected matrix: the expensive, serial part) runs only every second cycle of
+// q = 3 products -- between them the subspace just keeps converging under orth(G^3 V).  Same results layout as
+// k_subspace_eig.  grid (B), 256 threads; shared 2 n ldv... see subspace2_smem_doubles.
+__host__ __device__ inline size_t subspace2_smem_doubles(int n, int m) {
+  return 2 * (size_t)em_lds(n) * m + 3 * (size_t)m * m + 2 * (m + 2) + 64 + 2 * m + 64;
+}
+__global__ void k_subspace_eig2(double* __restrict__ Gall, double* __restrict__ Vall, const int* __restrict__ nbal, int T,
+                                int nmax, int r, int mmax, int maxit, double tol, int* __restrict__ iters_out) {
+  DFM_SMEM(sm);
+  int b = DFM_BX;
+  int nb = nbal[b];
+  int n = (nb <= T) ? nb : T;
+  int m = (mmax < n) ? mmax : n;
+  const int ldv = em_lds(n);
+  const double* G = Gall + (size_t)b * nmax * nmax;
+  double* Vg = Vall + (size_t)b * nmax * nmax;          // result: n x m in the first m columns (ld n)
+  double* Gd = Gall + (size_t)b * nmax * nmax;
+  double* V = sm; double* Y = V + (size_t)ldv * m;
+  double* H = Y + (size_t)ldv * m; double* W = H + m * m; double* S = W + m * m; double* cs = S + m * m;
+  double* red = cs + 2 * (m + 2);                        // 40
+  int* info = (int*)(red + 40);
+  double* theta = red + 44;                              // m
+  double* dinv = theta + m;                              // m
+  double* perm = dinv + m;                               // m (as doubles)
+  if (DFM_TID == 0) *info = 0;
+  // deterministic start: V[i][j] = hash-based pseudo-random in (-1, 1)   (same start as k_subspace_eig)
+  for (int e = DFM_TID; e < n * m; e += DFM_NT) {
+    unsigned h = (unsigned)e * 2654435761u + 12345u; h ^= h >> 15; h *= 2246822519u; h ^= h >> 13; h *= 3266489917u; h ^= h >> 16;
+    V[(e % n) + (size_t)ldv * (e / n)] = (double)(h & 0xffffff) / 8388608.0 - 1.0;
+  }
+  DFM_SYNC();
+  int it = 0;
+  double res = 1.0;
+  for (; it < maxit; ++it) {
+    // ---- orthonormalise V (CholQR, twice): S = V'V = L L', V <- V L^-T  (row-wise transposed solve)
+    for (int pass = 0; pass < 2; ++pass) {
+      wt_gemm(V, ldv, 1, V, ldv, 1, m, m, n, [&](int a, int c, double v) { S[a + m * c] = v; });
+      DFM_SYNC();
+      bm_symmetrize(S, m, m);
+      bc_chol(S, m, m, dinv, info);
+      bt_trsm_lower(S, m, m, dinv, V, ldv, n);
+    }
+    const bool rr = (it & 1) == 1 || it + 1 >= maxit;    // Rayleigh-Ritz + convergence test every second cycle
+    // ---- Y = G V
+    wt_gemm(G, 1, n, V, ldv, 1, n, m, n, [&](int i, int j, double v) { Y[i + (size_t)ldv * j] = v; });
+    DFM_SYNC();
+    if (rr) {
+      wt_gemm(V, ldv, 1, Y, ldv, 1, m, m, n, [&](int a, int c, double v) { H[a + m * c] = v; });
+      DFM_SYNC();
+      bm_symmetrize(H, m, m);
+      jacobi_core(H, W, m, cs, red, 40);
+      if (DFM_TID == 0) {                                 // Ritz values in descending order
+        for (int j = 0; j < m; ++j) {
+          int best = -1; double bv = -1e300;
+          for (int i = 0; i < m; ++i) { bool used = false; for (int l = 0; l < j; ++l) if ((int)perm[l] == i) used = true;
+            if (!used && H[i + m * i] > bv) { bv = H[i + m * i]; best = i; } }
+          perm[j] = (double)best; theta[j] = bv;
+        }
+      }
+      DFM_SYNC();
+      for (int e = DFM_TID; e < m * m; e += DFM_NT) { const int c = e % m, j = e / m; S[e] = W[c + m * (int)perm[j]]; }   // permuted rotation
+      DFM_SYNC();
+      // rotate both V and Y into the Ritz basis: through H/W-sized scratch is impossible (n x m): rotate V into Y's place
+      // after Y has been rotated in place row by row?  -- simpler and cheap on the tensor path: V' = V S (into scratch = Y
+      // is busy), so: first Y <- Y S via a second buffer = V is busy too.  Use the identity Y S = G (V S): rotate V into Y,
+      // swap, and recompute Y = G V.
+      wt_gemm(V, 1, ldv, S, m, 1, n, m, m, [&](int i, int j, double v) { Y[i + (size_t)ldv * j] = v; });
+      DFM_SYNC();
+      { double* sw = V; V = Y; Y = sw; }
+      wt_gemm(G, 1, n, V, ldv, 1, n, m, n, [&](int i, int j, double v) { Y[i + (size_t)ldv * j] = v; });
+      DFM_SYNC();
+      // ---- residuals of the leading r pairs
+      double rmax = 0.0;
+      for (int j = 0; j < r; ++j) {
+        double s_ = 0.0;
+        for (int i = DFM_TID; i < n; i += DFM_NT) { double d = Y[i + (size_t)ldv * j] - theta[j] * V[i + (size_t)ldv * j]; s_ += d * d; }
+        s_ = block_sum(s_, red);
+        rmax = fmax(rmax, sqrt(s_));
+      }
+      res = rmax / fabs(theta[0]);
+      if (res <= tol) { ++it; break; }
+    }
+    // next iterate: V <- normalised G^3 V (Y = G V is there)
+    for (int q_ = 0; q_ < 3; ++q_) {
+      if (q_ > 0) {
+        wt_gemm(G, 1, n, V, ldv, 1, n, m, n, [&](int i, int j, double v) { Y[i + (size_t)ldv * j] = v; });
+        DFM_SYNC();
+      }
+      // rescale the columns (plain power steps grow like lambda^q): keeps the Gram matrix of CholQR well scaled
+      for (int j = DFM_WARP; j < m; j += DFM_NWARP) {
+        double s_ = 0.0;
+        for (int i = DFM_LANE; i < n; i += DFM_WSZ) s_ += Y[i + (size_t)ldv * j] * Y[i + (size_t)ldv * j];
+#ifndef DFM_EMU
+        for (int o = 16; o > 0; o >>= 1) s_ += __shfl_xor_sync(0xffffffffu, s_, o);
+#endif
+        const double sc_ = (s_ > 0.0) ? 1.0 / sqrt(s_) : 1.0;
+        for (int i = DFM_LANE; i < n; i += DFM_WSZ) V[i + (size_t)ldv * j] = Y[i + (size_t)ldv * j] * sc_;
+      }
+      DFM_SYNC();
+    }
+  }
+  // ---- leave results where k_pca_finish looks for them
+  for (int e = DFM_TID; e < n * m; e += DFM_NT) Vg[e] = V[(e % n) + (size_t)ldv * (e / n)];
+  DFM_SYNC();
+  for (int i = DFM_TID; i < n; i += DFM_NT) Gd[i + (size_t)n * i] = (i < m) ? theta[i] : -1e300;
+  if (DFM_TID == 0 && iters_out) iters_out[b] = (res <= tol) ? it : -it;
+}
+
 // Pick the r largest eigenpairs and form scores.  grid (B), one block.
 // mode 0: score_j = Xb v_j ; mode 1: score_j = u_j * sqrt(lambda_j).  Sign: the entry of largest
 // magnitude of the right singular vector v_j is made positive.
@@ -411,10 +602,11 @@ __global__ void k_als_lambda(const double* __restrict__ Xs, const double* __rest
                              int nt_min, int mode, double* __restrict__ Lam, double* __restrict__ out2,
                              const double* __restrict__ FtF, int n_constr, const int* __restrict__ c_index,
                              const double* __restrict__ c_R, const double* __restrict__ c_r,
-                             const double* __restrict__ xstd, AlsState* st) {
+                             const double* __restrict__ xstd, AlsState* st, const int* __restrict__ only_missing = nullptr) {
   DFM_SMEM(sm);
   int i = DFM_BX, b = DFM_BY;
   if (st && st[b].done && mode == 0) return;
+  if (only_missing && !only_missing[b]) return;          // (EM initialisation: balanced panels take k_emb_mstep)
   const double* x = Xs + ((size_t)b * N + i) * T;
   const double* F = Fall + (size_t)b * T * r;
   int np = r * (r + 1) / 2;
