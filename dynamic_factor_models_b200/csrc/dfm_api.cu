@@ -572,12 +572,17 @@ static int run_pca(dfm_handle* h, const double* dXs, int T, int N, int r, int ba
   else {
     int m = std::min(nmax, pca_block(r));
     const size_t sm2 = subspace2_smem_doubles(nmax, m) * 8;
-    if (sm2 <= 110 * 1024 && !getenv("DFM_OLD_SUBSPACE")) {       // iterate in shared memory, products on the tensor path
+    if (sm2 <= 110 * 1024 && m <= 48 && !getenv("DFM_OLD_SUBSPACE")) {       // iterate in shared memory, products on the tensor path
       DFM_SET_SMEM(k_subspace_eig2, sm2);
       L(k_subspace_eig2, batch, 1, 256, sm2, G, V, nbal, T, nmax, r, m, 500, 1e-13, (int*)nullptr);
     } else L(k_subspace_eig, batch, 1, 256, (size_t)(3 * m * m + 3 * m + 72) * 8, G, V, Ysub, nbal, T, nmax, r, m, 500, 1e-13, (int*)nullptr);
   }
-  L(k_pca_finish, batch, 1, 128, (size_t)(r / 2 + 2 + 48 + N) * 8, dXs, T, N, bal_idx, nbal, G, V, nmax, r, dF, status, st);
+  {
+    const size_t smF = (size_t)(r / 2 + 2 + 48 + N) * 8, smFast = (size_t)(r / 2 + 2 + 48) * 8 + (size_t)em_lds(nmax) * r * 8 + 64;
+    if (N <= T && r <= 48 && smFast <= 100 * 1024 && !getenv("DFM_OLD_PCAFIN"))
+      L(k_pca_finish, batch, 1, 256, std::max(smF, smFast), dXs, T, N, bal_idx, nbal, G, V, nmax, r, dF, status, st, 1);
+    else L(k_pca_finish, batch, 1, 128, smF, dXs, T, N, bal_idx, nbal, G, V, nmax, r, dF, status, st, 0);
+  }
   return DFM_OK;
 }
 

@@ -391,6 +391,66 @@ __global__ void k_subspace_eig(double* __restrict__ Gall, double* __restrict__ V
   if (DFM_TID == 0 && iters_out) iters_out[b] = (res <= tol) ? it : -it;
 }
 
+// Y (n x m, ld ldv, shared) = G (n x n, ld n, global: L2 resident) * V (n x m, ld ldv, shared) on the tensor path.  One warp per
+// 8-row block of Y: its A fragments (rows of G) are read straight from L2, EIGHT k-steps ahead of the DMMAs (a fragment
+// load from L2 takes ~500 cycles: two in flight, as in the generic tile product, leave the loop latency bound), and each
+// fragment feeds all ceil(m / 8) <= 6 column tiles, whose B fragments come conflict-free from the shared iterate.
+__device__ __forceinline__ void gv_product(const double* __restrict__ G, int n, const double* V, double* Y, int ldv, int m);
+// general form: Y (rows x m, ld ldy) = A (rows x K, element (i, l) at A[i + lda * l], global) * V (K x m, ld ldv, shared)
+__device__ __forceinline__ void av_product(const double* __restrict__ G, int rows, int K, size_t lda, const double* V, int ldv, double* Y,
+                                           size_t ldy, int m) {
+#ifndef DFM_EMU
+  const int lr = DFM_LANE >> 2, lc = DFM_LANE & 3;
+  const int n = K;
+  const int nrb = (rows + 7) >> 3, nct = (m + 7) >> 3;
+  for (int rb = DFM_WARP; rb < nrb; rb += DFM_NWARP) {
+    const int row = rb * 8 + lr;
+    const bool rok = row < rows;
+    const double* gp = G + (rok ? row : 0);
+    double d[6][2];
+#pragma unroll
+    for (int ct = 0; ct < 6; ++ct) { d[ct][0] = 0.0; d[ct][1] = 0.0; }
+    for (int l0 = 0; l0 < n; l0 += 32) {
+      double a[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { const int l = l0 + 4 * q + lc; a[q] = (rok && l < n) ? gp[lda * l] : 0.0; }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int l = l0 + 4 * q + lc;
+        const bool lok = l < n;
+#pragma unroll
+        for (int ct = 0; ct < 6; ++ct) {
+          if (ct < nct) {
+            const int col = ct * 8 + lr;
+            const double bz = (lok && col < m) ? V[l + (size_t)ldv * col] : 0.0;
+            EM_DMMA(d[ct], a[q], bz);
+          }
+        }
+      }
+    }
+    if (rok) {
+#pragma unroll
+      for (int ct = 0; ct < 6; ++ct) {
+        const int col = ct * 8 + 2 * lc;
+        if (col < m) Y[row + ldy * col] = d[ct][0];
+        if (col + 1 < m) Y[row + ldy * (col + 1)] = d[ct][1];
+      }
+    }
+  }
+#else
+  for (int j = 0; j < m; ++j)
+    for (int i = 0; i < rows; ++i) {
+      double v = 0.0;
+      for (int l = 0; l < K; ++l) v += G[i + lda * l] * V[l + (size_t)ldv * j];
+      Y[i + ldy * j] = v;
+    }
+#endif
+  DFM_SYNC();
+}
+__device__ __forceinline__ void gv_product(const double* __restrict__ G, int n, const double* V, double* Y, int ldv, int m) {
+  av_product(G, n, n, (size_t)n, V, ldv, Y, (size_t)ldv, m);
+}
+
 // Shared-memory / tensor-core variant of k_subspace_eig for panels whose iterate fits shared memory (2 n m doubles):
 // the n x m iterate V and the product Y = G V stay in shared memory, every product (G V, V'V, V'Y, V W) is a DMMA tile
 // product (wt_gemm; G is read from L2), CholQR uses the block-cooperative Cholesky + transposed solves, and the
@@ -438,8 +498,7 @@ __global__ void k_subspace_eig2(double* __restrict__ Gall, double* __restrict__ 
     }
     const bool rr = (it & 1) == 1 || it + 1 >= maxit;    // Rayleigh-Ritz + convergence test every second cycle
     // ---- Y = G V
-    wt_gemm(G, 1, n, V, ldv, 1, n, m, n, [&](int i, int j, double v) { Y[i + (size_t)ldv * j] = v; });
-    DFM_SYNC();
+    gv_product(G, n, V, Y, ldv, m);
     if (rr) {
       wt_gemm(V, ldv, 1, Y, ldv, 1, m, m, n, [&](int a, int c, double v) { H[a + m * c] = v; });
       DFM_SYNC();
@@ -463,8 +522,7 @@ __global__ void k_subspace_eig2(double* __restrict__ Gall, double* __restrict__ 
       wt_gemm(V, 1, ldv, S, m, 1, n, m, m, [&](int i, int j, double v) { Y[i + (size_t)ldv * j] = v; });
       DFM_SYNC();
       { double* sw = V; V = Y; Y = sw; }
-      wt_gemm(G, 1, n, V, ldv, 1, n, m, n, [&](int i, int j, double v) { Y[i + (size_t)ldv * j] = v; });
-      DFM_SYNC();
+      gv_product(G, n, V, Y, ldv, m);
       // ---- residuals of the leading r pairs
       double rmax = 0.0;
       for (int j = 0; j < r; ++j) {
@@ -479,8 +537,7 @@ __global__ void k_subspace_eig2(double* __restrict__ Gall, double* __restrict__ 
     // next iterate: V <- normalised G^3 V (Y = G V is there)
     for (int q_ = 0; q_ < 3; ++q_) {
       if (q_ > 0) {
-        wt_gemm(G, 1, n, V, ldv, 1, n, m, n, [&](int i, int j, double v) { Y[i + (size_t)ldv * j] = v; });
-        DFM_SYNC();
+        gv_product(G, n, V, Y, ldv, m);
       }
       // rescale the columns (plain power steps grow like lambda^q): keeps the Gram matrix of CholQR well scaled
       for (int j = DFM_WARP; j < m; j += DFM_NWARP) {
@@ -508,7 +565,7 @@ __global__ void k_subspace_eig2(double* __restrict__ Gall, double* __restrict__ 
 __global__ void k_pca_finish(const double* __restrict__ Xs, int T, int N, const int* __restrict__ bal_idx,
                              const int* __restrict__ nbal, const double* __restrict__ Gall,
                              const double* __restrict__ Vall, int nmax, int r, double* __restrict__ score,
-                             int* __restrict__ status, AlsState* st) {
+                             int* __restrict__ status, AlsState* st, int fast_smem = 0) {
   DFM_SMEM(sm);
   int b = DFM_BX;
   int nb = nbal[b];
@@ -536,6 +593,28 @@ __global__ void k_pca_finish(const double* __restrict__ Xs, int T, int N, const 
     }
   }
   DFM_SYNC();
+  if (mode == 0 && nb == N && r <= 48 && fast_smem) {
+    // every column is balanced (idx = identity): scores = X Vr on the tensor path, Vr = the r selected eigenvectors with
+    // their signs, staged in shared memory
+    double* Vr = vtmp;                                   // n x r, ld em_lds(n)
+    const int ldr = em_lds(n);
+    for (int j = DFM_WARP; j < r; j += DFM_NWARP) {
+      const double* v = V + (size_t)n * order[j];
+      double best = 0.0, sg = 1.0; int bi = n;           // largest |entry|, first index on ties (as the scalar path)
+      for (int i = DFM_LANE; i < n; i += DFM_WSZ) if (fabs(v[i]) > best) { best = fabs(v[i]); sg = (v[i] < 0) ? -1.0 : 1.0; bi = i; }
+#ifndef DFM_EMU
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o), os = __shfl_xor_sync(0xffffffffu, sg, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; sg = os; bi = oi; }
+      }
+#endif
+      for (int i = DFM_LANE; i < n; i += DFM_WSZ) Vr[i + (size_t)ldr * j] = sg * v[i];
+    }
+    DFM_SYNC();
+    av_product(X, T, n, (size_t)T, Vr, ldr, sc, (size_t)T, r);
+    return;
+  }
   for (int j = 0; j < r; ++j) {
     const double* v = V + (size_t)n * order[j];
     if (mode == 0) {
