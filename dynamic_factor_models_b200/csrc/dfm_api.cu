@@ -226,7 +226,7 @@ static EmbPlan emb_plan(int T, int N, int r, int batch) {
   e.tsM = (T + e.tper - 1) / e.tper;
   if ((long long)e.nsE * batch > 65535 || (long long)e.tsM * batch > 65535) { e.on = false; return e; }
   e.smE = ((size_t)e.ncb * 8 * emb_pad(e.nper) + e.nper + 48) * 8;
-  e.smM = ((size_t)2 * r * r + (size_t)EMB_TILE * (r + 1) + 48) * 8;
+  e.smM = ((size_t)2 * r * r + (size_t)2 * EMB_TILE * (r + 1) + 96) * 8;
   return e;
 }
 template <int NCB>
@@ -256,7 +256,11 @@ static int run_em_general(dfm_handle* h, const double* x, const dfm_em_opts* o, 
   const int ntFS = (batch <= 296) ? 512 : 256;     // few panels: more warps for the parallel frozen runs; many: two CTAs per SM
   L(k_em_state_init, batch, 1, 1, 0, st);
   L(k_em_scan, N, batch, 64, 0, x, dL, T, N, r, st);
-  L(k_em_prep, batch, 1, 128, 0, dL, dR, N, r, p, dW, dlogR, dC, dA, dAn, dQ, dQn, st, mi, 0, 0);
+  L(k_em_prep, batch, 1, 128, 0, dL, dR, N, r, p, dW, dlogR, dC, dA, dAn, dQ, dQn, st, mi, 0, emb.on ? 1 : 0);
+  if (emb.on) {
+    L(k_emb_cinit, emb.ntM, batch, 256, 0, dL, dW, N, r, emb.Cpart, st);
+    L(k_emb_close, batch, 1, 256, 0, N, r, p, emb.ntM, emb.Cpart, dC, dA, dAn, dQ, dQn, st, mi, 0);
+  }
   // how many panels have missing data?  (decides which contraction kernels are launched at all: one sync, before the loop)
   int n_missing = batch;
   if (emb.on) {
@@ -289,7 +293,7 @@ static int run_em_general(dfm_handle* h, const double* x, const dfm_em_opts* o, 
         case 3: emb_launch_M<3>(h, emb, x, dFs, dSff, T, N, r, batch, dL, dR, dW, dlogR, st); break;
         default: emb_launch_M<4>(h, emb, x, dFs, dSff, T, N, r, batch, dL, dR, dW, dlogR, st); break;
       }
-      L(k_emb_close, batch, 1, 128, 0, N, r, p, emb.ntM, emb.Cpart, dC, dA, dAn, dQ, dQn, st, mi);
+      L(k_emb_close, batch, 1, 256, 0, N, r, p, emb.ntM, emb.Cpart, dC, dA, dAn, dQ, dQn, st, mi, 1);
     }
     if (any_missing || !emb.on) L(k_em_prep, batch, 1, 128, 0, dL, dR, N, r, p, dW, dlogR, dC, dA, dAn, dQ, dQn, st, mi, 1, emb_on);
     if (o->tol > 0 && ((it & 3) == 3)) {

@@ -88,6 +88,7 @@ __global__ void k_em_prep(const double* __restrict__ LamAll, const double* __res
     if (use && !(R[i] > 0.0)) st[b].status = 3;
   }
   DFM_SYNC();
+  if (skip_bal && !st[b].has_missing) return;            // (initial call on the multi-CTA path: C comes from k_emb_cinit + k_emb_close)
   for (int e = DFM_TID; e < r * r; e += DFM_NT) {
     int a = e % r, c = e / r;
     if (a < c) continue;

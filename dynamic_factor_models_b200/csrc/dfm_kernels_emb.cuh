@@ -132,7 +132,7 @@ __global__ void k_emb_contract(const double* __restrict__ Xall, const double* __
 }
 
 // M contraction + measurement M-step.  grid (ceil(N/64), tsplit * B), 256 threads.
-// Shared: r*r + 64*(r+1) + 64 + 48 doubles.  Spart [tsplit][B][N x r], sxxpart [tsplit][B][N]; counters [B][ceil(N/64)].
+// Shared: 2 r*r + 2 * 64*(r+1) + 96 doubles.  Spart [tsplit][B][N x r], sxxpart [tsplit][B][N]; counters [B][ceil(N/64)].
 // Cpart [B][ceil(N/64)][r x r]: this tile's share of C = Lam' R^-1 Lam (summed by k_emb_close).
 template <int NCB>
 __global__ void k_emb_mstep(const double* __restrict__ Xall, const double* __restrict__ Fs_, const double* __restrict__ SffAll_,
@@ -211,26 +211,32 @@ __global__ void k_emb_mstep(const double* __restrict__ Xall, const double* __res
   for (int e = DFM_TID; e < r * r; e += DFM_NT) { S[e] = SffAll_[(size_t)b * r * r + e]; S0[e] = S[e]; }
   DFM_SYNC();
   bm_chol(S, r, r, &flag[1]);
+  // split partials -> shared memory (all threads, independent loads), then one thread per series for the r x r solve
+  double* sxf = lamt + EMB_TILE * (r + 1) + 48;          // [64][r + 1]: S_xf,i and S_xx,i
+  for (int e = DFM_TID; e < EMB_TILE * (r + 1); e += DFM_NT) {
+    const int il = e % EMB_TILE, a = e / EMB_TILE, i = tile * EMB_TILE + il;
+    double v = 0.0;
+    if (i < N) {
+      if (a < r) { for (int s2 = 0; s2 < tsplit; ++s2) v += Spart[((size_t)(s2 * Bn + b) * r + a) * N + i]; }
+      else for (int s2 = 0; s2 < tsplit; ++s2) v += sxxpart[(size_t)(s2 * Bn + b) * N + i];
+    }
+    sxf[(size_t)il * (r + 1) + a] = v;
+  }
+  DFM_SYNC();
   for (int il = DFM_TID; il < EMB_TILE; il += DFM_NT) {
     const int i = tile * EMB_TILE + il;
     double* li = lamt + (size_t)il * (r + 1);
+    const double* sx = sxf + (size_t)il * (r + 1);
     for (int a = 0; a <= r; ++a) li[a] = 0.0;
     if (i >= N || is_nan(Lam[i]) || is_nan(R[i])) continue;
-    double sxx = 0.0;
-    for (int s2 = 0; s2 < tsplit; ++s2) sxx += sxxpart[(size_t)(s2 * Bn + b) * N + i];
-    for (int a = 0; a < r; ++a) {
-      double v = 0.0;
-      for (int s2 = 0; s2 < tsplit; ++s2) v += Spart[((size_t)(s2 * Bn + b) * r + a) * N + i];
-      li[a] = v;
-    }
+    const double sxx = sx[r];
+    for (int a = 0; a < r; ++a) li[a] = sx[a];
     double q1 = 0.0, q2 = 0.0;
-    // L y = sxf ; L' lam = y   (y and lam overwrite li; sxf is re-read from the partial sums for q1)
+    // L y = sxf ; L' lam = y   (y and lam overwrite li)
     for (int a = 0; a < r; ++a) { double v = li[a]; for (int c = 0; c < a; ++c) v -= S[a + r * c] * li[c]; li[a] = v / S[a + r * a]; }
     for (int a = r - 1; a >= 0; --a) { double v = li[a]; for (int c = a + 1; c < r; ++c) v -= S[c + r * a] * li[c]; li[a] = v / S[a + r * a]; }
     for (int a = 0; a < r; ++a) {
-      double sxf = 0.0;
-      for (int s2 = 0; s2 < tsplit; ++s2) sxf += Spart[((size_t)(s2 * Bn + b) * r + a) * N + i];
-      q1 += li[a] * sxf;
+      q1 += li[a] * sx[a];
       double v = 0.0;
       for (int c = 0; c < r; ++c) v += S0[a + r * c] * li[c];
       q2 += li[a] * v;
@@ -257,12 +263,14 @@ __global__ void k_emb_mstep(const double* __restrict__ Xall, const double* __res
 // convergence (as k_em_prep does), and C = sum of the tiles' shares.  grid (B), 128 threads.
 __global__ void k_emb_close(int N, int r, int p, int ntilesM, const double* __restrict__ Cpart, double* __restrict__ Call,
                             double* __restrict__ A, const double* __restrict__ Anew, double* __restrict__ Q,
-                            const double* __restrict__ Qnew, EmState* st, int max_iter) {
+                            const double* __restrict__ Qnew, EmState* st, int max_iter, int commit) {
   const int b = DFM_BX;
   if (st[b].done || st[b].has_missing) return;
   const int rk = r * r * p, rr = r * r;
-  for (int e = DFM_TID; e < rk; e += DFM_NT) A[(size_t)b * rk + e] = Anew[(size_t)b * rk + e];
-  for (int e = DFM_TID; e < rr; e += DFM_NT) Q[(size_t)b * rr + e] = Qnew[(size_t)b * rr + e];
+  if (commit) {
+    for (int e = DFM_TID; e < rk; e += DFM_NT) A[(size_t)b * rk + e] = Anew[(size_t)b * rk + e];
+    for (int e = DFM_TID; e < rr; e += DFM_NT) Q[(size_t)b * rr + e] = Qnew[(size_t)b * rr + e];
+  }
   for (int e = DFM_TID; e < rr; e += DFM_NT) {
     double v = 0.0;
     for (int tl = 0; tl < ntilesM; ++tl) v += Cpart[((size_t)b * ntilesM + tl) * rr + e];
@@ -273,9 +281,24 @@ __global__ void k_emb_close(int N, int r, int p, int ntilesM, const double* __re
     const int a = e % r, c = e / r;
     if (a > c) Call[(size_t)b * rr + c + r * a] = Call[(size_t)b * rr + a + r * c];
   }
-  if (DFM_TID == 0) {
+  if (DFM_TID == 0 && commit) {
     st[b].iters += 1;
     if (st[b].conv_pending || st[b].iters >= max_iter || st[b].status == 3) st[b].done = 1;
+  }
+}
+
+// C = Lam' R^-1 Lam of the INITIAL parameters, tile by tile (the iterations get it from k_emb_mstep).  grid (ceil(N/64), B).
+__global__ void k_emb_cinit(const double* __restrict__ LamAll, const double* __restrict__ Wall, int N, int r,
+                            double* __restrict__ Cpart, const EmState* st) {
+  const int tile = DFM_BX, b = DFM_BY, ntiles = DFM_GX;
+  if (st[b].done || st[b].has_missing) return;
+  const double* Lam = LamAll + (size_t)b * N * r; const double* W = Wall + (size_t)b * N * r;
+  const int i0 = tile * EMB_TILE, i1 = (i0 + EMB_TILE < N) ? i0 + EMB_TILE : N;
+  for (int e = DFM_TID; e < r * r; e += DFM_NT) {
+    const int a = e % r, c = e / r;
+    double v = 0.0;
+    for (int i = i0; i < i1; ++i) { const double w = W[i + (size_t)N * a]; if (!is_nan(w)) v += w * Lam[i + (size_t)N * c]; }
+    Cpart[((size_t)b * ntiles + tile) * r * r + e] = v;
   }
 }
 
