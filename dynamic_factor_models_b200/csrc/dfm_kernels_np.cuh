@@ -460,7 +460,12 @@ __device__ __forceinline__ void gv_product(const double* __restrict__ G, int n, 
 __host__ __device__ inline size_t subspace2_smem_doubles(int n, int m) {
   return 2 * (size_t)em_lds(n) * m + 3 * (size_t)m * m + 2 * (m + 2) + 64 + 2 * m + 64;
 }
-__global__ void k_subspace_eig2(double* __restrict__ Gall, double* __restrict__ Vall, const int* __restrict__ nbal, int T,
+#ifdef DFM_EMU
+#define SUB2_BOUNDS
+#else
+#define SUB2_BOUNDS __launch_bounds__(256, 2)
+#endif
+__global__ void SUB2_BOUNDS k_subspace_eig2(double* __restrict__ Gall, double* __restrict__ Vall, const int* __restrict__ nbal, int T,
                                 int nmax, int r, int mmax, int maxit, double tol, int* __restrict__ iters_out) {
   DFM_SMEM(sm);
   int b = DFM_BX;
