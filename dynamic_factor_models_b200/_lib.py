@@ -173,8 +173,8 @@ class Library:
         self.lib.dfm_profile_enable(self.h, int(on))
 
     def fs_prof(self, on=1):
-        """Arm (on=1) / read the section timers of k_em_filter_smooth; returns the 48 totals accumulated so far."""
-        out = (C.c_double * 48)()
+        """Arm (on=1) / read the section timers of k_em_filter_smooth; returns the 64 totals accumulated so far."""
+        out = (C.c_double * 64)()
         self.check(self.lib.dfm_debug_fs_prof(self.h, int(on), out), "dfm_debug_fs_prof")
         return list(out)
 

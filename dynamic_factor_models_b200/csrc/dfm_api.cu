@@ -481,11 +481,16 @@ int dfm_debug_fs_prof(dfm_handle* h, int on, double* out) {
 #ifndef DFM_EMU
   if (!h) return DFM_ERR_ARG;
   CK(cudaStreamSynchronize(h->stream));
-  long long v[48];
-  if (out) { CK(cudaMemcpyFromSymbol(v, dfm::g_fs_prof, sizeof(v))); for (int i = 0; i < 48; ++i) out[i] = (double)v[i]; }
-  memset(v, 0, sizeof(v));
+  long long v[48], w[16];
+  if (out) {
+    CK(cudaMemcpyFromSymbol(v, dfm::g_fs_prof, sizeof(v))); for (int i = 0; i < 48; ++i) out[i] = (double)v[i];
+    CK(cudaMemcpyFromSymbol(w, dfm::g_sub_prof, sizeof(w))); for (int i = 0; i < 16; ++i) out[48 + i] = (double)w[i];
+  }
+  memset(v, 0, sizeof(v)); memset(w, 0, sizeof(w));
   CK(cudaMemcpyToSymbol(dfm::g_fs_prof, v, sizeof(v)));
   CK(cudaMemcpyToSymbol(dfm::g_fs_prof_on, &on, sizeof(int)));
+  CK(cudaMemcpyToSymbol(dfm::g_sub_prof, w, sizeof(w)));
+  CK(cudaMemcpyToSymbol(dfm::g_sub_prof_on, &on, sizeof(int)));
 #else
   (void)h; (void)on; (void)out;
 #endif
@@ -577,8 +582,11 @@ static int run_pca(dfm_handle* h, const double* dXs, int T, int N, int r, int ba
     int m = std::min(nmax, pca_block(r));
     const size_t sm2 = subspace2_smem_doubles(nmax, m) * 8;
     if (sm2 <= 110 * 1024 && m <= 48 && !getenv("DFM_OLD_SUBSPACE")) {       // iterate in shared memory, products on the tensor path
-      DFM_SET_SMEM(k_subspace_eig2, sm2);
-      L(k_subspace_eig2, batch, 1, 256, sm2, G, V, nbal, T, nmax, r, m, 500, 1e-13, (int*)nullptr);
+      // (one CTA per SM, to keep the resident panels' Gram matrices inside L2, measured slower than two: 15.1 vs 11.5 ms
+      //  for the C5 shard; DFM_SUB2_ONE=1 pads the shared-memory request for that experiment)
+      size_t sm2r = getenv("DFM_SUB2_ONE") ? std::max(sm2, (size_t)116 * 1024) : sm2;
+      DFM_SET_SMEM(k_subspace_eig2, sm2r);
+      L(k_subspace_eig2, batch, 1, 256, sm2r, G, V, nbal, T, nmax, r, m, 500, 1e-13, (int*)nullptr);
     } else L(k_subspace_eig, batch, 1, 256, (size_t)(3 * m * m + 3 * m + 72) * 8, G, V, Ysub, nbal, T, nmax, r, m, 500, 1e-13, (int*)nullptr);
   }
   {

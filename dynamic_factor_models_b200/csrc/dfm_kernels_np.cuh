@@ -454,12 +454,22 @@ __device__ __forceinline__ void gv_product(const double* __restrict__ G, int n, 
 // Shared-memory / tensor-core variant of k_subspace_eig for panels whose iterate fits shared memory (2 n m doubles):
 // the n x m iterate V and the product Y = G V stay in shared memory, every product (G V, V'V, V'Y, V W) is a DMMA tile
 // product (wt_gemm; G is read from L2), CholQR uses the block-cooperative Cholesky + transposed solves, and the
-// Rayleigh-Ritz step (Jacobi on the m x m projected matrix: the expensive, serial part) runs only every second cycle of
-// q = 3 products -- between them the subspace just keeps converging under orth(G^3 V).  Same results layout as
+// Rayleigh-Ritz step (Jacobi on the m x m projected matrix: the expensive, serial part) runs after the third cycle of
+// q = 3 products and then every second cycle -- between them the subspace just keeps converging under orth(G^3 V).  Same results layout as
 // k_subspace_eig.  grid (B), 256 threads; shared 2 n ldv... see subspace2_smem_doubles.
 __host__ __device__ inline size_t subspace2_smem_doubles(int n, int m) {
   return 2 * (size_t)em_lds(n) * m + 3 * (size_t)m * m + 2 * (m + 2) + 64 + 2 * m + 64;
 }
+// diagnostics (dfm_debug_fs_prof slots 48..63): clock64 section totals of CTA 0 of k_subspace_eig2
+#ifndef DFM_EMU
+__device__ long long g_sub_prof[16];
+__device__ int g_sub_prof_on;
+#define SB_T0() long long sb_t_ = (g_sub_prof_on && blockIdx.x == 0 && threadIdx.x == 0) ? clock64() : 0
+#define SB_T(k_) do { if (g_sub_prof_on && blockIdx.x == 0 && threadIdx.x == 0) { long long n_ = clock64(); g_sub_prof[k_] += n_ - sb_t_; sb_t_ = n_; } } while (0)
+#else
+#define SB_T0() ((void)0)
+#define SB_T(k_) ((void)0)
+#endif
 #ifdef DFM_EMU
 #define SUB2_BOUNDS
 #else
@@ -492,29 +502,42 @@ __global__ void SUB2_BOUNDS k_subspace_eig2(double* __restrict__ Gall, double* _
   DFM_SYNC();
   int it = 0;
   double res = 1.0;
+  SB_T0();
   for (; it < maxit; ++it) {
     // ---- orthonormalise V (CholQR, twice): S = V'V = L L', V <- V L^-T  (row-wise transposed solve)
     for (int pass = 0; pass < 2; ++pass) {
       wt_gemm(V, ldv, 1, V, ldv, 1, m, m, n, [&](int a, int c, double v) { S[a + m * c] = v; });
       DFM_SYNC();
       bm_symmetrize(S, m, m);
+      SB_T(0);
       bc_chol(S, m, m, dinv, info);
+      SB_T(1);
       bt_trsm_lower(S, m, m, dinv, V, ldv, n);
+      SB_T(2);
     }
-    const bool rr = (it & 1) == 1 || it + 1 >= maxit;    // Rayleigh-Ritz + convergence test every second cycle
+    // Rayleigh-Ritz + convergence test: first after three cycles (9 products: a well separated factor spectrum has converged
+    // by then), afterwards every second cycle -- the Jacobi solve of the projected matrix is the expensive, serial part
+    const bool rr = (it >= 2 && ((it - 2) & 1) == 0) || it + 1 >= maxit;
     // ---- Y = G V
     gv_product(G, n, V, Y, ldv, m);
+    SB_T(3);
     if (rr) {
       wt_gemm(V, ldv, 1, Y, ldv, 1, m, m, n, [&](int a, int c, double v) { H[a + m * c] = v; });
       DFM_SYNC();
       bm_symmetrize(H, m, m);
+      SB_T(4);
+#ifndef DFM_EMU
+      { const int nsw = jacobi_core(H, W, m, cs, red, 40); if (g_sub_prof_on && blockIdx.x == 0 && threadIdx.x == 0) g_sub_prof[10] += nsw; }
+#else
       jacobi_core(H, W, m, cs, red, 40);
-      if (DFM_TID == 0) {                                 // Ritz values in descending order
+#endif
+      SB_T(5);
+      if (DFM_TID == 0) {                                 // Ritz values in descending order (selection with used flags in cs: O(m^2))
+        for (int i = 0; i < m; ++i) cs[i] = 0.0;
         for (int j = 0; j < m; ++j) {
           int best = -1; double bv = -1e300;
-          for (int i = 0; i < m; ++i) { bool used = false; for (int l = 0; l < j; ++l) if ((int)perm[l] == i) used = true;
-            if (!used && H[i + m * i] > bv) { bv = H[i + m * i]; best = i; } }
-          perm[j] = (double)best; theta[j] = bv;
+          for (int i = 0; i < m; ++i) { const double hv = H[i + m * i]; if (cs[i] == 0.0 && hv > bv) { bv = hv; best = i; } }
+          perm[j] = (double)best; theta[j] = bv; cs[best] = 1.0;
         }
       }
       DFM_SYNC();
@@ -537,6 +560,7 @@ __global__ void SUB2_BOUNDS k_subspace_eig2(double* __restrict__ Gall, double* _
         rmax = fmax(rmax, sqrt(s_));
       }
       res = rmax / fabs(theta[0]);
+      SB_T(6);
       if (res <= tol) { ++it; break; }
     }
     // next iterate: V <- normalised G^3 V (Y = G V is there)
@@ -556,7 +580,11 @@ __global__ void SUB2_BOUNDS k_subspace_eig2(double* __restrict__ Gall, double* _
       }
       DFM_SYNC();
     }
+    SB_T(7);
   }
+#ifndef DFM_EMU
+  if (g_sub_prof_on && blockIdx.x == 0 && threadIdx.x == 0) { g_sub_prof[8] += it; g_sub_prof[9] += 1; }
+#endif
   // ---- leave results where k_pca_finish looks for them
   for (int e = DFM_TID; e < n * m; e += DFM_NT) Vg[e] = V[(e % n) + (size_t)ldv * (e / n)];
   DFM_SYNC();
@@ -585,16 +613,23 @@ __global__ void k_pca_finish(const double* __restrict__ Xs, int T, int N, const 
   double* red = sm + ((r + 1) / 2 + 1);  // 33+
   double* vtmp = red + 40;               // nb doubles (mode 1)
   if (n < r) { if (DFM_TID == 0) { if (status) status[b] = 2; if (st) { st[b].status = 2; st[b].done = 1; } } return; }
-  if (DFM_TID == 0) {                    // selection of the r largest diagonal entries
-    for (int j = 0; j < r; ++j) {
-      int best = -1; double bv = -1e300;
-      for (int i = 0; i < n; ++i) {
+  if (DFM_WARP == 0) {                   // selection of the r largest diagonal entries: one warp, argmax by shuffles per pick
+    for (int j = 0; j < r; ++j) {            // (ties: the smallest index, as a serial scan with `>` gives)
+      int best = n; double bv = -1e300;
+      for (int i = DFM_LANE; i < n; i += DFM_WSZ) {
         bool used = false;
         for (int l = 0; l < j; ++l) if (order[l] == i) used = true;
         double v = G[i + (size_t)n * i];
-        if (!used && v > bv) { bv = v; best = i; }
+        if (!used && (v > bv || (v == bv && i < best))) { bv = v; best = i; }
       }
-      order[j] = best;
+#ifndef DFM_EMU
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oi = __shfl_xor_sync(0xffffffffu, best, o);
+        if (ov > bv || (ov == bv && oi < best)) { bv = ov; best = oi; }
+      }
+#endif
+      if (DFM_LANE == 0) order[j] = best;
+      DFM_WSYNC();
     }
   }
   DFM_SYNC();
