@@ -190,7 +190,7 @@ __device__ inline int jacobi_core(double* G, double* V, int n, double* cs, doubl
         if (i > j) off += v * v; else if (i == j) dg += v * v;
       }
     off = block_sum(off, red); dg = block_sum(dg, red);
-    if (off <= 1e-32 * dg) break;
+    if (off <= 1e-30 * dg) break;         // off-diagonal norm <= 1e-15 of the diagonal norm
     for (int s = 0; s < m - 1; ++s) {
       // phase 1: pairs and rotation angles of this round
       for (int i = DFM_TID; i < m / 2; i += DFM_NT) {
