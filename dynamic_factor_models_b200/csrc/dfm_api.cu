@@ -253,7 +253,8 @@ static int run_em_general(dfm_handle* h, const double* x, const dfm_em_opts* o, 
   int T = o->T, N = o->N, r = o->r, p = o->p, batch = o->batch, mi = o->max_iter;
   int np = r * (r + 1) / 2;
   int* dsrc = dnt + (size_t)batch * T;
-  const int ntFS = (batch <= 296) ? 512 : 256;     // few panels: more warps for the parallel frozen runs; many: two CTAs per SM
+  int ntFS = (batch <= 296) ? 512 : 256;           // few panels: more warps for the parallel frozen runs; many: two CTAs per SM
+  if (getenv("DFM_FS_THREADS")) ntFS = atoi(getenv("DFM_FS_THREADS"));      // (tuning knob: 256 or 512)
   L(k_em_state_init, batch, 1, 1, 0, st);
   L(k_em_scan, N, batch, 64, 0, x, dL, T, N, r, st);
   L(k_em_prep, batch, 1, 128, 0, dL, dR, N, r, p, dW, dlogR, dC, dA, dAn, dQ, dQn, st, mi, 0, emb.on ? 1 : 0);
