@@ -249,12 +249,15 @@ static int emb_launch_M(dfm_handle* h, const EmbPlan& e, const double* x, const 
 static int run_em_general(dfm_handle* h, const double* x, const dfm_em_opts* o, double* dL, double* dR, double* dA, double* dQ, double* dP0,
                           double* dAn, double* dQn, double* dW, double* dlogR, double* dC, double* dBt, double* dqt, double* dslr, int* dnt,
                           double* dCt, double* dzp, double* dzf, double* dPp, double* dPf, double* dFs, double* dPsF, double* dSff, double* dll,
-                          EmState* st, int* dit, int* dstat, int* active, int ntC, int nblkC, size_t smFS, int stgT, int want_psf, const EmbPlan& emb) {
+                          EmState* st, int* dit, int* dstat, int* active, int ntC, int nblkC, size_t smFS, int stgT, int want_psf, double* dxch, const EmbPlan& emb) {
   int T = o->T, N = o->N, r = o->r, p = o->p, batch = o->batch, mi = o->max_iter;
   int np = r * (r + 1) / 2;
   int* dsrc = dnt + (size_t)batch * T;
   int ntFS = (batch <= 296) ? 512 : 256;           // few panels: more warps for the parallel frozen runs; many: two CTAs per SM
   if (getenv("DFM_FS_THREADS")) ntFS = atoi(getenv("DFM_FS_THREADS"));      // (tuning knob: 256 or 512)
+  int ncl = 1;                                     // CTAs per panel (thread-block cluster) of the filter / smoother
+  if (dxch && !getenv("DFM_NO_CLUSTER")) { if (batch * 8 <= 148) ncl = 8; else if (batch * 4 <= 148) ncl = 4; else if (batch * 2 <= 148) ncl = 2; }
+  if (getenv("DFM_CLUSTER")) ncl = std::max(1, std::min(8, atoi(getenv("DFM_CLUSTER"))));
   L(k_em_state_init, batch, 1, 1, 0, st);
   L(k_em_scan, N, batch, 64, 0, x, dL, T, N, r, st);
   L(k_em_prep, batch, 1, 128, 0, dL, dR, N, r, p, dW, dlogR, dC, dA, dAn, dQ, dQn, st, mi, 0, emb.on ? 1 : 0);
@@ -284,8 +287,23 @@ static int run_em_general(dfm_handle* h, const double* x, const dfm_em_opts* o, 
         default: emb_launch_E<4>(h, emb, x, dW, dR, dlogR, T, N, r, batch, dBt, dqt, dslr, dnt, st); break;
       }
     }
+#ifndef DFM_EMU
+    if (ncl > 1) {
+      // few panels: a thread-block cluster per panel (the CTAs split the parallel phases of the frozen runs)
+      PROF_BEGIN("k_em_filter_smooth");
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)(batch * ncl)); cfg.blockDim = dim3((unsigned)ntFS); cfg.dynamicSmemBytes = smFS; cfg.stream = h->stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)ncl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      CK(cudaLaunchKernelEx(&cfg, k_em_filter_smooth, (const double*)dA, (const double*)dQ, (const double*)dP0, (const double*)dC,
+                            (const double*)dBt, (const double*)dqt, (const double*)dslr, (const int*)dnt, (const double*)dCt, T, r, p, dzp, dzf,
+                            dPp, dPf, dFs, dPsF, dSff, dAn, dQn, dll, mi, o->tol, st, dsrc, stgT, want_psf, dxch));
+      PROF_END(); h->launches++;
+    } else
+#endif
     L(k_em_filter_smooth, batch, 1, ntFS, smFS, dA, dQ, dP0, dC, dBt, dqt, dslr, dnt, dCt, T, r, p, dzp, dzf, dPp, dPf,
-      dFs, dPsF, dSff, dAn, dQn, dll, mi, o->tol, st, dsrc, stgT, want_psf);
+      dFs, dPsF, dSff, dAn, dQn, dll, mi, o->tol, st, dsrc, stgT, want_psf, (double*)nullptr);
     if (any_missing || !emb.on) L(k_em_mstep_series, N, batch, 64, (size_t)(2 * np + r + 8) * 8, x, dFs, dPsF, dSff, T, N, r, dL, dR, st, emb_on);
     if (any_bal && emb.on) {
       switch (emb.ncb) {
@@ -943,7 +961,7 @@ int dfm_em_kalman(dfm_handle* h, const double* X, const dfm_em_opts* o, const df
     double* dPFfull = out->PF ? a.get<double>(B * T * rr) : nullptr;
     double *dAn = nullptr, *dQn = nullptr, *dW = nullptr, *dlogR = nullptr, *dC = nullptr, *dBt = nullptr, *dqt = nullptr,
            *dslr = nullptr, *dCt = nullptr, *dzp = nullptr, *dzf = nullptr, *dPp = nullptr, *dPf = nullptr, *dSff = nullptr;
-    int* dnt = nullptr;
+    int* dnt = nullptr; double* dxch = nullptr;
     int* dflag = a.get<int>(4);
     int* dready = a.get<int>(kMaxReadyChunks);          // streaming host path: one "landed" flag per chunk of panels
     const size_t fused_off = a.off;                     // the fused kernels' scratch starts here (re-derived at launch time)
@@ -960,6 +978,7 @@ int dfm_em_kalman(dfm_handle* h, const double* X, const dfm_em_opts* o, const df
       dC = a.get<double>(B * rr); dBt = a.get<double>(B * T * r); dqt = a.get<double>(B * T); dslr = a.get<double>(B * T);
       dnt = a.get<int>(2 * B * T) /* n_t, then src_t of the frozen-step logic */; dCt = a.get<double>(B * T * np); dzp = a.get<double>(B * T * k); dzf = a.get<double>(B * T * k);
       dPp = a.get<double>(B * T * kk); dPf = a.get<double>(B * T * kk); dSff = a.get<double>(B * rr);
+      dxch = a.get<double>(B * (16 + 64 * (size_t)k + 16 * ((size_t)kk + rk)));      // cluster exchange (scalars, boundary states, Gram partials)
       if (emb.on) {
         emb.Bpart = a.get<double>((size_t)emb.nsE * B * T * r); emb.qpart = a.get<double>((size_t)emb.nsE * B * T);
         emb.Spart = a.get<double>((size_t)emb.tsM * B * N * r); emb.sxxpart = a.get<double>((size_t)emb.tsM * B * N);
@@ -1110,7 +1129,7 @@ int dfm_em_kalman(dfm_handle* h, const double* X, const dfm_em_opts* o, const df
         if (!init->P0) L(k_lyapunov, batch, 1, 128, (size_t)(3 * kk + 8) * 8, dA, dQ, r, p, dP0, 12);
         { long long n = (long long)B * mi; L(k_fill, (int)std::min<long long>((n + 255) / 256, 1024), 1, 256, 0, dll, n, DFM_NAN); }
         rc = run_em_general(h, xg, o, dL, dR, dA, dQ, dP0, dAn, dQn, dW, dlogR, dC, dBt, dqt, dslr, dnt, dCt, dzp, dzf, dPp, dPf, dFs, dPsF, dSff, dll, st, dit,
-                            dstat, active, ntC, nblkC, smFS, stgT, out->PF ? 1 : 0, emb);
+                            dstat, active, ntC, nblkC, smFS, stgT, out->PF ? 1 : 0, dxch, emb);
         if (rc) return rc;
         computed = true;
       }
@@ -1191,7 +1210,7 @@ int dfm_em_kalman(dfm_handle* h, const double* X, const dfm_em_opts* o, const df
 #endif
     } else {
       rc = run_em_general(h, x, o, dL, dR, dA, dQ, dP0, dAn, dQn, dW, dlogR, dC, dBt, dqt, dslr, dnt, dCt, dzp, dzf, dPp, dPf, dFs, dPsF, dSff, dll, st, dit,
-                          dstat, active, ntC, nblkC, smFS, stgT, out->PF ? 1 : 0, emb);
+                          dstat, active, ntC, nblkC, smFS, stgT, out->PF ? 1 : 0, dxch, emb);
       if (rc) return rc;
     }
     }   // !computed

@@ -227,6 +227,26 @@ __device__ int g_fs_prof_on;
 #else
 #define EM_NOINLINE __noinline__
 #endif
+// ---- thread-block CLUSTER per panel (few panels, e.g. C3): the CTAs of a cluster run the serial parts (explicit steps,
+// boundary chain) redundantly -- same inputs, same arithmetic, same results -- and split the parallel parts of the frozen
+// runs (tiles of the element-wise phases, chunks of the scan) by cluster rank; they exchange through global memory +
+// cluster barriers (barrier.cluster arrive.release / wait.acquire after a fence).  A plain launch is a cluster of one.
+#ifndef DFM_EMU
+__device__ __forceinline__ int cl_rank() { unsigned r_; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r_)); return (int)r_; }
+__device__ __forceinline__ int cl_size() { unsigned r_; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r_)); return (int)r_; }
+__device__ __forceinline__ void cl_sync(int nc) {
+  if (nc > 1) {
+    __threadfence();
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
+}
+#else
+__device__ __forceinline__ int cl_rank() { return 0; }
+__device__ __forceinline__ int cl_size() { return 1; }
+__device__ __forceinline__ void cl_sync(int) {}
+#endif
+
 #ifndef DFM_EMU
 // Tensor-core variant of the run scan for k <= 32 and a large workspace (one CTA per SM configurations): 64 chunks, 8 per warp
 // on warps 0..7.  A warp advances its 8 chunk recursions together: the step  Z <- Phi Z + U  with Z = [k x 8 chunks] is
@@ -238,7 +258,8 @@ __device__ int g_fs_prof_on;
 #define EM_SC_ZS 12
 template <int MB>
 __device__ EM_NOINLINE void em_run_scan_tc(double* __restrict__ zg, int k, int t_first, int L, int dir, const double* Phi,
-                                           const double* z_in, double* Rp, double* base, double* tmp, double* ws) {
+                                           const double* z_in, double* Rp, double* base, double* tmp, double* ws, int nc, int crank,
+                                           double* xbnd) {
   constexpr int KBX = 2 * MB, KR = 8 * MB;             // k-chunks and (zero padded) state rows of a warp's tile
   const int NCH = 8 * EM_SC_NW;
   const int Lc = (L + NCH - 1) / NCH;
@@ -260,10 +281,11 @@ __device__ EM_NOINLINE void em_run_scan_tc(double* __restrict__ zg, int k, int t
   }
   FS_T(27);
   double* bnd = ws + (size_t)EM_SC_NW * 2 * KR * EM_SC_ZS;             // [64][k]: e_c, then in_c
-  const int lr = DFM_LANE >> 2, lc = DFM_LANE & 3, w = DFM_WARP;
+  const int lr = DFM_LANE >> 2, lc = DFM_LANE & 3, wl = DFM_WARP;
+  const int w = wl * nc + crank;                        // virtual warp of the cluster: 8 chunks each, EM_SC_NW in total
   for (int pass = 1; pass <= 2; ++pass) {
     if (w < EM_SC_NW) {
-      double* cur = ws + (size_t)w * 2 * KR * EM_SC_ZS; double* nxt = cur + (size_t)KR * EM_SC_ZS;
+      double* cur = ws + (size_t)wl * 2 * KR * EM_SC_ZS; double* nxt = cur + (size_t)KR * EM_SC_ZS;
       double aP[MB][KBX];
 #pragma unroll
       for (int mb = 0; mb < MB; ++mb)
@@ -335,15 +357,19 @@ __device__ EM_NOINLINE void em_run_scan_tc(double* __restrict__ zg, int k, int t
         __syncwarp();
         double* sw = cur; cur = nxt; nxt = sw;
       }
-      if (pass == 1)
-        for (int e = DFM_LANE; e < k * 8; e += 32) { const int i = e >> 3, n = e & 7; bnd[(size_t)(8 * w + n) * k + i] = cur[i * EM_SC_ZS + n]; }
+      if (pass == 1) {
+        double* dst = (nc > 1) ? xbnd : bnd;             // (cluster: end states go through global memory)
+        for (int e = DFM_LANE; e < k * 8; e += 32) { const int i = e >> 3, n = e & 7; dst[(size_t)(8 * w + n) * k + i] = cur[i * EM_SC_ZS + n]; }
+      }
     }
     DFM_SYNC();
+    cl_sync(nc);
     FS_T(27 + pass);
     if (pass == 1) {
+      if (nc > 1) { for (int e = DFM_TID; e < NCH * k; e += DFM_NT) bnd[e] = xbnd[e]; DFM_SYNC(); }
       // incoming states on warp 0: in_0 = z_in, in_{c+1} = Phi^Lc in_c + e_c  (row i of Phi^Lc in the registers of lane i,
       // zero padded to 32 x 32 so that the step has no bounds tests; bnd[c] is overwritten by in_c)
-      if (w == 0) {
+      if (wl == 0) {
         double* inc = ws;                               // 32 doubles (warp 0's idle tile)
         const int i = DFM_LANE;
         const bool iok = i < k;
@@ -371,20 +397,22 @@ __device__ EM_NOINLINE void em_run_scan_tc(double* __restrict__ zg, int k, int t
 #endif
 
 __device__ EM_NOINLINE void em_run_scan(double* __restrict__ zg, int k, int t_first, int L, int dir, const double* Phi,
-                                   const double* z_in, double* Rp, double* base, double* tmp, double* wb, double* ws, int ws_doubles) {
+                                   const double* z_in, double* Rp, double* base, double* tmp, double* wb, double* ws, int ws_doubles,
+                                   int nc, int crank, double* xbnd) {
 #ifndef DFM_EMU
   if (k <= 32 && DFM_NWARP >= EM_SC_NW && ws_doubles >= EM_SC_NW * 2 * 8 * ((k + 7) >> 3) * EM_SC_ZS + 8 * EM_SC_NW * k && L >= 256) {
     switch ((k + 7) >> 3) {
-      case 1: em_run_scan_tc<1>(zg, k, t_first, L, dir, Phi, z_in, Rp, base, tmp, ws); break;
-      case 2: em_run_scan_tc<2>(zg, k, t_first, L, dir, Phi, z_in, Rp, base, tmp, ws); break;
-      case 3: em_run_scan_tc<3>(zg, k, t_first, L, dir, Phi, z_in, Rp, base, tmp, ws); break;
-      default: em_run_scan_tc<4>(zg, k, t_first, L, dir, Phi, z_in, Rp, base, tmp, ws); break;
+      case 1: em_run_scan_tc<1>(zg, k, t_first, L, dir, Phi, z_in, Rp, base, tmp, ws, nc, crank, xbnd); break;
+      case 2: em_run_scan_tc<2>(zg, k, t_first, L, dir, Phi, z_in, Rp, base, tmp, ws, nc, crank, xbnd); break;
+      case 3: em_run_scan_tc<3>(zg, k, t_first, L, dir, Phi, z_in, Rp, base, tmp, ws, nc, crank, xbnd); break;
+      default: em_run_scan_tc<4>(zg, k, t_first, L, dir, Phi, z_in, Rp, base, tmp, ws, nc, crank, xbnd); break;
     }
     return;
   }
 #else
   (void)ws; (void)ws_doubles;
 #endif
+  (void)nc; (void)crank; (void)xbnd;                   // (this variant is not split: the CTAs of a cluster run it redundantly)
   const int Lc = (L + EM_RUN_NCH - 1) / EM_RUN_NCH;
   FS_T0();
   // Rp = Phi^Lc
@@ -560,9 +588,10 @@ __global__ void EM_FS_BOUNDS k_em_filter_smooth(const double* __restrict__ Aall,
                                    double* __restrict__ Pf_, double* __restrict__ Fs_, double* __restrict__ PsF_,
                                    double* __restrict__ SffAll_, double* __restrict__ Anew_, double* __restrict__ Qnew_,
                                    double* __restrict__ loglik_, int max_iter, double tol, EmState* st, int* __restrict__ src_,
-                                   int stg_T, int want_psf) {
+                                   int stg_T, int want_psf, double* __restrict__ xch_) {
   DFM_SMEM(sm);
-  int b = DFM_BX;
+  const int NC = cl_size(), crank = cl_rank();           // cluster per panel (1 for a plain launch)
+  int b = DFM_BX / NC;
   if (st[b].done) return;
   int k = r * p, kk = k * k, rr = r * r, rk = r * k, np = r * (r + 1) / 2;
   double* M = sm;            double* Pp = M + kk;      double* Pf = Pp + kk;    double* T1 = Pf + kk;
@@ -584,6 +613,10 @@ __global__ void EM_FS_BOUNDS k_em_filter_smooth(const double* __restrict__ Aall,
   double* dvS = dvL + 64;
   double* ldS_sh = red + 40; // log det of the last explicit step, for all threads
   int* src = src_ + (size_t)b * T;
+  // cluster exchange buffers of this panel (global): [0..15] scalars by rank, then 64 k boundary states, then NC x (kk + rk) Gram partials
+  double* xch = xch_ ? xch_ + (size_t)b * (16 + 64 * (size_t)k + 16 * ((size_t)kk + rk)) : nullptr;
+  double* xbnd = xch ? xch + 16 : nullptr;
+  double* xgram = xch ? xch + 16 + 64 * (size_t)k : nullptr;
   const double* A = Aall + (size_t)b * rk; const double* Qg = Qall + (size_t)b * rr;
   const double* P0 = P0all + (size_t)b * kk; const double* Cg = Call + (size_t)b * rr;
   const double* Bt = Bt_ + (size_t)b * T * r; const double* qt = qt_ + (size_t)b * T;
@@ -657,7 +690,8 @@ __global__ void EM_FS_BOUNDS k_em_filter_smooth(const double* __restrict__ Aall,
         double* Bs = stg;                           // [r][TTp]        b_t of the tile (component-major)
         double* Zs = Bs + (size_t)r * TTp;          // [TT + 1][lds]   zf_{t0-1} .. zf_{t0+len-1}
         double* Zq = Zs + (size_t)(TT + 1) * lds;   // [TT][lds]       zp of the tile
-        for (int t0 = t; t0 < t1; t0 += TT) {                                    // u_t = Kb b_t  -> zfg
+        for (int t0 = t, ti = 0; t0 < t1; t0 += TT, ++ti) {                      // u_t = Kb b_t  -> zfg
+          if (ti % NC != crank) continue;                                        // (tiles dealt to the CTAs of the cluster)
           const int len = (t1 - t0 < TT) ? t1 - t0 : TT;
           DFM_SYNC();
 #pragma unroll 4
@@ -666,12 +700,15 @@ __global__ void EM_FS_BOUNDS k_em_filter_smooth(const double* __restrict__ Aall,
           wt_gemm(Bs, 1, TTp, Pf, 1, k, len, k, r, [&](int m, int n, double v) { zfg[(size_t)(t0 + m) * k + n] = v; });
         }
         DFM_SYNC();
+        cl_sync(NC);
         FS_T(22);
-        em_run_scan(zfg, k, t, Lr, +1, T1, zf, T2, T3, Psn, wb, stg, stg_doubles);                  // (T2, T3, Psn are free between explicit steps)
+        em_run_scan(zfg, k, t, Lr, +1, T1, zf, T2, T3, Psn, wb, stg, stg_doubles, NC, crank, xbnd);   // (T2, T3, Psn are free between explicit steps)
+        cl_sync(NC);
         FS_T(23);
         double llp = 0.0;
         const double ldS_ = *ldS_sh;
-        for (int t0 = t; t0 < t1; t0 += TT) {                                    // zp_t = M zf_{t-1}, likelihood terms
+        for (int t0 = t, ti = 0; t0 < t1; t0 += TT, ++ti) {                      // zp_t = M zf_{t-1}, likelihood terms
+          if (ti % NC != crank) continue;
           const int len = (t1 - t0 < TT) ? t1 - t0 : TT;
           DFM_SYNC();
 #pragma unroll 4
@@ -694,7 +731,15 @@ __global__ void EM_FS_BOUNDS k_em_filter_smooth(const double* __restrict__ Aall,
             llp += -0.5 * term;
           });
         }
-        ll += block_sum(llp, red);
+        if (NC > 1) {                                      // likelihood terms of the cluster's CTAs, summed in rank order by everyone
+          const double lp = block_sum(llp, red);
+          if (DFM_TID == 0) xch[crank] = lp;
+          cl_sync(NC);
+          double tot = 0.0;
+          for (int c = 0; c < NC; ++c) tot += xch[c];
+          ll += tot;
+          cl_sync(NC);                                     // (xch[0..NC) is reused by the next run)
+        } else ll += block_sum(llp, red);
         for (int e = DFM_TID; e < k; e += DFM_NT) zf[e] = zfg[(size_t)(t1 - 1) * k + e];
         DFM_SYNC();
         t = t1 - 1;
@@ -843,7 +888,8 @@ __global__ void EM_FS_BOUNDS k_em_filter_smooth(const double* __restrict__ Aall,
         // zs_t = J zs_{t+1} + v_t,  v_t = zf_t - J zp_{t+1}   (J is in T3)
         const int lds = em_lds(k);
         double* Zq = stg;                              // [TT][lds]      zp_{t0+1} .. zp_{t0+len}
-        for (int t0 = tl; t0 <= t; t0 += TT) {
+        for (int t0 = tl, ti = 0; t0 <= t; t0 += TT, ++ti) {
+          if (ti % NC != crank) continue;
           const int len = (t - t0 + 1 < TT) ? t - t0 + 1 : TT;
           DFM_SYNC();
           {
@@ -855,8 +901,10 @@ __global__ void EM_FS_BOUNDS k_em_filter_smooth(const double* __restrict__ Aall,
           wt_gemm(Zq, lds, 1, T3, 1, k, len, k, k, [&](int m, int n, double v) { zfg[(size_t)(t0 + m) * k + n] -= v; });
         }
         DFM_SYNC();
+        cl_sync(NC);
         FS_T(24);
-        em_run_scan(zfg, k, t, Lr, -1, T3, zsn, T1, Pf, T2, wb, stg, stg_doubles);                 // (T1, Pf, T2 are free here; zfg now holds zs_t)
+        em_run_scan(zfg, k, t, Lr, -1, T3, zsn, T1, Pf, T2, wb, stg, stg_doubles, NC, crank, xbnd);   // (T1, Pf, T2 are free here; zfg now holds zs_t)
+        cl_sync(NC);
         FS_T(25);
         // Gram sums of the smoothed means: S00 (k x k), S11 (r x k) as DMMA products over tiles of zs rows staged in shared
         // memory; a warp's output tiles stay in registers over the tiles of the run
@@ -870,8 +918,10 @@ __global__ void EM_FS_BOUNDS k_em_filter_smooth(const double* __restrict__ Aall,
 #else
         const bool in_regs = false;
 #endif
+        const int NCg = in_regs ? NC : 1, crg = in_regs ? crank : 0;      // (the plain-sum path is not split over the cluster)
         double* Zs = stg;                              // [TT + 1][lds]   zs_{t0} .. zs_{t0+len}
-        for (int t0 = tl; t0 <= t; t0 += TT) {
+        for (int t0 = tl, ti = 0; t0 <= t; t0 += TT, ++ti) {
+          if (ti % NCg != crg) continue;
           const int len = (t - t0 + 1 < TT) ? t - t0 + 1 : TT;
           DFM_SYNC();
           {
@@ -903,7 +953,23 @@ __global__ void EM_FS_BOUNDS k_em_filter_smooth(const double* __restrict__ Aall,
         FS_T(26);
         // zs_tl (k) -> tv for the Sff2 correction; fold the register sums into the shared accumulators
         for (int e = DFM_TID; e < k; e += DFM_NT) tv[e] = zfg[(size_t)tl * k + e];
-        if (in_regs) {
+        if (in_regs && NC > 1) {
+          // partial Gram sums of the cluster's CTAs through global memory, added in rank order by everyone
+          double* mine = xgram + (size_t)crank * (kk + rk);
+          wt_acc_visit(k, k, 0, acc, [&](int i, int j, double v) { mine[i + k * j] = v; });
+          wt_acc_visit(r, k, nt00, acc, [&](int i, int j, double v) { mine[kk + i + r * j] = v; });
+          DFM_SYNC();
+          cl_sync(NC);
+          for (int e = DFM_TID; e < kk + rk; e += DFM_NT) {
+            double v = 0.0;
+            for (int c = 0; c < NC; ++c) v += xgram[(size_t)c * (kk + rk) + e];
+            if (e < kk) {
+              S00[e] += v;
+              const int i = e % k, j = e / k;
+              if (i < r && j < r) { SffA[i + r * j] += v; Sff2[i + r * j] += v; }
+            } else S11[e - kk] += v;
+          }
+        } else if (in_regs) {
           wt_acc_visit(k, k, 0, acc, [&](int i, int j, double v) {
             S00[i + k * j] += v;
             if (i < r && j < r) { SffA[i + r * j] += v; Sff2[i + r * j] += v; }            // r x r block of the same Gram sum
@@ -1007,7 +1073,7 @@ __global__ void EM_FS_BOUNDS k_em_filter_smooth(const double* __restrict__ Aall,
   for (int e = DFM_TID; e < rk; e += DFM_NT) Anew_[(size_t)b * rk + e] = Wm[e];
   for (int e = DFM_TID; e < rr; e += DFM_NT) { Qnew_[(size_t)b * rr + e] = T4[e]; SffAll_[(size_t)b * rr + e] = SffA[e]; }
   FS_T(6);
-  if (DFM_TID == 0) {
+  if (DFM_TID == 0 && crank == 0) {                  // (one CTA of the cluster updates the panel's state: the update is not idempotent)
     int it = st[b].iters;
     loglik_[(size_t)b * max_iter + it] = ll;
     st[b].ll_prev = st[b].ll; st[b].ll = ll;
