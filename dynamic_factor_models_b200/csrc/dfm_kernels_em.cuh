@@ -309,53 +309,60 @@ __device__ EM_NOINLINE void em_run_scan_tc(double* __restrict__ zg, int k, int t
         nxt[i * EM_SC_ZS + n] = 0.0;
       }
       __syncwarp();
-      const double* pA = zg + tA * k + lr; const double* pB = zg + tB * k + lr;
-      for (int q = 0; q < 4; ++q) {
+      double* pA = zg + tA * k + lr; double* pB = zg + tB * k + lr;
+      // u_t of two steps ahead in registers (an L2 round trip is longer than a step; prefetch.global.L1 did not hide it)
+      double cuA[2][MB], cuB[2][MB];
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
 #pragma unroll
         for (int mb = 0; mb < MB; ++mb) {
-          if (rok[mb] && q < lenA) asm volatile("prefetch.global.L1 [%0];" ::"l"(pA + q * dk + mb * 8));
-          if (rok[mb] && q < lenB) asm volatile("prefetch.global.L1 [%0];" ::"l"(pB + q * dk + mb * 8));
+          cuA[q][mb] = (rok[mb] && q < lenA) ? pA[q * dk + mb * 8] : 0.0;
+          cuB[q][mb] = (rok[mb] && q < lenB) ? pB[q * dk + mb * 8] : 0.0;
         }
-      }
-      for (int s_ = 0; s_ < Lc; ++s_) {
-        const bool okA = s_ < lenA, okB = s_ < lenB;
-        double* gA = const_cast<double*>(pA) + s_ * dk; double* gB = const_cast<double*>(pB) + s_ * dk;
-        double uA[MB], uB[MB];
+      for (int s2 = 0; s2 < Lc; s2 += 2) {
+        double nA[2][MB], nB[2][MB];
 #pragma unroll
-        for (int mb = 0; mb < MB; ++mb) {
-          uA[mb] = (rok[mb] && okA) ? gA[mb * 8] : 0.0;
-          uB[mb] = (rok[mb] && okB) ? gB[mb * 8] : 0.0;
-        }
-        if (s_ + 4 < lenA) {
+        for (int q = 0; q < 2; ++q)
 #pragma unroll
-          for (int mb = 0; mb < MB; ++mb) if (rok[mb]) asm volatile("prefetch.global.L1 [%0];" ::"l"(gA + 4 * dk + mb * 8));
-        }
-        if (s_ + 4 < lenB) {
+          for (int mb = 0; mb < MB; ++mb) {
+            const int sn = s2 + 2 + q;
+            nA[q][mb] = (rok[mb] && sn < lenA) ? pA[sn * dk + mb * 8] : 0.0;
+            nB[q][mb] = (rok[mb] && sn < lenB) ? pB[sn * dk + mb * 8] : 0.0;
+          }
 #pragma unroll
-          for (int mb = 0; mb < MB; ++mb) if (rok[mb]) asm volatile("prefetch.global.L1 [%0];" ::"l"(gB + 4 * dk + mb * 8));
-        }
-        double d[MB][2];
+        for (int q = 0; q < 2; ++q) {
+          const int s_ = s2 + q;
+          if (s_ < Lc) {
+            const bool okA = s_ < lenA, okB = s_ < lenB;
+            double* gA = pA + s_ * dk; double* gB = pB + s_ * dk;
+            double d[MB][2];
 #pragma unroll
-        for (int mb = 0; mb < MB; ++mb) { d[mb][0] = 0.0; d[mb][1] = 0.0; }
-        double bz[KBX];
+            for (int mb = 0; mb < MB; ++mb) { d[mb][0] = 0.0; d[mb][1] = 0.0; }
+            double bz[KBX];
 #pragma unroll
-        for (int kb = 0; kb < KBX; ++kb) bz[kb] = cur[(kb * 4 + lc) * EM_SC_ZS + lr];
+            for (int kb = 0; kb < KBX; ++kb) bz[kb] = cur[(kb * 4 + lc) * EM_SC_ZS + lr];
 #pragma unroll
-        for (int kb = 0; kb < KBX; ++kb)
+            for (int kb = 0; kb < KBX; ++kb)
 #pragma unroll
-          for (int mb = 0; mb < MB; ++mb) EM_DMMA(d[mb], aP[mb][kb], bz[kb]);
+              for (int mb = 0; mb < MB; ++mb) EM_DMMA(d[mb], aP[mb][kb], bz[kb]);
 #pragma unroll
-        for (int mb = 0; mb < MB; ++mb) {
-          const int i = mb * 8 + lr;
-          const double vA = d[mb][0] + uA[mb], vB = d[mb][1] + uB[mb];
-          nxt[i * EM_SC_ZS + 2 * lc] = vA; nxt[i * EM_SC_ZS + 2 * lc + 1] = vB;       // (rows >= k: 0 + 0)
-          if (pass == 2 && rok[mb]) {
-            if (okA) gA[mb * 8] = vA;
-            if (okB) gB[mb * 8] = vB;
+            for (int mb = 0; mb < MB; ++mb) {
+              const int i = mb * 8 + lr;
+              const double vA = d[mb][0] + cuA[q][mb], vB = d[mb][1] + cuB[q][mb];
+              nxt[i * EM_SC_ZS + 2 * lc] = vA; nxt[i * EM_SC_ZS + 2 * lc + 1] = vB;       // (rows >= k: 0 + 0)
+              if (pass == 2 && rok[mb]) {
+                if (okA) gA[mb * 8] = vA;
+                if (okB) gB[mb * 8] = vB;
+              }
+            }
+            __syncwarp();
+            double* sw = cur; cur = nxt; nxt = sw;
           }
         }
-        __syncwarp();
-        double* sw = cur; cur = nxt; nxt = sw;
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+          for (int mb = 0; mb < MB; ++mb) { cuA[q][mb] = nA[q][mb]; cuB[q][mb] = nB[q][mb]; }
       }
       if (pass == 1) {
         double* dst = (nc > 1) ? xbnd : bnd;             // (cluster: end states go through global memory)
