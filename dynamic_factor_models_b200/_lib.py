@@ -63,7 +63,7 @@ def default_library_path():
 EXPORTS = ["dfm_version", "dfm_status_string", "dfm_create", "dfm_create_on_stream", "dfm_destroy", "dfm_sync",
            "dfm_launch_count", "dfm_last_error", "dfm_profile_enable", "dfm_profile_query", "dfm_profile_reset",
            "dfm_profile_kernel_name", "dfm_debug_fs_prof", "dfm_standardize", "dfm_pca_score", "dfm_estimate_factor",
-           "dfm_estimate_loading", "dfm_estimate_loading_ex", "dfm_estimate_var", "dfm_irf", "dfm_em_kalman", "dfm_em_init_from_factors",
+           "dfm_estimate_loading", "dfm_estimate_loading_ex", "dfm_estimate_var", "dfm_irf", "dfm_instability", "dfm_em_kalman", "dfm_em_init_from_factors",
            "dfm_simulate_panels", "dfm_bootstrap_panels", "dfm_bootstrap_irf", "dfm_percentiles", "dfm_allgather_results", "dfm_shard_range"]
 
 
@@ -356,6 +356,19 @@ class Library:
                                     B, MEM_HOST, _ptr(out)), "dfm_irf")
         o = out.reshape(B, ns_, H, r).transpose(0, 3, 2, 1)      # -> (B, r, H, n_shock)
         return np.ascontiguousarray(o if b else o[0])
+
+    def instability(self, data, F, T_break, q=6, ccut=0.15, min_obs=80, want_q0=False):
+        """Chow / QLR statistics (HAC, q lags) of the regression of every column of data (T, ns) on F (T, r); NaN = missing.
+        Returns dict(chow, qlr[, qlr0], status)."""
+        data = np.asarray(data, float); F = np.asarray(F, float)
+        T, ns = data.shape; r = F.shape[1]
+        chow = np.empty(ns); qlr = np.empty(ns); qlr0 = np.empty(ns) if want_q0 else None; st = np.zeros(ns, np.int32)
+        self.check(self.lib.dfm_instability(self.h, _ptr(to_cm(data)), _ptr(to_cm(F)), T, ns, r, q, T_break, C.c_double(ccut), min_obs, MEM_HOST,
+                                            _ptr(chow), _ptr(qlr), _ptr(qlr0), st.ctypes.data_as(c_ip)), "dfm_instability")
+        out = dict(chow=chow, qlr=qlr, status=st)
+        if want_q0:
+            out["qlr0"] = qlr0
+        return out
 
     def em_init_from_factors(self, Xs, F, p=1):
         Xs = np.asarray(Xs, float); F = np.asarray(F, float); b = Xs.shape[0] if Xs.ndim == 3 else None

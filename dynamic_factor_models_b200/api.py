@@ -261,3 +261,15 @@ def estimate_factor_numbers(m, max_nfac, lib=None):
         out.update(tss=d.fes.tss, nobs=d.fes.nobs, T=d.fes.T)
     out.update(bn_icp=bn, ssr_static=ssr_s, R2_static=R2_s, aw_icp=aw, ssr_dynamic=ssr_d)
     return out
+
+
+# ---------------------------------------------------------------------------------------------- f4: instability tests
+def instability_tests(m, lastpre, q=6, ccut=0.15, min_obs=80, lib=None, want_q0=False):
+    """Chow and QLR statistics of every series of `m.data` regressed on `m.factor` (compute_chow / compute_qlr with
+    regress_hac / hac / form_hscrc, dfm_functions.ipynb; the per-series loop of Stock_Watson.ipynb Table 4(a)): break after
+    the first `lastpre` rows that survive drop_missing_row, Bartlett HAC with q lags, QLR over the central 1 - 2 ccut of
+    the sample.  Series with fewer than min_obs observations on either side of row `lastpre` are NaN.  Returns (chow, qlr)
+    or (chow, qlr, qlr0)."""
+    lib = lib or get_library()
+    out = lib.instability(m.data, m.factor, lastpre, q=q, ccut=ccut, min_obs=min_obs, want_q0=want_q0)
+    return (out["chow"], out["qlr"], out["qlr0"]) if want_q0 else (out["chow"], out["qlr"])

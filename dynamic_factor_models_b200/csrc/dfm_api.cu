@@ -10,6 +10,7 @@
 #include "dfm_kernels_fused2.cuh"
 #include "dfm_kernels_als_masked.cuh"
 #include "dfm_kernels_rep.cuh"
+#include "dfm_kernels_inst.cuh"
 #include <algorithm>
 #include <new>
 #include <thread>
@@ -1343,6 +1344,35 @@ int dfm_bootstrap_irf(dfm_handle* h, const dfm_boot_opts* o, const double* F0, c
 }
 
 // ------------------------------------------------------------------------------------ (f)3: percentile bands
+// ------------------------------------------------------------------------------------ f4: instability tests
+int dfm_instability(dfm_handle* h, const double* data, const double* F, int T, int ns, int r, int q, int T_break, double ccut,
+                    int min_obs, int mem, double* chow, double* qlr, double* qlr0, int* status) {
+  if (!h || !data || !F || !chow || !qlr || T <= 2 || ns <= 0 || r <= 0 || r > 16 || q < 0 || q > 7 || T_break <= 0 || T_break >= T ||
+      !(ccut > 0.0 && ccut < 0.5) || min_obs < 0)
+    return fail(h, DFM_ERR_ARG, "dfm_instability: bad argument (r <= 16, q <= 7, 0 < ccut < 0.5)");
+  const size_t smem = inst_smem_doubles(T, r) * 8;
+  if (smem > kMaxSmem) return fail(h, DFM_ERR_UNSUPPORTED, "dfm_instability: T x r too large for one CTA per series");
+  CK(cudaSetDevice(h->device));
+  for (int pass = 0; pass < 2; ++pass) {
+    Arena a(pass ? h->ws : nullptr);
+    double* dD = mem == DFM_MEM_HOST ? a.get<double>((size_t)T * ns) : nullptr;
+    double* dF = mem == DFM_MEM_HOST ? a.get<double>((size_t)T * r) : nullptr;
+    double* dc = a.get<double>(ns); double* dq = a.get<double>(ns); double* dq0 = a.get<double>(ns); int* dst = a.get<int>(ns);
+    if (!pass) { int rc = ensure_ws(h, a.off); if (rc) return rc; continue; }
+    const double *x, *f;
+    int rc = stage_in(h, data, dD, (size_t)T * ns, mem, &x); if (rc) return rc;
+    rc = stage_in(h, F, dF, (size_t)T * r, mem, &f); if (rc) return rc;
+    CK(cudaMemsetAsync(dst, 0, ns * sizeof(int), h->stream));
+    DFM_SET_SMEM(k_instability, smem);
+    L(k_instability, ns, 1, 256, smem, x, f, T, ns, r, q, T_break, ccut, min_obs, dc, dq, qlr0 ? dq0 : (double*)nullptr, dst);
+    rc = copy_out(h, chow, dc, ns, mem); if (rc) return rc;
+    rc = copy_out(h, qlr, dq, ns, mem); if (rc) return rc;
+    if (qlr0) { rc = copy_out(h, qlr0, dq0, ns, mem); if (rc) return rc; }
+    if (status) { rc = copy_out(h, status, dst, ns, mem); if (rc) return rc; }
+  }
+  return finish(h, mem);
+}
+
 int dfm_percentiles(dfm_handle* h, const double* recs, long long n, int d, const double* q, int nq, int mem, double* out) {
   if (!h || !recs || !q || !out || n <= 0 || d <= 0 || nq <= 0 || nq > 64) return fail(h, DFM_ERR_ARG, "dfm_percentiles: bad argument");
   for (int k = 0; k < nq; ++k) if (!(q[k] >= 0.0 && q[k] <= 100.0)) return fail(h, DFM_ERR_ARG, "dfm_percentiles: q outside [0, 100]");

@@ -143,6 +143,17 @@ int dfm_estimate_loading_ex(dfm_handle* h, const double* data, const double* F, 
 int dfm_estimate_var(dfm_handle* h, const double* F, int T, int r, int p, int withconst, int batch, int mem,
                      double* betahat, double* resid, double* seps, double* M, double* Q, double* G);
 
+/* ---- f4: instability tests of the loadings: compute_chow / compute_qlr / regress_hac / hac / form_hscrc (dfm_functions.ipynb)
+ * and the per-series loop of Stock_Watson.ipynb Table 4(a) ------------------------------------------------------------- */
+/* For every series i of data (T x ns column-major, NaN = missing): rows with a missing y or factor are dropped
+ * (drop_missing_row([y X])); chow[i] = Wald statistic of the break-dummy interactions in the regression of y on
+ * [F, F .* D] with Bartlett HAC(q) covariance, D = 1 after the first T_break kept rows (the notebook applies the row number
+ * of the break date to the rows that survive the drop); qlr[i] = max of that statistic over the break rows
+ * floor(ccut Td) .. Td - floor(ccut Td); qlr0 (may be NULL) the same with q = 0.  NaN where y has fewer than min_obs
+ * observations before or after row T_break.  status (may be NULL): 3 where a covariance was not positive definite. */
+int dfm_instability(dfm_handle* h, const double* data, const double* F, int T, int ns, int r, int q, int T_break, double ccut,
+                    int min_obs, int mem, double* chow /*ns*/, double* qlr /*ns*/, double* qlr0 /*ns or NULL*/, int* status /*ns or NULL*/);
+
 /* ---- a11: impulse_response / compute_irf_single_shock!, :793-825 ----------------------- */
 /* irf[:, h, j] = Q M^h G[:, shock_ids[j]],  h = 0..H-1;  irf is r x H x n_shock column-major. */
 int dfm_irf(dfm_handle* h, const double* M, const double* Q, const double* G, int k, int r, int H,

@@ -357,3 +357,67 @@ def estimate_factor_numbers(m, max_nfac):
         out.update(tss=d.fes.tss, nobs=d.fes.nobs, T=d.fes.T)
     out.update(bn_icp=bn, ssr_static=ssr_s, R2_static=R2_s, aw_icp=aw, ssr_dynamic=ssr_d)
     return out
+
+
+# ----------------------------------------------------------------- f4: instability tests (HAC / Chow / QLR)
+def form_kernel(q):
+    """form_kernel(q::Integer)  dfm_functions.ipynb (Bartlett weights 1 - i/(q+1), i = 0..q)."""
+    return np.array([1.0 - i / (q + 1.0) for i in range(q + 1)])
+
+
+def form_hscrc(z, X, kernel, q):
+    """form_hscrc: HAC sandwich (X'X)^-1 [sum_i k_i (z'z_lag + z_lag'z)] (X'X)^-T."""
+    k = X.shape[1]; T = z.shape[0]
+    v = np.zeros((k, k))
+    for i in range(-q, 1):
+        r2 = T + i
+        v = v + kernel[-i] * z[0:r2].T @ z[-i:r2 - i]
+    for i in range(1, q + 1):
+        v = v + kernel[i] * z[i:T].T @ z[0:T - i]
+    XX = X.T @ X
+    return np.linalg.solve(XX, np.linalg.solve(XX, v.T).T)          # XX \ v / XX'
+
+
+def hac(u, X, q):
+    z = X * u[:, None]
+    vbeta = form_hscrc(z, X, form_kernel(q), q)
+    return vbeta, np.sqrt(np.diag(vbeta))
+
+
+def regress_hac(y, X, q):
+    betahat, ehat = ols(y, X)
+    vbeta, se = hac(ehat, X, q)
+    return betahat, vbeta, se
+
+
+def compute_chow(y, X, q, T_break):
+    """compute_chow: Wald statistic of the break-dummy interactions with HAC(q) covariance."""
+    k = X.shape[1]; T = len(y)
+    D = np.concatenate([np.zeros(T_break), np.ones(T - T_break)])
+    betahat, vbeta, _ = regress_hac(y, np.column_stack([X, X * D[:, None]]), q)
+    gamma = betahat[k:]
+    v1 = vbeta[k:, k:]
+    return float(gamma @ np.linalg.solve(v1, gamma))
+
+
+def compute_qlr(y, X2, ccut, q):
+    """compute_qlr(y, nothing, X2, ccut, q): sup of the Chow statistics over the central break dates (q = 0 and HAC(q))."""
+    T = len(y)
+    n1t = int(np.floor(ccut * T)); n2t = T - n1t
+    lr = [compute_chow(y, X2, 0, tb) for tb in range(n1t, n2t + 1)]
+    lrr = [compute_chow(y, X2, q, tb) for tb in range(n1t, n2t + 1)]
+    return max(lr), max(lrr)
+
+
+def instability_tests(m, lastpre, q=6, ccut=0.15, min_obs=80):
+    """The per-series loop of Stock_Watson.ipynb Table 4(a): Chow (break after `lastpre` rows of the rows that survive
+    drop_missing_row -- the notebook's convention) and QLR statistics of the regression of each series on m.factor."""
+    X = m.factor
+    chow = np.full(m.ns, np.nan); qlr = np.full(m.ns, np.nan)
+    for i in range(m.ns):
+        y = m.data[:, i]
+        if (~np.isnan(y[:lastpre])).sum() >= min_obs and (~np.isnan(y[lastpre:])).sum() >= min_obs:
+            yx, _ = drop_missing_row(np.column_stack([y, X]))
+            chow[i] = compute_chow(yx[:, 0], yx[:, 1:], q, lastpre)
+            qlr[i] = compute_qlr(yx[:, 0], yx[:, 1:], ccut, q)[1]
+    return chow, qlr

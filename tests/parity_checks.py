@@ -393,3 +393,23 @@ def check_em_block_missing(lib, path=1):
     np.testing.assert_allclose(got["F"], ref["F"], rtol=1e-8, atol=1e-10)
     np.testing.assert_allclose(got["Lam"], ref["Lam"], rtol=1e-8, atol=1e-10)
     np.testing.assert_allclose(got["A"], ref["A"], rtol=1e-8, atol=1e-10)
+
+
+def check_instability(lib, panels, r=4, series=None):
+    """f4: Chow / QLR statistics (HAC) on the hom_fac_1 panel vs the oracle (pinned on the notebook's Table 4(a))."""
+    import dynamic_factor_models_b200 as D
+    data, incl = panels["all_bpdata"], panels["all_inclcode"]
+    mo = R.DFMModel(data, incl, 20, 40, 3, 224, 0, r, 1e-8, 4, 4)
+    R.estimate_factor(mo, computeR2=False)
+    cols = np.arange(data.shape[1]) if series is None else np.asarray(series)
+    sub = R.DFMModel(data[:, cols], np.ones(len(cols), int), 20, 40, 3, 224, 0, r, 1e-8, 4, 4)
+    sub.factor[:] = mo.factor
+    chow_o, qlr_o = R.instability_tests(sub, 104)
+    mg = D.DFMModel(data[:, cols], np.ones(len(cols), int), 20, 40, 3, 224, 0, r, 1e-8, 4, 4)
+    mg.factor[:] = mo.factor                                   # same regressors: the test isolates the instability kernels
+    chow_g, qlr_g = D.instability_tests(mg, 104, lib=lib)
+    assert np.array_equal(np.isnan(chow_o), np.isnan(chow_g)) and np.array_equal(np.isnan(qlr_o), np.isnan(qlr_g))
+    ok = ~np.isnan(chow_o)
+    assert ok.sum() >= 1
+    np.testing.assert_allclose(chow_g[ok], chow_o[ok], rtol=1e-8)
+    np.testing.assert_allclose(qlr_g[ok], qlr_o[ok], rtol=1e-8)

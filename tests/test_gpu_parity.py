@@ -35,6 +35,8 @@ def test_bootstrap_panels(lib, panels): P.check_bootstrap_panels(lib, panels)
 def test_percentiles(lib): P.check_percentiles(lib)
 def test_percentiles_1000(lib): P.check_percentiles(lib, n=1000, d=1536)
 def test_var_missing_rows(lib): P.check_var_missing_rows(lib)
+def test_instability_r4(lib, panels): P.check_instability(lib, panels, r=4, series=list(range(0, 207, 9)))
+def test_instability_r8(lib, panels): P.check_instability(lib, panels, r=8, series=list(range(3, 207, 17)))
 def test_em_p1_balanced(lib): P.check_em(lib, p=1, miss=0.0, path=1)
 def test_em_p2_missing(lib): P.check_em(lib, p=2, miss=0.12, path=1)
 def test_em_p1_missing(lib): P.check_em(lib, p=1, miss=0.1, path=1, rep=10)
@@ -251,3 +253,18 @@ def test_pipelined_host_path_with_missing_data_falls_back(lib):
         del os.environ["DFM_NO_PIPELINE"]
     for k in ("F", "Lam", "loglik"):
         np.testing.assert_allclose(got[k], ref[k], rtol=1e-12, atol=1e-13)
+
+
+def test_table4a_through_gpu(lib, panels, notebook_tables):
+    """Golden Table 4(a) (Stock_Watson.ipynb): rejection rates of the Chow / QLR tests, r = 4 and 8, factors AND test
+    statistics from the GPU path (dfm_estimate_factor -> dfm_instability)."""
+    from scipy.stats import chi2
+    import dynamic_factor_models_b200 as D
+    qlr_thresh = {4: 4 * np.array([5.12, 4.09, 3.59]), 8: 8 * np.array([3.57, 2.98, 2.69])}
+    for r, key in ((4, "chow_qlr_r4"), (8, "chow_qlr_r8")):
+        m = D.DFMModel(panels["all_bpdata"], panels["all_inclcode"], 20, 40, 3, 224, 0, r, 1e-8, 4, 4)
+        D.estimate_factor(m, computeR2=False, lib=lib)
+        chow, qlr = D.instability_tests(m, 104, lib=lib)
+        ok = ~np.isnan(chow)
+        got = [[np.mean(chow[ok] > chi2.ppf(lv, r)), np.mean(qlr[ok] > th)] for lv, th in zip((0.99, 0.95, 0.9), qlr_thresh[r])]
+        np.testing.assert_allclose(np.array(got), np.array(notebook_tables["table4"][key]), atol=1e-6)

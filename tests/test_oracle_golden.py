@@ -97,3 +97,18 @@ def test_table5_canonical_correlations(panels, notebook_tables, vset):
     ok = ~np.isnan(np.column_stack([v.resid, m.factor_var_model.resid])).any(1)
     res = _canonical_correlations(v.resid[ok], m.factor_var_model.resid[ok])
     np.testing.assert_allclose(res, gold["resid"], rtol=5e-5, atol=5e-7)
+
+
+@pytest.mark.slow
+def test_table4a_instability_rejection_rates(panels, notebook_tables):
+    """Stock_Watson.ipynb Table 4(a): share of series whose Chow / QLR statistic (HAC, 6 lags; break 1984Q4) exceeds the
+    1 / 5 / 10 % critical values, r = 4 and 8 -- pins compute_chow, compute_qlr, regress_hac, hac, form_hscrc."""
+    from scipy.stats import chi2
+    qlr_thresh = {4: 4 * np.array([5.12, 4.09, 3.59]), 8: 8 * np.array([3.57, 2.98, 2.69])}
+    for r, key in ((4, "chow_qlr_r4"), (8, "chow_qlr_r8")):
+        m = model(panels["all_bpdata"], panels["all_inclcode"], r)
+        R.estimate_factor(m, computeR2=False)
+        chow, qlr = R.instability_tests(m, 104)
+        ok = ~np.isnan(chow)
+        got = [[np.mean(chow[ok] > chi2.ppf(lv, r)), np.mean(qlr[ok] > th)] for lv, th in zip((0.99, 0.95, 0.9), qlr_thresh[r])]
+        np.testing.assert_allclose(np.array(got), np.array(notebook_tables["table4"][key]), atol=1e-6)
