@@ -130,6 +130,21 @@ function impulse_response(varm, shock_ids::AbstractVector, H::Integer)
     return irf
 end
 
+"""Replaces the per-series loop of Table 4(a) (`compute_chow` / `compute_qlr` on `drop_missing_row([y X])`, Stock_Watson.ipynb):
+Chow and QLR statistics (Bartlett HAC, `q` lags) of every series of `m.data` regressed on `m.factor`; `missing` where the
+series has fewer than `min_obs` observations before or after row `lastpre`."""
+function instability_tests(m, lastpre::Integer; q::Integer = 6, ccut::Real = 0.15, min_obs::Integer = 80)
+    h = gethandle()
+    data = tonan(m.data); F = tonan(m.factor)
+    T, ns = size(data); r = size(F, 2)
+    chow = Vector{Float64}(undef, ns); qlr = Vector{Float64}(undef, ns)
+    check(ccall((:dfm_instability, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Cint, Cint, Cint, Cint, Cdouble, Cint, Cint,
+                 Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cint}),
+                h, data, F, T, ns, r, q, lastpre, Float64(ccut), min_obs, MEM_HOST, chow, qlr, C_NULL, C_NULL), "dfm_instability")
+    return frommissing(chow), frommissing(qlr)
+end
+
 """`estimate!(m, ::NonParametric)` (dfm_functions.ipynb:530-543) and the `Parametric` slot of :23."""
 function estimate!(m, method = Main.NonParametric(); lam_constr_f = nothing, lam_constr_fl = nothing,
                    max_iter::Integer = 50, tol::Real = 1e-6)
