@@ -419,5 +419,6 @@ def instability_tests(m, lastpre, q=6, ccut=0.15, min_obs=80):
         if (~np.isnan(y[:lastpre])).sum() >= min_obs and (~np.isnan(y[lastpre:])).sum() >= min_obs:
             yx, _ = drop_missing_row(np.column_stack([y, X]))
             chow[i] = compute_chow(yx[:, 0], yx[:, 1:], q, lastpre)
-            qlr[i] = compute_qlr(yx[:, 0], yx[:, 1:], ccut, q)[1]
+            Td = yx.shape[0]; n1t = int(np.floor(ccut * Td))            # = compute_qlr(...)[2] (lmr); its q = 0 twin is not needed here
+            qlr[i] = max(compute_chow(yx[:, 0], yx[:, 1:], q, tb) for tb in range(n1t, Td - n1t + 1))
     return chow, qlr
