@@ -241,6 +241,7 @@ static int emb_launch_E(dfm_handle* h, const EmbPlan& e, const double* x, const 
 template <int NCB>
 static int emb_launch_M(dfm_handle* h, const EmbPlan& e, const double* x, const double* dFs, const double* dSff, int T, int N, int r, int batch,
                         double* dL, double* dR, double* dW, double* dlogR, EmState* st) {
+  DFM_SET_SMEM(k_emb_mstep<NCB>, e.smM);
   L(k_emb_mstep<NCB>, e.ntM, e.tsM * batch, 256, e.smM, x, dFs, dSff, T, N, r, e.tsM, e.tper, batch, e.Spart, e.sxxpart,
     e.counters + (size_t)batch * e.ntE, dL, dR, dW, dlogR, e.Cpart, st);
   return DFM_OK;

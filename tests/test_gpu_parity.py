@@ -48,6 +48,7 @@ def test_em_block_missing_frozen(lib): P.check_em_block_missing(lib)
 def test_em_r12_long_run(lib): P.check_em(lib, N=50, r=12, T=420, p=1, miss=0.0, iters=3, path=1)      # run scan: 2 row blocks of the state
 def test_em_p4_balanced_long_run(lib): P.check_em(lib, N=40, r=8, T=330, p=4, miss=0.0, iters=2, path=1)   # companion state k = 32
 def test_em_r20_balanced(lib): P.check_em(lib, N=120, r=20, T=300, p=1, miss=0.0, iters=2, path=1)       # three DMMA column blocks
+def test_em_r28_balanced(lib): P.check_em(lib, N=90, r=28, T=300, p=1, miss=0.0, iters=2, path=1)        # four column blocks, 51 KB M-step tile
 def test_em_batch(lib): P.check_em_batch(lib, path=1)
 def test_als_batch(lib): P.check_als_batch(lib)
 def test_als_balanced_fused(lib): P.check_als_balanced(lib)
