@@ -298,10 +298,16 @@ static int run_em_general(dfm_handle* h, const double* x, const dfm_em_opts* o, 
       cudaLaunchAttribute at[1];
       at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)ncl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
-      CK(cudaLaunchKernelEx(&cfg, k_em_filter_smooth, (const double*)dA, (const double*)dQ, (const double*)dP0, (const double*)dC,
+      cudaError_t ce = cudaLaunchKernelEx(&cfg, k_em_filter_smooth, (const double*)dA, (const double*)dQ, (const double*)dP0, (const double*)dC,
                             (const double*)dBt, (const double*)dqt, (const double*)dslr, (const int*)dnt, (const double*)dCt, T, r, p, dzp, dzf,
-                            dPp, dPf, dFs, dPsF, dSff, dAn, dQn, dll, mi, o->tol, st, dsrc, stgT, want_psf, dxch));
+                            dPp, dPf, dFs, dPsF, dSff, dAn, dQn, dll, mi, o->tol, st, dsrc, stgT, want_psf, dxch);
       PROF_END(); h->launches++;
+      if (ce != cudaSuccess) {                       // the cluster could not be placed: run the plain one-CTA-per-panel launch instead
+        (void)cudaGetLastError();
+        ncl = 1;
+        L(k_em_filter_smooth, batch, 1, ntFS, smFS, dA, dQ, dP0, dC, dBt, dqt, dslr, dnt, dCt, T, r, p, dzp, dzf, dPp, dPf,
+          dFs, dPsF, dSff, dAn, dQn, dll, mi, o->tol, st, dsrc, stgT, want_psf, (double*)nullptr);
+      }
     } else
 #endif
     L(k_em_filter_smooth, batch, 1, ntFS, smFS, dA, dQ, dP0, dC, dBt, dqt, dslr, dnt, dCt, T, r, p, dzp, dzf, dPp, dPf,
