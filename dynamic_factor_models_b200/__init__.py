@@ -8,7 +8,7 @@ creating a handle raises if the library or a CUDA device is missing.
 """
 from ._lib import Library, DFMError, default_library_path  # noqa: F401
 from .api import (  # noqa: F401
-    instability_tests,
+    instability_tests, fitted_value_correlations,
     DFMModel, VARModel, FactorEstimateStats, NonParametric, Parametric, LambdaConstraint,
     construct_constraint, estimate, estimate_factor, estimate_factor_loading, estimate_var,
     impulse_response, bai_ng_criterion, amengual_watson_test, estimate_factor_numbers,

@@ -63,7 +63,7 @@ def default_library_path():
 EXPORTS = ["dfm_version", "dfm_status_string", "dfm_create", "dfm_create_on_stream", "dfm_destroy", "dfm_sync",
            "dfm_launch_count", "dfm_last_error", "dfm_profile_enable", "dfm_profile_query", "dfm_profile_reset",
            "dfm_profile_kernel_name", "dfm_debug_fs_prof", "dfm_standardize", "dfm_pca_score", "dfm_estimate_factor",
-           "dfm_estimate_loading", "dfm_estimate_loading_ex", "dfm_estimate_var", "dfm_irf", "dfm_instability", "dfm_em_kalman", "dfm_em_init_from_factors",
+           "dfm_estimate_loading", "dfm_estimate_loading_ex", "dfm_estimate_var", "dfm_irf", "dfm_instability", "dfm_fit_correlation", "dfm_em_kalman", "dfm_em_init_from_factors",
            "dfm_simulate_panels", "dfm_bootstrap_panels", "dfm_bootstrap_irf", "dfm_percentiles", "dfm_allgather_results", "dfm_shard_range"]
 
 
@@ -369,6 +369,15 @@ class Library:
         if want_q0:
             out["qlr0"] = qlr0
         return out
+
+    def fit_correlation(self, data, F, F_alt, T_break, min_obs=80):
+        """cor(yhat on F, yhat on F_alt) per column of data (Table 4(a), lower half)."""
+        data = np.asarray(data, float); F = np.asarray(F, float); Fa = np.asarray(F_alt, float)
+        T, ns = data.shape; r = F.shape[1]
+        cor = np.empty(ns); st = np.zeros(ns, np.int32)
+        self.check(self.lib.dfm_fit_correlation(self.h, _ptr(to_cm(data)), _ptr(to_cm(F)), _ptr(to_cm(Fa)), T, ns, r, T_break, min_obs, MEM_HOST,
+                                                _ptr(cor), st.ctypes.data_as(c_ip)), "dfm_fit_correlation")
+        return cor
 
     def em_init_from_factors(self, Xs, F, p=1):
         Xs = np.asarray(Xs, float); F = np.asarray(F, float); b = Xs.shape[0] if Xs.ndim == 3 else None

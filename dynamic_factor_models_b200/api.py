@@ -273,3 +273,9 @@ def instability_tests(m, lastpre, q=6, ccut=0.15, min_obs=80, lib=None, want_q0=
     lib = lib or get_library()
     out = lib.instability(m.data, m.factor, lastpre, q=q, ccut=ccut, min_obs=min_obs, want_q0=want_q0)
     return (out["chow"], out["qlr"], out["qlr0"]) if want_q0 else (out["chow"], out["qlr"])
+
+
+def fitted_value_correlations(m, m_alt, lastpre, min_obs=80, lib=None):
+    """cor(yhat, yhat_alt) per series: fitted values of `m.data` on `m.factor` and on `m_alt.factor` (Table 4(a), lower half)."""
+    lib = lib or get_library()
+    return lib.fit_correlation(m.data, m.factor, m_alt.factor, lastpre, min_obs=min_obs)

@@ -1380,6 +1380,30 @@ int dfm_instability(dfm_handle* h, const double* data, const double* F, int T, i
   return finish(h, mem);
 }
 
+int dfm_fit_correlation(dfm_handle* h, const double* data, const double* F, const double* F_alt, int T, int ns, int r, int T_break,
+                        int min_obs, int mem, double* cor, int* status) {
+  if (!h || !data || !F || !F_alt || !cor || T <= 2 || ns <= 0 || r <= 0 || r > 48 || T_break <= 0 || T_break >= T || min_obs < 0)
+    return fail(h, DFM_ERR_ARG, "dfm_fit_correlation: bad argument");
+  CK(cudaSetDevice(h->device));
+  for (int pass = 0; pass < 2; ++pass) {
+    Arena a(pass ? h->ws : nullptr);
+    double* dD = mem == DFM_MEM_HOST ? a.get<double>((size_t)T * ns) : nullptr;
+    double* dF = mem == DFM_MEM_HOST ? a.get<double>((size_t)T * r) : nullptr;
+    double* dFa = mem == DFM_MEM_HOST ? a.get<double>((size_t)T * r) : nullptr;
+    double* dc = a.get<double>(ns); int* dst = a.get<int>(ns);
+    if (!pass) { int rc = ensure_ws(h, a.off); if (rc) return rc; continue; }
+    const double *x, *f, *fa;
+    int rc = stage_in(h, data, dD, (size_t)T * ns, mem, &x); if (rc) return rc;
+    rc = stage_in(h, F, dF, (size_t)T * r, mem, &f); if (rc) return rc;
+    rc = stage_in(h, F_alt, dFa, (size_t)T * r, mem, &fa); if (rc) return rc;
+    CK(cudaMemsetAsync(dst, 0, ns * sizeof(int), h->stream));
+    L(k_fit_corr, ns, 1, 128, (size_t)(2 * (r * r + 2 * r) + 64 + 48 + 8) * 8, x, f, fa, T, ns, r, T_break, min_obs, dc, dst);
+    rc = copy_out(h, cor, dc, ns, mem); if (rc) return rc;
+    if (status) { rc = copy_out(h, status, dst, ns, mem); if (rc) return rc; }
+  }
+  return finish(h, mem);
+}
+
 int dfm_percentiles(dfm_handle* h, const double* recs, long long n, int d, const double* q, int nq, int mem, double* out) {
   if (!h || !recs || !q || !out || n <= 0 || d <= 0 || nq <= 0 || nq > 64) return fail(h, DFM_ERR_ARG, "dfm_percentiles: bad argument");
   for (int k = 0; k < nq; ++k) if (!(q[k] >= 0.0 && q[k] <= 100.0)) return fail(h, DFM_ERR_ARG, "dfm_percentiles: q outside [0, 100]");

@@ -148,4 +148,60 @@ __global__ void k_instability(const double* __restrict__ data, const double* __r
   }
 }
 
+// Fitted-value correlations of Table 4(a): for every series, yhat = F bhat and yhat_alt = F_alt bhat_alt with bhat from
+// ols_skipmissing(y, F, Balanced()) (rows with a missing y or factor dropped; no intercept), correlation over the rows where
+// both fitted values exist.  NaN for series that fail the min_obs rule of the instability loop.  grid (ns), 128 threads;
+// shared 2 (r*r + 2 r) + 64 + 48 doubles.
+__global__ void k_fit_corr(const double* __restrict__ data, const double* __restrict__ Fall, const double* __restrict__ Falt, int T, int ns,
+                           int r, int T_break, int min_obs, double* __restrict__ cor, int* __restrict__ status) {
+  DFM_SMEM(sm);
+  const int i = DFM_BX;
+  const double* y = data + (size_t)i * T;
+  double* S = sm; double* Sa = S + r * r; double* c = Sa + r * r; double* ca = c + r; double* dv = ca + r;   // dv: r (shared by the two factorisations)
+  double* red = dv + 64;
+  int* info = (int*)(red + 44);
+  double npre = 0.0, npost = 0.0;
+  for (int t = DFM_TID; t < T; t += DFM_NT) if (!is_nan(y[t])) { if (t < T_break) npre += 1.0; else npost += 1.0; }
+  npre = block_sum(npre, red); npost = block_sum(npost, red);
+  if (DFM_TID == 0) info[0] = 0;
+  if (npre < (double)min_obs || npost < (double)min_obs) { if (DFM_TID == 0) cor[i] = DFM_NAN; return; }
+  // normal equations of the two regressions (rows with y and all factors of that set present)
+  for (int e = DFM_TID; e < 2 * (r * r + r); e += DFM_NT) {
+    const int which = e / (r * r + r), ee = e % (r * r + r);
+    const double* F = which ? Falt : Fall;
+    double s = 0.0;
+    for (int t = 0; t < T; ++t) {
+      if (is_nan(y[t])) continue;
+      bool ok = true;
+      for (int a = 0; a < r && ok; ++a) ok = !is_nan(F[t + (size_t)T * a]);
+      if (!ok) continue;
+      if (ee < r * r) s += F[t + (size_t)T * (ee % r)] * F[t + (size_t)T * (ee / r)];
+      else s += F[t + (size_t)T * (ee - r * r)] * y[t];
+    }
+    if (ee < r * r) (which ? Sa : S)[ee] = s; else (which ? ca : c)[ee - r * r] = s;
+  }
+  DFM_SYNC();
+  bc_chol(S, r, r, dv, info);
+  bt_trsm_lower(S, r, r, dv, c, 1, 1); bt_trsm_lowerT(S, r, r, dv, c, 1, 1);
+  bc_chol(Sa, r, r, dv, info);
+  bt_trsm_lower(Sa, r, r, dv, ca, 1, 1); bt_trsm_lowerT(Sa, r, r, dv, ca, 1, 1);
+  // correlation of the fitted values over the rows where both factor sets exist (two passes: means, then moments)
+  double n = 0.0, s1 = 0.0, s2 = 0.0;
+  for (int t = DFM_TID; t < T; t += DFM_NT) {
+    double a1 = 0.0, a2 = 0.0; bool ok = true;
+    for (int a = 0; a < r; ++a) { const double f = Fall[t + (size_t)T * a], g = Falt[t + (size_t)T * a]; if (is_nan(f) || is_nan(g)) ok = false; a1 += f * c[a]; a2 += g * ca[a]; }
+    if (ok) { n += 1.0; s1 += a1; s2 += a2; }
+  }
+  n = block_sum(n, red); s1 = block_sum(s1, red); s2 = block_sum(s2, red);
+  const double m1 = s1 / n, m2 = s2 / n;
+  double v11 = 0.0, v22 = 0.0, v12 = 0.0;
+  for (int t = DFM_TID; t < T; t += DFM_NT) {
+    double a1 = 0.0, a2 = 0.0; bool ok = true;
+    for (int a = 0; a < r; ++a) { const double f = Fall[t + (size_t)T * a], g = Falt[t + (size_t)T * a]; if (is_nan(f) || is_nan(g)) ok = false; a1 += f * c[a]; a2 += g * ca[a]; }
+    if (ok) { v11 += (a1 - m1) * (a1 - m1); v22 += (a2 - m2) * (a2 - m2); v12 += (a1 - m1) * (a2 - m2); }
+  }
+  v11 = block_sum(v11, red); v22 = block_sum(v22, red); v12 = block_sum(v12, red);
+  if (DFM_TID == 0) { cor[i] = (n >= 2.0) ? v12 / sqrt(v11 * v22) : DFM_NAN; if (info[0] && status) status[i] = 3; }
+}
+
 }  // namespace dfm

@@ -154,6 +154,12 @@ int dfm_estimate_var(dfm_handle* h, const double* F, int T, int r, int p, int wi
 int dfm_instability(dfm_handle* h, const double* data, const double* F, int T, int ns, int r, int q, int T_break, double ccut,
                     int min_obs, int mem, double* chow /*ns*/, double* qlr /*ns*/, double* qlr0 /*ns or NULL*/, int* status /*ns or NULL*/);
 
+/* Second half of the Table 4(a) loop: cor[i] = correlation between the fitted values of series i on F (full-sample factors)
+ * and on F_alt (factors of another sample; NaN rows outside it), each from ols_skipmissing(y, X, Balanced()) without
+ * intercept, over the rows where both fitted values exist.  Same min_obs rule (NaN otherwise). */
+int dfm_fit_correlation(dfm_handle* h, const double* data, const double* F, const double* F_alt, int T, int ns, int r, int T_break,
+                        int min_obs, int mem, double* cor /*ns*/, int* status /*ns or NULL*/);
+
 /* ---- a11: impulse_response / compute_irf_single_shock!, :793-825 ----------------------- */
 /* irf[:, h, j] = Q M^h G[:, shock_ids[j]],  h = 0..H-1;  irf is r x H x n_shock column-major. */
 int dfm_irf(dfm_handle* h, const double* M, const double* Q, const double* G, int k, int r, int H,

@@ -422,3 +422,19 @@ def instability_tests(m, lastpre, q=6, ccut=0.15, min_obs=80):
             Td = yx.shape[0]; n1t = int(np.floor(ccut * Td))            # = compute_qlr(...)[2] (lmr); its q = 0 twin is not needed here
             qlr[i] = max(compute_chow(yx[:, 0], yx[:, 1:], q, tb) for tb in range(n1t, Td - n1t + 1))
     return chow, qlr
+
+
+def fitted_value_correlations(m, m_alt, lastpre, min_obs=80):
+    """Second half of the per-series loop of Table 4(a): correlation between the fitted values of the regression of each
+    series on the full-sample factors (m.factor) and on the factors of another sample (m_alt.factor), over the rows where
+    both exist (ols_skipmissing(y, X, Balanced()); yhat = X*bhat; drop_missing_row; cor)."""
+    X, Xa = m.factor, m_alt.factor
+    out = np.full(m.ns, np.nan)
+    for i in range(m.ns):
+        y = m.data[:, i]
+        if (~np.isnan(y[:lastpre])).sum() >= min_obs and (~np.isnan(y[lastpre:])).sum() >= min_obs:
+            yh = X @ ols_skipmissing_balanced(y, X)[0]
+            ya = Xa @ ols_skipmissing_balanced(y, Xa)[0]
+            both, _ = drop_missing_row(np.column_stack([yh, ya]))
+            out[i] = np.corrcoef(both[:, 0], both[:, 1])[0, 1]
+    return out

@@ -413,3 +413,17 @@ def check_instability(lib, panels, r=4, series=None):
     assert ok.sum() >= 1
     np.testing.assert_allclose(chow_g[ok], chow_o[ok], rtol=1e-8)
     np.testing.assert_allclose(qlr_g[ok], qlr_o[ok], rtol=1e-8)
+
+
+def check_fit_correlation(lib, panels, r=4):
+    """f4, lower half of Table 4(a): cor(yhat_full, yhat_pre/post) per series vs the oracle (same factors on both sides)."""
+    data, incl = panels["all_bpdata"], panels["all_inclcode"]
+    ms = [R.DFMModel(data, incl, 20, 40, i0, i1, 0, r, 1e-8, 4, 4) for i0, i1 in ((3, 224), (3, 104), (105, 224))]
+    for m in ms:
+        R.estimate_factor(m, computeR2=False)
+    for alt in ms[1:]:
+        ref = R.fitted_value_correlations(ms[0], alt, 104)
+        got = D.fitted_value_correlations(ms[0], alt, 104, lib=lib)
+        assert np.array_equal(np.isnan(ref), np.isnan(got))
+        ok = ~np.isnan(ref)
+        np.testing.assert_allclose(got[ok], ref[ok], rtol=1e-9, atol=1e-11)

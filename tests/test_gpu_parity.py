@@ -35,6 +35,7 @@ def test_bootstrap_panels(lib, panels): P.check_bootstrap_panels(lib, panels)
 def test_percentiles(lib): P.check_percentiles(lib)
 def test_percentiles_1000(lib): P.check_percentiles(lib, n=1000, d=1536)
 def test_var_missing_rows(lib): P.check_var_missing_rows(lib)
+def test_fit_correlation(lib, panels): P.check_fit_correlation(lib, panels)
 def test_instability_r4(lib, panels): P.check_instability(lib, panels, r=4, series=list(range(0, 207, 9)))
 def test_instability_r8(lib, panels): P.check_instability(lib, panels, r=8, series=list(range(3, 207, 17)))
 def test_em_p1_balanced(lib): P.check_em(lib, p=1, miss=0.0, path=1)
@@ -269,3 +270,11 @@ def test_table4a_through_gpu(lib, panels, notebook_tables):
         ok = ~np.isnan(chow)
         got = [[np.mean(chow[ok] > chi2.ppf(lv, r)), np.mean(qlr[ok] > th)] for lv, th in zip((0.99, 0.95, 0.9), qlr_thresh[r])]
         np.testing.assert_allclose(np.array(got), np.array(notebook_tables["table4"][key]), atol=1e-6)
+        # lower half: quantiles of cor(yhat_full, yhat_pre) and cor(yhat_full, yhat_post), factors re-estimated on the sub-samples
+        alts = [D.DFMModel(panels["all_bpdata"], panels["all_inclcode"], 20, 40, i0, i1, 0, r, 1e-8, 4, 4) for i0, i1 in ((3, 104), (105, 224))]
+        cors = []
+        for ma in alts:
+            D.estimate_factor(ma, computeR2=False, lib=lib)
+            c = D.fitted_value_correlations(m, ma, 104, lib=lib)
+            cors.append(np.quantile(c[~np.isnan(c)], [0.05, 0.25, 0.50, 0.75, 0.95]))
+        np.testing.assert_allclose(np.array(cors), np.array(notebook_tables["table4"]["cor_r%d" % r]), atol=2e-6)

@@ -112,3 +112,17 @@ def test_table4a_instability_rejection_rates(panels, notebook_tables):
         ok = ~np.isnan(chow)
         got = [[np.mean(chow[ok] > chi2.ppf(lv, r)), np.mean(qlr[ok] > th)] for lv, th in zip((0.99, 0.95, 0.9), qlr_thresh[r])]
         np.testing.assert_allclose(np.array(got), np.array(notebook_tables["table4"][key]), atol=1e-6)
+
+
+@pytest.mark.slow
+def test_table4a_fitted_value_correlations(panels, notebook_tables):
+    """Stock_Watson.ipynb Table 4(a), lower half: quantiles over the series of cor(yhat_full, yhat_pre) and
+    cor(yhat_full, yhat_post) (factors re-estimated on 1959Q3-1984Q4 / 1985Q1-2014Q4), r = 4 and 8."""
+    pct = [0.05, 0.25, 0.50, 0.75, 0.95]
+    for r, key in ((4, "cor_r4"), (8, "cor_r8")):
+        ms = [model(panels["all_bpdata"], panels["all_inclcode"], r, i0, i1) for i0, i1 in ((3, 224), (3, 104), (105, 224))]
+        for m in ms:
+            R.estimate_factor(m, computeR2=False)
+        got = [np.quantile(c[~np.isnan(c)], pct) for c in (R.fitted_value_correlations(ms[0], ms[1], 104),
+                                                           R.fitted_value_correlations(ms[0], ms[2], 104))]
+        np.testing.assert_allclose(np.array(got), np.array(notebook_tables["table4"][key]), atol=2e-6)
