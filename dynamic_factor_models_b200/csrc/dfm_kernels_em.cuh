@@ -1021,9 +1021,17 @@ __global__ void EM_FS_BOUNDS k_em_filter_smooth(const double* __restrict__ Aall,
       DFM_SYNC();
       bc_chol(T2, k, k, dvL, info);
       FS_T(20);
-      bt_trsm_lower(T2, k, k, dvL, T3, k, k);
+      // J = (Pf M') Pp^-1 = (Pf M') U U',  U = L^-T:  U' = L^-1 by forward substitution on the rows of the identity (thread per
+      // row, registers), then two tensor-core products -- the back substitution, whose row stays in shared memory, cost
+      // 16 K cycles at k = 32
+      for (int e = DFM_TID; e < kk; e += DFM_NT) { const int j = e % k, a = e / k; Pp[e] = (j == a) ? 1.0 : 0.0; }
+      DFM_SYNC();
+      bt_trsm_lower(T2, k, k, dvL, Pp, k, k);                                   // Pp[j + k a] = (L^-1)[a, j]  (= U[j, a])
       FS_T(21);
-      bt_trsm_lowerT(T2, k, k, dvL, T3, k, k);                                  // T3 = J
+      wt_gemm(T3, 1, k, Pp, k, 1, k, k, k, [&](int i, int j, double v) { T2[i + k * j] = v; });      // (Pf M') U
+      DFM_SYNC();
+      wt_gemm(T2, 1, k, Pp, 1, k, k, k, k, [&](int i, int j, double v) { T3[i + k * j] = v; });      // ... U' = J
+      DFM_SYNC();
       jpp = sp; jpf = sf;
     }
     FS_T(15);
