@@ -105,14 +105,20 @@ __global__ void k_instability(const double* __restrict__ data, const double* __r
   int* info = (int*)(red + 44);
   int* idx = (int*)(red + 48);            // [T] kept rows
   int* cnt = info + 1;                    // [1] Td, [2] n_pre, [3] n_post
+  // row flags in parallel (bit 0: y observed, bit 1: y and every factor observed), then one thread compacts them
+  for (int t = DFM_TID; t < T; t += DFM_NT) {
+    const bool yok = !is_nan(y[t]);
+    bool ok = yok;
+    for (int a = 0; a < r && ok; ++a) ok = !is_nan(Fall[t + (size_t)T * a]);
+    idx[t] = (yok ? 1 : 0) | (ok ? 2 : 0);
+  }
+  DFM_SYNC();
   if (DFM_TID == 0) {
     int Td = 0, npre = 0, npost = 0;
     for (int t = 0; t < T; ++t) {
-      const bool yok = !is_nan(y[t]);
-      if (yok) { if (t < T_break) ++npre; else ++npost; }
-      bool ok = yok;
-      for (int a = 0; a < r && ok; ++a) ok = !is_nan(Fall[t + (size_t)T * a]);
-      if (ok) idx[Td++] = t;
+      const int f = idx[t];
+      if (f & 1) { if (t < T_break) ++npre; else ++npost; }
+      if (f & 2) idx[Td++] = t;                       // (Td <= t: in-place compaction)
     }
     info[0] = 0; cnt[0] = Td; cnt[1] = npre; cnt[2] = npost;
   }
