@@ -174,8 +174,13 @@ static int make_panel_tmap(dfm_handle* h, const double* X, int T, long long rows
   cuuint64_t dims[2] = {(cuuint64_t)T, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)T * 8};
   cuuint32_t box[2] = {F2_TS, 8 * F2_SBS}, es[2] = {1, 1};
+  CUtensorMapL2promotion l2p = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+  if (const char* e_ = getenv("DFM_TMAP_L2")) {           // A/B knob: 0 none, 1 64 B, 2 128 B, 3 256 B (default)
+    const int v_ = atoi(e_);
+    l2p = v_ == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v_ == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : v_ == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+  }
   CUresult rc = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)X, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_SWIZZLE_NONE, l2p, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (rc != CUDA_SUCCESS) { snprintf(h->err, sizeof(h->err), "cuTensorMapEncodeTiled failed (%d)", (int)rc); return DFM_ERR_CUDA; }
   return DFM_OK;
 #endif
