@@ -145,6 +145,18 @@ function instability_tests(m, lastpre::Integer; q::Integer = 6, ccut::Real = 0.1
     return frommissing(chow), frommissing(qlr)
 end
 
+"""Second half of the Table 4(a) loop: `cor(yhat, yhat_alt)` per series, fitted values on `m.factor` and on `m_alt.factor`."""
+function fitted_value_correlations(m, m_alt, lastpre::Integer; min_obs::Integer = 80)
+    h = gethandle()
+    data = tonan(m.data); F = tonan(m.factor); Fa = tonan(m_alt.factor)
+    T, ns = size(data); r = size(F, 2)
+    cor = Vector{Float64}(undef, ns)
+    check(ccall((:dfm_fit_correlation, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Cint, Cint, Cint, Cint, Cint, Ptr{Cdouble}, Ptr{Cint}),
+                h, data, F, Fa, T, ns, r, lastpre, min_obs, MEM_HOST, cor, C_NULL), "dfm_fit_correlation")
+    return frommissing(cor)
+end
+
 """`estimate!(m, ::NonParametric)` (dfm_functions.ipynb:530-543) and the `Parametric` slot of :23."""
 function estimate!(m, method = Main.NonParametric(); lam_constr_f = nothing, lam_constr_fl = nothing,
                    max_iter::Integer = 50, tol::Real = 1e-6)
