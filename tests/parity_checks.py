@@ -427,3 +427,24 @@ def check_fit_correlation(lib, panels, r=4):
         assert np.array_equal(np.isnan(ref), np.isnan(got))
         ok = ~np.isnan(ref)
         np.testing.assert_allclose(got[ok], ref[ok], rtol=1e-9, atol=1e-11)
+
+
+def check_cluster_sizes(lib, N=160, r=12, T=700):
+    """General path, few panels: the thread-block cluster split of the frozen runs (8 / 2 CTAs per panel) gives the result of the
+    single-CTA launch (different summation order of the tile partials only).  (The emulation build has no clusters.)"""
+    import os
+    X, _ = simulate_panel(N, r, T, rep=5)
+    m = R.DFMModel(X, np.ones(N, int), 20, 40, 1, T, 0, r, 1e-8, 4, 1)
+    R.estimate_factor(m, max_iter=2, computeR2=False)
+    Lam, Rv, A, Q = K.init_from_factors(X, m.factor, 1)
+    outs = {}
+    for nc in ("1", "2", "8"):
+        os.environ["DFM_CLUSTER"] = nc
+        try:
+            outs[nc] = lib.em_kalman(X, Lam, Rv, A, Q, p=1, max_iter=4, path=1, want_PF=False)
+        finally:
+            del os.environ["DFM_CLUSTER"]
+    for nc in ("2", "8"):
+        np.testing.assert_allclose(outs[nc]["loglik"], outs["1"]["loglik"], rtol=1e-12)
+        np.testing.assert_allclose(outs[nc]["F"], outs["1"]["F"], rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(outs[nc]["Lam"], outs["1"]["Lam"], rtol=1e-9, atol=1e-11)

@@ -278,3 +278,6 @@ def test_table4a_through_gpu(lib, panels, notebook_tables):
             c = D.fitted_value_correlations(m, ma, 104, lib=lib)
             cors.append(np.quantile(c[~np.isnan(c)], [0.05, 0.25, 0.50, 0.75, 0.95]))
         np.testing.assert_allclose(np.array(cors), np.array(notebook_tables["table4"]["cor_r%d" % r]), atol=2e-6)
+
+
+def test_cluster_sizes_agree(lib): P.check_cluster_sizes(lib)
