@@ -1,9 +1,14 @@
 // dfm_kernels_em.cuh -- GENERAL (any r, p with k = r*p <= 48, any N, T, missing data) kernels of the
 // state-space EM, row a' of SURVEY.md section 8.  No reference code exists for this path
 // (dfm_functions.ipynb:23 is an empty placeholder); the spec is oracle/kalman_em.py.
-// One EM iteration = k_em_prep -> k_em_contract -> k_em_filter_smooth -> k_em_mstep_series.
-// The fused small-k fast path lives in dfm_kernels_fused.cuh; this file is also the path the host-emulation
-// tests exercise.
+// One EM iteration = contraction -> k_em_filter_smooth -> measurement M-step -> closing step:
+//   panels with missing data:  k_em_contract (masked C_t) -> k_em_filter_smooth -> k_em_mstep_series -> k_em_prep
+//   balanced panels (r <= 32):  k_emb_contract -> k_em_filter_smooth -> k_emb_mstep -> k_emb_close   (dfm_kernels_emb.cuh)
+// k_em_filter_smooth (one CTA, or a thread-block cluster, per panel) holds the filter, the smoother and the transition
+// M-step: explicit covariance steps, frozen steps, and frozen RUNS as parallel-in-time scans on the tensor path
+// (em_run_scan_tc); the small dense helpers it uses (block-cooperative Cholesky, transposed solves, DMMA tile products)
+// live in dfm_common.cuh.  The fused small-k fast path lives in dfm_kernels_fused*.cuh; this file is also the path the
+// host-emulation tests exercise (DMMA loops have plain twins under DFM_EMU).
 #pragma once
 #include "dfm_common.cuh"
 
