@@ -448,3 +448,30 @@ def check_cluster_sizes(lib, N=160, r=12, T=700):
         np.testing.assert_allclose(outs[nc]["loglik"], outs["1"]["loglik"], rtol=1e-12)
         np.testing.assert_allclose(outs[nc]["F"], outs["1"]["F"], rtol=1e-9, atol=1e-11)
         np.testing.assert_allclose(outs[nc]["Lam"], outs["1"]["Lam"], rtol=1e-9, atol=1e-11)
+
+
+def check_instability_edges(lib):
+    """f4 edge cases: a series with too few observations on one side of the break -> NaN (as the notebook's rule), an
+    all-missing series -> NaN, bad arguments -> status 1 (no exception from the kernel side, DFMError from the binding)."""
+    rng = np.random.default_rng(3)
+    T, r = 180, 3
+    F = rng.standard_normal((T, r)); F[:4] = np.nan                         # factor rows outside the estimation window
+    Y = F @ rng.standard_normal((r, 4)) + 0.5 * rng.standard_normal((T, 4))
+    Y[np.isnan(Y)] = np.nan
+    Y[:, 1] = np.nan                                                         # all missing
+    Y[:70, 2] = np.nan                                                       # 20 observations before the break row 90: < 80
+    out = lib.instability(Y, F, 90, q=4, ccut=0.15, min_obs=80)
+    assert np.isfinite(out["chow"][0]) and np.isfinite(out["qlr"][0]) and out["qlr"][0] >= out["chow"][0] * (1 - 1e-12)
+    assert np.isnan(out["chow"][1]) and np.isnan(out["qlr"][1]) and np.isnan(out["chow"][2])
+    assert np.isfinite(out["chow"][3])
+    m = type("M", (), {})(); m.data = Y; m.factor = F; m.ns = 4
+    chow_o, qlr_o = R.instability_tests(m, 90, q=4)
+    ok = ~np.isnan(chow_o)
+    np.testing.assert_allclose(out["chow"][ok], chow_o[ok], rtol=1e-8); np.testing.assert_allclose(out["qlr"][ok], qlr_o[ok], rtol=1e-8)
+    for bad in (dict(T_break=0), dict(T_break=T), dict(ccut=0.6), dict(q=9)):
+        kw = dict(T_break=90, q=4, ccut=0.15); kw.update(bad)
+        try:
+            lib.instability(Y, F, kw["T_break"], q=kw["q"], ccut=kw["ccut"])
+            raise AssertionError("bad argument accepted: %r" % (bad,))
+        except D.DFMError as e:
+            assert e.code == 1

@@ -36,6 +36,7 @@ def test_percentiles(lib): P.check_percentiles(lib)
 def test_var_missing_rows(lib): P.check_var_missing_rows(lib)
 def test_cluster_sizes_call_shape(lib): P.check_cluster_sizes(lib, N=40, r=4, T=120)      # (no clusters under emulation: checks the call path)
 def test_fit_correlation(lib, panels): P.check_fit_correlation(lib, panels)
+def test_instability_edges(lib): P.check_instability_edges(lib)
 def test_instability_few_series(lib, panels): P.check_instability(lib, panels, r=4, series=[5, 60])
 def test_em_p1_balanced(lib): P.check_em(lib, p=1, miss=0.0)
 def test_em_p2_missing(lib): P.check_em(lib, p=2, miss=0.12)

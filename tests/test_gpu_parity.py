@@ -36,6 +36,7 @@ def test_percentiles(lib): P.check_percentiles(lib)
 def test_percentiles_1000(lib): P.check_percentiles(lib, n=1000, d=1536)
 def test_var_missing_rows(lib): P.check_var_missing_rows(lib)
 def test_fit_correlation(lib, panels): P.check_fit_correlation(lib, panels)
+def test_instability_edges(lib): P.check_instability_edges(lib)
 def test_instability_r4(lib, panels): P.check_instability(lib, panels, r=4, series=list(range(0, 207, 9)))
 def test_instability_r8(lib, panels): P.check_instability(lib, panels, r=8, series=list(range(3, 207, 17)))
 def test_em_p1_balanced(lib): P.check_em(lib, p=1, miss=0.0, path=1)
